@@ -1,0 +1,439 @@
+#!/usr/bin/env python3
+"""Benchmark of the batched differential-IK hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one ``solve_ik`` pass over one batch of B = 65536 UR5 instances per
+GPU (FrameTask(tool0) + PostureTask + default limits, examples/arm_ur5.py).
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement".
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "IK solves/sec (batch=65536 per GPU, UR5 6-DOF, FrameTask+PostureTask, default limits)"
+UNIT = "IK steps/s"
+BYTES_PER_STEP = 96  # q 24 B + frame target 48 B read, v 24 B written
+L2_BYTES = 126 * 1024 * 1024
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, all host cores
+# ---------------------------------------------------------------------------
+
+_CPU_CTX = {}
+
+
+def _cpu_init():
+    from oracle import kinematics as okin
+    from pink_b200 import workloads
+    from pink_b200.robots import load_robot_description
+
+    robot = load_robot_description("ur5_description")
+    table = robot.model.table()
+    _CPU_CTX.update(table=table, model=robot.model, okin=okin, wl=workloads,
+                    frame=table.frame_names.index("tool0"))
+
+
+def _cpu_chunk(args):
+    """Solve instances [lo, hi) of the seeded workload with the oracle."""
+    seed, n, lo, hi = args
+    if not _CPU_CTX:
+        _cpu_init()
+    from oracle import ik as oik
+
+    table, model, okin, wl, f = (_CPU_CTX[k] for k in ("table", "model", "okin", "wl", "frame"))
+    q, T = cpu_workload(table, okin, wl, f, n, seed)
+    tasks = [
+        {"type": "frame", "frame": f, "cost": np.ones(6), "gain": 1.0, "lm_damping": 1.0,
+         "target": (T[lo:hi, :, :3], T[lo:hi, :, 3])},
+        {"type": "posture", "cost": 1e-3, "gain": 1.0, "lm_damping": 0.0,
+         "target": wl.ur5_posture_reference(model)},
+    ]
+    t0 = time.perf_counter()
+    v, status = oik.solve_ik_batch(table, q[lo:hi], tasks, wl.UR5_DT, wl.UR5_DAMPING)
+    return time.perf_counter() - t0, float(np.abs(v).sum())
+
+
+def cpu_workload(table, okin, wl, f, n, seed):
+    rng = np.random.default_rng(seed)
+    q = wl.sample_configurations(table, n, rng)
+    qt = wl.perturb_configurations(table, q, rng)
+    R, p = okin.frame_placement(table, okin.forward_kinematics(table, qt), f)
+    T = np.concatenate([R, p[:, :, None]], axis=2).astype(np.float32).astype(np.float64)
+    return q.astype(np.float32).astype(np.float64), T
+
+
+def cpu_throughput(per_core: int, cores: int, seed: int, pool=None):
+    """IK steps/s of the oracle over ``cores`` processes, ``per_core`` instances each."""
+    import multiprocessing as mp
+
+    n = per_core * cores
+    jobs = [(seed, n, i * per_core, (i + 1) * per_core) for i in range(cores)]
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init)
+    try:
+        t0 = time.perf_counter()
+        pool.map(_cpu_chunk, jobs)
+        wall = time.perf_counter() - t0
+    finally:
+        if own:
+            pool.close()
+            pool.join()
+    return n / wall, wall, n
+
+
+def run_reference_arm(args):
+    """``--impl reference``: the reference's CPU path (oracle port; Pink,
+    Pinocchio and quadprog are not installable offline) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    cores = os.cpu_count() or 1
+    per_core = args.cpu_sample
+    pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init)
+    try:
+        for _ in range(args.warmup):
+            cpu_throughput(max(8, per_core // 8), cores, 1, pool)
+        t0 = time.perf_counter()
+        total = 0
+        for k in range(args.steps):
+            _, _, n = cpu_throughput(per_core, cores, 100 + k, pool)
+            total += n
+        wall = time.perf_counter() - t0
+    finally:
+        pool.close()
+        pool.join()
+    value = total / wall
+    sample = f"{per_core * cores} seeded UR5 instances per step ({per_core} per core), per-instance fp64 loop"
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, cpu=True),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, cpu=False):
+    cfg = {
+        "workload": "UR5 6-DOF (hand-authored URDF), FrameTask(tool0, 1, 1, lm_damping=1) + PostureTask(1e-3), "
+                    "ConfigurationLimit + VelocityLimit, dt=1/200, damping=1e-12 (examples/arm_ur5.py)",
+        "batch_per_gpu": args.batch,
+        "targets": "reachable: FK(q + N(0, 0.3^2)) clipped to limits; seed 20260922",
+    }
+    if not cpu:
+        cfg["l2"] = f"rotating {args.nbuf} input/output sets ({args.nbuf * args.batch * BYTES_PER_STEP / 2**20:.0f} MiB > 126 MiB L2)"
+    return cfg
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+                for name, val in zip(names, s[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(mx)) if mx else None,
+            "reasons": sorted(reasons),
+            "samples": len(sm),
+        }
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from pink_b200 import FrameTask, PostureTask, _cabi, workloads
+    from pink_b200.engine import get_engine
+    from pink_b200.limits import ConfigurationLimit, VelocityLimit
+    from pink_b200.robots import load_robot_description
+    from pink_b200.solve_ik import describe_problem
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; pink_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    # model constants: built on rank 0, broadcast over NCCL (north_star), then
+    # turned into device tables by every rank
+    from pink_b200 import parallel
+
+    robot = load_robot_description("ur5_description") if rank == 0 else None
+    model = parallel.broadcast_model(robot.model if rank == 0 else None, device)
+    eng = get_engine(model, device)
+    table = eng.table
+    B, NBUF = args.batch, args.nbuf
+    f = table.frame_names.index("tool0")
+
+    # seeded synthetic inputs, one set per buffer; rank r owns shard r of the job
+    rng = np.random.default_rng(workloads.SEED + 1000 * rank)
+    qs, ts, vs, ss = [], [], [], []
+    for b in range(NBUF):
+        q = workloads.sample_configurations(table, B, rng)
+        qt = workloads.perturb_configurations(table, q, rng)
+        q_d = torch.as_tensor(q, dtype=torch.float32, device=device)
+        oMf, _ = eng.forward_kinematics(torch.as_tensor(qt, dtype=torch.float32, device=device))
+        qs.append(q_d)
+        ts.append(oMf[:, f].reshape(B, 12).contiguous())
+        vs.append(torch.empty((B, 6), dtype=torch.float32, device=device))
+        ss.append(torch.empty((B,), dtype=torch.int32, device=device))
+    frame_task = FrameTask("tool0", position_cost=1.0, orientation_cost=1.0, lm_damping=1.0)
+    frame_task.set_target(ts[0])
+    posture_task = PostureTask(cost=1e-3)
+    posture_task.set_target(workloads.ur5_posture_reference(model))
+    limits = [ConfigurationLimit(model), VelocityLimit(model)]
+    prob, _, _ = describe_problem(model, B, [frame_task, posture_task], workloads.UR5_DT, workloads.UR5_DAMPING,
+                                  limits, True)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(k):
+        i = k % NBUF
+        eng.solve_ik(prob, qs[i], ts[i], vs[i], ss[i])
+
+    # ---- device-resident throughput ("value") ---------------------------------
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    launches0 = _cabi.load().pk_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for k in range(args.steps):
+            step(k)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        # keep the GPU under the same load a little longer so the sampler sees it
+        t_end = time.time() + 0.6
+        k = 0
+        while time.time() < t_end:
+            step(k)
+            k += 1
+        torch.cuda.synchronize()
+    launches = _cabi.load().pk_launch_count() - launches0 - k
+    bad = int(sum(int((s != 0).sum().item()) for s in ss))
+
+    # same loop replayed from a CUDA graph: removes host launch latency from the
+    # per-kernel duration used for the roofline figure
+    g_ms = None
+    try:
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for k in range(NBUF):
+                    step(k)
+        torch.cuda.current_stream(device).wait_stream(side)
+        reps = max(1, args.steps // NBUF)
+        graph.replay()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(reps):
+            graph.replay()
+        g1.record()
+        barrier()
+        g_ms = g0.elapsed_time(g1) / (reps * NBUF)
+    except Exception as exc:  # pragma: no cover - graph capture is an optimisation only
+        print(f"[bench] CUDA graph timing skipped: {exc}", file=sys.stderr)
+
+    # ---- end to end through host buffers ("e2e") ---------------------------------
+    q_h = [torch.empty((B, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
+    t_h = [torch.empty((B, 12), dtype=torch.float32).pin_memory() for _ in range(2)]
+    v_h = [torch.empty((B, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
+    s_h = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
+    for i in range(2):
+        q_h[i].copy_(qs[i].cpu())
+        t_h[i].copy_(ts[i].cpu())
+
+    def e2e_step(k):
+        i = k % 2
+        eng.solve_ik_host(prob, q_h[i], t_h[i], v_h[i], s_h[i])
+
+    for k in range(max(3, args.warmup)):
+        e2e_step(k)
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = args.steps
+    h0.record()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    h1.record()
+    barrier()
+    e2e_ms = h0.elapsed_time(h1)
+    e2e_ok = bool(torch.allclose(v_h[0], vs[0].cpu(), atol=0, rtol=0)) if NBUF >= 1 else True
+
+    # ---- max over ranks -----------------------------------------------------------
+    times = torch.tensor([ms, e2e_ms, g_ms if g_ms is not None else 0.0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, g_ms_max = (float(x) for x in times.cpu())
+    if g_ms is not None:
+        g_ms = g_ms_max
+
+    # ---- solve + gather variant (multi-GPU only): v gathered on every rank --------
+    gather_ms = None
+    if world > 1:
+        gathered = torch.empty((world * B, 6), dtype=torch.float32, device=device)
+        for k in range(3):
+            step(k)
+            dist.all_gather_into_tensor(gathered, vs[k % NBUF])
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for k in range(args.steps):
+            step(k)
+            dist.all_gather_into_tensor(gathered, vs[k % NBUF])
+        a1.record()
+        barrier()
+        t = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gather_ms = float(t.item())
+
+    if rank == 0:
+        peak, peak_kind = load_peaks()
+        total_steps = world * B * args.steps
+        value = total_steps / (ms * 1e-3)
+        kern_ms = g_ms if g_ms is not None else ms / args.steps
+        achieved = B * BYTES_PER_STEP / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_kind": peak_kind,
+                "kernel": "pk::ik_chain_kernel<6>", "kernel_ms": kern_ms,
+                "timing": "CUDA graph replay of %d launches" % NBUF if g_ms is not None else "eager launches",
+                "algorithmic_bytes_per_launch": B * BYTES_PER_STEP,
+            },
+            "e2e": {
+                "value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": B * (6 + 12) * 4, "d2h_bytes_per_step": B * (6 + 1) * 4,
+                "ms_per_step": e2e_ms / e2e_steps, "bitwise_equal_to_device_path": e2e_ok,
+                "api": "pk_solve_ik_batched_host (pinned host buffers, chunked H2D / kernel / D2H overlap)",
+            },
+            "nonzero_status": bad,
+        }
+        if gather_ms is not None:
+            line["solve_plus_allgather"] = {"value": total_steps / (gather_ms * 1e-3), "unit": UNIT}
+        if not args.no_cpu and world == 1:
+            cores = os.cpu_count() or 1
+            cv, wall, n = cpu_throughput(args.cpu_sample, cores, 7)
+            line["cpu_baseline"] = {
+                "value": cv, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{n} seeded UR5 instances ({args.cpu_sample} per core, {wall:.1f} s wall), "
+                          "fp64 oracle port of the reference path (Pink/Pinocchio/quadprog unavailable offline)",
+            }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--nbuf", type=int, default=32)
+    ap.add_argument("--cpu-sample", type=int, default=1500, help="oracle instances per host core")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

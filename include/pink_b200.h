@@ -1,0 +1,187 @@
+/*
+ * pink_b200 -- C ABI of the batched differential-IK engine (sm_100a).
+ *
+ * The reference (stephane-caron/pink, /root/reference) is pure Python and has
+ * no FFI: its boundary for this path is the Python API
+ *   pink.solve_ik(configuration, tasks, dt, solver, damping, limits, ...)
+ *     -> pink/solve_ik.py:206-275
+ *   pink.build_ik(...) -> qpsolvers.Problem(P, q, G, h, A, b)
+ *     -> pink/solve_ik.py:152-203
+ *   pink.Configuration.update / get_frame_jacobian / get_transform_frame_to_world
+ *     -> pink/configuration.py:131-164, 203-254
+ *   Task.compute_error / compute_jacobian -> pink/tasks/task.py:66-113
+ * Each entry point below names the reference interface it evaluates for a
+ * whole batch of independent instances.  The Python classes in pink_b200/
+ * (same names and arguments as the reference's) marshal into these calls
+ * through ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it
+ *    asynchronously, no host synchronisation, no allocation on the hot path;
+ *  - the caller owns every buffer; device entry points take DEVICE pointers,
+ *    *_host entry points take HOST pointers (pinned for best throughput) and
+ *    perform the H2D / D2H copies themselves on `stream`;
+ *  - return value: 0 on success, non-zero for API misuse / CUDA errors
+ *    (message via pk_last_error()).  Per-instance numerical outcomes never
+ *    fail the call; they are reported in status[].
+ *  - SE(3) values are 12 floats, row-major [R | p] (3 rows of 4);
+ *    twists and Jacobian rows are [linear(3); angular(3)];
+ *    free-flyer q = [x y z qx qy qz qw | joints], v = [v(3) w(3) | rates].
+ */
+#ifndef PINK_B200_H
+#define PINK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PK_ABI_VERSION 1
+
+#define PK_MAX_JOINTS 58  /* 1-dof joints (free-flyer excluded)            */
+#define PK_MAX_NV 64      /* PK_MAX_JOINTS + 6 (active sets are 64-bit masks) */
+#define PK_MAX_FRAMES 256
+#define PK_MAX_TASKS 12
+#define PK_MAX_SHARED 192 /* floats of targets shared by all instances     */
+
+/* per-instance status bits written by the solve entry points */
+#define PK_STATUS_OK 0
+#define PK_STATUS_NO_SOLUTION 1   /* pink.exceptions.NoSolutionFound (solve_ik.py:271-273) */
+#define PK_STATUS_OUT_OF_LIMITS 2 /* NotWithinConfigurationLimits (configuration.py:186-194) */
+#define PK_STATUS_NOT_POSDEF 4    /* Hessian not positive definite in fp32 */
+#define PK_STATUS_ITER_LIMIT 8    /* active-set iteration cap hit; v is feasible, maybe sub-optimal */
+
+/* joint types */
+#define PK_JOINT_REVOLUTE 0
+#define PK_JOINT_PRISMATIC 1
+
+/* task types (pink/tasks/{frame,relative_frame,posture,com}_task.py) */
+#define PK_TASK_FRAME 0
+#define PK_TASK_RELATIVE_FRAME 1
+#define PK_TASK_POSTURE 2
+#define PK_TASK_COM 3
+
+/* bodies: -2 universe, -1 root body (floating base if free_flyer, else the
+ * universe), j >= 0 the body moved by 1-dof joint j                        */
+
+typedef struct PkModelDesc {
+  int32_t njoints;      /* number of 1-dof joints, parents-first order   */
+  int32_t free_flyer;   /* 1: root is a free-flyer ("root_joint")        */
+  int32_t nq;           /* njoints (+7)                                   */
+  int32_t nv;           /* njoints (+6)                                   */
+  const int32_t* parent;        /* [njoints] parent body (-1 or joint index) */
+  const int32_t* jtype;         /* [njoints] PK_JOINT_*                   */
+  const double* joint_placement;/* [njoints][12] placement in parent body */
+  const double* axis;           /* [njoints][3] unit axis in joint frame  */
+  int32_t nframes;
+  const int32_t* frame_body;    /* [nframes] body the frame is fixed to   */
+  const double* frame_placement;/* [nframes][12]                          */
+  const double* mass;           /* [njoints+1] by body+1 (root body first)*/
+  const double* com;            /* [njoints+1][3] CoM in body frame       */
+} PkModelDesc;
+
+typedef struct PkTaskDesc {
+  int32_t type;          /* PK_TASK_*                                     */
+  int32_t frame;         /* frame index (FRAME / RELATIVE_FRAME)          */
+  int32_t root;          /* root frame index (RELATIVE_FRAME)             */
+  int32_t target_offset; /* float offset of the target: inside one row of
+                            `targets` (per instance) or inside
+                            PkProblemDesc.shared (target_shared = 1).
+                            frame: 12 floats [R|p]; posture: nq; com: 3   */
+  int32_t target_shared;
+  float cost[6];         /* frame: [pos(3), ori(3)]; com: [3]; posture: cost[0] */
+  float gain;            /* Task.gain   (pink/tasks/task.py:146)          */
+  float lm_damping;      /* Task.lm_damping (pink/tasks/task.py:160)      */
+} PkTaskDesc;
+
+typedef struct PkProblemDesc {
+  int32_t ntasks;
+  PkTaskDesc tasks[PK_MAX_TASKS];
+  float dt;              /* solve_ik(..., dt)                             */
+  float damping;         /* solve_ik(..., damping)                        */
+  int32_t target_stride; /* floats per instance in `targets`              */
+  int32_t safety_break;  /* 1: out-of-limit instances are not solved and
+                            get PK_STATUS_OUT_OF_LIMITS; 0: flagged but solved */
+  /* Box inequality rows, per tangent index i (q index = i + nq - nv):
+   *   ConfigurationLimit (pink/limits/configuration_limit.py:108-121):
+   *      +dq_i <= cfg_gain (cfg_hi[i] - q_i),  -dq_i <= -cfg_gain (cfg_lo[i] - q_i)
+   *   VelocityLimit (pink/limits/velocity_limit.py:115-121):
+   *      +-dq_i <= dt * vel[i]
+   * +-INFINITY disables a row.                                            */
+  float cfg_gain;
+  float cfg_lo[PK_MAX_NV];
+  float cfg_hi[PK_MAX_NV];
+  float vel[PK_MAX_NV];
+  /* Configuration.check_limits (pink/configuration.py:181-201), tolerance
+   * already applied by the caller: flagged if q_i < chk_lo[i] or > chk_hi[i] */
+  float chk_lo[PK_MAX_NV];
+  float chk_hi[PK_MAX_NV];
+  float shared[PK_MAX_SHARED];
+} PkProblemDesc;
+
+typedef struct PkModel PkModel; /* opaque; immutable after creation */
+
+int pk_abi_version(void);
+const char* pk_last_error(void); /* thread-local */
+
+/* Build device-resident constant tables of a model on CUDA device `device`. */
+int pk_model_create(const PkModelDesc* desc, int device, PkModel** out);
+void pk_model_destroy(PkModel* model);
+
+/* pink.solve_ik for B instances (pink/solve_ik.py:206-275).
+ *   q[B][nq], targets[B][target_stride] -> v[B][nv], status[B] (may be NULL). */
+int pk_solve_ik_batched(const PkModel* model, const PkProblemDesc* prob,
+                        const float* q, const float* targets, float* v,
+                        int32_t* status, int64_t B, void* stream);
+
+/* Same through HOST buffers: H2D of q/targets, solve, D2H of v/status, all on
+ * `stream`, chunked so copies overlap the kernels.  Returns after enqueueing;
+ * the caller synchronises the stream before reading v.                     */
+int pk_solve_ik_batched_host(PkModel* model, const PkProblemDesc* prob,
+                             const float* q_host, const float* targets_host,
+                             float* v_host, int32_t* status_host, int64_t B,
+                             void* stream);
+
+/* pink.build_ik for B instances (pink/solve_ik.py:152-203):
+ *   H[B][nv][nv], c[B][nv], h[B][4][nv] with rows
+ *   [cfg upper, cfg lower, vel upper, vel lower] (the right-hand sides of
+ *   G = [P;-P;P;-P], +INFINITY where the row does not exist).             */
+int pk_build_ik_batched(const PkModel* model, const PkProblemDesc* prob,
+                        const float* q, const float* targets, float* H,
+                        float* c, float* h, int64_t B, void* stream);
+
+/* Task.compute_error / compute_jacobian of task `task_index`
+ * (pink/tasks/task.py:66-113): e[B][k], J[B][k][nv]; k = 6 frame tasks,
+ * 3 com, nv - root_nv posture.                                             */
+int pk_task_terms_batched(const PkModel* model, const PkProblemDesc* prob,
+                          int32_t task_index, const float* q,
+                          const float* targets, float* e, float* J, int64_t B,
+                          void* stream);
+
+/* Configuration.update (pink/configuration.py:163-164): frame placements
+ * oMf[B][nframes][12]; `com` [B][3] optional (pin.centerOfMass).           */
+int pk_forward_kinematics_batched(const PkModel* model, const float* q,
+                                  float* oMf, float* com, int64_t B,
+                                  void* stream);
+
+/* Configuration.get_frame_jacobian (pink/configuration.py:203-236), LOCAL:
+ * J[B][6][nv].                                                             */
+int pk_frame_jacobian_batched(const PkModel* model, int32_t frame,
+                              const float* q, float* J, int64_t B,
+                              void* stream);
+
+/* Configuration.integrate (pink/configuration.py:273-283):
+ * q_out = q (+) v * dt, quaternion renormalised.                           */
+int pk_integrate_batched(const PkModel* model, const float* q, const float* v,
+                         float dt, float* q_out, int64_t B, void* stream);
+
+/* Number of kernels this library has launched in the calling process
+ * (instrumentation for bench.py's gpu_launches).                           */
+int64_t pk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINK_B200_H */

@@ -80,6 +80,19 @@ def _slice_task(task, i):
     return t
 
 
+def _slice_task_range(task, lo, hi):
+    """Task restricted to instances ``[lo, hi)`` (shared targets untouched)."""
+    tgt = task.get("target")
+    t = dict(task)
+    if task["type"] in ("frame", "relative_frame"):
+        R, p = np.asarray(tgt[0]), np.asarray(tgt[1])
+        t["target"] = (R[lo:hi] if R.ndim == 3 else R, p[lo:hi] if p.ndim == 2 else p)
+    else:
+        a = np.asarray(tgt)
+        t["target"] = a[lo:hi] if a.ndim == 2 else a
+    return t
+
+
 def solve_ik(m, q, tasks, dt, damping=1e-12, limits=None, safety_break=True):
     """One IK step of one instance: ``(v, status)``.
 

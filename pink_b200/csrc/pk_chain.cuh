@@ -1,0 +1,205 @@
+// One IK step of a fixed-base serial chain, one instance per thread, all state in
+// registers (UR5-class arms: nq = nv = NJ <= 8).
+//
+// Path (reference file:line):
+//   Configuration.check_limits            pink/configuration.py:181-201
+//   FK + LOCAL frame Jacobian             pink/configuration.py:163-164, 233-235
+//   FrameTask error / Jacobian            pink/tasks/frame_task.py:176-227
+//   PostureTask error / Jacobian          pink/tasks/posture_task.py:100-129
+//   Task.compute_qp_objective             pink/tasks/task.py:145-166
+//   H = damping I + sum H_t, c = sum c_t  pink/solve_ik.py:55-60
+//   ConfigurationLimit / VelocityLimit    pink/limits/configuration_limit.py:108-121,
+//                                         pink/limits/velocity_limit.py:115-121
+//   QP solve, v = dq / dt                 pink/solve_ik.py:270-275
+//
+// The parameter block is passed by value as a kernel argument, i.e. it lives in
+// the constant bank: every thread reads the same address at the same time, so
+// model constants cost no registers and no memory traffic.
+#pragma once
+
+#include "pk_math.cuh"
+#include "pk_lsq.cuh"
+
+namespace pk {
+
+constexpr int kChainMaxFrameTasks = 2;
+
+struct ChainJoint {
+  float X[12];  // placement in the parent joint frame, row-major [R | p]
+  float ax, ay, az;
+  int type;  // PK_JOINT_*
+};
+
+struct ChainFrameTask {
+  int body;       // joint index the frame is fixed to (-1: world)
+  float X[12];    // frame placement in that body
+  float cost[6];  // [pos(3), ori(3)]
+  float gain, lm;
+  int tgt_off;
+  int tgt_shared;
+};
+
+template <int NJ>
+struct ChainParams {
+  ChainJoint joint[NJ];
+  int n_frame_tasks;
+  ChainFrameTask ft[kChainMaxFrameTasks];
+  int has_posture;
+  float posture_w2, posture_gain, posture_lm;
+  int posture_off, posture_shared;
+  float dt, inv_dt, damping;
+  float cfg_gain;
+  float cfg_lo[NJ], cfg_hi[NJ], vel[NJ], chk_lo[NJ], chk_hi[NJ];
+  int target_stride;
+  int safety_break;
+  float shared[12 * kChainMaxFrameTasks + NJ];
+};
+
+// NFT = number of FrameTasks (compile time, so that the stacked Jacobian has a
+// static shape and stays in registers).
+template <int NJ, int NFT>
+PK_HD void ik_step_chain(const ChainParams<NJ>& P, const float (&q)[NJ], const float* __restrict__ trow,
+                         float (&v)[NJ], int& status_out) {
+  static_assert(NFT >= 0 && NFT <= kChainMaxFrameTasks, "unsupported number of frame tasks");
+  constexpr int K = 6 * NFT;
+  constexpr int KA = K > 0 ? K : 1;
+  int status = 0;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+    if (q[j] < P.chk_lo[j] || q[j] > P.chk_hi[j]) status |= PK_STATUS_OUT_OF_LIMITS;
+  if (status && P.safety_break) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) v[j] = 0.f;
+    status_out = status;
+    return;
+  }
+
+  // ---- forward kinematics: oMi[j] = oMi[j-1] X_j exp(S_j q_j) -----------------
+  SE3f T = identity_se3();
+  V3 pj[NJ], wj[NJ];  // world origin and world axis of every joint
+  SE3f Tf[NFT > 0 ? NFT : 1];
+#pragma unroll
+  for (int t = 0; t < NFT; ++t) Tf[t] = load_se3(P.ft[t].X);  // frames fixed to the world body
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const ChainJoint& Jn = P.joint[j];
+    const V3 axis = v3(Jn.ax, Jn.ay, Jn.az);
+    SE3f X = load_se3(Jn.X);
+    SE3f Tl;
+    if (Jn.type == PK_JOINT_REVOLUTE) {
+      float s, c;
+      sincos_f(q[j], &s, &c);
+      Tl.R = mul(X.R, rot_axis(axis, s, c));
+      Tl.p = X.p;
+    } else {
+      Tl.R = X.R;
+      Tl.p = X.p + mul(X.R, q[j] * axis);
+    }
+    T = compose(T, Tl);
+    pj[j] = T.p;
+    wj[j] = mul(T.R, axis);
+#pragma unroll
+    for (int t = 0; t < NFT; ++t)
+      if (P.ft[t].body == j) Tf[t] = compose(T, load_se3(P.ft[t].X));
+  }
+
+  // ---- objective in square-root form: rows of A / b are W J and W alpha e ----------
+  float A[KA][NJ];
+  float b[KA];
+  float diag = P.damping;  // damping + sum of Levenberg-Marquardt terms
+
+#pragma unroll
+  for (int t = 0; t < NFT; ++t) {
+    const ChainFrameTask& Kt = P.ft[t];
+    const SE3f Tt = load_se3(Kt.tgt_shared ? (P.shared + Kt.tgt_off) : (trow + Kt.tgt_off));
+    // e = log6(T_b^-1 T_t)
+    const SE3f Tbt = act_inv(Tf[t], Tt);
+    Log3 L = log3(Tbt.R);
+    float e[6];
+    log6(Tbt, L, e);
+    // J = -Jlog6(T_t^-1 T_b) bJ_b ;  log3(R^T) = -log3(R), same angle and coefficients
+    SE3f Ttb;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) Ttb.R.m[3 * i + k] = Tbt.R.m[3 * k + i];
+    Ttb.p = -1.f * mul(Ttb.R, Tbt.p);
+    L.w = -1.f * L.w;
+    M3 Am, Bm;
+    jlog6(Ttb, L, Am, Bm);
+
+    float mu = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float ew = Kt.cost[k] * Kt.gain * e[k];
+      b[6 * t + k] = ew;
+      mu = fmaf(ew, ew, mu);
+    }
+    diag = fmaf(Kt.lm, mu, diag);
+
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      V3 lin, ang;
+      if (P.joint[j].type == PK_JOINT_REVOLUTE) {
+        ang = wj[j];
+        lin = cross(wj[j], Tf[t].p - pj[j]);
+      } else {
+        ang = v3(0.f, 0.f, 0.f);
+        lin = wj[j];
+      }
+      const V3 jl = mulT(Tf[t].R, lin);
+      const V3 ja = mulT(Tf[t].R, ang);
+      const V3 tl = mul(Am, jl) + mul(Bm, ja);
+      const V3 ta = mul(Am, ja);
+      const float on = (j <= Kt.body) ? -1.f : 0.f;  // joints past the frame do not move it
+      A[6 * t + 0][j] = on * Kt.cost[0] * tl.x;
+      A[6 * t + 1][j] = on * Kt.cost[1] * tl.y;
+      A[6 * t + 2][j] = on * Kt.cost[2] * tl.z;
+      A[6 * t + 3][j] = on * Kt.cost[3] * ta.x;
+      A[6 * t + 4][j] = on * Kt.cost[4] * ta.y;
+      A[6 * t + 5][j] = on * Kt.cost[5] * ta.z;
+    }
+  }
+
+  // diagonal part: posture rows w (x_j + alpha e_j) and sqrt(diag) x_j merged into d_j x_j + beta_j
+  float d[NJ], beta[NJ];
+  {
+    float se = 0.f;
+    float pe[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      pe[j] = 0.f;
+      if (P.has_posture) {
+        const float* qref = P.posture_shared ? (P.shared + P.posture_off) : (trow + P.posture_off);
+        pe[j] = q[j] - qref[j];
+        se = fmaf(pe[j], pe[j], se);
+      }
+    }
+    const float w2 = P.has_posture ? P.posture_w2 : 0.f;
+    diag = fmaf(P.posture_lm * P.posture_gain * P.posture_gain * w2, se, diag);
+    const float dd = sqrtf(w2 + diag);
+    const float k = (dd > 0.f) ? P.posture_gain * w2 / dd : 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      d[j] = dd;
+      beta[j] = k * pe[j];
+    }
+  }
+
+  // ---- box rows ------------------------------------------------------------------
+  float lo[NJ], hi[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const float vb = P.dt * P.vel[j];
+    hi[j] = fminf(P.cfg_gain * (P.cfg_hi[j] - q[j]), vb);
+    lo[j] = fmaxf(P.cfg_gain * (P.cfg_lo[j] - q[j]), -vb);
+  }
+
+  float x[NJ];
+  status |= BoxLSQ<K, NJ, true>::run(A, b, d, beta, lo, hi, K, NJ, x);
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) v[j] = x[j] * P.inv_dt;
+  status_out = status;
+}
+
+}  // namespace pk

@@ -1,0 +1,371 @@
+// General IK step: any joint tree (optional free-flyer), any mix of FrameTask /
+// RelativeFrameTask / PostureTask / ComTask, box limits.  One instance per thread
+// with run-time sized per-thread arrays.  This is the path every model can take;
+// it also backs the export entry points (build_ik, task terms, FK, frame Jacobian).
+// The register-resident chain kernel (pk_chain.cuh) and the warp-cooperative tree
+// kernel (pk_tree.cuh) are specialisations that must agree with it.
+//
+// Reference path: see the list at the top of pk_chain.cuh, plus
+//   RelativeFrameTask   pink/tasks/relative_frame_task.py:173-246
+//   ComTask             pink/tasks/com_task.py:120-148
+//   free-flyer columns  pink/configuration.py:220-228
+#pragma once
+
+#include "pk_math.cuh"
+#include "pk_lsq.cuh"
+
+namespace pk {
+
+// Device-resident constant tables of a model (pointers into one device buffer).
+struct DevModel {
+  int njoints, free_flyer, nq, nv, nframes;
+  const int* parent;       // [njoints]
+  const int* jtype;        // [njoints]
+  const float* jX;         // [njoints][12]
+  const float* axis;       // [njoints][3]
+  const int* frame_body;   // [nframes]
+  const float* fX;         // [nframes][12]
+  const float* mass;       // [njoints + 1]
+  const float* com;        // [njoints + 1][3]
+  const uint64_t* anc;     // [njoints + 2] joints on the path to body b (index b + 2)
+  float total_mass;
+};
+
+struct DevTask {
+  int type, frame, root, tgt_off, tgt_shared, body, root_body;
+  float cost[6];
+  float gain, lm;
+};
+
+// Problem description as the kernels read it (filled from PkProblemDesc).
+struct DevProblem {
+  int ntasks;
+  DevTask tasks[PK_MAX_TASKS];
+  float dt, inv_dt, damping, cfg_gain;
+  int target_stride, safety_break;
+  float cfg_lo[PK_MAX_NV], cfg_hi[PK_MAX_NV], vel[PK_MAX_NV], chk_lo[PK_MAX_NV], chk_hi[PK_MAX_NV];
+  float shared[PK_MAX_SHARED];
+};
+
+// Optional per-instance outputs of the export entry points (nullptr = skip).
+struct GenericOut {
+  float* v;        // [nv]
+  int32_t* status; // [1]
+  float* H;        // [nv][nv]
+  float* c;        // [nv]
+  float* h;        // [4][nv]
+  float* e;        // [k]   of task `task_index`
+  float* J;        // [k][nv]
+  int task_index;
+  float* oMf;      // [nframes][12]
+  float* com;      // [3]
+  float* Jf;       // [6][nv] LOCAL Jacobian of frame `jac_frame`
+  int jac_frame;
+};
+
+constexpr int kGenericMaxRows = 48;  // stacked task rows (6 per frame task, 3 per CoM task)
+
+template <int NJMAX, int NVMAX>
+struct Generic {
+  SE3f root;
+  SE3f Tw[NJMAX];
+
+  PK_HD SE3f body_placement(int body) const {
+    if (body == -2) return identity_se3();
+    if (body == -1) return root;
+    return Tw[body];
+  }
+
+  PK_HD void forward_kinematics(const DevModel& M, const float* q) {
+    int rq = 0;
+    root = identity_se3();
+    if (M.free_flyer) {
+      root.p = v3(q[0], q[1], q[2]);
+      root.R = quat_to_matrix(q[3], q[4], q[5], q[6]);
+      rq = 7;
+    }
+    for (int j = 0; j < M.njoints; ++j) {
+      const SE3f X = load_se3(M.jX + 12 * j);
+      const V3 axis = v3(M.axis[3 * j], M.axis[3 * j + 1], M.axis[3 * j + 2]);
+      SE3f Tl;
+      if (M.jtype[j] == PK_JOINT_REVOLUTE) {
+        float s, c;
+        sincos_f(q[rq + j], &s, &c);
+        Tl.R = mul(X.R, rot_axis(axis, s, c));
+        Tl.p = X.p;
+      } else {
+        Tl.R = X.R;
+        Tl.p = X.p + mul(X.R, q[rq + j] * axis);
+      }
+      const int par = M.parent[j];
+      Tw[j] = compose(par < 0 ? root : Tw[par], Tl);
+    }
+  }
+
+  // Column `i` (tangent index) of the LOCAL Jacobian of a frame placed at Tf on `body`.
+  PK_HD void frame_jac_col(const DevModel& M, int body, const SE3f& Tf, int i, V3& lin, V3& ang) const {
+    lin = v3(0.f, 0.f, 0.f);
+    ang = v3(0.f, 0.f, 0.f);
+    const int rv = M.free_flyer ? 6 : 0;
+    if (i < rv) {
+      if (body == -2) return;
+      // Ad_{(oM_root^-1 oMf)^-1}: base twist seen from the frame
+      const SE3f Trf = act_inv(root, Tf);
+      const V3 ek = v3(i % 3 == 0 ? 1.f : 0.f, i % 3 == 1 ? 1.f : 0.f, i % 3 == 2 ? 1.f : 0.f);
+      if (i < 3) {
+        lin = mulT(Trf.R, ek);
+      } else {
+        lin = mulT(Trf.R, cross(ek, Trf.p));
+        ang = mulT(Trf.R, ek);
+      }
+      return;
+    }
+    const int j = i - rv;
+    if (body < 0 || !((M.anc[body + 2] >> j) & 1ull)) return;
+    const V3 axis = v3(M.axis[3 * j], M.axis[3 * j + 1], M.axis[3 * j + 2]);
+    const V3 aw = mul(Tw[j].R, axis);
+    if (M.jtype[j] == PK_JOINT_REVOLUTE) {
+      lin = mulT(Tf.R, cross(aw, Tf.p - Tw[j].p));
+      ang = mulT(Tf.R, aw);
+    } else {
+      lin = mulT(Tf.R, aw);
+    }
+  }
+
+  PK_HD V3 center_of_mass(const DevModel& M) const {
+    V3 acc = v3(0.f, 0.f, 0.f);
+    for (int b = -1; b < M.njoints; ++b) {
+      const float m = M.mass[b + 1];
+      if (m == 0.f) continue;
+      const SE3f T = body_placement(b);
+      const V3 cl = v3(M.com[3 * (b + 1)], M.com[3 * (b + 1) + 1], M.com[3 * (b + 1) + 2]);
+      acc = acc + m * (mul(T.R, cl) + T.p);
+    }
+    return (1.f / M.total_mass) * acc;
+  }
+
+  // One step. `q` [nq], `trow` per-instance targets.
+  PK_HD void step(const DevModel& M, const DevProblem& P, const float* q, const float* trow, const GenericOut& out) {
+    const int nv = M.nv;
+    const int rq = M.free_flyer ? 7 : 0;
+    const int rv = M.free_flyer ? 6 : 0;
+    int status = 0;
+    for (int i = rv; i < nv; ++i) {
+      const float qi = q[i + rq - rv];
+      if (qi < P.chk_lo[i] || qi > P.chk_hi[i]) status |= PK_STATUS_OUT_OF_LIMITS;
+    }
+    const bool skip = status && P.safety_break;
+
+    forward_kinematics(M, q);
+
+    if (out.oMf) {
+      for (int f = 0; f < M.nframes; ++f) {
+        const SE3f Tf = compose(body_placement(M.frame_body[f]), load_se3(M.fX + 12 * f));
+        store_se3(Tf, out.oMf + 12 * f);
+      }
+    }
+    if (out.com) {
+      const V3 cm = center_of_mass(M);
+      out.com[0] = cm.x; out.com[1] = cm.y; out.com[2] = cm.z;
+    }
+    if (out.Jf) {
+      const int f = out.jac_frame;
+      const int body = M.frame_body[f];
+      const SE3f Tf = compose(body_placement(body), load_se3(M.fX + 12 * f));
+      for (int i = 0; i < nv; ++i) {
+        V3 lin, ang;
+        frame_jac_col(M, body, Tf, i, lin, ang);
+        out.Jf[0 * nv + i] = lin.x; out.Jf[1 * nv + i] = lin.y; out.Jf[2 * nv + i] = lin.z;
+        out.Jf[3 * nv + i] = ang.x; out.Jf[4 * nv + i] = ang.y; out.Jf[5 * nv + i] = ang.z;
+      }
+    }
+    if (!P.ntasks && !out.v && !out.H) {
+      if (out.status) *out.status = status;
+      return;
+    }
+
+    // square-root form of the objective: rows of A / b, diagonal terms d / beta
+    float A[kGenericMaxRows][NVMAX];
+    float b[kGenericMaxRows];
+    float d[NVMAX], beta[NVMAX];
+    float pw2[NVMAX], pc[NVMAX];  // posture contributions to H_ii and c_i
+    for (int i = 0; i < nv; ++i) { pw2[i] = 0.f; pc[i] = 0.f; }
+    int K = 0;
+    float diag = P.damping;
+    float Jw[6][NVMAX];
+
+    for (int t = 0; t < P.ntasks; ++t) {
+      const DevTask& Kt = P.tasks[t];
+      const float* tgt = Kt.tgt_shared ? (P.shared + Kt.tgt_off) : (trow + Kt.tgt_off);
+      const bool want = (out.e != nullptr || out.J != nullptr) && out.task_index == t;
+      if (Kt.type == PK_TASK_POSTURE) {
+        // e = (q (-) q*)[root_nv:], J = I[root_nv:, :]
+        const float w2 = Kt.cost[0] * Kt.cost[0];
+        float se = 0.f;
+        for (int i = rv; i < nv; ++i) {
+          const float e = q[i + rq - rv] - tgt[i + rq - rv];
+          se = fmaf(e, e, se);
+          pw2[i] += w2;
+          pc[i] = fmaf(Kt.gain * w2, e, pc[i]);
+          if (want && out.e) out.e[i - rv] = e;
+        }
+        diag = fmaf(Kt.lm * Kt.gain * Kt.gain * w2, se, diag);
+        if (want && out.J)
+          for (int r = 0; r < nv - rv; ++r)
+            for (int i = 0; i < nv; ++i) out.J[r * nv + i] = (i == r + rv) ? 1.f : 0.f;
+        continue;
+      }
+      int k = 6;
+      float e[6];
+      if (Kt.type == PK_TASK_COM) {
+        k = 3;
+        const V3 cm = center_of_mass(M);
+        e[0] = cm.x - tgt[0]; e[1] = cm.y - tgt[1]; e[2] = cm.z - tgt[2];
+        e[3] = e[4] = e[5] = 0.f;
+        // subtree masses and first moments, leaves to root
+        float sm[NJMAX];
+        V3 smc[NJMAX];
+        for (int j = 0; j < M.njoints; ++j) {
+          const V3 cl = v3(M.com[3 * (j + 1)], M.com[3 * (j + 1) + 1], M.com[3 * (j + 1) + 2]);
+          sm[j] = M.mass[j + 1];
+          smc[j] = sm[j] * (mul(Tw[j].R, cl) + Tw[j].p);
+        }
+        for (int j = M.njoints - 1; j >= 0; --j) {
+          const int par = M.parent[j];
+          if (par >= 0) { sm[par] += sm[j]; smc[par] = smc[par] + smc[j]; }
+        }
+        const float invM = 1.f / M.total_mass;
+        for (int i = 0; i < nv; ++i) {
+          V3 col = v3(0.f, 0.f, 0.f);
+          if (i < rv) {
+            const V3 ek = v3(i % 3 == 0 ? 1.f : 0.f, i % 3 == 1 ? 1.f : 0.f, i % 3 == 2 ? 1.f : 0.f);
+            if (i < 3) col = mul(root.R, ek);
+            else col = mul(root.R, cross(ek, mulT(root.R, cm - root.p)));
+          } else {
+            const int j = i - rv;
+            if (sm[j] > 0.f) {
+              const V3 axis = v3(M.axis[3 * j], M.axis[3 * j + 1], M.axis[3 * j + 2]);
+              const V3 aw = mul(Tw[j].R, axis);
+              if (M.jtype[j] == PK_JOINT_REVOLUTE)
+                col = (sm[j] * invM) * cross(aw, (1.f / sm[j]) * smc[j] - Tw[j].p);
+              else
+                col = (sm[j] * invM) * aw;
+            }
+          }
+          Jw[0][i] = col.x; Jw[1][i] = col.y; Jw[2][i] = col.z;
+        }
+      } else {
+        const SE3f Tf = compose(body_placement(Kt.body), load_se3(M.fX + 12 * Kt.frame));
+        const SE3f Tt = load_se3(tgt);
+        M3 Am, Bm;
+        float sign;
+        SE3f Trf;  // relative task: frame in root-frame coordinates
+        SE3f Tr;
+        if (Kt.type == PK_TASK_FRAME) {
+          const SE3f Tbt = act_inv(Tf, Tt);
+          Log3 L = log3(Tbt.R);
+          log6(Tbt, L, e);
+          SE3f Ttb;
+          for (int a = 0; a < 3; ++a)
+            for (int c2 = 0; c2 < 3; ++c2) Ttb.R.m[3 * a + c2] = Tbt.R.m[3 * c2 + a];
+          Ttb.p = -1.f * mul(Ttb.R, Tbt.p);
+          L.w = -1.f * L.w;
+          jlog6(Ttb, L, Am, Bm);
+          sign = -1.f;
+          Trf = identity_se3();
+          Tr = identity_se3();
+        } else {
+          Tr = compose(body_placement(Kt.root_body), load_se3(M.fX + 12 * Kt.root));
+          Trf = act_inv(Tr, Tf);
+          const SE3f Ttf = act_inv(Tt, Trf);
+          const Log3 L = log3(Ttf.R);
+          log6(Ttf, L, e);
+          jlog6(Ttf, L, Am, Bm);
+          sign = 1.f;
+        }
+        for (int i = 0; i < nv; ++i) {
+          V3 lin, ang;
+          frame_jac_col(M, Kt.body, Tf, i, lin, ang);
+          if (Kt.type == PK_TASK_RELATIVE_FRAME) {
+            V3 rl, ra;
+            frame_jac_col(M, Kt.root_body, Tr, i, rl, ra);
+            // Ad_{T_rf^-1} [rl; ra] = [R^T (rl - p x ra); R^T ra]
+            lin = lin - mulT(Trf.R, rl - cross(Trf.p, ra));
+            ang = ang - mulT(Trf.R, ra);
+          }
+          const V3 tl = sign * (mul(Am, lin) + mul(Bm, ang));
+          const V3 ta = sign * mul(Am, ang);
+          Jw[0][i] = tl.x; Jw[1][i] = tl.y; Jw[2][i] = tl.z;
+          Jw[3][i] = ta.x; Jw[4][i] = ta.y; Jw[5][i] = ta.z;
+        }
+      }
+      if (want) {
+        if (out.e)
+          for (int r = 0; r < k; ++r) out.e[r] = e[r];
+        if (out.J)
+          for (int r = 0; r < k; ++r)
+            for (int i = 0; i < nv; ++i) out.J[r * nv + i] = Jw[r][i];
+      }
+      float mu = 0.f;
+      for (int r = 0; r < k; ++r) {
+        const float ew = Kt.cost[r] * Kt.gain * e[r];
+        mu = fmaf(ew, ew, mu);
+        if (Kt.cost[r] == 0.f) continue;  // zero cost == row deleted (tests/test_frame_task.py:143-181)
+        if (K < kGenericMaxRows) {
+          b[K] = ew;
+          for (int i = 0; i < nv; ++i) A[K][i] = Kt.cost[r] * Jw[r][i];
+        }
+        ++K;
+      }
+      diag = fmaf(Kt.lm, mu, diag);
+    }
+    if (K > kGenericMaxRows) { status |= PK_STATUS_NOT_POSDEF; K = kGenericMaxRows; }
+    for (int i = 0; i < nv; ++i) {
+      const float dd = sqrtf(pw2[i] + diag);
+      d[i] = dd;
+      beta[i] = dd > 0.f ? pc[i] / dd : 0.f;
+    }
+
+    float lo[NVMAX], hi[NVMAX];
+    for (int i = 0; i < nv; ++i) {
+      const float qi = (i >= rv) ? q[i + rq - rv] : 0.f;
+      const float vb = P.dt * P.vel[i];
+      const float ch = P.cfg_gain * (P.cfg_hi[i] - qi);
+      const float cl = P.cfg_gain * (P.cfg_lo[i] - qi);
+      hi[i] = fminf(ch, vb);
+      lo[i] = fmaxf(cl, -vb);
+      if (out.h) {
+        out.h[0 * nv + i] = ch;
+        out.h[1 * nv + i] = -cl;
+        out.h[2 * nv + i] = vb;
+        out.h[3 * nv + i] = vb;
+      }
+    }
+    if (out.H)
+      for (int i = 0; i < nv; ++i)
+        for (int j = 0; j < nv; ++j) {
+          float s = (i == j) ? d[i] * d[i] : 0.f;
+          for (int r = 0; r < K; ++r) s = fmaf(A[r][i], A[r][j], s);
+          out.H[i * nv + j] = s;
+        }
+    if (out.c)
+      for (int i = 0; i < nv; ++i) {
+        float s = d[i] * beta[i];
+        for (int r = 0; r < K; ++r) s = fmaf(A[r][i], b[r], s);
+        out.c[i] = s;
+      }
+
+    if (out.v) {
+      float x[NVMAX];
+      if (skip) {
+        for (int i = 0; i < nv; ++i) out.v[i] = 0.f;
+      } else {
+        status |= BoxLSQ<kGenericMaxRows, NVMAX, false>::run(A, b, d, beta, lo, hi, K, nv, x);
+        for (int i = 0; i < nv; ++i) out.v[i] = x[i] * P.inv_dt;
+      }
+    }
+    if (out.status) *out.status = status;
+  }
+};
+
+}  // namespace pk

@@ -1,0 +1,218 @@
+// Per-instance QP of the IK step, solved in square-root (least-squares) form.
+//
+// pink.solve_ik hands qpsolvers the strictly convex QP (pink/solve_ik.py:202,270)
+//
+//     minimise 1/2 x^T H x + c^T x   subject to  G x <= h
+//
+// with H = sum_t (W_t J_t)^T (W_t J_t) + (damping + sum_t mu_t) I and
+// c = sum_t alpha_t (W_t J_t)^T W_t e_t (pink/tasks/task.py:145-166,
+// pink/solve_ik.py:55-60).  When the rows of G come from ConfigurationLimit and
+// VelocityLimit they are all +-e_i (pink/limits/configuration_limit.py:119,
+// pink/limits/velocity_limit.py:119): the feasible set is a box lo <= x <= hi.
+//
+// H is a Gram matrix.  With A the stacked weighted task Jacobians (K x n), b the
+// stacked weighted errors, and the diagonal terms (posture task, damping, LM)
+// folded into d_i x_i + beta_i, the same problem reads
+//
+//     minimise 1/2 |A x + b|^2 + 1/2 sum_i (d_i x_i + beta_i)^2,  lo <= x <= hi
+//
+// (H = A^T A + diag(d^2), c = A^T b + d*beta).  Working on [diag(d); A] instead of
+// H halves the exponent of the condition number, which is what makes fp32 viable:
+// cond(H) reaches 1e6..1e7 on the reference's own humanoid examples (CoM cost 200
+// next to posture cost 0.1) while cond([D; A]) stays ~1e3.
+//
+// Method: primal active set on the box.  Every equality-constrained subproblem is
+// a linear least-squares problem on the free coordinates, solved from scratch by
+// Householder QR of [diag(d); A] with the diagonal block ON TOP: the reflection of
+// column k only involves row k and the K dense rows, so a factorisation costs
+// ~2 (K+1) n^2 flops (about what forming H and its Cholesky would) and needs no
+// up/down-dating.  Fixed coordinates are masked (unit diagonal, zero column), so
+// indices stay static and, for compile-time sizes, everything lives in registers.
+// Multipliers come from the factored gradient A^T (A x + b) + d (d x + beta), whose
+// rounding error scales with the residual, not with |H| |x|.
+//
+// The minimiser of a strictly convex QP is unique, so the result equals what
+// quadprog's Goldfarb-Idnani iteration returns (the parity target).
+#pragma once
+
+#include "pk_math.cuh"
+
+#include "../../include/pink_b200.h"
+
+namespace pk {
+
+// Packed lower triangle (used for the exported Hessian).
+PK_HD constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+// KMAX x N capacity.  FIXED: K == KMAX and n == N at compile time (all loops
+// unrolled, constant indices => registers); else run-time sizes, rolled loops.
+template <int KMAX, int N, bool FIXED>
+struct BoxLSQ {
+  static constexpr int UN = FIXED ? N : 1;
+  static constexpr int UK = FIXED ? (KMAX > 0 ? KMAX : 1) : 1;
+  static constexpr int KA = KMAX > 0 ? KMAX : 1;
+  static constexpr int NU = N * (N - 1) / 2 > 0 ? N * (N - 1) / 2 : 1;
+
+  PK_HD static constexpr int ut(int k, int j) { return k * N - k * (k + 1) / 2 + (j - k - 1); }  // j > k
+
+  // Least squares on the free coordinates with x fixed on `act`.  y receives the
+  // full solution (fixed entries copied from x).  Returns false if singular.
+  static PK_HD bool eqp(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N], const float (&beta)[N],
+                        int K_, int n_, uint64_t act, const float (&x)[N], float (&y)[N]) {
+    const int K = FIXED ? KMAX : K_;
+    const int n = FIXED ? N : n_;
+    float Aw[KA][N];
+    float zb[KA];
+    float Rd[N], Ru[NU], zt[N];
+    bool ok = true;
+    // masked copy, right-hand side = b + A_act x_act
+#pragma unroll(UK)
+    for (int r = 0; r < K; ++r) {
+      float s = b[r];
+#pragma unroll(UN)
+      for (int j = 0; j < n; ++j) {
+        const bool fx = (act >> j) & 1ull;
+        Aw[r][j] = fx ? 0.f : A[r][j];
+        if (fx) s = fmaf(A[r][j], x[j], s);
+      }
+      zb[r] = s;
+    }
+#pragma unroll(UN)
+    for (int k = 0; k < n; ++k) {
+      const bool fx = (act >> k) & 1ull;
+      float sigma = 0.f;
+#pragma unroll(UK)
+      for (int r = 0; r < K; ++r) sigma = fmaf(Aw[r][k], Aw[r][k], sigma);
+      const float alpha = fx ? 1.f : d[k];
+      zt[k] = fx ? -x[k] : beta[k];
+      const float norm = sqrtf(fmaf(alpha, alpha, sigma));
+      ok = ok && (norm > 0.f);
+      const float v0 = alpha + norm;                      // alpha >= 0: no cancellation
+      const float tau = (sigma > 0.f) ? 1.f / (norm * v0) : 0.f;  // 2 / |v|^2
+      Rd[k] = (sigma > 0.f) ? -norm : alpha;
+#pragma unroll(UN)
+      for (int j = k + 1; j < n; ++j) {
+        float s = 0.f;
+#pragma unroll(UK)
+        for (int r = 0; r < K; ++r) s = fmaf(Aw[r][k], Aw[r][j], s);
+        s *= tau;
+        Ru[ut(k, j)] = -s * v0;
+#pragma unroll(UK)
+        for (int r = 0; r < K; ++r) Aw[r][j] = fmaf(-s, Aw[r][k], Aw[r][j]);
+      }
+      float s = v0 * zt[k];
+#pragma unroll(UK)
+      for (int r = 0; r < K; ++r) s = fmaf(Aw[r][k], zb[r], s);
+      s *= tau;
+      zt[k] = fmaf(-s, v0, zt[k]);
+#pragma unroll(UK)
+      for (int r = 0; r < K; ++r) zb[r] = fmaf(-s, Aw[r][k], zb[r]);
+    }
+    // R y = -zt
+#pragma unroll(UN)
+    for (int kk = 0; kk < n; ++kk) {
+      const int k = n - 1 - kk;
+      float s = -zt[k];
+#pragma unroll(UN)
+      for (int j = k + 1; j < n; ++j) s = fmaf(-Ru[ut(k, j)], y[j], s);
+      y[k] = ((act >> k) & 1ull) ? x[k] : s / Rd[k];
+    }
+    return ok;
+  }
+
+  // Returns status bits (0, NOT_POSDEF, NO_SOLUTION, ITER_LIMIT).
+  static PK_HD int run(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N], const float (&beta)[N],
+                       const float (&lo)[N], const float (&hi)[N], int K_, int n_, float (&x)[N]) {
+    const int K = FIXED ? KMAX : K_;
+    const int n = FIXED ? N : n_;
+    int status = 0;
+    // infeasible box <=> quadprog reports no solution
+#pragma unroll(UN)
+    for (int i = 0; i < n; ++i) {
+      x[i] = 0.f;
+      if (lo[i] > hi[i]) status |= PK_STATUS_NO_SOLUTION;
+    }
+    if (status) return status;
+    float y[N];
+    if (!eqp(A, b, d, beta, K, n, 0ull, x, y)) status |= PK_STATUS_NOT_POSDEF;
+    uint64_t at_hi = 0ull, at_lo = 0ull;
+#pragma unroll(UN)
+    for (int i = 0; i < n; ++i) {
+      if (y[i] > hi[i]) { at_hi |= (1ull << i); x[i] = hi[i]; }
+      else if (y[i] < lo[i]) { at_lo |= (1ull << i); x[i] = lo[i]; }
+      else x[i] = y[i];
+    }
+    if ((at_hi | at_lo) == 0ull) return status;
+
+    const int max_iter = 3 * n + 8;
+    for (int it = 0;; ++it) {
+      if (it >= max_iter) { status |= PK_STATUS_ITER_LIMIT; break; }
+      const uint64_t act = at_hi | at_lo;
+      eqp(A, b, d, beta, K, n, act, x, y);
+      // longest feasible step from x towards y
+      float step = 1.f;
+      int blk = -1;
+      bool blk_hi = false;
+#pragma unroll(UN)
+      for (int i = 0; i < n; ++i) {
+        if (!((act >> i) & 1ull)) {
+          const float dlt = y[i] - x[i];
+          if (y[i] > hi[i]) {
+            const float a = (hi[i] - x[i]) / dlt;
+            if (a < step) { step = a; blk = i; blk_hi = true; }
+          } else if (y[i] < lo[i]) {
+            const float a = (lo[i] - x[i]) / dlt;
+            if (a < step) { step = a; blk = i; blk_hi = false; }
+          }
+        }
+      }
+      if (blk >= 0) {
+        step = fmaxf(step, 0.f);
+#pragma unroll(UN)
+        for (int i = 0; i < n; ++i) {
+          if (!((act >> i) & 1ull)) {
+            x[i] = fmaf(step, y[i] - x[i], x[i]);
+            if (i == blk) x[i] = blk_hi ? hi[i] : lo[i];
+          }
+        }
+        if (blk_hi) at_hi |= (1ull << blk); else at_lo |= (1ull << blk);
+        continue;
+      }
+#pragma unroll(UN)
+      for (int i = 0; i < n; ++i) x[i] = y[i];
+      // multipliers from the factored gradient g = A^T (A x + b) + d (d x + beta)
+      float rho[KA];
+#pragma unroll(UK)
+      for (int r = 0; r < K; ++r) {
+        float s = b[r];
+#pragma unroll(UN)
+        for (int j = 0; j < n; ++j) s = fmaf(A[r][j], x[j], s);
+        rho[r] = s;
+      }
+      float worst = 0.f;
+      int rel = -1;
+#pragma unroll(UN)
+      for (int i = 0; i < n; ++i) {
+        if ((act >> i) & 1ull) {
+          const float rt = fmaf(d[i], x[i], beta[i]);
+          float g = d[i] * rt;
+          float gabs = fabsf(g);
+#pragma unroll(UK)
+          for (int r = 0; r < K; ++r) {
+            g = fmaf(A[r][i], rho[r], g);
+            gabs = fmaf(fabsf(A[r][i]), fabsf(rho[r]), gabs);
+          }
+          const float lam = ((at_hi >> i) & 1ull) ? -g : g;
+          // release only multipliers that are negative beyond the rounding of g
+          if (lam < -4e-6f * gabs && lam < worst) { worst = lam; rel = i; }
+        }
+      }
+      if (rel < 0) break;
+      at_hi &= ~(1ull << rel);
+      at_lo &= ~(1ull << rel);
+    }
+    return status;
+  }
+};
+
+}  // namespace pk

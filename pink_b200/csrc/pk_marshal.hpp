@@ -1,0 +1,226 @@
+// Host-side marshalling shared by the CUDA library (pk_cabi.cu) and the CPU
+// test harness (tests/hostsim): PkModelDesc -> flat fp32 tables, PkProblemDesc ->
+// DevProblem / ChainParams, kernel eligibility.  Plain C++, no CUDA calls.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pink_b200.h"
+#include "pk_chain.cuh"
+#include "pk_generic.cuh"
+
+namespace pk {
+
+struct HostModel {
+  int njoints = 0, free_flyer = 0, nq = 0, nv = 0, nframes = 0;
+  std::vector<int> parent, jtype, frame_body;
+  std::vector<float> jX, axis, fX, mass, com;
+  std::vector<uint64_t> anc;
+  float total_mass = 0.f;
+  bool serial_chain = false;
+
+  // DevModel whose pointers alias the host vectors (CPU harness only).
+  DevModel host_view() const {
+    DevModel d{};
+    d.njoints = njoints; d.free_flyer = free_flyer; d.nq = nq; d.nv = nv; d.nframes = nframes;
+    d.parent = parent.data(); d.jtype = jtype.data(); d.jX = jX.data(); d.axis = axis.data();
+    d.frame_body = frame_body.data(); d.fX = fX.data(); d.mass = mass.data(); d.com = com.data();
+    d.anc = anc.data(); d.total_mass = total_mass;
+    return d;
+  }
+};
+
+// Returns an empty string on success, else the error message.
+inline std::string build_host_model(const PkModelDesc* d, HostModel* m) {
+  if (!d || !m) return "null model description";
+  if (d->njoints < 0 || d->njoints > PK_MAX_JOINTS) return "njoints out of range";
+  if (d->nframes < 0 || d->nframes > PK_MAX_FRAMES) return "nframes out of range";
+  const int nj = d->njoints;
+  const int ff = d->free_flyer ? 1 : 0;
+  if (d->nq != nj + 7 * ff || d->nv != nj + 6 * ff) return "nq/nv inconsistent with njoints/free_flyer";
+  m->njoints = nj;
+  m->free_flyer = ff;
+  m->nq = d->nq;
+  m->nv = d->nv;
+  m->nframes = d->nframes;
+  m->parent.assign(d->parent, d->parent + nj);
+  m->jtype.assign(d->jtype, d->jtype + nj);
+  m->jX.resize(12 * nj);
+  m->axis.resize(3 * nj);
+  for (int i = 0; i < 12 * nj; ++i) m->jX[i] = (float)d->joint_placement[i];
+  for (int j = 0; j < nj; ++j) {
+    const double* a = d->axis + 3 * j;
+    const double n = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    if (!(n > 0.0)) return "zero joint axis";
+    for (int k = 0; k < 3; ++k) m->axis[3 * j + k] = (float)(a[k] / n);
+    if (m->parent[j] >= j || m->parent[j] < -1) return "joints must be ordered parents-first";
+    if (m->jtype[j] != PK_JOINT_REVOLUTE && m->jtype[j] != PK_JOINT_PRISMATIC) return "unknown joint type";
+  }
+  m->frame_body.assign(d->frame_body, d->frame_body + d->nframes);
+  for (int f = 0; f < d->nframes; ++f)
+    if (m->frame_body[f] < -2 || m->frame_body[f] >= nj) return "frame body out of range";
+  m->fX.resize(12 * d->nframes);
+  for (int i = 0; i < 12 * d->nframes; ++i) m->fX[i] = (float)d->frame_placement[i];
+  m->mass.resize(nj + 1);
+  m->com.resize(3 * (nj + 1));
+  double total = 0.0;
+  for (int b = 0; b <= nj; ++b) {
+    m->mass[b] = d->mass ? (float)d->mass[b] : 0.f;
+    total += d->mass ? d->mass[b] : 0.0;
+    for (int k = 0; k < 3; ++k) m->com[3 * b + k] = d->com ? (float)d->com[3 * b + k] : 0.f;
+  }
+  m->total_mass = (float)total;
+  m->anc.assign(nj + 2, 0ull);
+  for (int j = 0; j < nj; ++j) {
+    const uint64_t up = m->parent[j] >= 0 ? m->anc[m->parent[j] + 2] : 0ull;
+    m->anc[j + 2] = up | (1ull << j);
+  }
+  m->serial_chain = !ff && nj >= 1;
+  for (int j = 0; j < nj; ++j)
+    if (m->parent[j] != j - 1) m->serial_chain = false;
+  return "";
+}
+
+inline int target_size(const HostModel& m, const PkTaskDesc& t) {
+  switch (t.type) {
+    case PK_TASK_FRAME:
+    case PK_TASK_RELATIVE_FRAME: return 12;
+    case PK_TASK_POSTURE: return m.nq;
+    case PK_TASK_COM: return 3;
+    default: return -1;
+  }
+}
+
+inline std::string make_dev_problem(const HostModel& m, const PkProblemDesc* p, DevProblem* out) {
+  if (!p) return "null problem";
+  if (p->ntasks < 0 || p->ntasks > PK_MAX_TASKS) return "ntasks out of range";
+  if (!(p->dt > 0.f)) return "dt must be positive";
+  if (p->target_stride < 0) return "negative target_stride";
+  DevProblem& P = *out;
+  memset(&P, 0, sizeof(P));
+  P.ntasks = p->ntasks;
+  for (int t = 0; t < p->ntasks; ++t) {
+    const PkTaskDesc& s = p->tasks[t];
+    DevTask& d = P.tasks[t];
+    const int ts = target_size(m, s);
+    if (ts < 0) return "unknown task type";
+    const int limit = s.target_shared ? PK_MAX_SHARED : p->target_stride;
+    if (s.target_offset < 0 || s.target_offset + ts > limit) return "task target does not fit its buffer";
+    d.type = s.type;
+    d.frame = s.frame;
+    d.root = s.root;
+    d.tgt_off = s.target_offset;
+    d.tgt_shared = s.target_shared ? 1 : 0;
+    d.body = d.root_body = -2;
+    if (s.type == PK_TASK_FRAME || s.type == PK_TASK_RELATIVE_FRAME) {
+      if (s.frame < 0 || s.frame >= m.nframes) return "task frame index out of range";
+      d.body = m.frame_body[s.frame];
+    }
+    if (s.type == PK_TASK_RELATIVE_FRAME) {
+      if (s.root < 0 || s.root >= m.nframes) return "task root frame index out of range";
+      d.root_body = m.frame_body[s.root];
+    }
+    for (int k = 0; k < 6; ++k) {
+      if (s.cost[k] < 0.f) return "negative task cost";
+      d.cost[k] = s.cost[k];
+    }
+    d.gain = s.gain;
+    d.lm = s.lm_damping;
+  }
+  P.dt = p->dt;
+  P.inv_dt = 1.f / p->dt;
+  P.damping = p->damping;
+  P.cfg_gain = p->cfg_gain;
+  P.target_stride = p->target_stride;
+  P.safety_break = p->safety_break ? 1 : 0;
+  for (int i = 0; i < PK_MAX_NV; ++i) {
+    const bool in = i < m.nv;
+    P.cfg_lo[i] = in ? p->cfg_lo[i] : -INFINITY;
+    P.cfg_hi[i] = in ? p->cfg_hi[i] : INFINITY;
+    P.vel[i] = in ? p->vel[i] : INFINITY;
+    P.chk_lo[i] = in ? p->chk_lo[i] : -INFINITY;
+    P.chk_hi[i] = in ? p->chk_hi[i] : INFINITY;
+  }
+  memcpy(P.shared, p->shared, sizeof(P.shared));
+  return "";
+}
+
+// Does the register-resident chain kernel cover this (model, problem)?
+inline bool chain_eligible(const HostModel& m, const DevProblem& P) {
+  if (!m.serial_chain || m.njoints > 7 || m.njoints < 2) return false;
+  int nf = 0, np = 0;
+  for (int t = 0; t < P.ntasks; ++t) {
+    const DevTask& d = P.tasks[t];
+    if (d.type == PK_TASK_FRAME) {
+      if (d.body == -2) return false;
+      ++nf;
+    } else if (d.type == PK_TASK_POSTURE) {
+      ++np;
+    } else {
+      return false;
+    }
+  }
+  if (nf > kChainMaxFrameTasks || np > 1) return false;
+  int shared_need = 0;
+  for (int t = 0; t < P.ntasks; ++t)
+    if (P.tasks[t].tgt_shared)
+      shared_need = std::max(shared_need, P.tasks[t].tgt_off + (P.tasks[t].type == PK_TASK_FRAME ? 12 : m.nq));
+  return shared_need <= 12 * kChainMaxFrameTasks + m.njoints;
+}
+
+template <int NJ>
+void make_chain_params(const HostModel& m, const DevProblem& P, ChainParams<NJ>* out) {
+  ChainParams<NJ>& C = *out;
+  memset(&C, 0, sizeof(C));
+  for (int j = 0; j < NJ; ++j) {
+    memcpy(C.joint[j].X, &m.jX[12 * j], sizeof(float) * 12);
+    C.joint[j].ax = m.axis[3 * j];
+    C.joint[j].ay = m.axis[3 * j + 1];
+    C.joint[j].az = m.axis[3 * j + 2];
+    C.joint[j].type = m.jtype[j];
+    C.cfg_lo[j] = P.cfg_lo[j];
+    C.cfg_hi[j] = P.cfg_hi[j];
+    C.vel[j] = P.vel[j];
+    C.chk_lo[j] = P.chk_lo[j];
+    C.chk_hi[j] = P.chk_hi[j];
+  }
+  for (int t = 0; t < kChainMaxFrameTasks; ++t) {
+    // inert defaults so that unused slots are well defined
+    const float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    memcpy(C.ft[t].X, I, sizeof(I));
+    C.ft[t].body = -1;
+  }
+  for (int t = 0; t < P.ntasks; ++t) {
+    const DevTask& d = P.tasks[t];
+    if (d.type == PK_TASK_FRAME) {
+      ChainFrameTask& f = C.ft[C.n_frame_tasks++];
+      f.body = d.body;
+      memcpy(f.X, &m.fX[12 * d.frame], sizeof(float) * 12);
+      memcpy(f.cost, d.cost, sizeof(float) * 6);
+      f.gain = d.gain;
+      f.lm = d.lm;
+      f.tgt_off = d.tgt_off;
+      f.tgt_shared = d.tgt_shared;
+    } else {
+      C.has_posture = 1;
+      C.posture_w2 = d.cost[0] * d.cost[0];
+      C.posture_gain = d.gain;
+      C.posture_lm = d.lm;
+      C.posture_off = d.tgt_off;
+      C.posture_shared = d.tgt_shared;
+    }
+  }
+  C.dt = P.dt;
+  C.inv_dt = P.inv_dt;
+  C.damping = P.damping;
+  C.cfg_gain = P.cfg_gain;
+  C.target_stride = P.target_stride;
+  C.safety_break = P.safety_break;
+  memcpy(C.shared, P.shared, sizeof(C.shared));
+}
+
+}  // namespace pk

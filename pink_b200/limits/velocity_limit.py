@@ -1,0 +1,53 @@
+"""Velocity limit (``/root/reference/pink/limits/velocity_limit.py``)."""
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from ..exceptions import PinkError
+from .limit import Limit
+
+
+class VelocityLimit(Limit):
+    r"""Rows :math:`\pm P \Delta q \leq \mathrm{d}t\, v_{max}`."""
+
+    def __init__(self, model, velocity_limit: Optional[np.ndarray] = None):
+        if velocity_limit is None:
+            velocity_limit = model.velocityLimit
+        else:
+            velocity_limit = np.asarray(velocity_limit, dtype=float).flatten()
+            if model.nv > 0 and velocity_limit.shape[0] != model.nv:
+                raise PinkError(f"{velocity_limit.shape=} but {model.nv=}")
+        has_velocity_limit = np.logical_and(velocity_limit < 1e20, velocity_limit > 1e-10)
+        joints = [
+            joint
+            for joint in model.joints
+            if joint.idx_v >= 0
+            and has_velocity_limit[slice(joint.idx_v, joint.idx_v + joint.nv)].all()
+        ]
+        index_list: List[int] = []
+        for joint in joints:
+            index_list.extend(range(joint.idx_v, joint.idx_v + joint.nv))
+        indices = np.array(index_list, dtype=np.int64)
+        indices.setflags(write=False)
+        dim = len(indices)
+        self.indices = indices
+        self.joints = joints
+        self.model = model
+        self.projection_matrix = np.eye(model.nv)[indices] if dim > 0 else None
+        self.velocity_limit = velocity_limit
+
+    def box_bounds(self) -> np.ndarray:
+        """Per-tangent-index velocity bound (+inf where no row exists)."""
+        v = np.full(self.model.nv, np.inf)
+        for i in self.indices:
+            v[i] = self.velocity_limit[i]
+        return v
+
+    def compute_qp_inequalities(self, configuration, dt: float) -> Optional[Tuple]:
+        """``velocity_limit.py:90-121``, evaluated by the CUDA library."""
+        if self.projection_matrix is None:
+            return None
+        from ..solve_ik import _limit_rows
+
+        return _limit_rows(configuration, [self], dt)

@@ -1,0 +1,89 @@
+"""Seeded synthetic inputs of the BASELINE configurations.
+
+Pure numpy sampling (fp64); forward kinematics of the sampled "target
+configurations" is done by the caller (the CUDA library in ``bench.py``, the
+oracle in the tests) so that this module carries no kinematics of its own.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+SEED = 20260922
+
+# examples/arm_ur5.py:33-63
+UR5_TASKS = dict(frame="tool0", position_cost=1.0, orientation_cost=1.0, lm_damping=1.0, posture_cost=1e-3)
+UR5_DT = 1.0 / 200.0
+UR5_DAMPING = 1e-12
+
+
+def ur5_posture_reference(model) -> np.ndarray:
+    """``q_ref`` of ``examples/arm_ur5.py:46-51``: pan = lift = elbow = 1."""
+    q = np.zeros(model.nq)
+    for name in ("shoulder_pan_joint", "shoulder_lift_joint", "elbow_joint"):
+        q[model.joints[model.getJointId(name)].idx_q] = 1.0
+    return q
+
+
+def _finite_limits(table):
+    rq = 7 if table.free_flyer else 0
+    lo = np.array(table.q_min[rq:], dtype=np.float64)
+    hi = np.array(table.q_max[rq:], dtype=np.float64)
+    lo = np.where(np.isfinite(lo), lo, -np.pi)
+    hi = np.where(np.isfinite(hi), hi, np.pi)
+    return lo, hi
+
+
+def random_quaternions(n: int, rng) -> np.ndarray:
+    """Uniform unit quaternions ``[x, y, z, w]``."""
+    q = rng.normal(size=(n, 4))
+    return q / np.linalg.norm(q, axis=1, keepdims=True)
+
+
+def sample_configurations(table, B: int, rng, near_limit_fraction: float = 0.05) -> np.ndarray:
+    """``q ~ U(0.9 q_min, 0.9 q_max)`` per joint, about 5 % of the instances
+    pushed to within 1e-2 rad of a position limit on one joint; free-flyer:
+    position ``U([-0.5, 0.5]^3)``, uniform random orientation."""
+    lo, hi = _finite_limits(table)
+    nj = lo.shape[0]
+    qj = rng.uniform(0.9 * lo, 0.9 * hi, size=(B, nj))
+    n_near = int(round(near_limit_fraction * B))
+    if n_near and nj:
+        rows = rng.choice(B, size=n_near, replace=False)
+        cols = rng.integers(0, nj, size=n_near)
+        upper = rng.random(n_near) < 0.5
+        gap = rng.uniform(0.0, 1e-2, size=n_near)
+        qj[rows, cols] = np.where(upper, hi[cols] - gap, lo[cols] + gap)
+    if not table.free_flyer:
+        return qj
+    base = np.concatenate([rng.uniform(-0.5, 0.5, size=(B, 3)), random_quaternions(B, rng)], axis=1)
+    return np.concatenate([base, qj], axis=1)
+
+
+def perturb_configurations(table, q: np.ndarray, rng, sigma: float = 0.3) -> np.ndarray:
+    """``q + delta`` with ``delta ~ N(0, sigma^2)`` on the joints, clipped into the
+    limits; the frame poses at these configurations are the *reachable* targets."""
+    lo, hi = _finite_limits(table)
+    rq = 7 if table.free_flyer else 0
+    out = np.array(q, dtype=np.float64)
+    out[:, rq:] = np.clip(out[:, rq:] + rng.normal(0.0, sigma, size=out[:, rq:].shape), lo, hi)
+    return out
+
+
+def random_poses(B: int, rng, half_extent: float = 1.2) -> np.ndarray:
+    """*Unreachable* targets: ``p ~ U([-h, h]^3)``, ``R`` uniform on SO(3);
+    returns ``[B, 3, 4]`` rows ``[R | p]``."""
+    q = random_quaternions(B, rng)
+    x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = np.empty((B, 3, 3))
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z)
+    R[:, 0, 1] = 2 * (x * y - z * w)
+    R[:, 0, 2] = 2 * (x * z + y * w)
+    R[:, 1, 0] = 2 * (x * y + z * w)
+    R[:, 1, 1] = 1 - 2 * (x * x + z * z)
+    R[:, 1, 2] = 2 * (y * z - x * w)
+    R[:, 2, 0] = 2 * (x * z - y * w)
+    R[:, 2, 1] = 2 * (y * z + x * w)
+    R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    p = rng.uniform(-half_extent, half_extent, size=(B, 3))
+    return np.concatenate([R, p[:, :, None]], axis=2)

@@ -1,0 +1,157 @@
+"""Shared fixtures: seeded workloads, product-side task objects and the matching
+oracle task dicts, tolerance checks."""
+
+import numpy as np
+import torch
+
+from oracle import ik as oik
+from oracle import kinematics as okin
+from pink_b200 import ComTask, FrameTask, PostureTask, RelativeFrameTask, workloads
+from pink_b200.limits import ConfigurationLimit, VelocityLimit
+from pink_b200.model import JointModelFreeFlyer
+from pink_b200.robots import load_robot_description
+
+# fp32 CUDA vs fp64 oracle on identical inputs
+V_ATOL, V_RTOL = 2e-4, 2e-3
+
+
+def load(name):
+    root = None if name.startswith("ur5") else JointModelFreeFlyer()
+    robot = load_robot_description(name, root_joint=root)
+    return robot, robot.model, robot.model.table()
+
+
+def frame_targets(table, q_target, frame_name):
+    """[B, 3, 4] fp32 poses of `frame_name` at configurations `q_target` (oracle FK)."""
+    fk = okin.forward_kinematics(table, q_target)
+    R, p = okin.frame_placement(table, fk, table.frame_names.index(frame_name))
+    return np.concatenate([R, p[:, :, None]], axis=2).astype(np.float32)
+
+
+class Scenario:
+    """A (model, tasks, limits, inputs) bundle in both product and oracle form."""
+
+    def __init__(self, name, robot, model, table, q, tasks, oracle_tasks, dt, damping, limits="default",
+                 safety_break=True):
+        self.name, self.robot, self.model, self.table = name, robot, model, table
+        self.q32 = np.ascontiguousarray(q, dtype=np.float32)
+        self.q64 = self.q32.astype(np.float64)
+        self.tasks, self.oracle_tasks = tasks, oracle_tasks
+        self.dt, self.damping, self.safety_break = dt, damping, safety_break
+        if limits == "default":
+            self.limits = [ConfigurationLimit(model), VelocityLimit(model)]
+            self.oracle_limits = None
+        else:
+            self.limits = []
+            self.oracle_limits = []
+
+    @property
+    def B(self):
+        return self.q32.shape[0]
+
+    def problem(self):
+        from pink_b200.solve_ik import describe_problem
+
+        prob, parts, descs = describe_problem(self.model, self.B, self.tasks, self.dt, self.damping, self.limits,
+                                              self.safety_break)
+        targets = torch.cat([p.cpu().float() for p in parts], dim=1).numpy() if parts else None
+        return prob, targets, descs
+
+    def oracle_solve(self, n=None):
+        n = self.B if n is None else min(n, self.B)
+        tasks = [oik._slice_task_range(t, 0, n) for t in self.oracle_tasks]
+        return oik.solve_ik_batch(self.table, self.q64[:n], tasks, self.dt, self.damping, self.oracle_limits,
+                                  self.safety_break)
+
+    def oracle_build(self):
+        return oik.build_ik(self.table, self.q64, self.oracle_tasks, self.dt, self.damping, self.oracle_limits)
+
+
+def ur5_scenario(B, kind="reachable", seed=workloads.SEED, lm_damping=1.0, posture_cost=1e-3, out_of_limits=0):
+    robot, model, table = load("ur5_description")
+    rng = np.random.default_rng(seed)
+    q = workloads.sample_configurations(table, B, rng)
+    if out_of_limits:
+        rows = rng.choice(B, size=out_of_limits, replace=False)
+        q[rows, 2] = table.q_max[2] + rng.uniform(1e-3, 0.2, size=out_of_limits)
+    if kind == "reachable":
+        T = frame_targets(table, workloads.perturb_configurations(table, q, rng), "tool0")
+    elif kind == "unreachable":
+        T = workloads.random_poses(B, rng).astype(np.float32)
+    else:  # at target: zero error
+        T = frame_targets(table, q.astype(np.float32).astype(np.float64), "tool0")
+    q_ref = workloads.ur5_posture_reference(model)
+    ft = FrameTask("tool0", position_cost=1.0, orientation_cost=1.0, lm_damping=lm_damping)
+    ft.set_target(torch.as_tensor(T))
+    pt = PostureTask(cost=posture_cost)
+    pt.set_target(q_ref)
+    T64 = T.astype(np.float64)
+    f = table.frame_names.index("tool0")
+    otasks = [
+        {"type": "frame", "frame": f, "cost": np.ones(6), "gain": 1.0, "lm_damping": lm_damping,
+         "target": (T64[:, :, :3], T64[:, :, 3])},
+        {"type": "posture", "cost": posture_cost, "gain": 1.0, "lm_damping": 0.0, "target": q_ref},
+    ]
+    return Scenario(f"ur5-{kind}", robot, model, table, q, [ft, pt], otasks, workloads.UR5_DT, workloads.UR5_DAMPING)
+
+
+def humanoid_scenario(name, B, seed=workloads.SEED, sigma=0.15, with_com=False, with_relative=False):
+    """Draco3-class (examples/humanoid_draco3.py:69-91) or G1-class
+    (examples/humanoid_g1_com.py:45-74) task sets on the synthetic trees."""
+    robot, model, table = load(name)
+    rng = np.random.default_rng(seed)
+    q = workloads.sample_configurations(table, B, rng, near_limit_fraction=0.05)
+    qt = workloads.perturb_configurations(table, q, rng, sigma=sigma)
+    if name.startswith("draco3"):
+        specs = [("l_foot_contact", 1.0, 1.0), ("torso_com_link", 1.0, 0.0), ("r_foot_contact", 1.0, 1.0),
+                 ("r_hand_contact", 4.0, 4.0)]
+        posture_cost, damping = 1e-1, 1e-12
+    else:
+        specs = [("pelvis", 0.0, 10.0), ("right_ankle_roll_link", [2.0, 2.0, 200.0], 10.0),
+                 ("left_ankle_roll_link", [2.0, 2.0, 200.0], 10.0), ("right_wrist_yaw_link", 4.0, 0.0),
+                 ("left_wrist_yaw_link", 4.0, 0.0)]
+        posture_cost, damping = 1e-1, 0.01
+    tasks, otasks = [], []
+    for frame, pc, oc in specs:
+        T = frame_targets(table, qt, frame)
+        t = FrameTask(frame, position_cost=pc, orientation_cost=oc)
+        t.set_target(torch.as_tensor(T))
+        tasks.append(t)
+        T64 = T.astype(np.float64)
+        otasks.append({"type": "frame", "frame": table.frame_names.index(frame), "cost": np.array(t.cost),
+                       "gain": 1.0, "lm_damping": 0.0, "target": (T64[:, :, :3], T64[:, :, 3])})
+    q_ref = q[0].copy()
+    pt = PostureTask(cost=posture_cost)
+    pt.set_target(q_ref)
+    tasks.append(pt)
+    otasks.append({"type": "posture", "cost": posture_cost, "gain": 1.0, "lm_damping": 0.0, "target": q_ref})
+    if with_com:
+        com = okin.center_of_mass(table, okin.forward_kinematics(table, qt)).astype(np.float32)
+        ct = ComTask(cost=200.0)
+        ct.set_target(torch.as_tensor(com))
+        tasks.append(ct)
+        otasks.append({"type": "com", "cost": np.full(3, 200.0), "gain": 1.0, "lm_damping": 0.0,
+                       "target": com.astype(np.float64)})
+    if with_relative:
+        a, b = ("l_hand_contact", "r_hand_contact") if name.startswith("draco3") else ("left_wrist_yaw_link", "right_wrist_yaw_link")
+        fkt = okin.forward_kinematics(table, qt)
+        Ra, pa = okin.frame_placement(table, fkt, table.frame_names.index(a))
+        Rb, pb = okin.frame_placement(table, fkt, table.frame_names.index(b))
+        from oracle import lie
+
+        Rr, pr = lie.se3_act_inv(Rb, pb, Ra, pa)
+        T = np.concatenate([Rr, pr[:, :, None]], axis=2).astype(np.float32)
+        rt = RelativeFrameTask(a, b, position_cost=2.0, orientation_cost=0.5, lm_damping=1e-3, gain=0.8)
+        rt.set_target(torch.as_tensor(T))
+        tasks.append(rt)
+        T64 = T.astype(np.float64)
+        otasks.append({"type": "relative_frame", "frame": table.frame_names.index(a), "root": table.frame_names.index(b),
+                       "cost": np.array(rt.cost), "gain": 0.8, "lm_damping": 1e-3,
+                       "target": (T64[:, :, :3], T64[:, :, 3])})
+    return Scenario(name, robot, model, table, q, tasks, otasks, 1.0 / 200.0, damping, safety_break=False)
+
+
+def within_tolerance(v, v_ref, atol=V_ATOL, rtol=V_RTOL):
+    """Per-instance boolean: every coordinate within atol + rtol |v_ref|."""
+    err = np.abs(np.asarray(v, dtype=np.float64) - v_ref)
+    return (err <= atol + rtol * np.abs(v_ref)).all(axis=-1)

@@ -1,0 +1,152 @@
+// CPU build of the kernel bodies (pk_chain.cuh / pk_generic.cuh) for the test
+// suite ONLY: lets `pytest -m "not gpu"` exercise the exact fp32 arithmetic and
+// control flow of the CUDA kernels against the fp64 oracle on machines without
+// a GPU.  It is never loaded by the product package (pink_b200/_cabi.py loads
+// libpink_b200.so and nothing else) and is not a fallback.
+#include <cstdint>
+#include <cstring>
+#include <string>
+
+#include "../../include/pink_b200.h"
+#include "../../pink_b200/csrc/pk_marshal.hpp"
+
+namespace {
+thread_local std::string g_err;
+int fail(const std::string& m) { g_err = m; return 1; }
+
+template <int NJ>
+void run_chain(const pk::HostModel& hm, const pk::DevProblem& P, const float* q, const float* targets, float* v,
+               int32_t* status, int64_t B) {
+  pk::ChainParams<NJ> C;
+  pk::make_chain_params<NJ>(hm, P, &C);
+  for (int64_t i = 0; i < B; ++i) {
+    float qi[NJ], vi[NJ];
+    for (int k = 0; k < NJ; ++k) qi[k] = q[i * NJ + k];
+    int st = 0;
+    const float* trow = targets + i * (int64_t)P.target_stride;
+    switch (C.n_frame_tasks) {
+      case 0: pk::ik_step_chain<NJ, 0>(C, qi, trow, vi, st); break;
+      case 1: pk::ik_step_chain<NJ, 1>(C, qi, trow, vi, st); break;
+      default: pk::ik_step_chain<NJ, 2>(C, qi, trow, vi, st); break;
+    }
+    for (int k = 0; k < NJ; ++k) v[i * NJ + k] = vi[k];
+    if (status) status[i] = st;
+  }
+}
+
+struct Args {
+  const float* q; const float* targets; float* v; int32_t* status; float* H; float* c; float* h;
+  float* e; float* J; int task_index; int task_k; float* oMf; float* com; float* Jf; int jac_frame;
+};
+
+void run_generic(const pk::HostModel& hm, const pk::DevProblem& P, const Args& A, int64_t B) {
+  const pk::DevModel M = hm.host_view();
+  const int nv = M.nv;
+  static thread_local pk::Generic<PK_MAX_JOINTS, PK_MAX_NV> G;
+  for (int64_t i = 0; i < B; ++i) {
+    pk::GenericOut out;
+    out.v = A.v ? A.v + i * nv : nullptr;
+    out.status = A.status ? A.status + i : nullptr;
+    out.H = A.H ? A.H + i * nv * nv : nullptr;
+    out.c = A.c ? A.c + i * nv : nullptr;
+    out.h = A.h ? A.h + i * 4 * nv : nullptr;
+    out.e = A.e ? A.e + i * A.task_k : nullptr;
+    out.J = A.J ? A.J + i * A.task_k * nv : nullptr;
+    out.task_index = A.task_index;
+    out.oMf = A.oMf ? A.oMf + i * M.nframes * 12 : nullptr;
+    out.com = A.com ? A.com + i * 3 : nullptr;
+    out.Jf = A.Jf ? A.Jf + i * 6 * nv : nullptr;
+    out.jac_frame = A.jac_frame;
+    G.step(M, P, A.q + i * M.nq, A.targets ? A.targets + i * (int64_t)P.target_stride : nullptr, out);
+  }
+}
+}  // namespace
+
+extern "C" {
+
+const char* hs_last_error(void) { return g_err.c_str(); }
+
+int hs_model_create(const PkModelDesc* d, void** out) {
+  pk::HostModel* m = new pk::HostModel();
+  const std::string e = pk::build_host_model(d, m);
+  if (!e.empty()) { delete m; return fail(e); }
+  *out = m;
+  return 0;
+}
+void hs_model_destroy(void* m) { delete (pk::HostModel*)m; }
+
+// path: 0 auto (same selection as the CUDA library), 1 force the general path
+int hs_solve_ik(void* model, const PkProblemDesc* prob, const float* q, const float* targets, float* v,
+                int32_t* status, int64_t B, int path, int* used_chain) {
+  const pk::HostModel& hm = *(pk::HostModel*)model;
+  pk::DevProblem P;
+  const std::string e = pk::make_dev_problem(hm, prob, &P);
+  if (!e.empty()) return fail(e);
+  const bool chain = path == 0 && pk::chain_eligible(hm, P);
+  if (used_chain) *used_chain = chain ? 1 : 0;
+  if (chain) {
+    switch (hm.njoints) {
+      case 2: run_chain<2>(hm, P, q, targets, v, status, B); return 0;
+      case 3: run_chain<3>(hm, P, q, targets, v, status, B); return 0;
+      case 4: run_chain<4>(hm, P, q, targets, v, status, B); return 0;
+      case 5: run_chain<5>(hm, P, q, targets, v, status, B); return 0;
+      case 6: run_chain<6>(hm, P, q, targets, v, status, B); return 0;
+      case 7: run_chain<7>(hm, P, q, targets, v, status, B); return 0;
+    }
+  }
+  Args A{};
+  A.q = q; A.targets = targets; A.v = v; A.status = status; A.task_index = -1;
+  run_generic(hm, P, A, B);
+  return 0;
+}
+
+int hs_build_ik(void* model, const PkProblemDesc* prob, const float* q, const float* targets, float* H, float* c,
+                float* h, int64_t B) {
+  const pk::HostModel& hm = *(pk::HostModel*)model;
+  pk::DevProblem P;
+  const std::string e = pk::make_dev_problem(hm, prob, &P);
+  if (!e.empty()) return fail(e);
+  Args A{};
+  A.q = q; A.targets = targets; A.H = H; A.c = c; A.h = h; A.task_index = -1;
+  run_generic(hm, P, A, B);
+  return 0;
+}
+
+int hs_task_terms(void* model, const PkProblemDesc* prob, int task_index, const float* q, const float* targets,
+                  float* eo, float* J, int64_t B) {
+  const pk::HostModel& hm = *(pk::HostModel*)model;
+  pk::DevProblem P;
+  const std::string e = pk::make_dev_problem(hm, prob, &P);
+  if (!e.empty()) return fail(e);
+  if (task_index < 0 || task_index >= P.ntasks) return fail("task_index out of range");
+  Args A{};
+  A.q = q; A.targets = targets; A.e = eo; A.J = J; A.task_index = task_index;
+  const int type = P.tasks[task_index].type;
+  A.task_k = type == PK_TASK_COM ? 3 : (type == PK_TASK_POSTURE ? hm.nv - (hm.free_flyer ? 6 : 0) : 6);
+  run_generic(hm, P, A, B);
+  return 0;
+}
+
+int hs_forward_kinematics(void* model, const float* q, float* oMf, float* com, int64_t B) {
+  const pk::HostModel& hm = *(pk::HostModel*)model;
+  pk::DevProblem P;
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < PK_MAX_NV; ++i) { P.chk_lo[i] = -INFINITY; P.chk_hi[i] = INFINITY; }
+  Args A{};
+  A.q = q; A.oMf = oMf; A.com = com; A.task_index = -1;
+  run_generic(hm, P, A, B);
+  return 0;
+}
+
+int hs_frame_jacobian(void* model, int frame, const float* q, float* J, int64_t B) {
+  const pk::HostModel& hm = *(pk::HostModel*)model;
+  if (frame < 0 || frame >= hm.nframes) return fail("frame index out of range");
+  pk::DevProblem P;
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < PK_MAX_NV; ++i) { P.chk_lo[i] = -INFINITY; P.chk_hi[i] = INFINITY; }
+  Args A{};
+  A.q = q; A.Jf = J; A.jac_frame = frame; A.task_index = -1;
+  run_generic(hm, P, A, B);
+  return 0;
+}
+}

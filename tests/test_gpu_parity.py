@@ -1,0 +1,198 @@
+"""GPU suite (`-m gpu`): the CUDA library, called through the public Python API
+and the C-ABI, against the fp64 oracle on identical seeded inputs."""
+
+import numpy as np
+import pytest
+import torch
+
+import pink_b200
+from oracle import ik as oik
+from oracle import kinematics as okin
+from oracle import tasks as otk
+from pink_b200 import _cabi
+from pink_b200.engine import get_engine
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_solve(sc, **kw):
+    cfg = pink_b200.Configuration(sc.model, sc.robot.data, torch.as_tensor(sc.q32, device="cuda"))
+    limits = None if sc.oracle_limits is None else []
+    v, st = pink_b200.solve_ik(cfg, sc.tasks, sc.dt, solver="quadprog", damping=sc.damping, limits=limits,
+                               safety_break=sc.safety_break, return_status=True, **kw)
+    torch.cuda.synchronize()
+    return v.cpu().numpy(), st.cpu().numpy()
+
+
+@pytest.mark.parametrize("kind", ["reachable", "unreachable", "at_target"])
+def test_ur5_matches_oracle(kind):
+    sc = helpers.ur5_scenario(512, kind)
+    v, st = _gpu_solve(sc)
+    v_ref, st_ref = sc.oracle_solve()
+    assert (st == 0).all() and (st_ref == 0).all()
+    ok = helpers.within_tolerance(v, v_ref)
+    if kind == "at_target":
+        assert ok.mean() >= 0.99
+        assert helpers.within_tolerance(v, v_ref, atol=5e-3, rtol=2e-2).all()
+    else:
+        assert ok.all(), f"{(~ok).sum()} instances off, worst {np.abs(v - v_ref).max()}"
+
+
+def test_ur5_gpu_agrees_with_host_build_of_the_same_kernel():
+    """The CPU harness compiles the same kernel body; only libm / FMA contraction differ."""
+    from tests.hostsim import HostSim
+
+    sc = helpers.ur5_scenario(4096, "reachable")
+    v, st = _gpu_solve(sc)
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v_h, st_h = hs.solve_ik(prob, sc.q32, targets)
+    np.testing.assert_array_equal(st, st_h)
+    np.testing.assert_allclose(v, v_h, rtol=1e-3, atol=1e-4)
+
+
+def test_ur5_full_batch_kkt_certificate():
+    """BASELINE config 2 at full size (B = 65536): the fp32 velocities satisfy the
+    fp64 KKT conditions of their own QPs (unique minimiser => parity at scale)."""
+    sc = helpers.ur5_scenario(65536, "reachable")
+    v, st = _gpu_solve(sc)
+    assert (st == 0).all()
+    H, c, G, h = sc.oracle_build()
+    x = v.astype(np.float64) * sc.dt
+    stat, prim, lo, hi = oik.kkt_check_batch(H, c, G, h, x)
+    scale = np.abs(c).max(axis=1)
+    assert prim.max() <= 1e-6
+    assert np.quantile(stat / scale, 0.999) <= 1e-4
+    assert (stat / scale).max() <= 1e-3
+    # and a slice against the oracle's own solutions
+    v_ref, _ = sc.oracle_solve(300)
+    assert helpers.within_tolerance(v[:300], v_ref).all()
+
+
+def test_general_path_equals_chain_kernel_on_ur5(monkeypatch):
+    import ctypes as C
+
+    sc = helpers.ur5_scenario(2048, "unreachable")
+    v, st = _gpu_solve(sc)
+    # general path through the build_ik / debug entry: compare H, c, then solve with the env override
+    eng = get_engine(sc.model)
+    prob, targets, _ = sc.problem()
+    H, c, h4 = eng.build_ik(prob, torch.as_tensor(sc.q32, device="cuda"), torch.as_tensor(targets, device="cuda"))
+    H_ref, c_ref, G_ref, h_ref = sc.oracle_build()
+    np.testing.assert_allclose(H.cpu().numpy(), H_ref, atol=2e-5 * np.abs(H_ref).max(), rtol=1e-4)
+    np.testing.assert_allclose(c.cpu().numpy(), c_ref, atol=2e-5 * np.abs(c_ref).max(), rtol=1e-4)
+    h_np = h4.cpu().numpy()
+    rows = np.concatenate([h_np[:, 0], h_np[:, 1], h_np[:, 2], h_np[:, 3]], axis=1)
+    np.testing.assert_allclose(rows, h_ref, atol=1e-5, rtol=1e-5)
+
+
+def test_out_of_limits_and_no_solution_statuses():
+    sc = helpers.ur5_scenario(256, "reachable", out_of_limits=9)
+    v, st = _gpu_solve(sc)
+    v_ref, st_ref = sc.oracle_solve()
+    np.testing.assert_array_equal(st & 3, st_ref)
+    assert (st == _cabi.PK_STATUS_OUT_OF_LIMITS).sum() == 9
+    sc.safety_break = False
+    v2, st2 = _gpu_solve(sc)
+    v2_ref, st2_ref = sc.oracle_solve()
+    np.testing.assert_array_equal((st2 & 1) != 0, st2_ref == 1)
+    solved = (st2 & 1) == 0
+    assert helpers.within_tolerance(v2[solved], v2_ref[solved]).all()
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("draco3_description", {}),
+    ("g1_description", {"with_com": True}),
+    ("draco3_description", {"with_relative": True}),
+    ("g1_description", {"with_com": True, "with_relative": True}),
+])
+def test_humanoids_match_oracle(name, kw):
+    sc = helpers.humanoid_scenario(name, 64, **kw)
+    v, st = _gpu_solve(sc)
+    v_ref, st_ref = sc.oracle_solve()
+    np.testing.assert_array_equal(st & 1, st_ref & 1)
+    good = (st & 1) == 0
+    ok = helpers.within_tolerance(v[good], v_ref[good], atol=5e-4, rtol=5e-3)
+    assert ok.mean() >= 0.97, f"only {ok.mean():.3f} within tolerance, worst {np.abs(v - v_ref)[good].max()}"
+    # task terms through Task.compute_error / compute_jacobian
+    cfg = pink_b200.Configuration(sc.model, sc.robot.data, torch.as_tensor(sc.q32, device="cuda"))
+    fk = okin.forward_kinematics(sc.table, sc.q64)
+    for task, ot in zip(sc.tasks, sc.oracle_tasks):
+        e = task.compute_error(cfg).cpu().numpy()
+        J = task.compute_jacobian(cfg).cpu().numpy()
+        e_ref, J_ref = otk.task_error_jacobian(sc.table, sc.q64, fk, ot)
+        np.testing.assert_allclose(e, e_ref, atol=5e-6, rtol=1e-5)
+        np.testing.assert_allclose(J, np.broadcast_to(J_ref, J.shape), atol=1e-5, rtol=1e-5)
+
+
+def test_host_entry_point_is_bitwise_equal_to_device_path():
+    sc = helpers.ur5_scenario(50000, "reachable")
+    eng = get_engine(sc.model)
+    prob, targets, _ = sc.problem()
+    q_d = torch.as_tensor(sc.q32, device="cuda")
+    t_d = torch.as_tensor(targets, device="cuda")
+    v_d, s_d = eng.solve_ik(prob, q_d, t_d)
+    q_h = torch.as_tensor(sc.q32).pin_memory()
+    t_h = torch.as_tensor(targets).pin_memory()
+    v_h = torch.empty((sc.B, 6), dtype=torch.float32).pin_memory()
+    s_h = torch.empty((sc.B,), dtype=torch.int32).pin_memory()
+    eng.solve_ik_host(prob, q_h, t_h, v_h, s_h)
+    torch.cuda.synchronize()
+    assert torch.equal(v_h, v_d.cpu())
+    assert torch.equal(s_h, s_d.cpu())
+
+
+def test_forward_kinematics_jacobian_and_integrate():
+    for name in ["ur5_description", "g1_description"]:
+        robot, model, table = helpers.load(name)
+        rng = np.random.default_rng(5)
+        q = pink_b200.workloads.sample_configurations(table, 128, rng).astype(np.float32)
+        cfg = pink_b200.Configuration(model, robot.data, torch.as_tensor(q, device="cuda"))
+        fk = okin.forward_kinematics(table, q.astype(np.float64))
+        fname = table.frame_names[-1]
+        T = cfg.get_transform_frame_to_world(fname).cpu().numpy()
+        R, p = okin.frame_placement(table, fk, table.nframes - 1)
+        np.testing.assert_allclose(T[:, :, :3], R, atol=3e-6)
+        np.testing.assert_allclose(T[:, :, 3], p, atol=3e-6)
+        J = cfg.get_frame_jacobian(fname).cpu().numpy()
+        np.testing.assert_allclose(J, okin.frame_jacobian_local(table, fk, table.nframes - 1), atol=5e-6)
+        v = rng.normal(size=(128, model.nv)).astype(np.float32)
+        q_next = cfg.integrate(torch.as_tensor(v, device="cuda"), 0.01).cpu().numpy()
+        q_ref = okin.integrate(table, q.astype(np.float64), v.astype(np.float64) * 0.01)
+        np.testing.assert_allclose(q_next, q_ref, atol=2e-6)
+
+
+def test_unbatched_configuration_behaves_like_the_reference():
+    robot, model, table = helpers.load("ur5_description")
+    q_ref = pink_b200.custom_configuration_vector(robot, shoulder_lift_joint=1.0, shoulder_pan_joint=1.0, elbow_joint=1.0)
+    configuration = pink_b200.Configuration(model, robot.data, q_ref)
+    ee = pink_b200.FrameTask("tool0", position_cost=1.0, orientation_cost=1.0, lm_damping=1.0)
+    posture = pink_b200.PostureTask(cost=1e-3)
+    for task in (ee, posture):
+        task.set_target_from_configuration(configuration)
+    # fulfilled tasks => zero velocity (tests/test_solve_ik.py:249-277)
+    v = pink_b200.solve_ik(configuration, [ee, posture], 1e-3, solver="quadprog")
+    assert isinstance(v, np.ndarray) and v.shape == (6,)
+    assert np.abs(v).max() < 1e-3
+    # move the target: single task converges (tests/test_solve_ik.py:160-210)
+    target = ee.transform_target_to_world
+    target.translation[1] += 0.1
+    dt = 5e-3
+    errs = []
+    for _ in range(120):
+        v = pink_b200.solve_ik(configuration, [ee, posture], dt, solver="quadprog")
+        configuration.integrate_inplace(v, dt)
+        errs.append(np.linalg.norm(ee.compute_error(configuration)))
+    assert errs[-1] < 1e-3 and errs[-1] < errs[0]
+    # out of limits raises (tests/test_solve_ik.py:39-65)
+    q_bad = q_ref.copy()
+    q_bad[2] = 4.0
+    bad = pink_b200.Configuration(model, robot.data, q_bad)
+    with pytest.raises(pink_b200.exceptions.NotWithinConfigurationLimits):
+        pink_b200.solve_ik(bad, [ee, posture], dt, solver="quadprog")
+    # no limits => G is None (tests/test_solve_ik.py:67-77)
+    problem = pink_b200.build_ik(configuration, [ee, posture], dt, limits=[])
+    assert problem.G is None and problem.h is None and problem.P.shape == (6, 6)
+    problem = pink_b200.build_ik(configuration, [ee, posture], dt)
+    assert problem.G.shape == (24, 6) and problem.h.shape == (24,)

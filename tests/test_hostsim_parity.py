@@ -1,0 +1,152 @@
+"""CPU suite: the kernel bodies (fp32, compiled for the host by tests/hostsim)
+against the fp64 oracle.  These run the same source the GPU runs, so logic and
+numerics of the CUDA path are covered without a device; the `-m gpu` twins in
+test_gpu_parity.py repeat them through the real library."""
+
+import numpy as np
+import pytest
+
+from oracle import ik as oik
+from tests import helpers
+from tests.hostsim import HostSim
+
+
+@pytest.mark.parametrize("kind", ["reachable", "unreachable", "at_target"])
+def test_ur5_chain_kernel_matches_oracle(kind):
+    sc = helpers.ur5_scenario(400, kind)
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v, st = hs.solve_ik(prob, sc.q32, targets)
+    assert hs.used_chain, "UR5 frame+posture must take the register-resident chain kernel"
+    v_ref, st_ref = sc.oracle_solve()
+    assert (st == 0).all() and (st_ref == 0).all()
+    ok = helpers.within_tolerance(v, v_ref)
+    if kind == "at_target":
+        # e ~ 1e-7 is at the fp32 resolution of forward kinematics and H = J^T J + 1e-6 I
+        # is as ill-conditioned as it gets (lm_damping inert at zero error): the noise
+        # floor is |dv| ~ 2e-7 |J^-1| / dt, see DESIGN.md "Numerics"
+        assert ok.mean() >= 0.99
+        assert helpers.within_tolerance(v, v_ref, atol=5e-3, rtol=2e-2).all()
+    else:
+        assert ok.all(), f"{(~ok).sum()} instances off, worst {np.abs(v - v_ref).max()}"
+
+
+def test_ur5_general_path_is_bitwise_equal_to_chain_kernel():
+    sc = helpers.ur5_scenario(300, "reachable")
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v1, s1 = hs.solve_ik(prob, sc.q32, targets)
+    v2, s2 = hs.solve_ik(prob, sc.q32, targets, general_path=True)
+    assert not hs.used_chain
+    np.testing.assert_array_equal(s1, s2)
+    # same arithmetic, different register allocation / association: tiny differences allowed
+    np.testing.assert_allclose(v1, v2, rtol=1e-5, atol=1e-5)
+
+
+def test_ur5_full_batch_kkt_certificate():
+    """Size-independent property at a large batch: the fp32 solution satisfies
+    the fp64 KKT conditions of its own QP (unique minimiser => parity)."""
+    sc = helpers.ur5_scenario(20000, "reachable")
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v, st = hs.solve_ik(prob, sc.q32, targets)
+    assert (st == 0).all()
+    H, c, G, h = sc.oracle_build()
+    x = v.astype(np.float64) * sc.dt
+    stat, prim, lo, hi = oik.kkt_check_batch(H, c, G, h, x)
+    scale = np.abs(c).max(axis=1)
+    assert prim.max() <= 1e-6
+    assert np.quantile(stat / scale, 0.999) <= 1e-4
+    assert (stat / scale).max() <= 1e-3
+
+
+def test_ur5_out_of_limits_and_safety_break():
+    sc = helpers.ur5_scenario(200, "reachable", out_of_limits=7)
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v, st = hs.solve_ik(prob, sc.q32, targets)
+    v_ref, st_ref = sc.oracle_solve()
+    np.testing.assert_array_equal(st & 3, st_ref)
+    assert (st == 2).sum() == 7
+    assert np.abs(v[st == 2]).max() == 0.0
+    ok = helpers.within_tolerance(v, v_ref)
+    assert ok.all()
+    # safety_break=False: flagged but solved (configuration.py:195-201)
+    sc.safety_break = False
+    prob, targets, _ = sc.problem()
+    v2, st2 = hs.solve_ik(prob, sc.q32, targets)
+    v2_ref, st2_ref = sc.oracle_solve()
+    flagged = (st2 & 2) != 0
+    assert flagged.sum() == 7
+    # instances too far outside have an empty box: NoSolutionFound in both
+    np.testing.assert_array_equal((st2 & 1) != 0, st2_ref == 1)
+    solved = (st2 & 1) == 0
+    assert helpers.within_tolerance(v2[solved], v2_ref[solved]).all()
+
+
+def test_ur5_no_limits_is_unconstrained_minimiser():
+    sc = helpers.ur5_scenario(100, "reachable")
+    sc.limits, sc.oracle_limits = [], []
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v, st = hs.solve_ik(prob, sc.q32, targets)
+    H, c, G, h = sc.oracle_build()
+    assert G is None
+    x_ref = -np.linalg.solve(H, c[..., None])[..., 0]
+    np.testing.assert_allclose(v * sc.dt, x_ref, rtol=2e-3, atol=2e-6)
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("draco3_description", {}),
+    ("g1_description", {"with_com": True}),
+    ("draco3_description", {"with_relative": True}),
+])
+def test_humanoid_general_path_matches_oracle(name, kw):
+    sc = helpers.humanoid_scenario(name, 24, **kw)
+    hs = HostSim(sc.model)
+    prob, targets, descs = sc.problem()
+    # objective and limit rows
+    H, c, h4 = hs.build_ik(prob, sc.q32, targets)
+    H_ref, c_ref, G_ref, h_ref = sc.oracle_build()
+    scale = np.abs(H_ref).max()
+    np.testing.assert_allclose(H, H_ref, atol=2e-5 * scale, rtol=1e-4)
+    np.testing.assert_allclose(c, c_ref, atol=2e-5 * np.abs(c_ref).max(), rtol=1e-4)
+    # per-task error / Jacobian
+    from oracle import kinematics as okin, tasks as otk
+
+    fk = okin.forward_kinematics(sc.table, sc.q64)
+    for k, (ot, d) in enumerate(zip(sc.oracle_tasks, descs)):
+        e, J = hs.task_terms(prob, k, d["k"], sc.q32, targets)
+        e_ref, J_ref = otk.task_error_jacobian(sc.table, sc.q64, fk, ot)
+        np.testing.assert_allclose(e, e_ref, atol=5e-6, rtol=1e-5)
+        np.testing.assert_allclose(J, np.broadcast_to(J_ref, J.shape), atol=1e-5, rtol=1e-5)
+    # velocities
+    v, st = hs.solve_ik(prob, sc.q32, targets)
+    v_ref, st_ref = sc.oracle_solve()
+    np.testing.assert_array_equal(st & 1, st_ref & 1)
+    good = (st & 1) == 0
+    ok = helpers.within_tolerance(v[good], v_ref[good], atol=5e-4, rtol=5e-3)
+    assert ok.mean() >= 0.95, f"only {ok.mean():.3f} within tolerance, worst {np.abs(v - v_ref)[good].max()}"
+
+
+def test_forward_kinematics_and_frame_jacobian_exports():
+    from oracle import kinematics as okin
+
+    for name in ["ur5_description", "g1_description"]:
+        robot, model, table = helpers.load(name)
+        rng = np.random.default_rng(3)
+        from pink_b200 import workloads
+
+        q = workloads.sample_configurations(table, 16, rng)
+        hs = HostSim(model)
+        oMf, com = hs.forward_kinematics(q)
+        fk = okin.forward_kinematics(table, q.astype(np.float32).astype(np.float64))
+        for f in range(table.nframes):
+            R, p = okin.frame_placement(table, fk, f)
+            np.testing.assert_allclose(oMf[:, f, :, :3], R, atol=3e-6)
+            np.testing.assert_allclose(oMf[:, f, :, 3], p, atol=3e-6)
+        if table.mass.sum() > 0:
+            np.testing.assert_allclose(com, okin.center_of_mass(table, fk), atol=3e-6)
+        f = table.nframes - 1
+        J = hs.frame_jacobian(f, q)
+        np.testing.assert_allclose(J, okin.frame_jacobian_local(table, fk, f), atol=5e-6)

@@ -37,97 +37,92 @@ def load_peaks():
 
 
 # ---------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path, all host cores
+# CPU arm: the oracle's C port of the reference path, all host cores
 # ---------------------------------------------------------------------------
 
-_CPU_CTX = {}
 
+class CpuArm:
+    """fp64 CPU implementation of the same step (oracle/c/pink_oracle.c: dense H,
+    Goldfarb-Idnani QP with Givens updates, pthreads).  Pink + Pinocchio + quadprog
+    cannot be installed offline, so this port stands in for them."""
 
-def _cpu_init():
-    from oracle import kinematics as okin
-    from pink_b200 import workloads
-    from pink_b200.robots import load_robot_description
+    def __init__(self, batch, seed=20260922):
+        from oracle import cport
+        from oracle import kinematics as okin
+        from pink_b200 import workloads as wl
+        from pink_b200.robots import load_robot_description
 
-    robot = load_robot_description("ur5_description")
-    table = robot.model.table()
-    _CPU_CTX.update(table=table, model=robot.model, okin=okin, wl=workloads,
-                    frame=table.frame_names.index("tool0"))
+        robot = load_robot_description("ur5_description")
+        table = robot.model.table()
+        f = table.frame_names.index("tool0")
+        rng = np.random.default_rng(seed)
+        q = wl.sample_configurations(table, batch, rng)
+        qt = wl.perturb_configurations(table, q, rng)
+        R, p = okin.frame_placement(table, okin.forward_kinematics(table, qt), f)
+        self.T = np.concatenate([R, p[:, :, None]], axis=2).astype(np.float32).astype(np.float64)[:, None]
+        self.q = q.astype(np.float32).astype(np.float64)
+        tasks = [
+            {"type": "frame", "frame": f, "cost": np.ones(6), "gain": 1.0, "lm_damping": 1.0},
+            {"type": "posture", "cost": 1e-3, "gain": 1.0, "lm_damping": 0.0,
+             "target": wl.ur5_posture_reference(robot.model)},
+        ]
+        self.port = cport.CPort(table, tasks, wl.UR5_DT, wl.UR5_DAMPING)
+        self.batch = batch
+        self.table, self.model, self.wl = table, robot.model, wl
 
-
-def _cpu_chunk(args):
-    """Solve instances [lo, hi) of the seeded workload with the oracle."""
-    seed, n, lo, hi = args
-    if not _CPU_CTX:
-        _cpu_init()
-    from oracle import ik as oik
-
-    table, model, okin, wl, f = (_CPU_CTX[k] for k in ("table", "model", "okin", "wl", "frame"))
-    q, T = cpu_workload(table, okin, wl, f, n, seed)
-    tasks = [
-        {"type": "frame", "frame": f, "cost": np.ones(6), "gain": 1.0, "lm_damping": 1.0,
-         "target": (T[lo:hi, :, :3], T[lo:hi, :, 3])},
-        {"type": "posture", "cost": 1e-3, "gain": 1.0, "lm_damping": 0.0,
-         "target": wl.ur5_posture_reference(model)},
-    ]
-    t0 = time.perf_counter()
-    v, status = oik.solve_ik_batch(table, q[lo:hi], tasks, wl.UR5_DT, wl.UR5_DAMPING)
-    return time.perf_counter() - t0, float(np.abs(v).sum())
-
-
-def cpu_workload(table, okin, wl, f, n, seed):
-    rng = np.random.default_rng(seed)
-    q = wl.sample_configurations(table, n, rng)
-    qt = wl.perturb_configurations(table, q, rng)
-    R, p = okin.frame_placement(table, okin.forward_kinematics(table, qt), f)
-    T = np.concatenate([R, p[:, :, None]], axis=2).astype(np.float32).astype(np.float64)
-    return q.astype(np.float32).astype(np.float64), T
-
-
-def cpu_throughput(per_core: int, cores: int, seed: int, pool=None):
-    """IK steps/s of the oracle over ``cores`` processes, ``per_core`` instances each."""
-    import multiprocessing as mp
-
-    n = per_core * cores
-    jobs = [(seed, n, i * per_core, (i + 1) * per_core) for i in range(cores)]
-    own = pool is None
-    if own:
-        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init)
-    try:
+    def step(self, threads):
         t0 = time.perf_counter()
-        pool.map(_cpu_chunk, jobs)
-        wall = time.perf_counter() - t0
-    finally:
-        if own:
-            pool.close()
-            pool.join()
-    return n / wall, wall, n
+        v, st = self.port.solve(self.q, self.T, threads=threads)
+        return time.perf_counter() - t0, v, st
+
+    def python_port_rate(self, n=200):
+        """The numpy per-instance loop (structure of the reference's Python path), 1 core."""
+        from oracle import ik as oik
+
+        f = self.table.frame_names.index("tool0")
+        tasks = [
+            {"type": "frame", "frame": f, "cost": np.ones(6), "gain": 1.0, "lm_damping": 1.0,
+             "target": (self.T[:n, 0, :, :3], self.T[:n, 0, :, 3])},
+            {"type": "posture", "cost": 1e-3, "gain": 1.0, "lm_damping": 0.0,
+             "target": self.wl.ur5_posture_reference(self.model)},
+        ]
+        t0 = time.perf_counter()
+        oik.solve_ik_batch(self.table, self.q[:n], tasks, self.wl.UR5_DT, self.wl.UR5_DAMPING)
+        return n / (time.perf_counter() - t0)
+
+
+def cpu_baseline_block(batch, passes=5):
+    cores = os.cpu_count() or 1
+    arm = CpuArm(batch)
+    arm.step(cores)  # warm-up (page faults, thread start)
+    wall = sum(arm.step(cores)[0] for _ in range(passes))
+    one = arm.step(1)[0]
+    return {
+        "value": batch * passes / wall, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{passes} passes over the same {batch}-instance UR5 workload, fp64 C port of the reference path "
+                  f"(dense H, Goldfarb-Idnani QP), {cores} pthreads; Pink/Pinocchio/quadprog are not installable offline",
+        "one_core": batch / one,
+        "python_loop_one_core": arm.python_port_rate(),
+    }
 
 
 def run_reference_arm(args):
-    """``--impl reference``: the reference's CPU path (oracle port; Pink,
-    Pinocchio and quadprog are not installable offline) on all host cores."""
+    """``--impl reference``: the reference's CPU path on all host cores (the
+    oracle's C port; the real stack cannot be installed offline)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
-
     cores = os.cpu_count() or 1
-    per_core = args.cpu_sample
-    pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init)
-    try:
-        for _ in range(args.warmup):
-            cpu_throughput(max(8, per_core // 8), cores, 1, pool)
-        t0 = time.perf_counter()
-        total = 0
-        for k in range(args.steps):
-            _, _, n = cpu_throughput(per_core, cores, 100 + k, pool)
-            total += n
-        wall = time.perf_counter() - t0
-    finally:
-        pool.close()
-        pool.join()
-    value = total / wall
-    sample = f"{per_core * cores} seeded UR5 instances per step ({per_core} per core), per-instance fp64 loop"
+    arm = CpuArm(args.batch)
+    for _ in range(max(args.warmup, 1)):
+        arm.step(cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        arm.step(cores)
+    wall = time.perf_counter() - t0
+    value = args.batch * args.steps / wall
+    sample = (f"every step = the full {args.batch}-instance workload, fp64 C port of the reference path "
+              f"(oracle/c/pink_oracle.c), {cores} pthreads")
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -405,13 +400,7 @@ def run_gpu_arm(args):
         if gather_ms is not None:
             line["solve_plus_allgather"] = {"value": total_steps / (gather_ms * 1e-3), "unit": UNIT}
         if not args.no_cpu and world == 1:
-            cores = os.cpu_count() or 1
-            cv, wall, n = cpu_throughput(args.cpu_sample, cores, 7)
-            line["cpu_baseline"] = {
-                "value": cv, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{n} seeded UR5 instances ({args.cpu_sample} per core, {wall:.1f} s wall), "
-                          "fp64 oracle port of the reference path (Pink/Pinocchio/quadprog unavailable offline)",
-            }
+            line["cpu_baseline"] = cpu_baseline_block(B)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -420,12 +409,11 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--nbuf", type=int, default=32)
-    ap.add_argument("--cpu-sample", type=int, default=1500, help="oracle instances per host core")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

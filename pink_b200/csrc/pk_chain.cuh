@@ -196,7 +196,7 @@ PK_HD void ik_step_chain(const ChainParams<NJ>& P, const float (&q)[NJ], const f
   }
 
   float x[NJ];
-  status |= BoxLSQ<K, NJ, true>::run(A, b, d, beta, lo, hi, K, NJ, x);
+  status |= BoxLSQChol<K, NJ>::run(A, b, d, beta, lo, hi, x);
 #pragma unroll
   for (int j = 0; j < NJ; ++j) v[j] = x[j] * P.inv_dt;
   status_out = status;

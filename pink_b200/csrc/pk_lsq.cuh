@@ -148,7 +148,14 @@ struct BoxLSQ {
     for (int it = 0;; ++it) {
       if (it >= max_iter) { status |= PK_STATUS_ITER_LIMIT; break; }
       const uint64_t act = at_hi | at_lo;
-      eqp(A, b, d, beta, K, n, act, x, y);
+      const uint64_t all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+      if (act == all) {
+        // every coordinate sits on a bound: nothing to solve
+#pragma unroll(UN)
+        for (int i = 0; i < n; ++i) y[i] = x[i];
+      } else {
+        eqp(A, b, d, beta, K, n, act, x, y);
+      }
       // longest feasible step from x towards y
       float step = 1.f;
       int blk = -1;
@@ -210,6 +217,227 @@ struct BoxLSQ {
       if (rel < 0) break;
       at_hi &= ~(1ull << rel);
       at_lo &= ~(1ull << rel);
+    }
+    return status;
+  }
+};
+
+// ---------------------------------------------------------------------------------
+// Register-resident variant for small compile-time sizes (the chain kernel).
+//
+// Same problem and same active-set logic as BoxLSQ, different linear algebra: the
+// equality-constrained subproblems are solved by a Cholesky factorisation of the
+// masked Gram matrix H = A^T A + diag(d^2) (~250 instructions for n = 6 instead of
+// ~1800 for the Householder sweep, which dominated the kernel in the first ncu
+// capture, profiles/r1a), and the squared conditioning this costs is bought back
+// at the end by two steps of iterative refinement with the FACTORED gradient
+// A^T (A x + b) + d (d x + beta) (corrected semi-normal equations): the residual is
+// formed from A, never from H, so its rounding error scales with |A x + b|.
+// Multipliers always come from that factored gradient.  Skipped work: no solve at
+// all while every coordinate sits on a bound (78 % of the UR5 benchmark instances
+// end there), and the first multiplier pass releases every wrong-signed bound at
+// once instead of one per iteration.
+// ---------------------------------------------------------------------------------
+template <int K, int N>
+struct BoxLSQChol {
+  static constexpr int KA = K > 0 ? K : 1;
+  static constexpr int NT = N * (N + 1) / 2;
+  static constexpr uint32_t ALL = (1u << N) - 1u;
+
+  // Cholesky of the masked H (act bit => identity row/column).
+  static PK_HD bool factor(const float (&H)[NT], uint32_t act, float (&L)[NT], float (&inv)[N]) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const bool fj = !((act >> j) & 1u);
+      float dj = fj ? H[tri(j, j)] : 1.f;
+#pragma unroll
+      for (int k = 0; k < j; ++k) dj = fmaf(-L[tri(j, k)], L[tri(j, k)], dj);
+      ok = ok && (dj > 0.f);
+      const float r = rsqrtf(fmaxf(dj, 1e-30f));
+      inv[j] = r;
+      L[tri(j, j)] = dj * r;
+#pragma unroll
+      for (int i = j + 1; i < N; ++i) {
+        const bool fi = !((act >> i) & 1u);
+        float s = (fi && fj) ? H[tri(i, j)] : 0.f;
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fmaf(-L[tri(i, k)], L[tri(j, k)], s);
+        L[tri(i, j)] = s * r;
+      }
+    }
+    return ok;
+  }
+
+  static PK_HD void solve(const float (&L)[NT], const float (&inv)[N], float (&y)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float s = y[i];
+#pragma unroll
+      for (int k = 0; k < i; ++k) s = fmaf(-L[tri(i, k)], y[k], s);
+      y[i] = s * inv[i];
+    }
+#pragma unroll
+    for (int ii = 0; ii < N; ++ii) {
+      const int i = N - 1 - ii;
+      float s = y[i];
+#pragma unroll
+      for (int k = i + 1; k < N; ++k) s = fmaf(-L[tri(k, i)], y[k], s);
+      y[i] = s * inv[i];
+    }
+  }
+
+  // g = A^T (A x + b) + d (d x + beta), gabs = rounding scale of each entry
+  static PK_HD void gradient(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N],
+                             const float (&beta)[N], const float (&x)[N], float (&g)[N], float (&gabs)[N]) {
+    float rho[KA];
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      float s = b[r];
+#pragma unroll
+      for (int j = 0; j < N; ++j) s = fmaf(A[r][j], x[j], s);
+      rho[r] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float rt = fmaf(d[i], x[i], beta[i]);
+      float s = d[i] * rt;
+      float sa = fabsf(s);
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+        s = fmaf(A[r][i], rho[r], s);
+        sa = fmaf(fabsf(A[r][i]), fabsf(rho[r]), sa);
+      }
+      g[i] = s;
+      gabs[i] = sa;
+    }
+  }
+
+  static PK_HD int run(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N], const float (&beta)[N],
+                       const float (&lo)[N], const float (&hi)[N], float (&x)[N]) {
+    int status = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      x[i] = 0.f;
+      if (lo[i] > hi[i]) status |= PK_STATUS_NO_SOLUTION;
+    }
+    if (status) return status;
+    // Gram matrix and linear term
+    float H[NT], c[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        float s = (i == j) ? d[i] * d[i] : 0.f;
+#pragma unroll
+        for (int r = 0; r < K; ++r) s = fmaf(A[r][i], A[r][j], s);
+        H[tri(i, j)] = s;
+      }
+      float s = d[i] * beta[i];
+#pragma unroll
+      for (int r = 0; r < K; ++r) s = fmaf(A[r][i], b[r], s);
+      c[i] = s;
+    }
+    float L[NT], inv[N], y[N];
+    uint32_t fact_act = 0u;
+    if (!factor(H, 0u, L, inv)) status |= PK_STATUS_NOT_POSDEF;
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = -c[i];
+    solve(L, inv, y);
+    uint32_t at_hi = 0u, at_lo = 0u;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (y[i] > hi[i]) { at_hi |= (1u << i); x[i] = hi[i]; }
+      else if (y[i] < lo[i]) { at_lo |= (1u << i); x[i] = lo[i]; }
+      else x[i] = y[i];
+    }
+    if ((at_hi | at_lo) != 0u) {
+      const int max_iter = 3 * N + 8;
+      for (int it = 0;; ++it) {
+        if (it >= max_iter) { status |= PK_STATUS_ITER_LIMIT; break; }
+        const uint32_t act = at_hi | at_lo;
+        if (act != ALL) {
+          // EQP on the working set: H_FF y_F = -(c_F + H_FA x_A)
+          factor(H, act, L, inv);
+          fact_act = act;
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            float s = -c[i];
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+              if ((act >> j) & 1u) s = fmaf(-H[tri(i, j)], x[j], s);
+            y[i] = ((act >> i) & 1u) ? x[i] : s;
+          }
+          solve(L, inv, y);
+          float step = 1.f;
+          int blk = -1;
+          bool blk_hi = false;
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            if (!((act >> i) & 1u)) {
+              const float dlt = y[i] - x[i];
+              if (y[i] > hi[i]) {
+                const float a = (hi[i] - x[i]) / dlt;
+                if (a < step) { step = a; blk = i; blk_hi = true; }
+              } else if (y[i] < lo[i]) {
+                const float a = (lo[i] - x[i]) / dlt;
+                if (a < step) { step = a; blk = i; blk_hi = false; }
+              }
+            }
+          }
+          if (blk >= 0) {
+            step = fmaxf(step, 0.f);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              if (!((act >> i) & 1u)) {
+                x[i] = fmaf(step, y[i] - x[i], x[i]);
+                if (i == blk) x[i] = blk_hi ? hi[i] : lo[i];
+              }
+            }
+            if (blk_hi) at_hi |= (1u << blk); else at_lo |= (1u << blk);
+            continue;
+          }
+#pragma unroll
+          for (int i = 0; i < N; ++i) x[i] = y[i];
+        }
+        // multipliers of the active bounds
+        float g[N], gabs[N];
+        gradient(A, b, d, beta, x, g, gabs);
+        float worst = 0.f;
+        int rel = -1;
+        uint32_t neg = 0u;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          if ((act >> i) & 1u) {
+            const float lam = ((at_hi >> i) & 1u) ? -g[i] : g[i];
+            if (lam < -4e-6f * gabs[i]) {
+              neg |= (1u << i);
+              if (lam < worst) { worst = lam; rel = i; }
+            }
+          }
+        }
+        if (rel < 0) break;
+        // first pass: release every wrong-signed bound; afterwards one at a time
+        const uint32_t drop = (it == 0) ? neg : (1u << rel);
+        at_hi &= ~drop;
+        at_lo &= ~drop;
+      }
+    }
+    // iterative refinement on the final free set with the factored gradient
+    const uint32_t act = at_hi | at_lo;
+    if (act != ALL) {
+      if (fact_act != act) factor(H, act, L, inv);
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        float g[N], gabs[N];
+        gradient(A, b, d, beta, x, g, gabs);
+#pragma unroll
+        for (int i = 0; i < N; ++i) y[i] = ((act >> i) & 1u) ? 0.f : -g[i];
+        solve(L, inv, y);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+          if (!((act >> i) & 1u)) x[i] = fminf(fmaxf(x[i] + y[i], lo[i]), hi[i]);
+      }
     }
     return status;
   }

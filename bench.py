@@ -254,8 +254,10 @@ def run_gpu_arm(args):
     posture_task = PostureTask(cost=1e-3)
     posture_task.set_target(workloads.ur5_posture_reference(model))
     limits = [ConfigurationLimit(model), VelocityLimit(model)]
-    prob, _, _ = describe_problem(model, B, [frame_task, posture_task], workloads.UR5_DT, workloads.UR5_DAMPING,
-                                  limits, True)
+    from pink_b200 import BatchedIK
+
+    ik = BatchedIK(model, [frame_task, posture_task], workloads.UR5_DT, damping=workloads.UR5_DAMPING,
+                   limits=limits, safety_break=True, device=device, batch_size=B)
     torch.cuda.synchronize()
 
     def barrier():
@@ -265,7 +267,7 @@ def run_gpu_arm(args):
 
     def step(k):
         i = k % NBUF
-        eng.solve_ik(prob, qs[i], ts[i], vs[i], ss[i])
+        ik.solve(qs[i], ts[i], vs[i], ss[i])
 
     # ---- device-resident throughput ("value") ---------------------------------
     for k in range(args.warmup):
@@ -327,7 +329,7 @@ def run_gpu_arm(args):
 
     def e2e_step(k):
         i = k % 2
-        eng.solve_ik_host(prob, q_h[i], t_h[i], v_h[i], s_h[i])
+        ik.solve_host(q_h[i], t_h[i], v_h[i], s_h[i])
 
     for k in range(max(3, args.warmup)):
         e2e_step(k)
@@ -393,7 +395,7 @@ def run_gpu_arm(args):
                 "value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": B * (6 + 12) * 4, "d2h_bytes_per_step": B * (6 + 1) * 4,
                 "ms_per_step": e2e_ms / e2e_steps, "bitwise_equal_to_device_path": e2e_ok,
-                "api": "pk_solve_ik_batched_host (pinned host buffers, chunked H2D / kernel / D2H overlap)",
+                "api": "BatchedIK.solve_host -> pk_solve_ik_prepared_host (pinned host buffers; mode %s)" % os.environ.get("PK_HOST_MODE", "0"),
             },
             "nonzero_status": bad,
         }

@@ -136,6 +136,20 @@ int pk_solve_ik_batched(const PkModel* model, const PkProblemDesc* prob,
                         const float* q, const float* targets, float* v,
                         int32_t* status, int64_t B, void* stream);
 
+/* Prepared form for hot loops: validate and marshal the problem once, then every
+ * call costs one kernel launch.  A PkProblem is immutable and tied to the model
+ * it was created for.                                                      */
+typedef struct PkProblem PkProblem;
+int pk_problem_create(const PkModel* model, const PkProblemDesc* prob, PkProblem** out);
+void pk_problem_destroy(PkProblem* problem);
+int pk_solve_ik_prepared(const PkModel* model, const PkProblem* problem,
+                         const float* q, const float* targets, float* v,
+                         int32_t* status, int64_t B, void* stream);
+int pk_solve_ik_prepared_host(PkModel* model, const PkProblem* problem,
+                              const float* q_host, const float* targets_host,
+                              float* v_host, int32_t* status_host, int64_t B,
+                              void* stream);
+
 /* Same through HOST buffers: H2D of q/targets, solve, D2H of v/status, all on
  * `stream`, chunked so copies overlap the kernels.  Returns after enqueueing;
  * the caller synchronises the stream before reading v.                     */

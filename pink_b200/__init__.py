@@ -7,6 +7,7 @@ runs in hand-written CUDA kernels behind the C-ABI of ``include/pink_b200.h``;
 there is no CPU fallback.
 """
 
+from .batched import BatchedIK
 from .configuration import Configuration
 from .exceptions import PinkError
 from .model import JointModelFreeFlyer, Model, RobotWrapper, load_urdf
@@ -18,6 +19,7 @@ from .utils import custom_configuration_vector
 __version__ = "0.1.0"
 
 __all__ = [
+    "BatchedIK",
     "ComTask",
     "Configuration",
     "FrameTask",

@@ -173,38 +173,237 @@ extern "C" void pk_model_destroy(PkModel* m) {
 
 namespace pk {
 
+// Chain kernel: one instance per thread up to the QP data, then the data-dependent
+// active-set rounds run on warps COMPACTED across the CTA.
+//
+// Why: on the UR5 benchmark a lane needs 0.93 active-set rounds on average but a
+// warp pays the maximum over its 32 lanes (3.65 on average); in the first captures
+// (profiles/r01a, r01b) 68-77 % of all issued instructions belonged to QP rounds
+// running with 6-12 of 32 lanes active.  So: every lane first tries the cheap
+// uniform exits in place (no bound active; or every coordinate clamped and all
+// multipliers of the right sign).  Lanes that still need work park their whole QP
+// (state + the factored objective A, b, beta, d) in shared memory, word-major, one
+// slot per thread, and keep nothing in registers.  Then, round after round, the
+// unfinished slots of the CTA are ranked with ballot + popc and the first `total`
+// threads each advance ONE slot by one step of its state machine (active-set round,
+// or the final polish): full warps instead of sparse ones.
 template <int NJ, int NFT>
-__global__ void __launch_bounds__(128) ik_chain_kernel(const __grid_constant__ ChainParams<NJ> P,
-                                                       const float* __restrict__ q,
-                                                       const float* __restrict__ targets,
-                                                       float* __restrict__ v, int32_t* __restrict__ status,
-                                                       int64_t B) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B) return;
-  float qi[NJ], vi[NJ];
-  const float* qrow = q + i * NJ;
-  if constexpr (NJ % 2 == 0) {
+struct ChainSlots {
+  static constexpr int K = 6 * NFT;
+  static constexpr int NT = NJ * (NJ + 1) / 2;
+  static constexpr int kConst = NT + 3 * NJ + 1;  // H, c, lo, hi, gtol
+  static constexpr int kVar = NJ + 5;             // x, at_hi, at_lo, cond, status, rounds
+  static constexpr int kObj = K * NJ + K + NJ + 1;  // A, b, beta, d
+  static constexpr int kWords = kConst + kVar + kObj;
+  // CTA size: as many warps as fit ~96 KB of slots, at most 7 (2 CTAs/SM = 448
+  // threads/SM, which holds 65536 instances on 148 SMs in a single wave)
+  static constexpr int kFit = (96 * 1024 / (kWords * 4)) / 32 * 32;
+  static constexpr int BLOCK = kFit >= 224 ? 224 : (kFit >= 64 ? kFit : 64);
+  static constexpr size_t kSmemBytes = (size_t)kWords * BLOCK * 4;
+};
+
+template <int NJ, int NFT>
+struct SlotIO {
+  using L = ChainSlots<NJ, NFT>;
+  static constexpr int BLOCK = L::BLOCK;
+  static constexpr int K = L::K;
+  static constexpr int KA = K > 0 ? K : 1;
+  static constexpr int NT = L::NT;
+  static __device__ __forceinline__ float& at(float* sm, int word, int slot) { return sm[word * BLOCK + slot]; }
+
+  static __device__ __forceinline__ void store_const(float* sm, int slot, const BoxState<NJ>& S) {
 #pragma unroll
-    for (int k = 0; k < NJ / 2; ++k) {
-      const float2 t = __ldg(reinterpret_cast<const float2*>(qrow) + k);
-      qi[2 * k] = t.x;
-      qi[2 * k + 1] = t.y;
+    for (int k = 0; k < NT; ++k) at(sm, k, slot) = S.H[k];
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      at(sm, NT + k, slot) = S.c[k];
+      at(sm, NT + NJ + k, slot) = S.lo[k];
+      at(sm, NT + 2 * NJ + k, slot) = S.hi[k];
     }
-  } else {
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) qi[k] = __ldg(qrow + k);
+    at(sm, NT + 3 * NJ, slot) = S.gtol;
   }
-  int st;
-  ik_step_chain<NJ, NFT>(P, qi, targets + i * (int64_t)P.target_stride, vi, st);
+  static __device__ __forceinline__ void load_const(float* sm, int slot, BoxState<NJ>& S) {
+#pragma unroll
+    for (int k = 0; k < NT; ++k) S.H[k] = at(sm, k, slot);
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      S.c[k] = at(sm, NT + k, slot);
+      S.lo[k] = at(sm, NT + NJ + k, slot);
+      S.hi[k] = at(sm, NT + 2 * NJ + k, slot);
+    }
+    S.gtol = at(sm, NT + 3 * NJ, slot);
+  }
+  static __device__ __forceinline__ void store_var(float* sm, int slot, const BoxState<NJ>& S) {
+    constexpr int base = L::kConst;
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) at(sm, base + k, slot) = S.x[k];
+    at(sm, base + NJ, slot) = __uint_as_float(S.at_hi);
+    at(sm, base + NJ + 1, slot) = __uint_as_float(S.at_lo);
+    at(sm, base + NJ + 2, slot) = S.cond;
+    at(sm, base + NJ + 3, slot) = __int_as_float(S.status);
+    at(sm, base + NJ + 4, slot) = __int_as_float(S.rounds);
+  }
+  static __device__ __forceinline__ void load_var(float* sm, int slot, BoxState<NJ>& S) {
+    constexpr int base = L::kConst;
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) S.x[k] = at(sm, base + k, slot);
+    S.at_hi = __float_as_uint(at(sm, base + NJ, slot));
+    S.at_lo = __float_as_uint(at(sm, base + NJ + 1, slot));
+    S.cond = at(sm, base + NJ + 2, slot);
+    S.status = __float_as_int(at(sm, base + NJ + 3, slot));
+    S.rounds = __float_as_int(at(sm, base + NJ + 4, slot));
+  }
+  static __device__ __forceinline__ void store_obj(float* sm, int slot, const ChainStep<NJ, NFT>& C) {
+    constexpr int base = L::kConst + L::kVar;
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) at(sm, base + r * NJ + j, slot) = C.A[r][j];
+      at(sm, base + K * NJ + r, slot) = C.b[r];
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) at(sm, base + K * NJ + K + j, slot) = C.beta[j];
+    at(sm, base + K * NJ + K + NJ, slot) = C.d[0];
+  }
+  static __device__ __forceinline__ void load_obj(float* sm, int slot, float (&A)[KA][NJ], float (&b)[KA],
+                                                  float (&d)[NJ], float (&beta)[NJ]) {
+    constexpr int base = L::kConst + L::kVar;
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) A[r][j] = at(sm, base + r * NJ + j, slot);
+      b[r] = at(sm, base + K * NJ + r, slot);
+    }
+    const float dd = at(sm, base + K * NJ + K + NJ, slot);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      beta[j] = at(sm, base + K * NJ + K + j, slot);
+      d[j] = dd;
+    }
+  }
+};
+
+template <int NJ, int NFT>
+__global__ void __launch_bounds__(ChainSlots<NJ, NFT>::BLOCK, 2)
+    ik_chain_kernel(const __grid_constant__ ChainParams<NJ> P, const float* __restrict__ q,
+                    const float* __restrict__ targets, float* __restrict__ v, int32_t* __restrict__ status,
+                    int64_t B) {
+  using IO = SlotIO<NJ, NFT>;
+  constexpr int BLOCK = IO::BLOCK;
+  constexpr int NW = BLOCK / 32;
+  constexpr int KA = IO::KA;
+  using QP = BoxLSQChol<6 * NFT, NJ>;
+  using State = BoxState<NJ>;
+  extern __shared__ __align__(16) float sm[];
+  __shared__ int list[BLOCK];
+  __shared__ signed char phase[BLOCK];  // 0 done, 1 needs a round, 2 needs the polish
+  __shared__ int wcount[NW];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int64_t i = (int64_t)blockIdx.x * BLOCK + tid;
+  const bool valid = i < B;
+
+  int st = 0;
+  bool skip = true;
+  int ph = 0;
+  float x[NJ];
+#pragma unroll
+  for (int k = 0; k < NJ; ++k) x[k] = 0.f;
+  if (valid) {
+    ChainStep<NJ, NFT> C;
+    State S;
+    float qi[NJ];
+    const float* qrow = q + i * NJ;
+    if constexpr (NJ % 2 == 0) {
+#pragma unroll
+      for (int k = 0; k < NJ / 2; ++k) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(qrow) + k);
+        qi[2 * k] = t.x;
+        qi[2 * k + 1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NJ; ++k) qi[k] = __ldg(qrow + k);
+    }
+    st = C.assemble(P, qi, targets + i * (int64_t)P.target_stride, skip);
+    if (!skip) {
+      bool more = QP::init(C.A, C.b, C.d, C.beta, C.lo, C.hi, S);
+      // cheap exits in place: every coordinate clamped => one multiplier check
+      if (more && (S.at_hi | S.at_lo) == QP::ALL) {
+        more = QP::round(S);
+        if (!more) more = QP::polish(C.A, C.b, C.d, C.beta, S);
+        ph = more ? 1 : 0;
+      } else {
+        // interior and well-conditioned => nothing left; otherwise park
+        ph = more ? 1 : (((S.at_hi | S.at_lo) == 0u && S.cond <= 1e3f) ? 0 : 2);
+      }
+      if (ph != 0) {
+        IO::store_const(sm, tid, S);
+        IO::store_var(sm, tid, S);
+        IO::store_obj(sm, tid, C);
+      } else {
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) x[k] = S.x[k];
+        st |= S.status;
+      }
+    }
+  }
+  const bool parked = ph != 0;
+  phase[tid] = (signed char)ph;
+
+  // ---- compacted state machine --------------------------------------------------------
+  for (;;) {
+    __syncthreads();
+    const bool unfinished = phase[tid] != 0;
+    const unsigned ball = __ballot_sync(0xffffffffu, unfinished);
+    if (lane == 0) wcount[warp] = __popc(ball);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      const int c = wcount[k];
+      if (k < warp) base += c;
+      total += c;
+    }
+    if (total == 0) break;
+    if (unfinished) list[base + __popc(ball & ((1u << lane) - 1u))] = tid;
+    __syncthreads();
+    if (tid < total) {
+      const int slot = list[tid];
+      State T;
+      IO::load_const(sm, slot, T);
+      IO::load_var(sm, slot, T);
+      int next;
+      if (phase[slot] == 1) {
+        next = QP::round(T) ? 1 : 2;
+      } else {
+        float A[KA][NJ], b[KA], d[NJ], beta[NJ];
+        IO::load_obj(sm, slot, A, b, d, beta);
+        next = QP::polish(A, b, d, beta, T) ? 1 : 0;
+      }
+      IO::store_var(sm, slot, T);
+      phase[slot] = (signed char)next;
+    }
+  }
+
+  if (!valid) return;
+  if (parked) {
+    constexpr int base = ChainSlots<NJ, NFT>::kConst;
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) x[k] = IO::at(sm, base + k, tid);
+    st |= __float_as_int(IO::at(sm, base + NJ + 3, tid));
+  }
   float* vrow = v + i * NJ;
   if constexpr (NJ % 2 == 0) {
 #pragma unroll
-    for (int k = 0; k < NJ / 2; ++k) reinterpret_cast<float2*>(vrow)[k] = make_float2(vi[2 * k], vi[2 * k + 1]);
+    for (int k = 0; k < NJ / 2; ++k)
+      reinterpret_cast<float2*>(vrow)[k] = make_float2(x[2 * k] * P.inv_dt, x[2 * k + 1] * P.inv_dt);
   } else {
 #pragma unroll
-    for (int k = 0; k < NJ; ++k) vrow[k] = vi[k];
+    for (int k = 0; k < NJ; ++k) vrow[k] = x[k] * P.inv_dt;
   }
-  if (status) status[i] = st;
+  if (status) status[i] = st & 0xff;
 }
 
 // General path: one instance per thread, per-thread arrays in local memory.
@@ -305,21 +504,31 @@ int env_int(const char* name, int dflt) {
   return s ? atoi(s) : dflt;
 }
 
-template <int NJ>
-int launch_chain(const PkModel* m, const pk::DevProblem& P, const float* q, const float* targets, float* v,
-                 int32_t* status, int64_t B, cudaStream_t stream) {
-  pk::ChainParams<NJ> C;
-  pk::make_chain_params<NJ>(m->hm, P, &C);
-  static const int block = std::min(128, std::max(32, env_int("PK_CHAIN_BLOCK", 64)));
-  const int64_t grid = (B + block - 1) / block;
-  switch (C.n_frame_tasks) {
-    case 0: pk::ik_chain_kernel<NJ, 0><<<(unsigned)grid, block, 0, stream>>>(C, q, targets, v, status, B); break;
-    case 1: pk::ik_chain_kernel<NJ, 1><<<(unsigned)grid, block, 0, stream>>>(C, q, targets, v, status, B); break;
-    default: pk::ik_chain_kernel<NJ, 2><<<(unsigned)grid, block, 0, stream>>>(C, q, targets, v, status, B); break;
+template <int NJ, int NFT>
+int launch_chain_nft(const pk::ChainParams<NJ>& C, const float* q, const float* targets, float* v, int32_t* status,
+                     int64_t B, cudaStream_t stream) {
+  using L = pk::ChainSlots<NJ, NFT>;
+  static bool configured = false;  // opt in to > 48 KB of dynamic shared memory once per instantiation
+  if (!configured) {
+    PK_CUDA(cudaFuncSetAttribute(pk::ik_chain_kernel<NJ, NFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)L::kSmemBytes));
+    configured = true;
   }
+  const int64_t grid = (B + L::BLOCK - 1) / L::BLOCK;
+  pk::ik_chain_kernel<NJ, NFT><<<(unsigned)grid, L::BLOCK, L::kSmemBytes, stream>>>(C, q, targets, v, status, B);
   g_launches.fetch_add(1);
   PK_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int NJ>
+int launch_chain(const pk::ChainParams<NJ>& C, const float* q, const float* targets, float* v, int32_t* status,
+                 int64_t B, cudaStream_t stream) {
+  switch (C.n_frame_tasks) {
+    case 0: return launch_chain_nft<NJ, 0>(C, q, targets, v, status, B, stream);
+    case 1: return launch_chain_nft<NJ, 1>(C, q, targets, v, status, B, stream);
+    default: return launch_chain_nft<NJ, 2>(C, q, targets, v, status, B, stream);
+  }
 }
 
 int launch_generic(const PkModel* m, const pk::DevProblem& P, const pk::GenericArgs& A, int64_t B,
@@ -337,18 +546,64 @@ int launch_generic(const PkModel* m, const pk::DevProblem& P, const pk::GenericA
   return 0;
 }
 
-int solve_device(const PkModel* m, const pk::DevProblem& P, const float* q, const float* targets, float* v,
+}  // namespace
+
+// A validated problem with its kernel parameter blocks precomputed, so that the
+// per-call host cost is one kernel launch.
+struct PkProblem {
+  pk::DevProblem P;
+  bool chain = false;
+  int nj = 0;
+  alignas(16) unsigned char chain_params[sizeof(pk::ChainParams<7>)];
+};
+
+namespace {
+
+template <int NJ>
+void fill_chain(const PkModel* m, PkProblem* pr) {
+  static_assert(sizeof(pk::ChainParams<NJ>) <= sizeof(pr->chain_params), "parameter block too small");
+  pk::make_chain_params<NJ>(m->hm, pr->P, reinterpret_cast<pk::ChainParams<NJ>*>(pr->chain_params));
+}
+
+int prepare_problem(const PkModel* m, const PkProblemDesc* desc, PkProblem* pr) {
+  if (!m) return fail("null model");
+  const std::string perr = pk::make_dev_problem(m->hm, desc, &pr->P);
+  if (!perr.empty()) return fail(perr);
+  static const int force_generic = env_int("PK_FORCE_GENERIC", 0);
+  pr->chain = !force_generic && pk::chain_eligible(m->hm, pr->P);
+  pr->nj = m->njoints;
+  if (pr->chain) {
+    switch (m->njoints) {
+      case 2: fill_chain<2>(m, pr); break;
+      case 3: fill_chain<3>(m, pr); break;
+      case 4: fill_chain<4>(m, pr); break;
+      case 5: fill_chain<5>(m, pr); break;
+      case 6: fill_chain<6>(m, pr); break;
+      case 7: fill_chain<7>(m, pr); break;
+      default: pr->chain = false;
+    }
+  }
+  return 0;
+}
+
+template <int NJ>
+int launch_chain_prepared(const PkProblem& pr, const float* q, const float* targets, float* v, int32_t* status,
+                          int64_t B, cudaStream_t stream) {
+  return launch_chain<NJ>(*reinterpret_cast<const pk::ChainParams<NJ>*>(pr.chain_params), q, targets, v, status, B,
+                          stream);
+}
+
+int solve_device(const PkModel* m, const PkProblem& pr, const float* q, const float* targets, float* v,
                  int32_t* status, int64_t B, cudaStream_t stream) {
   if (B == 0) return 0;
-  static const int force_generic = env_int("PK_FORCE_GENERIC", 0);
-  if (!force_generic && pk::chain_eligible(m->hm, P)) {
-    switch (m->njoints) {
-      case 2: return launch_chain<2>(m, P, q, targets, v, status, B, stream);
-      case 3: return launch_chain<3>(m, P, q, targets, v, status, B, stream);
-      case 4: return launch_chain<4>(m, P, q, targets, v, status, B, stream);
-      case 5: return launch_chain<5>(m, P, q, targets, v, status, B, stream);
-      case 6: return launch_chain<6>(m, P, q, targets, v, status, B, stream);
-      case 7: return launch_chain<7>(m, P, q, targets, v, status, B, stream);
+  if (pr.chain) {
+    switch (pr.nj) {
+      case 2: return launch_chain_prepared<2>(pr, q, targets, v, status, B, stream);
+      case 3: return launch_chain_prepared<3>(pr, q, targets, v, status, B, stream);
+      case 4: return launch_chain_prepared<4>(pr, q, targets, v, status, B, stream);
+      case 5: return launch_chain_prepared<5>(pr, q, targets, v, status, B, stream);
+      case 6: return launch_chain_prepared<6>(pr, q, targets, v, status, B, stream);
+      case 7: return launch_chain_prepared<7>(pr, q, targets, v, status, B, stream);
       default: break;
     }
   }
@@ -358,7 +613,7 @@ int solve_device(const PkModel* m, const pk::DevProblem& P, const float* q, cons
   A.v = v;
   A.status = status;
   A.task_index = -1;
-  return launch_generic(m, P, A, B, stream);
+  return launch_generic(m, pr.P, A, B, stream);
 }
 
 int check_common(const PkModel* m, const void* q, int64_t B) {
@@ -375,17 +630,49 @@ int check_common(const PkModel* m, const void* q, int64_t B) {
 // entry points
 // --------------------------------------------------------------------------------------
 
+extern "C" int pk_problem_create(const PkModel* m, const PkProblemDesc* desc, PkProblem** out) {
+  if (!out) return fail("null output");
+  PkProblem* pr = new PkProblem();
+  if (prepare_problem(m, desc, pr)) {
+    delete pr;
+    return 1;
+  }
+  *out = pr;
+  return 0;
+}
+
+extern "C" void pk_problem_destroy(PkProblem* pr) { delete pr; }
+
+static int solve_host_impl(PkModel* m, const PkProblem& pr, const float* q_host, const float* targets_host,
+                           float* v_host, int32_t* status_host, int64_t B, cudaStream_t stream);
+
+extern "C" int pk_solve_ik_prepared(const PkModel* m, const PkProblem* pr, const float* q, const float* targets,
+                                    float* v, int32_t* status, int64_t B, void* stream) {
+  if (check_common(m, q, B)) return 1;
+  if (!pr) return fail("null problem");
+  if (B > 0 && !v) return fail("null v");
+  if (B > 0 && pr->P.target_stride > 0 && !targets) return fail("null targets");
+  return solve_device(m, *pr, q, targets, v, status, B, (cudaStream_t)stream);
+}
+
+extern "C" int pk_solve_ik_prepared_host(PkModel* m, const PkProblem* pr, const float* q_host,
+                                         const float* targets_host, float* v_host, int32_t* status_host, int64_t B,
+                                         void* stream) {
+  if (check_common(m, q_host, B)) return 1;
+  if (!pr) return fail("null problem");
+  if (B > 0 && !v_host) return fail("null v");
+  if (B > 0 && pr->P.target_stride > 0 && !targets_host) return fail("null targets");
+  return solve_host_impl(m, *pr, q_host, targets_host, v_host, status_host, B, (cudaStream_t)stream);
+}
+
 extern "C" int pk_solve_ik_batched(const PkModel* m, const PkProblemDesc* prob, const float* q,
                                    const float* targets, float* v, int32_t* status, int64_t B, void* stream) {
   if (check_common(m, q, B)) return 1;
   if (B > 0 && !v) return fail("null v");
-  pk::DevProblem P;
-  {
-    const std::string perr = pk::make_dev_problem(m->hm, prob, &P);
-    if (!perr.empty()) return fail(perr);
-  }
-  if (B > 0 && P.target_stride > 0 && !targets) return fail("null targets");
-  return solve_device(m, P, q, targets, v, status, B, (cudaStream_t)stream);
+  PkProblem pr;
+  if (prepare_problem(m, prob, &pr)) return 1;
+  if (B > 0 && pr.P.target_stride > 0 && !targets) return fail("null targets");
+  return solve_device(m, pr, q, targets, v, status, B, (cudaStream_t)stream);
 }
 
 extern "C" int pk_solve_ik_batched_host(PkModel* m, const PkProblemDesc* prob, const float* q_host,
@@ -393,14 +680,32 @@ extern "C" int pk_solve_ik_batched_host(PkModel* m, const PkProblemDesc* prob, c
                                         int64_t B, void* stream_) {
   if (check_common(m, q_host, B)) return 1;
   if (B > 0 && !v_host) return fail("null v");
-  pk::DevProblem P;
-  {
-    const std::string perr = pk::make_dev_problem(m->hm, prob, &P);
-    if (!perr.empty()) return fail(perr);
-  }
-  if (B > 0 && P.target_stride > 0 && !targets_host) return fail("null targets");
+  PkProblem pr;
+  if (prepare_problem(m, prob, &pr)) return 1;
+  if (B > 0 && pr.P.target_stride > 0 && !targets_host) return fail("null targets");
+  return solve_host_impl(m, pr, q_host, targets_host, v_host, status_host, B, (cudaStream_t)stream_);
+}
+
+static int solve_host_impl(PkModel* m, const PkProblem& pr, const float* q_host, const float* targets_host,
+                           float* v_host, int32_t* status_host, int64_t B, cudaStream_t stream) {
   if (B == 0) return 0;
-  cudaStream_t stream = (cudaStream_t)stream_;
+  const pk::DevProblem& P = pr.P;
+  // Zero-copy mode: when every buffer is pinned (device-addressable under UVA) the
+  // kernel can pull q / targets over PCIe itself and push v / status back: one
+  // launch, no staging copies.  PK_HOST_MODE=1 selects it; default is staged DMA.
+  static const int host_mode = env_int("PK_HOST_MODE", 0);
+  if (host_mode == 1) {
+    auto pinned = [](const void* ptr) {
+      if (!ptr) return true;
+      cudaPointerAttributes a{};
+      return cudaPointerGetAttributes(&a, ptr) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer;
+    };
+    if (pinned(q_host) && pinned(targets_host) && pinned(v_host) && pinned(status_host)) {
+      PK_CUDA(cudaSetDevice(m->device));
+      return solve_device(m, pr, q_host, targets_host, v_host, status_host, B, stream);
+    }
+    cudaGetLastError();  // clear the error of a failed attribute query on pageable memory
+  }
   std::lock_guard<std::mutex> lock(m->mu);
   PK_CUDA(cudaSetDevice(m->device));
   const int ts = P.target_stride;
@@ -448,7 +753,7 @@ extern "C" int pk_solve_ik_batched_host(PkModel* m, const PkProblemDesc* prob, c
     if (ts > 0)
       PK_CUDA(cudaMemcpyAsync(m->st_t + b0 * ts, targets_host + b0 * ts, sizeof(float) * nb * ts,
                               cudaMemcpyHostToDevice, s));
-    if (solve_device(m, P, m->st_q + b0 * m->nq, m->st_t + b0 * ts, m->st_v + b0 * m->nv, m->st_s + b0, nb, s))
+    if (solve_device(m, pr, m->st_q + b0 * m->nq, m->st_t + b0 * ts, m->st_v + b0 * m->nv, m->st_s + b0, nb, s))
       return 1;
     PK_CUDA(cudaMemcpyAsync(v_host + b0 * m->nv, m->st_v + b0 * m->nv, sizeof(float) * nb * m->nv,
                             cudaMemcpyDeviceToHost, s));

@@ -57,22 +57,29 @@ struct ChainParams {
 
 // NFT = number of FrameTasks (compile time, so that the stacked Jacobian has a
 // static shape and stays in registers).
+//
+// ChainStep::assemble runs everything up to the QP data (limit check, FK, task
+// rows, box); the QP itself is BoxLSQChol (pk_lsq.cuh), either run to completion
+// in the same thread (ik_step_chain, used by the CPU harness and small batches) or
+// staged by the kernel so that its data-dependent rounds run on compacted warps.
 template <int NJ, int NFT>
-PK_HD void ik_step_chain(const ChainParams<NJ>& P, const float (&q)[NJ], const float* __restrict__ trow,
-                         float (&v)[NJ], int& status_out) {
+struct ChainStep {
   static_assert(NFT >= 0 && NFT <= kChainMaxFrameTasks, "unsupported number of frame tasks");
-  constexpr int K = 6 * NFT;
-  constexpr int KA = K > 0 ? K : 1;
+  static constexpr int K = 6 * NFT;
+  static constexpr int KA = K > 0 ? K : 1;
+  float A[KA][NJ];
+  float b[KA];
+  float d[NJ], beta[NJ], lo[NJ], hi[NJ];
+
+  // Returns status bits; `skip` is set when the instance must not be solved
+  // (outside limits with safety_break).
+  PK_HD int assemble(const ChainParams<NJ>& P, const float (&q)[NJ], const float* __restrict__ trow, bool& skip) {
   int status = 0;
 #pragma unroll
   for (int j = 0; j < NJ; ++j)
     if (q[j] < P.chk_lo[j] || q[j] > P.chk_hi[j]) status |= PK_STATUS_OUT_OF_LIMITS;
-  if (status && P.safety_break) {
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) v[j] = 0.f;
-    status_out = status;
-    return;
-  }
+  skip = status && P.safety_break;
+  if (skip) return status;
 
   // ---- forward kinematics: oMi[j] = oMi[j-1] X_j exp(S_j q_j) -----------------
   SE3f T = identity_se3();
@@ -104,8 +111,6 @@ PK_HD void ik_step_chain(const ChainParams<NJ>& P, const float (&q)[NJ], const f
   }
 
   // ---- objective in square-root form: rows of A / b are W J and W alpha e ----------
-  float A[KA][NJ];
-  float b[KA];
   float diag = P.damping;  // damping + sum of Levenberg-Marquardt terms
 
 #pragma unroll
@@ -162,7 +167,6 @@ PK_HD void ik_step_chain(const ChainParams<NJ>& P, const float (&q)[NJ], const f
   }
 
   // diagonal part: posture rows w (x_j + alpha e_j) and sqrt(diag) x_j merged into d_j x_j + beta_j
-  float d[NJ], beta[NJ];
   {
     float se = 0.f;
     float pe[NJ];
@@ -187,7 +191,6 @@ PK_HD void ik_step_chain(const ChainParams<NJ>& P, const float (&q)[NJ], const f
   }
 
   // ---- box rows ------------------------------------------------------------------
-  float lo[NJ], hi[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     const float vb = P.dt * P.vel[j];
@@ -195,8 +198,20 @@ PK_HD void ik_step_chain(const ChainParams<NJ>& P, const float (&q)[NJ], const f
     lo[j] = fmaxf(P.cfg_gain * (P.cfg_lo[j] - q[j]), -vb);
   }
 
+  return status;
+  }
+};
+
+template <int NJ, int NFT>
+PK_HD void ik_step_chain(const ChainParams<NJ>& P, const float (&q)[NJ], const float* __restrict__ trow,
+                         float (&v)[NJ], int& status_out) {
+  ChainStep<NJ, NFT> C;
+  bool skip;
+  int status = C.assemble(P, q, trow, skip);
   float x[NJ];
-  status |= BoxLSQChol<K, NJ>::run(A, b, d, beta, lo, hi, x);
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) x[j] = 0.f;
+  if (!skip) status |= BoxLSQChol<6 * NFT, NJ>::run(C.A, C.b, C.d, C.beta, C.lo, C.hi, x);
 #pragma unroll
   for (int j = 0; j < NJ; ++j) v[j] = x[j] * P.inv_dt;
   status_out = status;

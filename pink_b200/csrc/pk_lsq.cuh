@@ -225,35 +225,53 @@ struct BoxLSQ {
 // ---------------------------------------------------------------------------------
 // Register-resident variant for small compile-time sizes (the chain kernel).
 //
-// Same problem and same active-set logic as BoxLSQ, different linear algebra: the
-// equality-constrained subproblems are solved by a Cholesky factorisation of the
-// masked Gram matrix H = A^T A + diag(d^2) (~250 instructions for n = 6 instead of
-// ~1800 for the Householder sweep, which dominated the kernel in the first ncu
-// capture, profiles/r1a), and the squared conditioning this costs is bought back
-// at the end by two steps of iterative refinement with the FACTORED gradient
-// A^T (A x + b) + d (d x + beta) (corrected semi-normal equations): the residual is
-// formed from A, never from H, so its rounding error scales with |A x + b|.
-// Multipliers always come from that factored gradient.  Skipped work: no solve at
-// all while every coordinate sits on a bound (78 % of the UR5 benchmark instances
-// end there), and the first multiplier pass releases every wrong-signed bound at
-// once instead of one per iteration.
+// Same problem and same primal active-set logic as BoxLSQ, different linear
+// algebra, chosen from the first ncu captures (profiles/r01*): the Householder
+// sweep cost ~1800 instructions per subproblem and the QP was 77 % of the kernel.
+//  * Subproblems are Newton steps on the free coordinates with a Cholesky
+//    factorisation of the masked Gram matrix H = A^T A + diag(d^2) (~300
+//    instructions for n = 6), started from the current gradient H x + c.
+//  * The conditioning lost by squaring is bought back only where it matters: the
+//    final multipliers always come from the FACTORED gradient
+//    A^T (A x + b) + d (d x + beta) (rounding error ~ |A x + b|, not |H| |x|), and
+//    when the pivot ratio of the free block says it is ill-conditioned the free
+//    coordinates get two steps of iterative refinement with that gradient
+//    (corrected semi-normal equations).
+//  * No solve at all while every coordinate sits on a bound, and the first
+//    multiplier pass releases every wrong-signed bound at once.
+// The solver is split into init / round / polish so that a kernel can run the
+// data-dependent rounds on a compacted set of instances (see pk_cabi.cu).
 // ---------------------------------------------------------------------------------
+template <int N>
+struct BoxState {
+  static constexpr int NT = N * (N + 1) / 2;
+  float H[NT], c[N], lo[N], hi[N], x[N];
+  uint32_t at_hi, at_lo;
+  float gtol;  // absolute tolerance on multipliers inside the rounds
+  float cond;  // pivot ratio of the last factorisation of the free block
+  int status;
+  int rounds;
+};
+
 template <int K, int N>
 struct BoxLSQChol {
   static constexpr int KA = K > 0 ? K : 1;
   static constexpr int NT = N * (N + 1) / 2;
   static constexpr uint32_t ALL = (1u << N) - 1u;
+  static constexpr int kMaxRounds = 3 * N + 8;
+  using State = BoxState<N>;
 
-  // Cholesky of the masked H (act bit => identity row/column).
-  static PK_HD bool factor(const float (&H)[NT], uint32_t act, float (&L)[NT], float (&inv)[N]) {
-    bool ok = true;
+  // Cholesky of the masked H (act bit => identity row/column); returns the pivot
+  // ratio max/min over the free coordinates (0 if a pivot is not positive).
+  static PK_HD float factor(const float (&H)[NT], uint32_t act, float (&L)[NT], float (&inv)[N]) {
+    float pmax = 0.f, pmin = 3.0e38f;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       const bool fj = !((act >> j) & 1u);
       float dj = fj ? H[tri(j, j)] : 1.f;
 #pragma unroll
       for (int k = 0; k < j; ++k) dj = fmaf(-L[tri(j, k)], L[tri(j, k)], dj);
-      ok = ok && (dj > 0.f);
+      if (fj) { pmax = fmaxf(pmax, dj); pmin = fminf(pmin, dj); }
       const float r = rsqrtf(fmaxf(dj, 1e-30f));
       inv[j] = r;
       L[tri(j, j)] = dj * r;
@@ -266,7 +284,7 @@ struct BoxLSQChol {
         L[tri(i, j)] = s * r;
       }
     }
-    return ok;
+    return (pmin > 0.f) ? pmax / pmin : 0.f;
   }
 
   static PK_HD void solve(const float (&L)[NT], const float (&inv)[N], float (&y)[N]) {
@@ -287,9 +305,21 @@ struct BoxLSQChol {
     }
   }
 
+  // g = H x + c
+  static PK_HD void gradient_h(const State& S, float (&g)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float s = S.c[i];
+#pragma unroll
+      for (int j = 0; j < N; ++j) s = fmaf(S.H[tri(i, j)], S.x[j], s);
+      g[i] = s;
+    }
+  }
+
   // g = A^T (A x + b) + d (d x + beta), gabs = rounding scale of each entry
-  static PK_HD void gradient(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N],
-                             const float (&beta)[N], const float (&x)[N], float (&g)[N], float (&gabs)[N]) {
+  static PK_HD void gradient_factored(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N],
+                                      const float (&beta)[N], const float (&x)[N], float (&g)[N],
+                                      float (&gabs)[N]) {
     float rho[KA];
 #pragma unroll
     for (int r = 0; r < K; ++r) {
@@ -313,17 +343,22 @@ struct BoxLSQChol {
     }
   }
 
-  static PK_HD int run(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N], const float (&beta)[N],
-                       const float (&lo)[N], const float (&hi)[N], float (&x)[N]) {
-    int status = 0;
+  // Gram matrix, unconstrained minimiser, clamp.  Returns true if rounds are needed.
+  static PK_HD bool init(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N],
+                         const float (&beta)[N], const float (&lo)[N], const float (&hi)[N], State& S) {
+    S.status = 0;
+    S.rounds = 0;
+    S.at_hi = S.at_lo = 0u;
+    S.cond = 1.f;
+    S.gtol = 0.f;
+    bool infeasible = false;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      x[i] = 0.f;
-      if (lo[i] > hi[i]) status |= PK_STATUS_NO_SOLUTION;
+      S.lo[i] = lo[i];
+      S.hi[i] = hi[i];
+      S.x[i] = 0.f;
+      infeasible = infeasible || (lo[i] > hi[i]);
     }
-    if (status) return status;
-    // Gram matrix and linear term
-    float H[NT], c[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
 #pragma unroll
@@ -331,115 +366,167 @@ struct BoxLSQChol {
         float s = (i == j) ? d[i] * d[i] : 0.f;
 #pragma unroll
         for (int r = 0; r < K; ++r) s = fmaf(A[r][i], A[r][j], s);
-        H[tri(i, j)] = s;
+        S.H[tri(i, j)] = s;
       }
       float s = d[i] * beta[i];
 #pragma unroll
       for (int r = 0; r < K; ++r) s = fmaf(A[r][i], b[r], s);
-      c[i] = s;
+      S.c[i] = s;
+    }
+    if (infeasible) {  // empty box <=> quadprog reports no solution
+      S.status = PK_STATUS_NO_SOLUTION;
+      return false;
     }
     float L[NT], inv[N], y[N];
-    uint32_t fact_act = 0u;
-    if (!factor(H, 0u, L, inv)) status |= PK_STATUS_NOT_POSDEF;
+    S.cond = factor(S.H, 0u, L, inv);
+    if (!(S.cond > 0.f)) S.status |= PK_STATUS_NOT_POSDEF;
 #pragma unroll
-    for (int i = 0; i < N; ++i) y[i] = -c[i];
+    for (int i = 0; i < N; ++i) y[i] = -S.c[i];
     solve(L, inv, y);
-    uint32_t at_hi = 0u, at_lo = 0u;
+    float gs = 0.f;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      if (y[i] > hi[i]) { at_hi |= (1u << i); x[i] = hi[i]; }
-      else if (y[i] < lo[i]) { at_lo |= (1u << i); x[i] = lo[i]; }
-      else x[i] = y[i];
+      if (y[i] > hi[i]) { S.at_hi |= (1u << i); S.x[i] = hi[i]; }
+      else if (y[i] < lo[i]) { S.at_lo |= (1u << i); S.x[i] = lo[i]; }
+      else S.x[i] = y[i];
     }
-    if ((at_hi | at_lo) != 0u) {
-      const int max_iter = 3 * N + 8;
-      for (int it = 0;; ++it) {
-        if (it >= max_iter) { status |= PK_STATUS_ITER_LIMIT; break; }
-        const uint32_t act = at_hi | at_lo;
-        if (act != ALL) {
-          // EQP on the working set: H_FF y_F = -(c_F + H_FA x_A)
-          factor(H, act, L, inv);
-          fact_act = act;
+    // rounding scale of H x + c over the box reachable from here
 #pragma unroll
-          for (int i = 0; i < N; ++i) {
-            float s = -c[i];
+    for (int i = 0; i < N; ++i) {
+      float s = fabsf(S.c[i]);
 #pragma unroll
-            for (int j = 0; j < N; ++j)
-              if ((act >> j) & 1u) s = fmaf(-H[tri(i, j)], x[j], s);
-            y[i] = ((act >> i) & 1u) ? x[i] : s;
-          }
-          solve(L, inv, y);
-          float step = 1.f;
-          int blk = -1;
-          bool blk_hi = false;
+      for (int j = 0; j < N; ++j) s = fmaf(fabsf(S.H[tri(i, j)]), fabsf(S.x[j]), s);
+      gs = fmaxf(gs, s);
+    }
+    S.gtol = 4e-6f * gs;
+    return (S.at_hi | S.at_lo) != 0u;
+  }
+
+  // One active-set round: Newton step on the free set (with blocking), then release
+  // of wrong-signed bounds.  Returns true if another round is needed.
+  static PK_HD bool round(State& S) {
+    const bool first = S.rounds == 0;
+    if (++S.rounds > kMaxRounds) {
+      S.status |= PK_STATUS_ITER_LIMIT;
+      return false;
+    }
+    const uint32_t act = S.at_hi | S.at_lo;
+    float g[N];
+    if (act != ALL) {
+#ifdef PK_COUNT_ITERS
+      S.status += 256;
+#endif
+      gradient_h(S, g);
+      float L[NT], inv[N], y[N];
+      S.cond = factor(S.H, act, L, inv);
 #pragma unroll
-          for (int i = 0; i < N; ++i) {
-            if (!((act >> i) & 1u)) {
-              const float dlt = y[i] - x[i];
-              if (y[i] > hi[i]) {
-                const float a = (hi[i] - x[i]) / dlt;
-                if (a < step) { step = a; blk = i; blk_hi = true; }
-              } else if (y[i] < lo[i]) {
-                const float a = (lo[i] - x[i]) / dlt;
-                if (a < step) { step = a; blk = i; blk_hi = false; }
-              }
-            }
-          }
-          if (blk >= 0) {
-            step = fmaxf(step, 0.f);
+      for (int i = 0; i < N; ++i) y[i] = ((act >> i) & 1u) ? 0.f : -g[i];
+      solve(L, inv, y);
+      float step = 1.f;
+      int blk = -1;
+      bool blk_hi = false;
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-              if (!((act >> i) & 1u)) {
-                x[i] = fmaf(step, y[i] - x[i], x[i]);
-                if (i == blk) x[i] = blk_hi ? hi[i] : lo[i];
-              }
-            }
-            if (blk_hi) at_hi |= (1u << blk); else at_lo |= (1u << blk);
-            continue;
-          }
-#pragma unroll
-          for (int i = 0; i < N; ++i) x[i] = y[i];
-        }
-        // multipliers of the active bounds
-        float g[N], gabs[N];
-        gradient(A, b, d, beta, x, g, gabs);
-        float worst = 0.f;
-        int rel = -1;
-        uint32_t neg = 0u;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-          if ((act >> i) & 1u) {
-            const float lam = ((at_hi >> i) & 1u) ? -g[i] : g[i];
-            if (lam < -4e-6f * gabs[i]) {
-              neg |= (1u << i);
-              if (lam < worst) { worst = lam; rel = i; }
-            }
+      for (int i = 0; i < N; ++i) {
+        if (!((act >> i) & 1u)) {
+          const float xn = S.x[i] + y[i];
+          if (xn > S.hi[i]) {
+            const float a = (S.hi[i] - S.x[i]) / y[i];
+            if (a < step) { step = a; blk = i; blk_hi = true; }
+          } else if (xn < S.lo[i]) {
+            const float a = (S.lo[i] - S.x[i]) / y[i];
+            if (a < step) { step = a; blk = i; blk_hi = false; }
           }
         }
-        if (rel < 0) break;
-        // first pass: release every wrong-signed bound; afterwards one at a time
-        const uint32_t drop = (it == 0) ? neg : (1u << rel);
-        at_hi &= ~drop;
-        at_lo &= ~drop;
+      }
+      step = fmaxf(step, 0.f);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        if (!((act >> i) & 1u)) {
+          S.x[i] = fmaf(step, y[i], S.x[i]);
+          if (i == blk) S.x[i] = blk_hi ? S.hi[i] : S.lo[i];
+        }
+      }
+      if (blk >= 0) {
+        if (blk_hi) S.at_hi |= (1u << blk); else S.at_lo |= (1u << blk);
+        return true;
       }
     }
-    // iterative refinement on the final free set with the factored gradient
-    const uint32_t act = at_hi | at_lo;
-    if (act != ALL) {
-      if (fact_act != act) factor(H, act, L, inv);
+    // multipliers of the active bounds
+    gradient_h(S, g);
+    float worst = 0.f;
+    int rel = -1;
+    uint32_t neg = 0u;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if ((act >> i) & 1u) {
+        const float lam = ((S.at_hi >> i) & 1u) ? -g[i] : g[i];
+        if (lam < -S.gtol) {
+          neg |= (1u << i);
+          if (lam < worst) { worst = lam; rel = i; }
+        }
+      }
+    }
+    if (rel < 0) return false;
+    // first pass: release every wrong-signed bound; afterwards one at a time
+    const uint32_t drop = first ? neg : (1u << rel);
+    S.at_hi &= ~drop;
+    S.at_lo &= ~drop;
+    return true;
+  }
+
+  // Accurate acceptance test and refinement.  Returns true if more rounds are needed.
+  static PK_HD bool polish(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N],
+                           const float (&beta)[N], State& S) {
+    if (S.status & (PK_STATUS_NO_SOLUTION | PK_STATUS_ITER_LIMIT)) return false;
+    const uint32_t act = S.at_hi | S.at_lo;
+    if (act == 0u && S.cond <= 1e3f) return false;  // interior, well-conditioned: x is the plain solve
+    float g[N], gabs[N];
+    gradient_factored(A, b, d, beta, S.x, g, gabs);
+    float worst = 0.f;
+    int rel = -1;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if ((act >> i) & 1u) {
+        const float lam = ((S.at_hi >> i) & 1u) ? -g[i] : g[i];
+        if (lam < -4e-6f * gabs[i] && lam < worst) { worst = lam; rel = i; }
+      }
+    }
+    if (rel >= 0 && S.rounds < kMaxRounds) {
+      S.at_hi &= ~(1u << rel);
+      S.at_lo &= ~(1u << rel);
+      return true;
+    }
+    if (act != ALL && S.cond > 1e3f) {
+      // ill-conditioned free block: two refinement steps with the factored gradient
+      float L[NT], inv[N], y[N];
+      factor(S.H, act, L, inv);
 #pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
-        float g[N], gabs[N];
-        gradient(A, b, d, beta, x, g, gabs);
 #pragma unroll
         for (int i = 0; i < N; ++i) y[i] = ((act >> i) & 1u) ? 0.f : -g[i];
         solve(L, inv, y);
 #pragma unroll
         for (int i = 0; i < N; ++i)
-          if (!((act >> i) & 1u)) x[i] = fminf(fmaxf(x[i] + y[i], lo[i]), hi[i]);
+          if (!((act >> i) & 1u)) S.x[i] = fminf(fmaxf(S.x[i] + y[i], S.lo[i]), S.hi[i]);
+        if (pass == 0) gradient_factored(A, b, d, beta, S.x, g, gabs);
       }
     }
-    return status;
+    return false;
+  }
+
+  // Whole solve in one thread (no compaction).
+  static PK_HD int run(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N], const float (&beta)[N],
+                       const float (&lo)[N], const float (&hi)[N], float (&x)[N]) {
+    State S;
+    bool more = init(A, b, d, beta, lo, hi, S);
+    for (;;) {
+      while (more) more = round(S);
+      more = polish(A, b, d, beta, S);
+      if (!more) break;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = S.x[i];
+    return S.status;
   }
 };
 

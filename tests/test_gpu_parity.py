@@ -206,3 +206,28 @@ def test_unbatched_configuration_behaves_like_the_reference():
     assert problem.G is None and problem.h is None and problem.P.shape == (6, 6)
     problem = pink_b200.build_ik(configuration, [ee, posture], dt)
     assert problem.G.shape == (24, 6) and problem.h.shape == (24,)
+
+
+def test_prepared_solver_equals_solve_ik_and_host_modes(monkeypatch):
+    sc = helpers.ur5_scenario(30000, "reachable")
+    v, st = _gpu_solve(sc)
+    ik = pink_b200.BatchedIK(sc.model, sc.tasks, sc.dt, damping=sc.damping, batch_size=sc.B)
+    assert ik.target_stride == 12 and ik.target_layout == [(0, 0, 12)]
+    prob, targets, _ = sc.problem()
+    q_d = torch.as_tensor(sc.q32, device="cuda")
+    t_d = torch.as_tensor(targets, device="cuda")
+    v2, st2 = ik.solve(q_d, t_d)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(v2.cpu().numpy(), v)
+    np.testing.assert_array_equal(st2.cpu().numpy(), st)
+    q_h, t_h = torch.as_tensor(sc.q32).pin_memory(), torch.as_tensor(targets).pin_memory()
+    v_h = torch.empty((sc.B, 6), dtype=torch.float32).pin_memory()
+    s_h = torch.empty((sc.B,), dtype=torch.int32).pin_memory()
+    ik.solve_host(q_h, t_h, v_h, s_h)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(v_h.numpy(), v)
+    # pageable host memory takes the staged path as well
+    v_p = torch.empty((sc.B, 6), dtype=torch.float32)
+    ik.solve_host(torch.as_tensor(sc.q32), torch.as_tensor(targets), v_p, None)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(v_p.numpy(), v)

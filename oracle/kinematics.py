@@ -214,14 +214,29 @@ def integrate(m, q, dv):
     rq, rv = root_dims(m)
     out = np.array(np.broadcast_to(q, np.broadcast_shapes(q.shape[:-1], dv.shape[:-1]) + (m.nq,)))
     if m.free_flyer:
-        R0 = lie.quat_to_matrix(q[..., 3:7])
-        Re, pe = lie.exp6(dv[..., 0:6])
-        Rn, pn = lie.se3_mul(R0, q[..., 0:3], Re, pe)
-        out[..., 0:3] = pn
-        quat = lie.matrix_to_quat(Rn)
-        # keep the quaternion on the same hemisphere as the input one
-        flip = np.sum(quat * q[..., 3:7], axis=-1, keepdims=True) < 0.0
-        out[..., 3:7] = np.where(flip, -quat, quat)
+        # Pinocchio's SE(3) integration on [p, quaternion]: p += R V(w) v,
+        # quat <- quat * exp_quat(w), renormalised
+        quat0 = q[..., 3:7] / np.linalg.norm(q[..., 3:7], axis=-1, keepdims=True)
+        R0 = lie.quat_to_matrix(quat0)
+        _, pe = lie.exp6(dv[..., 0:6])
+        out[..., 0:3] = q[..., 0:3] + np.einsum("...ij,...j->...i", R0, pe)
+        w = dv[..., 3:6]
+        th = np.linalg.norm(w, axis=-1)
+        small = th < 1e-8
+        k = np.where(small, 0.5, np.sin(0.5 * th) / np.where(small, 1.0, th))
+        dq = np.concatenate([k[..., None] * w, np.cos(0.5 * th)[..., None]], axis=-1)
+        ax, ay, az, aw = (quat0[..., i] for i in range(4))
+        bx, by, bz, bw = (dq[..., i] for i in range(4))
+        quat = np.stack(
+            [
+                aw * bx + ax * bw + ay * bz - az * by,
+                aw * by - ax * bz + ay * bw + az * bx,
+                aw * bz + ax * by - ay * bx + az * bw,
+                aw * bw - ax * bx - ay * by - az * bz,
+            ],
+            axis=-1,
+        )
+        out[..., 3:7] = quat / np.linalg.norm(quat, axis=-1, keepdims=True)
     out[..., rq:] = q[..., rq:] + dv[..., rv:]
     return out
 

@@ -287,7 +287,7 @@ template <int NJ, int NFT>
 __global__ void __launch_bounds__(ChainSlots<NJ, NFT>::BLOCK, 2)
     ik_chain_kernel(const __grid_constant__ ChainParams<NJ> P, const float* __restrict__ q,
                     const float* __restrict__ targets, float* __restrict__ v, int32_t* __restrict__ status,
-                    int64_t B) {
+                    int64_t B, int rounds_per_sync) {
   using IO = SlotIO<NJ, NFT>;
   constexpr int BLOCK = IO::BLOCK;
   constexpr int NW = BLOCK / 32;
@@ -377,6 +377,7 @@ __global__ void __launch_bounds__(ChainSlots<NJ, NFT>::BLOCK, 2)
       int next;
       if (phase[slot] == 1) {
         next = QP::round(T) ? 1 : 2;
+        for (int r = 1; r < rounds_per_sync && next == 1; ++r) next = QP::round(T) ? 1 : 2;
       } else {
         float A[KA][NJ], b[KA], d[NJ], beta[NJ];
         IO::load_obj(sm, slot, A, b, d, beta);
@@ -402,6 +403,42 @@ __global__ void __launch_bounds__(ChainSlots<NJ, NFT>::BLOCK, 2)
   } else {
 #pragma unroll
     for (int k = 0; k < NJ; ++k) vrow[k] = x[k] * P.inv_dt;
+  }
+  if (status) status[i] = st & 0xff;
+}
+
+// Plain variant: the whole step, QP rounds included, in the owning thread (lanes of
+// a warp wait for the slowest QP).  Kept selectable (PK_CHAIN_MODE=0) so that the
+// compaction can be measured against it; see DESIGN.md "Kernels".
+template <int NJ, int NFT>
+__global__ void __launch_bounds__(128, 4)
+    ik_chain_kernel_plain(const __grid_constant__ ChainParams<NJ> P, const float* __restrict__ q,
+                          const float* __restrict__ targets, float* __restrict__ v, int32_t* __restrict__ status,
+                          int64_t B) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  float qi[NJ], vi[NJ];
+  const float* qrow = q + i * NJ;
+  if constexpr (NJ % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < NJ / 2; ++k) {
+      const float2 t = __ldg(reinterpret_cast<const float2*>(qrow) + k);
+      qi[2 * k] = t.x;
+      qi[2 * k + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) qi[k] = __ldg(qrow + k);
+  }
+  int st;
+  ik_step_chain<NJ, NFT>(P, qi, targets + i * (int64_t)P.target_stride, vi, st);
+  float* vrow = v + i * NJ;
+  if constexpr (NJ % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < NJ / 2; ++k) reinterpret_cast<float2*>(vrow)[k] = make_float2(vi[2 * k], vi[2 * k + 1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) vrow[k] = vi[k];
   }
   if (status) status[i] = st & 0xff;
 }
@@ -514,8 +551,17 @@ int launch_chain_nft(const pk::ChainParams<NJ>& C, const float* q, const float* 
                                  (int)L::kSmemBytes));
     configured = true;
   }
+  static const int mode = env_int("PK_CHAIN_MODE", 1);
+  if (mode == 0) {
+    const int64_t grid0 = (B + 127) / 128;
+    pk::ik_chain_kernel_plain<NJ, NFT><<<(unsigned)grid0, 128, 0, stream>>>(C, q, targets, v, status, B);
+    g_launches.fetch_add(1);
+    PK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int64_t grid = (B + L::BLOCK - 1) / L::BLOCK;
-  pk::ik_chain_kernel<NJ, NFT><<<(unsigned)grid, L::BLOCK, L::kSmemBytes, stream>>>(C, q, targets, v, status, B);
+  static const int rps = std::max(1, env_int("PK_ROUNDS_PER_SYNC", 1));
+  pk::ik_chain_kernel<NJ, NFT><<<(unsigned)grid, L::BLOCK, L::kSmemBytes, stream>>>(C, q, targets, v, status, B, rps);
   g_launches.fetch_add(1);
   PK_CUDA(cudaGetLastError());
   return 0;

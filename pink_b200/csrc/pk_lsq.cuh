@@ -242,6 +242,10 @@ struct BoxLSQ {
 // The solver is split into init / round / polish so that a kernel can run the
 // data-dependent rounds on a compacted set of instances (see pk_cabi.cu).
 // ---------------------------------------------------------------------------------
+#ifdef PK_COUNT_ITERS
+extern "C" void pk_count_nfree(int nfree, int round);
+#endif
+
 template <int N>
 struct BoxState {
   static constexpr int NT = N * (N + 1) / 2;
@@ -415,6 +419,7 @@ struct BoxLSQChol {
     if (act != ALL) {
 #ifdef PK_COUNT_ITERS
       S.status += 256;
+      pk_count_nfree(N - __builtin_popcount(act), S.rounds);
 #endif
       gradient_h(S, g);
       float L[NT], inv[N], y[N];

@@ -185,16 +185,29 @@ def test_unbatched_configuration_behaves_like_the_reference():
     v = pink_b200.solve_ik(configuration, [ee, posture], 1e-3, solver="quadprog")
     assert isinstance(v, np.ndarray) and v.shape == (6,)
     assert np.abs(v).max() < 1e-3
-    # move the target: single task converges (tests/test_solve_ik.py:160-210)
+    # move the target and close the loop (examples/arm_ur5.py:65-86): the fp32 engine must
+    # follow the fp64 oracle's trajectory step by step
+    from oracle import kinematics as okin2, tasks as otk2
+
     target = ee.transform_target_to_world
     target.translation[1] += 0.1
     dt = 5e-3
-    errs = []
-    for _ in range(120):
+    f = table.frame_names.index("tool0")
+    otasks = [{"type": "frame", "frame": f, "cost": np.ones(6), "gain": 1.0, "lm_damping": 1.0,
+               "target": (target.rotation.copy(), target.translation.copy())},
+              {"type": "posture", "cost": 1e-3, "gain": 1.0, "lm_damping": 0.0, "target": q_ref.copy()}]
+    q_o = q_ref.copy()
+    errs, errs_o = [], []
+    for _ in range(60):
         v = pink_b200.solve_ik(configuration, [ee, posture], dt, solver="quadprog")
         configuration.integrate_inplace(v, dt)
         errs.append(np.linalg.norm(ee.compute_error(configuration)))
-    assert errs[-1] < 1e-3 and errs[-1] < errs[0]
+        v_o, st_o = oik.solve_ik(table, q_o, otasks, dt)
+        q_o = okin2.integrate(table, q_o, v_o * dt)
+        errs_o.append(np.linalg.norm(otk2.frame_task_error(table, okin2.forward_kinematics(table, q_o), otasks[0])))
+    np.testing.assert_allclose(errs, errs_o, rtol=2e-3, atol=2e-5)
+    np.testing.assert_allclose(configuration.q, q_o, atol=2e-4)
+    assert errs[-1] < errs[0] and all(b <= a + 1e-6 for a, b in zip(errs, errs[1:]))
     # out of limits raises (tests/test_solve_ik.py:39-65)
     q_bad = q_ref.copy()
     q_bad[2] = 4.0

@@ -360,7 +360,7 @@ struct Generic {
       if (skip) {
         for (int i = 0; i < nv; ++i) out.v[i] = 0.f;
       } else {
-        status |= BoxLSQ<kGenericMaxRows, NVMAX, false>::run(A, b, d, beta, lo, hi, K, nv, x);
+        status |= BoxLSQ<kGenericMaxRows, NVMAX>::run(A, b, d, beta, lo, hi, K, nv, x);
         for (int i = 0; i < nv; ++i) out.v[i] = x[i] * P.inv_dt;
       }
     }

@@ -44,12 +44,13 @@ namespace pk {
 // Packed lower triangle (used for the exported Hessian).
 PK_HD constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
-// KMAX x N capacity.  FIXED: K == KMAX and n == N at compile time (all loops
-// unrolled, constant indices => registers); else run-time sizes, rolled loops.
-template <int KMAX, int N, bool FIXED>
+// General-path solver: run-time sizes K <= KMAX rows, n <= N coordinates, arrays
+// addressed dynamically (thread-local memory).  Every subproblem is solved on the
+// COMPACTED free set: with tight velocity limits most coordinates sit on a bound
+// (24 of 33 on the Draco3-class workload), so a factorisation costs
+// ~2 (K+1) |F|^2 instead of ~2 (K+1) n^2.
+template <int KMAX, int N>
 struct BoxLSQ {
-  static constexpr int UN = FIXED ? N : 1;
-  static constexpr int UK = FIXED ? (KMAX > 0 ? KMAX : 1) : 1;
   static constexpr int KA = KMAX > 0 ? KMAX : 1;
   static constexpr int NU = N * (N - 1) / 2 > 0 ? N * (N - 1) / 2 : 1;
 
@@ -58,76 +59,64 @@ struct BoxLSQ {
   // Least squares on the free coordinates with x fixed on `act`.  y receives the
   // full solution (fixed entries copied from x).  Returns false if singular.
   static PK_HD bool eqp(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N], const float (&beta)[N],
-                        int K_, int n_, uint64_t act, const float (&x)[N], float (&y)[N]) {
-    const int K = FIXED ? KMAX : K_;
-    const int n = FIXED ? N : n_;
-    float Aw[KA][N];
+                        int K, int n, uint64_t act, const float (&x)[N], float (&y)[N]) {
+    float Aw[KA][N];  // free columns, compacted
     float zb[KA];
     float Rd[N], Ru[NU], zt[N];
+    int idx[N];
     bool ok = true;
-    // masked copy, right-hand side = b + A_act x_act
-#pragma unroll(UK)
+    int nf = 0;
+    for (int j = 0; j < n; ++j) {
+      y[j] = x[j];
+      if (!((act >> j) & 1ull)) idx[nf++] = j;
+    }
+    // right-hand side = b + A_act x_act; compacted copy of the free columns
     for (int r = 0; r < K; ++r) {
       float s = b[r];
-#pragma unroll(UN)
-      for (int j = 0; j < n; ++j) {
-        const bool fx = (act >> j) & 1ull;
-        Aw[r][j] = fx ? 0.f : A[r][j];
-        if (fx) s = fmaf(A[r][j], x[j], s);
-      }
+      for (int j = 0; j < n; ++j)
+        if ((act >> j) & 1ull) s = fmaf(A[r][j], x[j], s);
       zb[r] = s;
+      for (int c = 0; c < nf; ++c) Aw[r][c] = A[r][idx[c]];
     }
-#pragma unroll(UN)
-    for (int k = 0; k < n; ++k) {
-      const bool fx = (act >> k) & 1ull;
+    for (int k = 0; k < nf; ++k) {
       float sigma = 0.f;
-#pragma unroll(UK)
       for (int r = 0; r < K; ++r) sigma = fmaf(Aw[r][k], Aw[r][k], sigma);
-      const float alpha = fx ? 1.f : d[k];
-      zt[k] = fx ? -x[k] : beta[k];
+      const float alpha = d[idx[k]];
+      zt[k] = beta[idx[k]];
       const float norm = sqrtf(fmaf(alpha, alpha, sigma));
       ok = ok && (norm > 0.f);
-      const float v0 = alpha + norm;                      // alpha >= 0: no cancellation
-      const float tau = (sigma > 0.f) ? 1.f / (norm * v0) : 0.f;  // 2 / |v|^2
+      const float v0 = alpha + norm;                               // alpha >= 0: no cancellation
+      const float tau = (sigma > 0.f) ? 1.f / (norm * v0) : 0.f;   // 2 / |v|^2
       Rd[k] = (sigma > 0.f) ? -norm : alpha;
-#pragma unroll(UN)
-      for (int j = k + 1; j < n; ++j) {
+      for (int j = k + 1; j < nf; ++j) {
         float s = 0.f;
-#pragma unroll(UK)
         for (int r = 0; r < K; ++r) s = fmaf(Aw[r][k], Aw[r][j], s);
         s *= tau;
         Ru[ut(k, j)] = -s * v0;
-#pragma unroll(UK)
         for (int r = 0; r < K; ++r) Aw[r][j] = fmaf(-s, Aw[r][k], Aw[r][j]);
       }
       float s = v0 * zt[k];
-#pragma unroll(UK)
       for (int r = 0; r < K; ++r) s = fmaf(Aw[r][k], zb[r], s);
       s *= tau;
       zt[k] = fmaf(-s, v0, zt[k]);
-#pragma unroll(UK)
       for (int r = 0; r < K; ++r) zb[r] = fmaf(-s, Aw[r][k], zb[r]);
     }
-    // R y = -zt
-#pragma unroll(UN)
-    for (int kk = 0; kk < n; ++kk) {
-      const int k = n - 1 - kk;
+    // R y_F = -zt
+    for (int kk = 0; kk < nf; ++kk) {
+      const int k = nf - 1 - kk;
       float s = -zt[k];
-#pragma unroll(UN)
-      for (int j = k + 1; j < n; ++j) s = fmaf(-Ru[ut(k, j)], y[j], s);
-      y[k] = ((act >> k) & 1ull) ? x[k] : s / Rd[k];
+      for (int j = k + 1; j < nf; ++j) s = fmaf(-Ru[ut(k, j)], zt[j], s);
+      zt[k] = (Rd[k] != 0.f) ? s / Rd[k] : 0.f;  // zt now holds the solution
+      y[idx[k]] = zt[k];
     }
     return ok;
   }
 
   // Returns status bits (0, NOT_POSDEF, NO_SOLUTION, ITER_LIMIT).
   static PK_HD int run(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N], const float (&beta)[N],
-                       const float (&lo)[N], const float (&hi)[N], int K_, int n_, float (&x)[N]) {
-    const int K = FIXED ? KMAX : K_;
-    const int n = FIXED ? N : n_;
+                       const float (&lo)[N], const float (&hi)[N], int K, int n, float (&x)[N]) {
     int status = 0;
     // infeasible box <=> quadprog reports no solution
-#pragma unroll(UN)
     for (int i = 0; i < n; ++i) {
       x[i] = 0.f;
       if (lo[i] > hi[i]) status |= PK_STATUS_NO_SOLUTION;
@@ -136,7 +125,6 @@ struct BoxLSQ {
     float y[N];
     if (!eqp(A, b, d, beta, K, n, 0ull, x, y)) status |= PK_STATUS_NOT_POSDEF;
     uint64_t at_hi = 0ull, at_lo = 0ull;
-#pragma unroll(UN)
     for (int i = 0; i < n; ++i) {
       if (y[i] > hi[i]) { at_hi |= (1ull << i); x[i] = hi[i]; }
       else if (y[i] < lo[i]) { at_lo |= (1ull << i); x[i] = lo[i]; }
@@ -144,23 +132,24 @@ struct BoxLSQ {
     }
     if ((at_hi | at_lo) == 0ull) return status;
 
-    const int max_iter = 3 * n + 8;
+    const uint64_t all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+    const int max_iter = 4 * n + 16;
     for (int it = 0;; ++it) {
       if (it >= max_iter) { status |= PK_STATUS_ITER_LIMIT; break; }
       const uint64_t act = at_hi | at_lo;
-      const uint64_t all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
       if (act == all) {
         // every coordinate sits on a bound: nothing to solve
-#pragma unroll(UN)
         for (int i = 0; i < n; ++i) y[i] = x[i];
       } else {
+#ifdef PK_COUNT_ITERS
+        status += 256;
+#endif
         eqp(A, b, d, beta, K, n, act, x, y);
       }
       // longest feasible step from x towards y
       float step = 1.f;
       int blk = -1;
       bool blk_hi = false;
-#pragma unroll(UN)
       for (int i = 0; i < n; ++i) {
         if (!((act >> i) & 1ull)) {
           const float dlt = y[i] - x[i];
@@ -175,7 +164,6 @@ struct BoxLSQ {
       }
       if (blk >= 0) {
         step = fmaxf(step, 0.f);
-#pragma unroll(UN)
         for (int i = 0; i < n; ++i) {
           if (!((act >> i) & 1ull)) {
             x[i] = fmaf(step, y[i] - x[i], x[i]);
@@ -185,38 +173,39 @@ struct BoxLSQ {
         if (blk_hi) at_hi |= (1ull << blk); else at_lo |= (1ull << blk);
         continue;
       }
-#pragma unroll(UN)
       for (int i = 0; i < n; ++i) x[i] = y[i];
       // multipliers from the factored gradient g = A^T (A x + b) + d (d x + beta)
       float rho[KA];
-#pragma unroll(UK)
       for (int r = 0; r < K; ++r) {
         float s = b[r];
-#pragma unroll(UN)
         for (int j = 0; j < n; ++j) s = fmaf(A[r][j], x[j], s);
         rho[r] = s;
       }
       float worst = 0.f;
       int rel = -1;
-#pragma unroll(UN)
+      uint64_t neg = 0ull;
       for (int i = 0; i < n; ++i) {
         if ((act >> i) & 1ull) {
           const float rt = fmaf(d[i], x[i], beta[i]);
           float g = d[i] * rt;
           float gabs = fabsf(g);
-#pragma unroll(UK)
           for (int r = 0; r < K; ++r) {
             g = fmaf(A[r][i], rho[r], g);
             gabs = fmaf(fabsf(A[r][i]), fabsf(rho[r]), gabs);
           }
           const float lam = ((at_hi >> i) & 1ull) ? -g : g;
           // release only multipliers that are negative beyond the rounding of g
-          if (lam < -4e-6f * gabs && lam < worst) { worst = lam; rel = i; }
+          if (lam < -4e-6f * gabs) {
+            neg |= (1ull << i);
+            if (lam < worst) { worst = lam; rel = i; }
+          }
         }
       }
       if (rel < 0) break;
-      at_hi &= ~(1ull << rel);
-      at_lo &= ~(1ull << rel);
+      // first pass: release every wrong-signed bound; afterwards one at a time
+      const uint64_t drop = (it == 0) ? neg : (1ull << rel);
+      at_hi &= ~drop;
+      at_lo &= ~drop;
     }
     return status;
   }
@@ -320,30 +309,46 @@ struct BoxLSQChol {
     }
   }
 
-  // g = A^T (A x + b) + d (d x + beta), gabs = rounding scale of each entry
-  static PK_HD void gradient_factored(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N],
-                                      const float (&beta)[N], const float (&x)[N], float (&g)[N],
-                                      float (&gabs)[N]) {
-    float rho[KA];
+  // Objective held in registers / thread-local arrays.
+  struct ArrayObjective {
+    const float (&A)[KA][N];
+    const float (&b)[KA];
+    const float (&d)[N];
+    const float (&beta)[N];
+    PK_HD void row(int r, float (&a)[N], float& br) const {
 #pragma unroll
-    for (int r = 0; r < K; ++r) {
-      float s = b[r];
-#pragma unroll
-      for (int j = 0; j < N; ++j) s = fmaf(A[r][j], x[j], s);
-      rho[r] = s;
+      for (int j = 0; j < N; ++j) a[j] = A[r][j];
+      br = b[r];
     }
+    PK_HD float diag(int i) const { return d[i]; }
+    PK_HD float lin(int i) const { return beta[i]; }
+  };
+
+  // g = A^T (A x + b) + d (d x + beta), gabs = rounding scale of each entry.  The
+  // objective is streamed row by row (Obj::row) so that a caller holding it in
+  // shared memory never needs all of A in registers.
+  template <class Obj>
+  static PK_HD void gradient_factored(const Obj& O, const float (&x)[N], float (&g)[N], float (&gabs)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const float rt = fmaf(d[i], x[i], beta[i]);
-      float s = d[i] * rt;
-      float sa = fabsf(s);
+      const float di = O.diag(i);
+      const float rt = fmaf(di, x[i], O.lin(i));
+      g[i] = di * rt;
+      gabs[i] = fabsf(g[i]);
+    }
 #pragma unroll
-      for (int r = 0; r < K; ++r) {
-        s = fmaf(A[r][i], rho[r], s);
-        sa = fmaf(fabsf(A[r][i]), fabsf(rho[r]), sa);
+    for (int r = 0; r < K; ++r) {
+      float a[N], br;
+      O.row(r, a, br);
+      float rho = br;
+#pragma unroll
+      for (int j = 0; j < N; ++j) rho = fmaf(a[j], x[j], rho);
+      const float ra = fabsf(rho);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        g[i] = fmaf(a[i], rho, g[i]);
+        gabs[i] = fmaf(fabsf(a[i]), ra, gabs[i]);
       }
-      g[i] = s;
-      gabs[i] = sa;
     }
   }
 
@@ -480,13 +485,13 @@ struct BoxLSQChol {
   }
 
   // Accurate acceptance test and refinement.  Returns true if more rounds are needed.
-  static PK_HD bool polish(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N],
-                           const float (&beta)[N], State& S) {
+  template <class Obj>
+  static PK_HD bool polish(const Obj& O, State& S) {
     if (S.status & (PK_STATUS_NO_SOLUTION | PK_STATUS_ITER_LIMIT)) return false;
     const uint32_t act = S.at_hi | S.at_lo;
     if (act == 0u && S.cond <= 1e3f) return false;  // interior, well-conditioned: x is the plain solve
     float g[N], gabs[N];
-    gradient_factored(A, b, d, beta, S.x, g, gabs);
+    gradient_factored(O, S.x, g, gabs);
     float worst = 0.f;
     int rel = -1;
 #pragma unroll
@@ -513,10 +518,16 @@ struct BoxLSQChol {
 #pragma unroll
         for (int i = 0; i < N; ++i)
           if (!((act >> i) & 1u)) S.x[i] = fminf(fmaxf(S.x[i] + y[i], S.lo[i]), S.hi[i]);
-        if (pass == 0) gradient_factored(A, b, d, beta, S.x, g, gabs);
+        if (pass == 0) gradient_factored(O, S.x, g, gabs);
       }
     }
     return false;
+  }
+
+  static PK_HD bool polish(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N],
+                           const float (&beta)[N], State& S) {
+    const ArrayObjective O{A, b, d, beta};
+    return polish(O, S);
   }
 
   // Whole solve in one thread (no compaction).

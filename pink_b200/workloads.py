@@ -87,3 +87,55 @@ def random_poses(B: int, rng, half_extent: float = 1.2) -> np.ndarray:
     R[:, 2, 2] = 1 - 2 * (x * x + y * y)
     p = rng.uniform(-half_extent, half_extent, size=(B, 3))
     return np.concatenate([R, p[:, :, None]], axis=2)
+
+
+# ---- humanoid configurations (BASELINE configs 3 and 4, without the barrier) -----------
+
+# examples/humanoid_draco3.py:69-91 (frame, position_cost, orientation_cost)
+DRACO3_FRAME_TASKS = [
+    ("l_foot_contact", 1.0, 1.0),
+    ("torso_com_link", 1.0, 0.0),
+    ("r_foot_contact", 1.0, 1.0),
+    ("r_hand_contact", 4.0, 4.0),
+]
+DRACO3_POSTURE_COST, DRACO3_DAMPING = 1e-1, 1e-12
+
+# examples/humanoid_g1_com.py:45-74, 106-113
+G1_FRAME_TASKS = [
+    ("pelvis", 0.0, 10.0),
+    ("right_ankle_roll_link", [2.0, 2.0, 200.0], 10.0),
+    ("left_ankle_roll_link", [2.0, 2.0, 200.0], 10.0),
+    ("right_wrist_yaw_link", 4.0, 0.0),
+    ("left_wrist_yaw_link", 4.0, 0.0),
+]
+G1_POSTURE_COST, G1_COM_COST, G1_DAMPING = 1e-1, 200.0, 0.01
+
+
+def humanoid_task_set(name: str, model, oMf_target, com_target=None):
+    """Task objects of the Draco3 / G1 examples with per-instance targets.
+
+    ``oMf_target`` is ``[B, nframes, 3, 4]`` (frame poses at the target
+    configurations, e.g. from ``Engine.forward_kinematics``); ``com_target``
+    ``[B, 3]`` for the G1 set.  Returns ``(tasks, damping)``.
+    """
+    from .tasks import ComTask, FrameTask, PostureTask
+
+    if name.startswith("draco3"):
+        specs, posture_cost, damping = DRACO3_FRAME_TASKS, DRACO3_POSTURE_COST, DRACO3_DAMPING
+    else:
+        specs, posture_cost, damping = G1_FRAME_TASKS, G1_POSTURE_COST, G1_DAMPING
+    tasks = []
+    for frame, pc, oc in specs:
+        t = FrameTask(frame, position_cost=pc, orientation_cost=oc)
+        t.set_target(oMf_target[:, model.getFrameId(frame)])
+        tasks.append(t)
+    posture = PostureTask(cost=posture_cost)
+    q_ref = np.zeros(model.nq)
+    q_ref[6] = 1.0
+    posture.set_target(q_ref)
+    tasks.append(posture)
+    if not name.startswith("draco3") and com_target is not None:
+        com = ComTask(cost=G1_COM_COST)
+        com.set_target(com_target)
+        tasks.append(com)
+    return tasks, damping

@@ -10,12 +10,12 @@ except Exception as e: print("$name", "ERR", e)
 PY
 }
 run plain PK_CHAIN_MODE=0
-run compact_rps1 PK_CHAIN_MODE=1 PK_ROUNDS_PER_SYNC=1
-run compact_rps2 PK_CHAIN_MODE=1 PK_ROUNDS_PER_SYNC=2
-run compact_rps3 PK_CHAIN_MODE=1 PK_ROUNDS_PER_SYNC=3
-run compact_rps8 PK_CHAIN_MODE=1 PK_ROUNDS_PER_SYNC=8
-run chunk8k PK_HOST_CHUNK=8192
+run sps1 PK_STEPS_PER_SYNC=1
+run sps2 PK_STEPS_PER_SYNC=2
+run sps4 PK_STEPS_PER_SYNC=4
+run sps8 PK_STEPS_PER_SYNC=8
+run sps32 PK_STEPS_PER_SYNC=32
+run chunk16k PK_HOST_CHUNK=16384
 run chunk32k PK_HOST_CHUNK=32768
-run chunk64k PK_HOST_CHUNK=65536
-timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -5
-PK_CHAIN_MODE=0 timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -3
+python scripts/pcie_probe.py > $OUT/pcie.txt 2>&1; cat $OUT/pcie.txt
+timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -3

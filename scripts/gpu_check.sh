@@ -11,7 +11,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 
 echo "smoke exit $?" >> $OUT/smoke.log
 timeout 600 python bench.py --steps 20000 --warmup 50 > $OUT/bench.json 2> $OUT/bench.err
 echo "bench exit $?" >> $OUT/bench.err
-PK_HOST_MODE=1 timeout 600 python bench.py --steps 5000 --warmup 20 --no-cpu > $OUT/bench_zerocopy.json 2>> $OUT/bench.err
+timeout 600 python scripts/bench_humanoids.py > $OUT/humanoids.json 2>> $OUT/bench.err
 timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/bench_reference.json 2>> $OUT/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 40 --warmup 3 --no-cpu --nbuf 4 > $OUT/ncu_launches.log 2>&1

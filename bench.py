@@ -224,6 +224,7 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
 
     # model constants: built on rank 0, broadcast over NCCL (north_star), then
@@ -382,7 +383,7 @@ def run_gpu_arm(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args),
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches) * world,
             "clocks": clocks.summary(),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

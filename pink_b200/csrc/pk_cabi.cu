@@ -107,6 +107,7 @@ extern "C" int pk_model_create(const PkModelDesc* d, int device, PkModel** out) 
   const size_t o_fX = reserve(sizeof(float) * 12 * std::max(d->nframes, 1), 16);
   const size_t o_mass = reserve(sizeof(float) * (nj + 1), 4);
   const size_t o_com = reserve(sizeof(float) * 3 * (nj + 1), 4);
+  const size_t o_depth = reserve(sizeof(int) * std::max(nj, 1), 4);
   std::vector<char> host(off, 0);
   memcpy(host.data() + o_anc, m->hm.anc.data(), sizeof(uint64_t) * (nj + 2));
   if (nj) {
@@ -121,6 +122,7 @@ extern "C" int pk_model_create(const PkModelDesc* d, int device, PkModel** out) 
   }
   memcpy(host.data() + o_mass, m->hm.mass.data(), sizeof(float) * (nj + 1));
   memcpy(host.data() + o_com, m->hm.com.data(), sizeof(float) * 3 * (nj + 1));
+  memcpy(host.data() + o_depth, m->hm.depth.data(), sizeof(int) * std::max(nj, 1));
 
   cudaError_t err = cudaSetDevice(device);
   if (err == cudaSuccess) err = cudaMalloc(&m->dev_buf, off);
@@ -147,6 +149,8 @@ extern "C" int pk_model_create(const PkModelDesc* d, int device, PkModel** out) 
   m->dev.mass = (const float*)(base + o_mass);
   m->dev.com = (const float*)(base + o_com);
   m->dev.total_mass = m->hm.total_mass;
+  m->dev.depth = (const int*)(base + o_depth);
+  m->dev.maxdepth = m->hm.maxdepth;
   *out = m;
   return 0;
 }
@@ -501,6 +505,22 @@ __global__ void __launch_bounds__(64) ik_generic_kernel(const DevModel M, const 
   G.step(M, P, A.q + i * M.nq, A.targets ? A.targets + i * (int64_t)P.target_stride : nullptr, out);
 }
 
+// Tree kernel: one instance per warp, per-instance state in the warp's slice of
+// dynamic shared memory (pk_tree.cuh).
+constexpr int kTreeWarpsPerBlock = 4;
+__global__ void __launch_bounds__(32 * kTreeWarpsPerBlock)
+    ik_tree_kernel(const DevModel M, const __grid_constant__ DevProblem P, const __grid_constant__ TreePlan L,
+                   const float* __restrict__ q, const float* __restrict__ targets, float* __restrict__ v,
+                   int32_t* __restrict__ status, int64_t B) {
+  extern __shared__ __align__(16) float tree_smem[];
+  const int warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * kTreeWarpsPerBlock + warp;
+  if (i >= B) return;
+  float* W = tree_smem + (size_t)warp * L.words;
+  TreeStep::run(M, P, L, q + i * L.nq, targets ? targets + i * (int64_t)L.stride : nullptr, W, v + i * L.nv,
+                status ? status + i : nullptr);
+}
+
 // q (+) v dt
 __global__ void integrate_kernel(int nq, int nv, int free_flyer, const float* __restrict__ q,
                                  const float* __restrict__ v, float dt, float* __restrict__ qo, int64_t B) {
@@ -615,6 +635,8 @@ int launch_generic(const PkModel* m, const pk::DevProblem& P, const pk::GenericA
 struct PkProblem {
   pk::DevProblem P;
   bool chain = false;
+  bool tree = false;
+  pk::TreePlan plan;
   int nj = 0;
   alignas(16) unsigned char chain_params[sizeof(pk::ChainParams<7>)];
 };
@@ -634,6 +656,10 @@ int prepare_problem(const PkModel* m, const PkProblemDesc* desc, PkProblem* pr) 
   static const int force_generic = env_int("PK_FORCE_GENERIC", 0);
   pr->chain = !force_generic && pk::chain_eligible(m->hm, pr->P);
   pr->nj = m->njoints;
+  static const int use_tree = env_int("PK_TREE", 1);
+  bool tree_ok = false;
+  pr->plan = pk::make_tree_plan(m->hm, pr->P, &tree_ok);
+  pr->tree = !force_generic && use_tree && !pr->chain && tree_ok;
   if (pr->chain) {
     switch (m->njoints) {
       case 2: fill_chain<2>(m, pr); break;
@@ -668,6 +694,20 @@ int solve_device(const PkModel* m, const PkProblem& pr, const float* q, const fl
       case 7: return launch_chain_prepared<7>(pr, q, targets, v, status, B, stream);
       default: break;
     }
+  }
+  if (pr.tree) {
+    const size_t smem = (size_t)pr.plan.words * 4 * pk::kTreeWarpsPerBlock;
+    static size_t configured = 0;
+    if (smem > configured) {
+      PK_CUDA(cudaFuncSetAttribute(pk::ik_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    const int64_t grid = (B + pk::kTreeWarpsPerBlock - 1) / pk::kTreeWarpsPerBlock;
+    pk::ik_tree_kernel<<<(unsigned)grid, 32 * pk::kTreeWarpsPerBlock, smem, stream>>>(m->dev, pr.P, pr.plan, q, targets, v,
+                                                                                      status, B);
+    g_launches.fetch_add(1);
+    PK_CUDA(cudaGetLastError());
+    return 0;
   }
   pk::GenericArgs A{};
   A.q = q;

@@ -28,6 +28,8 @@ struct DevModel {
   const float* mass;       // [njoints + 1]
   const float* com;        // [njoints + 1][3]
   const uint64_t* anc;     // [njoints + 2] joints on the path to body b (index b + 2)
+  const int* depth;        // [njoints] number of 1-dof ancestors
+  int maxdepth;
   float total_mass;
 };
 

@@ -12,12 +12,14 @@
 #include "../../include/pink_b200.h"
 #include "pk_chain.cuh"
 #include "pk_generic.cuh"
+#include "pk_tree.cuh"
 
 namespace pk {
 
 struct HostModel {
   int njoints = 0, free_flyer = 0, nq = 0, nv = 0, nframes = 0;
-  std::vector<int> parent, jtype, frame_body;
+  std::vector<int> parent, jtype, frame_body, depth;
+  int maxdepth = 0;
   std::vector<float> jX, axis, fX, mass, com;
   std::vector<uint64_t> anc;
   float total_mass = 0.f;
@@ -30,6 +32,7 @@ struct HostModel {
     d.parent = parent.data(); d.jtype = jtype.data(); d.jX = jX.data(); d.axis = axis.data();
     d.frame_body = frame_body.data(); d.fX = fX.data(); d.mass = mass.data(); d.com = com.data();
     d.anc = anc.data(); d.total_mass = total_mass;
+    d.depth = depth.data(); d.maxdepth = maxdepth;
     return d;
   }
 };
@@ -78,6 +81,12 @@ inline std::string build_host_model(const PkModelDesc* d, HostModel* m) {
   for (int j = 0; j < nj; ++j) {
     const uint64_t up = m->parent[j] >= 0 ? m->anc[m->parent[j] + 2] : 0ull;
     m->anc[j + 2] = up | (1ull << j);
+  }
+  m->depth.assign(nj > 0 ? nj : 1, 0);
+  m->maxdepth = 0;
+  for (int j = 0; j < nj; ++j) {
+    m->depth[j] = m->parent[j] >= 0 ? m->depth[m->parent[j]] + 1 : 0;
+    m->maxdepth = std::max(m->maxdepth, m->depth[j]);
   }
   m->serial_chain = !ff && nj >= 1;
   for (int j = 0; j < nj; ++j)
@@ -170,6 +179,65 @@ inline bool chain_eligible(const HostModel& m, const DevProblem& P) {
     if (P.tasks[t].tgt_shared)
       shared_need = std::max(shared_need, P.tasks[t].tgt_off + (P.tasks[t].type == PK_TASK_FRAME ? 12 : m.nq));
   return shared_need <= 12 * kChainMaxFrameTasks + m.njoints;
+}
+
+// Workspace layout of the warp-cooperative tree kernel; `ok` false if the problem
+// does not fit it (then the general path is used).
+inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok) {
+  TreePlan L;
+  memset(&L, 0, sizeof(L));
+  L.nj = m.njoints;
+  L.nq = m.nq;
+  L.nv = m.nv;
+  L.rq = m.free_flyer ? 7 : 0;
+  L.rv = m.free_flyer ? 6 : 0;
+  L.ntasks = P.ntasks;
+  L.stride = P.target_stride;
+  L.maxdepth = m.maxdepth;
+  int K = 0;
+  for (int t = 0; t < PK_MAX_TASKS; ++t) L.row_base[t] = -1;
+  for (int t = 0; t < P.ntasks; ++t) {
+    const DevTask& d = P.tasks[t];
+    if (d.type == PK_TASK_POSTURE) continue;
+    const int k = d.type == PK_TASK_COM ? 3 : 6;
+    int rows = 0;
+    for (int r = 0; r < k; ++r) rows += d.cost[r] != 0.f ? 1 : 0;
+    if (rows) {
+      L.row_base[t] = K;
+      K += rows;
+    }
+  }
+  L.K = K;
+  L.lda = L.nv | 1;
+  L.ldw = L.nv | 1;
+  int off = 0;
+  auto take = [&](int words) { const int at = off; off += (words + 3) / 4 * 4; return at; };
+  L.o_q = take(L.nq);
+  L.o_t = take(L.stride);
+  L.o_tw = take(kTwStride * (L.nj > 0 ? L.nj : 1));
+  L.o_root = take(12);
+  L.o_tf = take(kTreeTaskWords * (P.ntasks > 0 ? P.ntasks : 1));
+  L.o_A = take((K > 0 ? K : 1) * L.lda);
+  L.o_b = take(K);
+  L.o_d = take(L.nv);
+  L.o_beta = take(L.nv);
+  L.o_lo = take(L.nv);
+  L.o_hi = take(L.nv);
+  L.o_x = take(L.nv);
+  L.o_y = take(L.nv);
+  L.o_g = take(L.nv);
+  L.o_aw = take((K > 0 ? K : 1) * L.ldw);
+  L.o_ru = take(L.nv * L.ldw);
+  L.o_rd = take(L.nv);
+  L.o_zt = take(L.nv);
+  L.o_zb = take(K);
+  L.o_rho = take(K);
+  L.o_ys = take(L.nv);
+  L.o_idx = take(L.nv);
+  L.o_cw = take(3 * (L.nj + 1));
+  L.words = off;
+  *ok = m.njoints >= 1 && m.njoints <= kTreeMaxJoints && m.nv <= 64 && P.ntasks <= 32 && (size_t)L.words * 4 <= 48 * 1024;
+  return L;
 }
 
 template <int NJ>

@@ -1,0 +1,599 @@
+// Warp-cooperative IK step for joint trees (humanoids): one instance per warp,
+// lanes = joints / tangent columns / task rows, all per-instance state in the warp's
+// slice of shared memory.  Same arithmetic as the general path (pk_generic.cuh):
+// FK over the tree, FrameTask / RelativeFrameTask / PostureTask / ComTask rows in
+// square-root form, box limits, active-set QP with a Householder QR of the
+// compacted free columns of [diag(d); A].  Reference path: see pk_chain.cuh and
+// pk_generic.cuh headers.
+//
+// Written in the lane-block style of pk_warp.cuh so that tests/hostsim can run it
+// on the CPU.
+#pragma once
+
+#include "pk_generic.cuh"
+#include "pk_warp.cuh"
+
+namespace pk {
+
+constexpr int kTreeMaxJoints = 32;   // lanes = joints
+constexpr int kTreeTaskWords = 60;   // per task: Tf 12, A 9, B 9, e 6, Tr 12, Trf 12
+
+// Sizes and workspace offsets (in floats) of one instance; computed on the host.
+struct TreePlan {
+  int nj, nq, nv, rq, rv, K, ntasks, stride, lda, ldw, maxdepth;
+  int row_base[PK_MAX_TASKS];  // first row of A of each task (-1: none)
+  int o_q, o_t, o_tw, o_root, o_tf, o_A, o_b, o_d, o_beta, o_lo, o_hi, o_x, o_y, o_g, o_aw, o_ru, o_rd, o_zt, o_zb,
+      o_rho, o_ys, o_idx, o_cw, words;
+};
+
+constexpr int kTwStride = 13;  // 12 floats per joint transform, padded against bank conflicts
+
+struct TreeStep {
+  // ---- small accessors -------------------------------------------------------------
+  static PK_HD SE3f load_tw(const float* W, const TreePlan& L, int body) {
+    if (body == -2) return identity_se3();
+    if (body == -1) return load_se3(W + L.o_root);
+    return load_se3(W + L.o_tw + kTwStride * body);
+  }
+
+  // Column i of the LOCAL Jacobian of a frame at Tf on `body` (as Generic::frame_jac_col).
+  static PK_HD void jac_col(const DevModel& M, const float* W, const TreePlan& L, int body, const SE3f& Tf, int i,
+                            V3& lin, V3& ang) {
+    lin = v3(0.f, 0.f, 0.f);
+    ang = v3(0.f, 0.f, 0.f);
+    if (i < L.rv) {
+      if (body == -2) return;
+      const SE3f Trf = act_inv(load_se3(W + L.o_root), Tf);
+      const V3 ek = v3(i % 3 == 0 ? 1.f : 0.f, i % 3 == 1 ? 1.f : 0.f, i % 3 == 2 ? 1.f : 0.f);
+      if (i < 3) {
+        lin = mulT(Trf.R, ek);
+      } else {
+        lin = mulT(Trf.R, cross(ek, Trf.p));
+        ang = mulT(Trf.R, ek);
+      }
+      return;
+    }
+    const int j = i - L.rv;
+    if (body < 0 || !((M.anc[body + 2] >> j) & 1ull)) return;
+    const SE3f Tj = load_se3(W + L.o_tw + kTwStride * j);
+    const V3 axis = v3(M.axis[3 * j], M.axis[3 * j + 1], M.axis[3 * j + 2]);
+    const V3 aw = mul(Tj.R, axis);
+    if (M.jtype[j] == PK_JOINT_REVOLUTE) {
+      lin = mulT(Tf.R, cross(aw, Tf.p - Tj.p));
+      ang = mulT(Tf.R, aw);
+    } else {
+      lin = mulT(Tf.R, aw);
+    }
+  }
+
+  // ---- least squares on the free set (cooperative Householder QR) -------------------
+  // Rows of Aw are owned by lanes (r = l, l + 32, ...).  y receives the full solution.
+  static PK_HD bool eqp(float* W, const TreePlan& L, uint64_t act) {
+    const int n = L.nv, K = L.K;
+    float* A = W + L.o_A;
+    float* Aw = W + L.o_aw;
+    float* Ru = W + L.o_ru;
+    float* Rd = W + L.o_rd;
+    float* zt = W + L.o_zt;
+    float* zb = W + L.o_zb;
+    float* ys = W + L.o_ys;
+    int* idx = reinterpret_cast<int*>(W + L.o_idx);
+    const float* x = W + L.o_x;
+    float* y = W + L.o_y;
+    const float* bv = W + L.o_b;
+    const float* dv = W + L.o_d;
+    const float* beta = W + L.o_beta;
+    // free index list
+    int nf = 0;
+    for (int j = 0; j < n; ++j) nf += ((act >> j) & 1ull) ? 0 : 1;
+    PK_LANES(l) {
+      for (int i = l; i < n; i += 32) {
+        y[i] = x[i];
+        if (!((act >> i) & 1ull)) {
+          const uint64_t below = (i == 0) ? 0ull : (~act & ((1ull << i) - 1ull));
+#if defined(__CUDA_ARCH__)
+          const int pos = __popcll(below);
+#else
+          const int pos = __builtin_popcountll(below);
+#endif
+          idx[pos] = i;
+          zt[pos] = beta[i];
+        }
+      }
+    }
+    PK_WSYNC();
+    // right-hand side and compacted copy, row-parallel
+    PK_LANES(l) {
+      for (int r = l; r < K; r += 32) {
+        float s = bv[r];
+        for (int j = 0; j < n; ++j)
+          if ((act >> j) & 1ull) s = fmaf(A[r * L.lda + j], x[j], s);
+        zb[r] = s;
+        for (int c = 0; c < nf; ++c) Aw[r * L.ldw + c] = A[r * L.lda + idx[c]];
+      }
+    }
+    PK_WSYNC();
+    bool ok = true;
+    for (int k = 0; k < nf; ++k) {
+      LaneVar<float> part;
+      PK_LANES(l) {
+        float s = 0.f;
+        for (int r = l; r < K; r += 32) s = fmaf(Aw[r * L.ldw + k], Aw[r * L.ldw + k], s);
+        part[l] = s;
+      }
+      const float sigma = lane_sum(part);
+      const float alpha = dv[idx[k]];
+      const float norm = sqrtf(fmaf(alpha, alpha, sigma));
+      ok = ok && (norm > 0.f);
+      const float v0 = alpha + norm;
+      const float tau = (sigma > 0.f) ? 1.f / (norm * v0) : 0.f;
+      const float rdk = (sigma > 0.f) ? -norm : alpha;
+      for (int j = k + 1; j < nf; ++j) {
+        PK_LANES(l) {
+          float s = 0.f;
+          for (int r = l; r < K; r += 32) s = fmaf(Aw[r * L.ldw + k], Aw[r * L.ldw + j], s);
+          part[l] = s;
+        }
+        const float s = lane_sum(part) * tau;
+        PK_LANES(l) {
+          for (int r = l; r < K; r += 32) Aw[r * L.ldw + j] = fmaf(-s, Aw[r * L.ldw + k], Aw[r * L.ldw + j]);
+          if (l == 0) Ru[k * L.ldw + j] = -s * v0;
+        }
+      }
+      PK_LANES(l) {
+        float s = 0.f;
+        for (int r = l; r < K; r += 32) s = fmaf(Aw[r * L.ldw + k], zb[r], s);
+        part[l] = s;
+      }
+      const float ztk = zt[k];
+      const float s = fmaf(v0, ztk, lane_sum(part)) * tau;
+      PK_WSYNC();
+      PK_LANES(l) {
+        for (int r = l; r < K; r += 32) zb[r] = fmaf(-s, Aw[r * L.ldw + k], zb[r]);
+        if (l == 0) {
+          zt[k] = fmaf(-s, v0, ztk);
+          Rd[k] = rdk;
+        }
+      }
+    }
+    PK_WSYNC();
+    // R ys = -zt
+    for (int kk = 0; kk < nf; ++kk) {
+      const int k = nf - 1 - kk;
+      LaneVar<float> part;
+      PK_LANES(l) {
+        float s = 0.f;
+        for (int j = k + 1 + l; j < nf; j += 32) s = fmaf(Ru[k * L.ldw + j], ys[j], s);
+        part[l] = s;
+      }
+      const float rd = Rd[k];
+      const float yk = (rd != 0.f) ? (-zt[k] - lane_sum(part)) / rd : 0.f;
+      PK_WSYNC();
+      PK_LANES(l) {
+        if (l == 0) {
+          ys[k] = yk;
+          y[idx[k]] = yk;
+        }
+      }
+      PK_WSYNC();
+    }
+    return ok;
+  }
+
+  // ---- box-constrained least squares (as BoxLSQ::run, cooperative) ------------------
+  static PK_HD int solve_qp(float* W, const TreePlan& L) {
+    const int n = L.nv, K = L.K;
+    const float* A = W + L.o_A;
+    const float* bv = W + L.o_b;
+    const float* dv = W + L.o_d;
+    const float* beta = W + L.o_beta;
+    const float* lo = W + L.o_lo;
+    const float* hi = W + L.o_hi;
+    float* x = W + L.o_x;
+    float* y = W + L.o_y;
+    float* rho = W + L.o_rho;
+    int status = 0;
+    {
+      LaneVar<int> bad;
+      PK_LANES(l) {
+        int f = 0;
+        for (int i = l; i < n; i += 32) {
+          x[i] = 0.f;
+          if (lo[i] > hi[i]) f = 1;
+        }
+        bad[l] = f;
+      }
+      PK_WSYNC();
+      if (lane_or(bad)) return PK_STATUS_NO_SOLUTION;
+    }
+    if (!eqp(W, L, 0ull)) status |= PK_STATUS_NOT_POSDEF;
+    uint64_t at_hi, at_lo;
+    {
+      LaneVar<uint64_t> mh, ml;
+      PK_LANES(l) {
+        uint64_t h = 0ull, m = 0ull;
+        for (int i = l; i < n; i += 32) {
+          const float yi = y[i];
+          if (yi > hi[i]) { h |= (1ull << i); x[i] = hi[i]; }
+          else if (yi < lo[i]) { m |= (1ull << i); x[i] = lo[i]; }
+          else x[i] = yi;
+        }
+        mh[l] = h;
+        ml[l] = m;
+      }
+      at_hi = lane_or64(mh);
+      at_lo = lane_or64(ml);
+      PK_WSYNC();
+    }
+    if ((at_hi | at_lo) == 0ull) return status;
+
+    const uint64_t all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+    const int max_iter = 4 * n + 16;
+    for (int it = 0;; ++it) {
+      if (it >= max_iter) { status |= PK_STATUS_ITER_LIMIT; break; }
+      const uint64_t act = at_hi | at_lo;
+      if (act == all) {
+        PK_LANES(l) {
+          for (int i = l; i < n; i += 32) y[i] = x[i];
+        }
+        PK_WSYNC();
+      } else {
+        eqp(W, L, act);
+      }
+      // longest feasible step from x towards y
+      float step;
+      int blk;
+      {
+        LaneVar<float> sv;
+        LaneVar<int> si;
+        PK_LANES(l) {
+          float best = 1.f;
+          int bi = 0x7fffffff;
+          for (int i = l; i < n; i += 32) {
+            if (!((act >> i) & 1ull)) {
+              const float yi = y[i], xi = x[i];
+              float a = 2.f;
+              if (yi > hi[i]) a = (hi[i] - xi) / (yi - xi);
+              else if (yi < lo[i]) a = (lo[i] - xi) / (yi - xi);
+              if (a < best) { best = a; bi = i; }
+            }
+          }
+          sv[l] = best;
+          si[l] = bi;
+        }
+        lane_argmin(sv, si, step, blk);
+      }
+      if (blk != 0x7fffffff) {
+        step = fmaxf(step, 0.f);
+        const bool blk_hi = y[blk] > hi[blk];
+        PK_WSYNC();
+        PK_LANES(l) {
+          for (int i = l; i < n; i += 32) {
+            if (!((act >> i) & 1ull)) {
+              float xi = fmaf(step, y[i] - x[i], x[i]);
+              if (i == blk) xi = blk_hi ? hi[i] : lo[i];
+              x[i] = xi;
+            }
+          }
+        }
+        PK_WSYNC();
+        if (blk_hi) at_hi |= (1ull << blk); else at_lo |= (1ull << blk);
+        continue;
+      }
+      PK_LANES(l) {
+        for (int i = l; i < n; i += 32) x[i] = y[i];
+      }
+      PK_WSYNC();
+      // multipliers from the factored gradient: rho = A x + b (row-parallel) ...
+      PK_LANES(l) {
+        for (int r = l; r < K; r += 32) {
+          float s = bv[r];
+          for (int j = 0; j < n; ++j) s = fmaf(A[r * L.lda + j], x[j], s);
+          rho[r] = s;
+        }
+      }
+      PK_WSYNC();
+      // ... g_i = A[:, i] . rho + d_i (d_i x_i + beta_i) (column-parallel)
+      float worst;
+      int rel;
+      uint64_t neg;
+      {
+        LaneVar<float> wv;
+        LaneVar<int> wi;
+        LaneVar<uint64_t> nm;
+        PK_LANES(l) {
+          float best = 0.f;
+          int bi = 0x7fffffff;
+          uint64_t m = 0ull;
+          for (int i = l; i < n; i += 32) {
+            if ((act >> i) & 1ull) {
+              const float rt = fmaf(dv[i], x[i], beta[i]);
+              float g = dv[i] * rt;
+              float gabs = fabsf(g);
+              for (int r = 0; r < K; ++r) {
+                const float a = A[r * L.lda + i];
+                g = fmaf(a, rho[r], g);
+                gabs = fmaf(fabsf(a), fabsf(rho[r]), gabs);
+              }
+              const float lam = ((at_hi >> i) & 1ull) ? -g : g;
+              if (lam < -4e-6f * gabs) {
+                m |= (1ull << i);
+                if (lam < best) { best = lam; bi = i; }
+              }
+            }
+          }
+          wv[l] = best;
+          wi[l] = bi;
+          nm[l] = m;
+        }
+        lane_argmin(wv, wi, worst, rel);
+        neg = lane_or64(nm);
+      }
+      if (neg == 0ull) break;
+      const uint64_t drop = (it == 0) ? neg : (1ull << rel);
+      at_hi &= ~drop;
+      at_lo &= ~drop;
+    }
+    return status;
+  }
+
+  // ---- the whole step ----------------------------------------------------------------
+  static PK_HD void run(const DevModel& M, const DevProblem& P, const TreePlan& L, const float* __restrict__ qg,
+                        const float* __restrict__ tg, float* W, float* __restrict__ vg, int32_t* status_out) {
+    const int nj = L.nj, nv = L.nv, rq = L.rq, rv = L.rv;
+    float* qs = W + L.o_q;
+    float* ts = W + L.o_t;
+    float* A = W + L.o_A;
+    // ---- load q and targets (coalesced), limit check --------------------------------
+    int status = 0;
+    {
+      LaneVar<int> bad;
+      PK_LANES(l) {
+        for (int i = l; i < L.nq; i += 32) qs[i] = qg[i];
+        for (int i = l; i < L.stride; i += 32) ts[i] = tg[i];
+        int f = 0;
+        for (int i = rv + l; i < nv; i += 32) {
+          const float qi = qg[i + rq - rv];
+          if (qi < P.chk_lo[i] || qi > P.chk_hi[i]) f = 1;
+        }
+        bad[l] = f;
+      }
+      PK_WSYNC();
+      if (lane_or(bad)) status |= PK_STATUS_OUT_OF_LIMITS;
+    }
+    if (status && P.safety_break) {
+      PK_LANES(l) {
+        for (int i = l; i < nv; i += 32) vg[i] = 0.f;
+        if (l == 0 && status_out) *status_out = status;
+      }
+      return;
+    }
+    // ---- forward kinematics: local transforms in registers, tree sweep by depth ------
+    {
+      LaneVar<SE3f> Tl;
+      PK_LANES(l) {
+        if (l == 0) {
+          SE3f root = identity_se3();
+          if (M.free_flyer) {
+            root.p = v3(qs[0], qs[1], qs[2]);
+            root.R = quat_to_matrix(qs[3], qs[4], qs[5], qs[6]);
+          }
+          store_se3(root, W + L.o_root);
+        }
+        if (l < nj) {
+          const SE3f X = load_se3(M.jX + 12 * l);
+          const V3 axis = v3(M.axis[3 * l], M.axis[3 * l + 1], M.axis[3 * l + 2]);
+          SE3f T;
+          if (M.jtype[l] == PK_JOINT_REVOLUTE) {
+            float s, c;
+            sincos_f(qs[rq + l], &s, &c);
+            T.R = mul(X.R, rot_axis(axis, s, c));
+            T.p = X.p;
+          } else {
+            T.R = X.R;
+            T.p = X.p + mul(X.R, qs[rq + l] * axis);
+          }
+          Tl[l] = T;
+        }
+      }
+      PK_WSYNC();
+      for (int dep = 0; dep <= L.maxdepth; ++dep) {
+        PK_LANES(l) {
+          if (l < nj && M.depth[l] == dep) {
+            const int par = M.parent[l];
+            const SE3f Tp = load_tw(W, L, par < 0 ? -1 : par);
+            store_se3(compose(Tp, Tl[l]), W + L.o_tw + kTwStride * l);
+          }
+        }
+        PK_WSYNC();
+      }
+    }
+    // world CoM of every body (only if a CoM task exists)
+    bool has_com = false;
+    for (int t = 0; t < P.ntasks; ++t) has_com = has_com || (P.tasks[t].type == PK_TASK_COM);
+    if (has_com) {
+      PK_LANES(l) {
+        for (int b = l; b <= nj; b += 32) {  // index b: body b - 1
+          const SE3f T = load_tw(W, L, b - 1);
+          const V3 cl = v3(M.com[3 * b], M.com[3 * b + 1], M.com[3 * b + 2]);
+          const V3 c = mul(T.R, cl) + T.p;
+          W[L.o_cw + 3 * b] = c.x; W[L.o_cw + 3 * b + 1] = c.y; W[L.o_cw + 3 * b + 2] = c.z;
+        }
+      }
+      PK_WSYNC();
+    }
+    // ---- per-task quantities, one task per lane ------------------------------------------
+    PK_LANES(l) {
+      if (l < P.ntasks) {
+        const DevTask& Kt = P.tasks[l];
+        float* F = W + L.o_tf + kTreeTaskWords * l;
+        const float* tgt = Kt.tgt_shared ? (P.shared + Kt.tgt_off) : (ts + Kt.tgt_off);
+        if (Kt.type == PK_TASK_FRAME || Kt.type == PK_TASK_RELATIVE_FRAME) {
+          const SE3f Tf = compose(load_tw(W, L, Kt.body), load_se3(M.fX + 12 * Kt.frame));
+          const SE3f Tt = load_se3(tgt);
+          M3 Am, Bm;
+          float e[6];
+          SE3f Tr = identity_se3(), Trf = identity_se3();
+          if (Kt.type == PK_TASK_FRAME) {
+            const SE3f Tbt = act_inv(Tf, Tt);
+            Log3 Lg = log3(Tbt.R);
+            log6(Tbt, Lg, e);
+            SE3f Ttb;
+            for (int a = 0; a < 3; ++a)
+              for (int c = 0; c < 3; ++c) Ttb.R.m[3 * a + c] = Tbt.R.m[3 * c + a];
+            Ttb.p = -1.f * mul(Ttb.R, Tbt.p);
+            Lg.w = -1.f * Lg.w;
+            jlog6(Ttb, Lg, Am, Bm);
+          } else {
+            Tr = compose(load_tw(W, L, Kt.root_body), load_se3(M.fX + 12 * Kt.root));
+            Trf = act_inv(Tr, Tf);
+            const SE3f Ttf = act_inv(Tt, Trf);
+            const Log3 Lg = log3(Ttf.R);
+            log6(Ttf, Lg, e);
+            jlog6(Ttf, Lg, Am, Bm);
+          }
+          store_se3(Tf, F);
+          for (int k = 0; k < 9; ++k) { F[12 + k] = Am.m[k]; F[21 + k] = Bm.m[k]; }
+          for (int k = 0; k < 6; ++k) F[30 + k] = e[k];
+          store_se3(Tr, F + 36);
+          store_se3(Trf, F + 48);
+        } else if (Kt.type == PK_TASK_COM) {
+          V3 acc = v3(0.f, 0.f, 0.f);
+          for (int b = 0; b <= nj; ++b) {
+            const float m = M.mass[b];
+            acc = acc + m * v3(W[L.o_cw + 3 * b], W[L.o_cw + 3 * b + 1], W[L.o_cw + 3 * b + 2]);
+          }
+          const V3 cm = (1.f / M.total_mass) * acc;
+          F[0] = cm.x; F[1] = cm.y; F[2] = cm.z;
+          F[30] = cm.x - tgt[0]; F[31] = cm.y - tgt[1]; F[32] = cm.z - tgt[2];
+          F[33] = F[34] = F[35] = 0.f;
+        }
+      }
+    }
+    PK_WSYNC();
+    // ---- rows of A (column-parallel), b, diagonal terms -----------------------------------
+    float diag = P.damping;
+    for (int t = 0; t < P.ntasks; ++t) {
+      const DevTask& Kt = P.tasks[t];
+      const float* F = W + L.o_tf + kTreeTaskWords * t;
+      if (Kt.type == PK_TASK_POSTURE) {
+        const float* tgt = Kt.tgt_shared ? (P.shared + Kt.tgt_off) : (ts + Kt.tgt_off);
+        const float w2 = Kt.cost[0] * Kt.cost[0];
+        LaneVar<float> part;
+        PK_LANES(l) {
+          float s = 0.f;
+          for (int i = rv + l; i < nv; i += 32) {
+            const float e = qs[i + rq - rv] - tgt[i + rq - rv];
+            s = fmaf(e, e, s);
+          }
+          part[l] = s;
+        }
+        diag = fmaf(Kt.lm * Kt.gain * Kt.gain * w2, lane_sum(part), diag);
+        continue;
+      }
+      const int k = (Kt.type == PK_TASK_COM) ? 3 : 6;
+      float mu = 0.f;
+      for (int r = 0; r < k; ++r) {
+        const float ew = Kt.cost[r] * Kt.gain * F[30 + r];
+        mu = fmaf(ew, ew, mu);
+      }
+      diag = fmaf(Kt.lm, mu, diag);
+      const int base = L.row_base[t];
+      if (base < 0) continue;
+      PK_LANES(l) {
+        // b entries of this task (rows with non-zero cost are packed in order)
+        if (l == 0) {
+          int row = base;
+          for (int r = 0; r < k; ++r)
+            if (Kt.cost[r] != 0.f) W[L.o_b + row++] = Kt.cost[r] * Kt.gain * F[30 + r];
+        }
+        for (int i = l; i < nv; i += 32) {
+          float col[6];
+          if (Kt.type == PK_TASK_COM) {
+            const V3 cm = v3(F[0], F[1], F[2]);
+            V3 c = v3(0.f, 0.f, 0.f);
+            if (i < rv) {
+              const SE3f root = load_se3(W + L.o_root);
+              const V3 ek = v3(i % 3 == 0 ? 1.f : 0.f, i % 3 == 1 ? 1.f : 0.f, i % 3 == 2 ? 1.f : 0.f);
+              if (i < 3) c = mul(root.R, ek);
+              else c = mul(root.R, cross(ek, mulT(root.R, cm - root.p)));
+            } else {
+              const int j = i - rv;
+              float sm = 0.f;
+              V3 smc = v3(0.f, 0.f, 0.f);
+              for (int b = 1; b <= nj; ++b) {
+                if ((M.anc[b + 1] >> j) & 1ull) {
+                  const float m = M.mass[b];
+                  sm += m;
+                  smc = smc + m * v3(W[L.o_cw + 3 * b], W[L.o_cw + 3 * b + 1], W[L.o_cw + 3 * b + 2]);
+                }
+              }
+              if (sm > 0.f) {
+                const SE3f Tj = load_se3(W + L.o_tw + kTwStride * j);
+                const V3 axis = v3(M.axis[3 * j], M.axis[3 * j + 1], M.axis[3 * j + 2]);
+                const V3 aw = mul(Tj.R, axis);
+                const float invM = 1.f / M.total_mass;
+                if (M.jtype[j] == PK_JOINT_REVOLUTE) c = (sm * invM) * cross(aw, (1.f / sm) * smc - Tj.p);
+                else c = (sm * invM) * aw;
+              }
+            }
+            col[0] = c.x; col[1] = c.y; col[2] = c.z; col[3] = col[4] = col[5] = 0.f;
+          } else {
+            const SE3f Tf = load_se3(F);
+            M3 Am, Bm;
+            for (int q9 = 0; q9 < 9; ++q9) { Am.m[q9] = F[12 + q9]; Bm.m[q9] = F[21 + q9]; }
+            V3 lin, ang;
+            jac_col(M, W, L, Kt.body, Tf, i, lin, ang);
+            float sign = -1.f;
+            if (Kt.type == PK_TASK_RELATIVE_FRAME) {
+              const SE3f Tr = load_se3(F + 36);
+              const SE3f Trf = load_se3(F + 48);
+              V3 rl, ra;
+              jac_col(M, W, L, Kt.root_body, Tr, i, rl, ra);
+              lin = lin - mulT(Trf.R, rl - cross(Trf.p, ra));
+              ang = ang - mulT(Trf.R, ra);
+              sign = 1.f;
+            }
+            const V3 tl = sign * (mul(Am, lin) + mul(Bm, ang));
+            const V3 ta = sign * mul(Am, ang);
+            col[0] = tl.x; col[1] = tl.y; col[2] = tl.z; col[3] = ta.x; col[4] = ta.y; col[5] = ta.z;
+          }
+          int row = base;
+          for (int r = 0; r < k; ++r)
+            if (Kt.cost[r] != 0.f) A[(row++) * L.lda + i] = Kt.cost[r] * col[r];
+        }
+      }
+    }
+    // diagonal terms (posture tasks), box
+    PK_LANES(l) {
+      for (int i = l; i < nv; i += 32) {
+        float pw2 = 0.f, pc = 0.f;
+        const float qi = (i >= rv) ? qs[i + rq - rv] : 0.f;
+        for (int t = 0; t < P.ntasks; ++t) {
+          const DevTask& Kt = P.tasks[t];
+          if (Kt.type == PK_TASK_POSTURE && i >= rv) {
+            const float* tgt = Kt.tgt_shared ? (P.shared + Kt.tgt_off) : (ts + Kt.tgt_off);
+            const float w2 = Kt.cost[0] * Kt.cost[0];
+            pw2 += w2;
+            pc = fmaf(Kt.gain * w2, qi - tgt[i + rq - rv], pc);
+          }
+        }
+        const float dd = sqrtf(pw2 + diag);
+        W[L.o_d + i] = dd;
+        W[L.o_beta + i] = dd > 0.f ? pc / dd : 0.f;
+        const float vb = P.dt * P.vel[i];
+        W[L.o_hi + i] = fminf(P.cfg_gain * (P.cfg_hi[i] - qi), vb);
+        W[L.o_lo + i] = fmaxf(P.cfg_gain * (P.cfg_lo[i] - qi), -vb);
+      }
+    }
+    PK_WSYNC();
+    // ---- QP -------------------------------------------------------------------------------
+    status |= solve_qp(W, L);
+    PK_LANES(l) {
+      for (int i = l; i < nv; i += 32) vg[i] = W[L.o_x + i] * P.inv_dt;
+      if (l == 0 && status_out) *status_out = status;
+    }
+  }
+};
+
+}  // namespace pk

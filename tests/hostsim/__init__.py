@@ -73,7 +73,7 @@ class HostSim:
             a = a[None]
         return a
 
-    def solve_ik(self, prob, q, targets=None, general_path=False):
+    def solve_ik(self, prob, q, targets=None, general_path=False, path=None):
         q = self._f32(q)
         B = q.shape[0]
         t = None if targets is None else self._f32(targets)
@@ -81,8 +81,9 @@ class HostSim:
         st = np.zeros(B, dtype=np.int32)
         used = C.c_int(0)
         self._chk(lib().hs_solve_ik(self.handle, C.byref(prob), _p(q), _p(t), _p(v), _p(st),
-                                    C.c_int64(B), 1 if general_path else 0, C.byref(used)))
-        self.used_chain = bool(used.value)
+                                    C.c_int64(B), (1 if general_path else 0) if path is None else path, C.byref(used)))
+        self.used_chain = used.value == 1
+        self.used_tree = used.value == 2
         return v, st
 
     def build_ik(self, prob, q, targets=None):

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/pink_b200.h"
 #include "../../pink_b200/csrc/pk_marshal.hpp"
@@ -75,7 +76,7 @@ int hs_model_create(const PkModelDesc* d, void** out) {
 }
 void hs_model_destroy(void* m) { delete (pk::HostModel*)m; }
 
-// path: 0 auto (same selection as the CUDA library), 1 force the general path
+// path: 0 auto (same selection as the CUDA library), 1 force the general path, 2 force the tree kernel body
 int hs_solve_ik(void* model, const PkProblemDesc* prob, const float* q, const float* targets, float* v,
                 int32_t* status, int64_t B, int path, int* used_chain) {
   const pk::HostModel& hm = *(pk::HostModel*)model;
@@ -93,6 +94,20 @@ int hs_solve_ik(void* model, const PkProblemDesc* prob, const float* q, const fl
       case 6: run_chain<6>(hm, P, q, targets, v, status, B); return 0;
       case 7: run_chain<7>(hm, P, q, targets, v, status, B); return 0;
     }
+  }
+  if (path == 2 || (path == 0 && !chain)) {
+    bool ok = false;
+    const pk::TreePlan L = pk::make_tree_plan(hm, P, &ok);
+    if (ok) {
+      if (used_chain) *used_chain = 2;
+      const pk::DevModel M = hm.host_view();
+      std::vector<float> W(L.words);
+      for (int64_t i = 0; i < B; ++i)
+        pk::TreeStep::run(M, P, L, q + i * L.nq, targets ? targets + i * (int64_t)L.stride : nullptr, W.data(),
+                          v + i * L.nv, status ? status + i : nullptr);
+      return 0;
+    }
+    if (path == 2) return fail("problem does not fit the tree kernel");
   }
   Args A{};
   A.q = q; A.targets = targets; A.v = v; A.status = status; A.task_index = -1;

@@ -244,3 +244,19 @@ def test_prepared_solver_equals_solve_ik_and_host_modes(monkeypatch):
     ik.solve_host(torch.as_tensor(sc.q32), torch.as_tensor(targets), v_p, None)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(v_p.numpy(), v)
+
+
+@pytest.mark.parametrize("name,kw", [("draco3_description", {}), ("g1_description", {"with_com": True})])
+def test_tree_kernel_on_gpu_agrees_with_general_path_body(name, kw):
+    """Humanoids take the warp-cooperative tree kernel on the GPU; the general path
+    (run on the host build) must give the same velocities."""
+    from tests.hostsim import HostSim
+
+    sc = helpers.humanoid_scenario(name, 256, **kw)
+    v, st = _gpu_solve(sc)
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v_g, st_g = hs.solve_ik(prob, sc.q32, targets, path=1)
+    np.testing.assert_array_equal(st & 1, st_g & 1)
+    ok = helpers.within_tolerance(v, v_g.astype(np.float64), atol=1e-3, rtol=5e-3)
+    assert ok.mean() >= 0.98

@@ -150,3 +150,39 @@ def test_forward_kinematics_and_frame_jacobian_exports():
         f = table.nframes - 1
         J = hs.frame_jacobian(f, q)
         np.testing.assert_allclose(J, okin.frame_jacobian_local(table, fk, f), atol=5e-6)
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("draco3_description", {}),
+    ("g1_description", {"with_com": True}),
+    ("g1_description", {"with_com": True, "with_relative": True}),
+])
+def test_tree_kernel_body_matches_general_path_and_oracle(name, kw):
+    """The warp-cooperative tree kernel (pk_tree.cuh), run lane by lane on the host."""
+    sc = helpers.humanoid_scenario(name, 32, **kw)
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v_t, st_t = hs.solve_ik(prob, sc.q32, targets, path=2)
+    assert hs.used_tree
+    v_g, st_g = hs.solve_ik(prob, sc.q32, targets, path=1)
+    np.testing.assert_array_equal(st_t, st_g)
+    np.testing.assert_allclose(v_t, v_g, atol=2e-3, rtol=2e-3)
+    v_ref, st_ref = sc.oracle_solve()
+    good = (st_t & 1) == 0
+    ok = helpers.within_tolerance(v_t[good], v_ref[good], atol=5e-4, rtol=5e-3)
+    assert ok.mean() >= 0.95
+
+
+def test_tree_kernel_is_selected_for_humanoids_and_handles_limits():
+    sc = helpers.humanoid_scenario("draco3_description", 16)
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    hs.solve_ik(prob, sc.q32, targets)
+    assert hs.used_tree and not hs.used_chain
+    # out-of-limit instance with safety_break: flagged, zero velocity
+    q = sc.q32.copy()
+    q[3, 7 + 2] = sc.table.q_max[7 + 2] + 0.3
+    sc.safety_break = True
+    prob, targets, _ = sc.problem()
+    v, st = hs.solve_ik(prob, q, targets)
+    assert st[3] == 2 and np.abs(v[3]).max() == 0.0 and (st[np.arange(16) != 3] == 0).all()

@@ -150,6 +150,17 @@ int pk_solve_ik_prepared_host(PkModel* model, const PkProblem* problem,
                               float* v_host, int32_t* status_host, int64_t B,
                               void* stream);
 
+/* Closed loop of n_steps iterations of  v = solve_ik(q); q <- q (+) v dt
+ * (the loop of examples/arm_ur5.py:65-86 with fixed targets): q_out[B][nq] final
+ * configurations, v[B][nv] last velocities, status = OR over steps; an instance
+ * that fails a step keeps its configuration.  Serial chains run all steps in one
+ * launch with q resident in registers; other models alternate solve / integrate
+ * launches (status then reports the last step only).                        */
+int pk_rollout_prepared(const PkModel* model, const PkProblem* problem,
+                        const float* q, const float* targets, int32_t n_steps,
+                        float* q_out, float* v, int32_t* status, int64_t B,
+                        void* stream);
+
 /* Same through HOST buffers: H2D of q/targets, solve, D2H of v/status, all on
  * `stream`, chunked so copies overlap the kernels.  Returns after enqueueing;
  * the caller synchronises the stream before reading v.                     */

@@ -138,6 +138,7 @@ def declare(lib: C.CDLL, prefix: str = "pk_") -> None:
     lib.pk_problem_destroy.restype = None
     lib.pk_solve_ik_prepared.argtypes = [C.c_void_p, C.c_void_p, _FP, _FP, _FP, _FP, C.c_int64, C.c_void_p]
     lib.pk_solve_ik_prepared_host.argtypes = [C.c_void_p, C.c_void_p, _FP, _FP, _FP, _FP, C.c_int64, C.c_void_p]
+    lib.pk_rollout_prepared.argtypes = [C.c_void_p, C.c_void_p, _FP, _FP, C.c_int32, _FP, _FP, _FP, C.c_int64, C.c_void_p]
     lib.pk_build_ik_batched.argtypes = [C.c_void_p, C.POINTER(PkProblemDesc), _FP, _FP, _FP, _FP, _FP, C.c_int64, C.c_void_p]
     lib.pk_task_terms_batched.argtypes = [C.c_void_p, C.POINTER(PkProblemDesc), C.c_int32, _FP, _FP, _FP, _FP, C.c_int64, C.c_void_p]
     lib.pk_forward_kinematics_batched.argtypes = [C.c_void_p, _FP, _FP, _FP, C.c_int64, C.c_void_p]
@@ -157,6 +158,7 @@ EXPORTED_SYMBOLS = [
     "pk_problem_destroy",
     "pk_solve_ik_prepared",
     "pk_solve_ik_prepared_host",
+    "pk_rollout_prepared",
     "pk_build_ik_batched",
     "pk_task_terms_batched",
     "pk_forward_kinematics_batched",

@@ -88,3 +88,22 @@ class BatchedIK:
             _cabi.check(eng.lib.pk_solve_ik_prepared_host(eng.handle, self._handle, _addr(q), _addr(targets),
                                                           _addr(out), _addr(status), q.shape[0], _stream(eng.device)))
         return out, status
+
+    def rollout(self, q: torch.Tensor, targets: Optional[torch.Tensor], steps: int,
+                q_out: Optional[torch.Tensor] = None, v_out: Optional[torch.Tensor] = None,
+                status: Optional[torch.Tensor] = None):
+        """``steps`` iterations of ``v = solve_ik(q); q = q (+) v dt`` with fixed targets
+        (the loop of ``examples/arm_ur5.py:65-86``); serial chains keep ``q`` on chip
+        for the whole loop.  Returns ``(q_final, v_last, status)``."""
+        eng = self.engine
+        B = q.shape[0]
+        if q_out is None:
+            q_out = torch.empty_like(q)
+        if v_out is None:
+            v_out = torch.empty((B, self.nv), device=eng.device, dtype=torch.float32)
+        if status is None:
+            status = torch.empty((B,), device=eng.device, dtype=torch.int32)
+        with torch.cuda.device(eng.device):
+            _cabi.check(eng.lib.pk_rollout_prepared(eng.handle, self._handle, _addr(q), _addr(targets), int(steps),
+                                                    _addr(q_out), _addr(v_out), _addr(status), B, _stream(eng.device)))
+        return q_out, v_out, status

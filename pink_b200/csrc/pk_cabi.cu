@@ -304,7 +304,7 @@ template <int NJ, int NFT>
 __global__ void __launch_bounds__(ChainSlots<NJ, NFT>::BLOCK, 2)
     ik_chain_kernel(const __grid_constant__ ChainParams<NJ> P, const float* __restrict__ q,
                     const float* __restrict__ targets, float* __restrict__ v, int32_t* __restrict__ status,
-                    int64_t B, int steps_per_sync) {
+                    int64_t B, int steps_per_sync, int n_steps, float* __restrict__ q_out) {
   using IO = SlotIO<NJ, NFT>;
   constexpr int BLOCK = IO::BLOCK;
   constexpr int NW = BLOCK / 32;
@@ -321,16 +321,10 @@ __global__ void __launch_bounds__(ChainSlots<NJ, NFT>::BLOCK, 2)
   const int64_t i = (int64_t)blockIdx.x * BLOCK + tid;
   const bool valid = i < B;
 
-  int st = 0;
-  bool skip = true;
-  int ph = 0;
-  float x[NJ];
+  float qi[NJ];
 #pragma unroll
-  for (int k = 0; k < NJ; ++k) x[k] = 0.f;
+  for (int k = 0; k < NJ; ++k) qi[k] = 0.f;
   if (valid) {
-    ChainStep<NJ, NFT> C;
-    State S;
-    float qi[NJ];
     const float* qrow = q + i * NJ;
     if constexpr (NJ % 2 == 0) {
 #pragma unroll
@@ -343,78 +337,107 @@ __global__ void __launch_bounds__(ChainSlots<NJ, NFT>::BLOCK, 2)
 #pragma unroll
       for (int k = 0; k < NJ; ++k) qi[k] = __ldg(qrow + k);
     }
-    st = C.assemble(P, qi, targets + i * (int64_t)P.target_stride, skip);
-    if (!skip) {
-      bool more = QP::init(C.A, C.b, C.d, C.beta, C.lo, C.hi, S);
-      // cheap exits in place: every coordinate clamped => one multiplier check
-      if (more && (S.at_hi | S.at_lo) == QP::ALL) {
-        more = QP::round(S);
-        if (!more) more = QP::polish(C.A, C.b, C.d, C.beta, S);
-        ph = more ? 1 : 0;
-      } else {
-        // interior and well-conditioned => nothing left; otherwise park
-        ph = more ? 1 : (((S.at_hi | S.at_lo) == 0u && S.cond <= 1e3f) ? 0 : 2);
-      }
-      if (ph != 0) {
-        IO::store_const(sm, tid, S);
-        IO::store_var(sm, tid, S);
-        IO::store_obj(sm, tid, C);
-      } else {
-#pragma unroll
-        for (int k = 0; k < NJ; ++k) x[k] = S.x[k];
-        st |= S.status;
-      }
-    }
   }
-  const bool parked = ph != 0;
-  phase[tid] = (signed char)ph;
-
-  // ---- compacted state machine --------------------------------------------------------
-  for (;;) {
-    __syncthreads();
-    const bool unfinished = phase[tid] != 0;
-    const unsigned ball = __ballot_sync(0xffffffffu, unfinished);
-    if (lane == 0) wcount[warp] = __popc(ball);
-    __syncthreads();
-    int base = 0, total = 0;
+  // n_steps > 1: closed-loop rollout, q <- q (+) v dt after every step with q kept in
+  // registers (pink/configuration.py:285-293 after pink/solve_ik.py:274); an instance
+  // that fails a step (no solution / outside limits with safety_break) is frozen.
+  int st_all = 0;
+  float x[NJ];
 #pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      const int c = wcount[k];
-      if (k < warp) base += c;
-      total += c;
-    }
-    if (total == 0) break;
-    if (unfinished) list[base + __popc(ball & ((1u << lane) - 1u))] = tid;
-    __syncthreads();
-    if (tid < total) {
-      const int slot = list[tid];
-      State T;
-      IO::load_const(sm, slot, T);
-      IO::load_var(sm, slot, T);
-      // one barrier interval: up to `steps_per_sync` active-set rounds, or the polish.
-      // (Keeping the two in separate intervals lets the polish hold A in registers
-      // without spilling the round's Cholesky state: measured 24.2 us vs 29.2 us.)
-      int next;
-      if (phase[slot] == 1) {
-        next = QP::round(T) ? 1 : 2;
-        for (int step = 1; step < steps_per_sync && next == 1; ++step) next = QP::round(T) ? 1 : 2;
-      } else {
-        float A[KA][NJ], b[KA], d[NJ], beta[NJ];
-        IO::load_obj(sm, slot, A, b, d, beta);
-        next = QP::polish(A, b, d, beta, T) ? 1 : 0;
+  for (int k = 0; k < NJ; ++k) x[k] = 0.f;
+  for (int step_no = 0; step_no < n_steps; ++step_no) {
+    int st = 0;
+    bool skip = true;
+    int ph = 0;
+    const bool frozen =
+        (st_all & (PK_STATUS_NO_SOLUTION | PK_STATUS_NOT_POSDEF)) || ((st_all & PK_STATUS_OUT_OF_LIMITS) && P.safety_break);
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) x[k] = 0.f;
+    if (valid && !frozen) {
+      ChainStep<NJ, NFT> C;
+      State S;
+      st = C.assemble(P, qi, targets + i * (int64_t)P.target_stride, skip);
+      if (!skip) {
+        bool more = QP::init(C.A, C.b, C.d, C.beta, C.lo, C.hi, S);
+        // cheap exits in place: every coordinate clamped => one multiplier check
+        if (more && (S.at_hi | S.at_lo) == QP::ALL) {
+          more = QP::round(S);
+          if (!more) more = QP::polish(C.A, C.b, C.d, C.beta, S);
+          ph = more ? 1 : 0;
+        } else {
+          // interior and well-conditioned => nothing left; otherwise park
+          ph = more ? 1 : (((S.at_hi | S.at_lo) == 0u && S.cond <= 1e3f) ? 0 : 2);
+        }
+        if (ph != 0) {
+          IO::store_const(sm, tid, S);
+          IO::store_var(sm, tid, S);
+          IO::store_obj(sm, tid, C);
+        } else {
+#pragma unroll
+          for (int k = 0; k < NJ; ++k) x[k] = S.x[k];
+          st |= S.status;
+        }
       }
-      IO::store_var(sm, slot, T);
-      phase[slot] = (signed char)next;
     }
+    const bool parked = ph != 0;
+    phase[tid] = (signed char)ph;
+
+    // ---- compacted state machine ------------------------------------------------------
+    for (;;) {
+      __syncthreads();
+      const bool unfinished = phase[tid] != 0;
+      const unsigned ball = __ballot_sync(0xffffffffu, unfinished);
+      if (lane == 0) wcount[warp] = __popc(ball);
+      __syncthreads();
+      int base = 0, total = 0;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        const int c = wcount[k];
+        if (k < warp) base += c;
+        total += c;
+      }
+      if (total == 0) break;
+      if (unfinished) list[base + __popc(ball & ((1u << lane) - 1u))] = tid;
+      __syncthreads();
+      if (tid < total) {
+        const int slot = list[tid];
+        State T;
+        IO::load_const(sm, slot, T);
+        IO::load_var(sm, slot, T);
+        // one barrier interval: up to `steps_per_sync` active-set rounds, or the polish.
+        // (Keeping the two in separate intervals lets the polish hold A in registers
+        // without spilling the round's Cholesky state: measured 24.2 us vs 29.2 us.)
+        int next;
+        if (phase[slot] == 1) {
+          next = QP::round(T) ? 1 : 2;
+          for (int r = 1; r < steps_per_sync && next == 1; ++r) next = QP::round(T) ? 1 : 2;
+        } else {
+          float A[KA][NJ], b[KA], d[NJ], beta[NJ];
+          IO::load_obj(sm, slot, A, b, d, beta);
+          next = QP::polish(A, b, d, beta, T) ? 1 : 0;
+        }
+        IO::store_var(sm, slot, T);
+        phase[slot] = (signed char)next;
+      }
+    }
+
+    if (valid) {
+      if (parked) {
+        constexpr int base = ChainSlots<NJ, NFT>::kConst;
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) x[k] = IO::at(sm, base + k, tid);
+        st |= __float_as_int(IO::at(sm, base + NJ + 3, tid));
+      }
+      st_all |= st & 0xff;
+      if (n_steps > 1 || q_out) {
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) qi[k] += x[k];  // 1-dof joints: q (+) dq = q + dq
+      }
+    }
+    if (step_no + 1 < n_steps) __syncthreads();  // slots are reused by the next step
   }
 
   if (!valid) return;
-  if (parked) {
-    constexpr int base = ChainSlots<NJ, NFT>::kConst;
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) x[k] = IO::at(sm, base + k, tid);
-    st |= __float_as_int(IO::at(sm, base + NJ + 3, tid));
-  }
   float* vrow = v + i * NJ;
   if constexpr (NJ % 2 == 0) {
 #pragma unroll
@@ -424,7 +447,12 @@ __global__ void __launch_bounds__(ChainSlots<NJ, NFT>::BLOCK, 2)
 #pragma unroll
     for (int k = 0; k < NJ; ++k) vrow[k] = x[k] * P.inv_dt;
   }
-  if (status) status[i] = st & 0xff;
+  if (q_out) {
+    float* orow = q_out + i * NJ;
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) orow[k] = qi[k];
+  }
+  if (status) status[i] = st_all;
 }
 
 // Plain variant: the whole step, QP rounds included, in the owning thread (lanes of
@@ -579,7 +607,7 @@ int env_int(const char* name, int dflt) {
 
 template <int NJ, int NFT>
 int launch_chain_nft(const pk::ChainParams<NJ>& C, const float* q, const float* targets, float* v, int32_t* status,
-                     int64_t B, cudaStream_t stream) {
+                     int64_t B, cudaStream_t stream, int n_steps, float* q_out) {
   using L = pk::ChainSlots<NJ, NFT>;
   static bool configured = false;  // opt in to > 48 KB of dynamic shared memory once per instantiation
   if (!configured) {
@@ -588,7 +616,7 @@ int launch_chain_nft(const pk::ChainParams<NJ>& C, const float* q, const float* 
     configured = true;
   }
   static const int mode = env_int("PK_CHAIN_MODE", 1);
-  if (mode == 0) {
+  if (mode == 0 && n_steps == 1 && !q_out) {
     const int64_t grid0 = (B + 127) / 128;
     pk::ik_chain_kernel_plain<NJ, NFT><<<(unsigned)grid0, 128, 0, stream>>>(C, q, targets, v, status, B);
     g_launches.fetch_add(1);
@@ -597,7 +625,7 @@ int launch_chain_nft(const pk::ChainParams<NJ>& C, const float* q, const float* 
   }
   const int64_t grid = (B + L::BLOCK - 1) / L::BLOCK;
   static const int rps = std::max(1, env_int("PK_STEPS_PER_SYNC", 8));
-  pk::ik_chain_kernel<NJ, NFT><<<(unsigned)grid, L::BLOCK, L::kSmemBytes, stream>>>(C, q, targets, v, status, B, rps);
+  pk::ik_chain_kernel<NJ, NFT><<<(unsigned)grid, L::BLOCK, L::kSmemBytes, stream>>>(C, q, targets, v, status, B, rps, n_steps, q_out);
   g_launches.fetch_add(1);
   PK_CUDA(cudaGetLastError());
   return 0;
@@ -605,11 +633,11 @@ int launch_chain_nft(const pk::ChainParams<NJ>& C, const float* q, const float* 
 
 template <int NJ>
 int launch_chain(const pk::ChainParams<NJ>& C, const float* q, const float* targets, float* v, int32_t* status,
-                 int64_t B, cudaStream_t stream) {
+                 int64_t B, cudaStream_t stream, int n_steps = 1, float* q_out = nullptr) {
   switch (C.n_frame_tasks) {
-    case 0: return launch_chain_nft<NJ, 0>(C, q, targets, v, status, B, stream);
-    case 1: return launch_chain_nft<NJ, 1>(C, q, targets, v, status, B, stream);
-    default: return launch_chain_nft<NJ, 2>(C, q, targets, v, status, B, stream);
+    case 0: return launch_chain_nft<NJ, 0>(C, q, targets, v, status, B, stream, n_steps, q_out);
+    case 1: return launch_chain_nft<NJ, 1>(C, q, targets, v, status, B, stream, n_steps, q_out);
+    default: return launch_chain_nft<NJ, 2>(C, q, targets, v, status, B, stream, n_steps, q_out);
   }
 }
 
@@ -676,9 +704,9 @@ int prepare_problem(const PkModel* m, const PkProblemDesc* desc, PkProblem* pr) 
 
 template <int NJ>
 int launch_chain_prepared(const PkProblem& pr, const float* q, const float* targets, float* v, int32_t* status,
-                          int64_t B, cudaStream_t stream) {
+                          int64_t B, cudaStream_t stream, int n_steps = 1, float* q_out = nullptr) {
   return launch_chain<NJ>(*reinterpret_cast<const pk::ChainParams<NJ>*>(pr.chain_params), q, targets, v, status, B,
-                          stream);
+                          stream, n_steps, q_out);
 }
 
 int solve_device(const PkModel* m, const PkProblem& pr, const float* q, const float* targets, float* v,
@@ -765,6 +793,36 @@ extern "C" int pk_solve_ik_prepared_host(PkModel* m, const PkProblem* pr, const 
   if (B > 0 && !v_host) return fail("null v");
   if (B > 0 && pr->P.target_stride > 0 && !targets_host) return fail("null targets");
   return solve_host_impl(m, *pr, q_host, targets_host, v_host, status_host, B, (cudaStream_t)stream);
+}
+
+extern "C" int pk_rollout_prepared(const PkModel* m, const PkProblem* pr, const float* q, const float* targets,
+                                   int32_t n_steps, float* q_out, float* v, int32_t* status, int64_t B,
+                                   void* stream_) {
+  if (check_common(m, q, B)) return 1;
+  if (!pr) return fail("null problem");
+  if (n_steps < 1) return fail("n_steps must be >= 1");
+  if (B > 0 && (!v || !q_out)) return fail("null v or q_out");
+  if (B > 0 && pr->P.target_stride > 0 && !targets) return fail("null targets");
+  if (B == 0) return 0;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (pr->chain) {
+    switch (pr->nj) {
+      case 2: return launch_chain_prepared<2>(*pr, q, targets, v, status, B, stream, n_steps, q_out);
+      case 3: return launch_chain_prepared<3>(*pr, q, targets, v, status, B, stream, n_steps, q_out);
+      case 4: return launch_chain_prepared<4>(*pr, q, targets, v, status, B, stream, n_steps, q_out);
+      case 5: return launch_chain_prepared<5>(*pr, q, targets, v, status, B, stream, n_steps, q_out);
+      case 6: return launch_chain_prepared<6>(*pr, q, targets, v, status, B, stream, n_steps, q_out);
+      case 7: return launch_chain_prepared<7>(*pr, q, targets, v, status, B, stream, n_steps, q_out);
+      default: break;
+    }
+  }
+  // other models: the same closed loop as separate launches (solve, then integrate in place)
+  if (q_out != q) PK_CUDA(cudaMemcpyAsync(q_out, q, sizeof(float) * B * m->nq, cudaMemcpyDeviceToDevice, stream));
+  for (int s = 0; s < n_steps; ++s) {
+    if (solve_device(m, *pr, q_out, targets, v, status, B, stream)) return 1;
+    if (pk_integrate_batched(m, q_out, v, pr->P.dt, q_out, B, stream)) return 1;
+  }
+  return 0;
 }
 
 extern "C" int pk_solve_ik_batched(const PkModel* m, const PkProblemDesc* prob, const float* q,

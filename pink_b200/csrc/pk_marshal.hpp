@@ -236,7 +236,7 @@ inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok
   L.o_idx = take(L.nv);
   L.o_cw = take(3 * (L.nj + 1));
   L.words = off;
-  *ok = m.njoints >= 1 && m.njoints <= kTreeMaxJoints && m.nv <= 64 && P.ntasks <= 32 && (size_t)L.words * 4 <= 48 * 1024;
+  *ok = m.njoints >= 1 && m.njoints <= kTreeMaxJoints && m.nv <= 64 && P.ntasks <= 32 && K <= 64 && (size_t)L.words * 4 <= 48 * 1024;
   return L;
 }
 

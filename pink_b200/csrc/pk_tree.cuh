@@ -26,7 +26,8 @@ struct TreePlan {
       o_rho, o_ys, o_idx, o_cw, words;
 };
 
-constexpr int kTwStride = 13;  // 12 floats per joint transform, padded against bank conflicts
+constexpr int kTwStride = 13;     // 12 floats per joint transform, padded against bank conflicts
+constexpr int kMultiChange = 12;  // iterations with multi-add / multi-release before single steps
 
 struct TreeStep {
   // ---- small accessors -------------------------------------------------------------
@@ -102,24 +103,35 @@ struct TreeStep {
       }
     }
     PK_WSYNC();
-    // right-hand side and compacted copy, row-parallel
+    // right-hand side and compacted copy, row-parallel (two row slots per lane)
     PK_LANES(l) {
-      for (int r = l; r < K; r += 32) {
-        float s = bv[r];
-        for (int j = 0; j < n; ++j)
-          if ((act >> j) & 1ull) s = fmaf(A[r * L.lda + j], x[j], s);
-        zb[r] = s;
-        for (int c = 0; c < nf; ++c) Aw[r * L.ldw + c] = A[r * L.lda + idx[c]];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = l + 32 * h;
+        if (r < K) {
+          const float* Ar = A + r * L.lda;
+          float* Awr = Aw + r * L.ldw;
+          float s = bv[r];
+          for (int j = 0; j < n; ++j)
+            if ((act >> j) & 1ull) s = fmaf(Ar[j], x[j], s);
+          zb[r] = s;
+          for (int c = 0; c < nf; ++c) Awr[c] = Ar[idx[c]];
+        }
       }
     }
     PK_WSYNC();
     bool ok = true;
+    // Householder sweep.  K <= 64: every lane owns at most two rows (l and l + 32),
+    // kept in registers for column k; four columns j are reflected per pass so that
+    // the four shuffle reductions overlap.
     for (int k = 0; k < nf; ++k) {
-      LaneVar<float> part;
+      LaneVar<float> ak0, ak1, part;
       PK_LANES(l) {
-        float s = 0.f;
-        for (int r = l; r < K; r += 32) s = fmaf(Aw[r * L.ldw + k], Aw[r * L.ldw + k], s);
-        part[l] = s;
+        const float a0 = (l < K) ? Aw[l * L.ldw + k] : 0.f;
+        const float a1 = (l + 32 < K) ? Aw[(l + 32) * L.ldw + k] : 0.f;
+        ak0[l] = a0;
+        ak1[l] = a1;
+        part[l] = fmaf(a0, a0, a1 * a1);
       }
       const float sigma = lane_sum(part);
       const float alpha = dv[idx[k]];
@@ -128,28 +140,44 @@ struct TreeStep {
       const float v0 = alpha + norm;
       const float tau = (sigma > 0.f) ? 1.f / (norm * v0) : 0.f;
       const float rdk = (sigma > 0.f) ? -norm : alpha;
-      for (int j = k + 1; j < nf; ++j) {
+      for (int j = k + 1; j < nf; j += 4) {
+        LaneVar<float> c0[4], c1[4], p[4];
         PK_LANES(l) {
-          float s = 0.f;
-          for (int r = l; r < K; r += 32) s = fmaf(Aw[r * L.ldw + k], Aw[r * L.ldw + j], s);
-          part[l] = s;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const bool on = j + c < nf;
+            const float a0 = (on && l < K) ? Aw[l * L.ldw + j + c] : 0.f;
+            const float a1 = (on && l + 32 < K) ? Aw[(l + 32) * L.ldw + j + c] : 0.f;
+            c0[c][l] = a0;
+            c1[c][l] = a1;
+            p[c][l] = fmaf(ak0[l], a0, ak1[l] * a1);
+          }
         }
-        const float s = lane_sum(part) * tau;
+        float sc[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sc[c] = lane_sum(p[c]) * tau;
         PK_LANES(l) {
-          for (int r = l; r < K; r += 32) Aw[r * L.ldw + j] = fmaf(-s, Aw[r * L.ldw + k], Aw[r * L.ldw + j]);
-          if (l == 0) Ru[k * L.ldw + j] = -s * v0;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (j + c < nf) {
+              if (l < K) Aw[l * L.ldw + j + c] = fmaf(-sc[c], ak0[l], c0[c][l]);
+              if (l + 32 < K) Aw[(l + 32) * L.ldw + j + c] = fmaf(-sc[c], ak1[l], c1[c][l]);
+              if (l == 0) Ru[k * L.ldw + j + c] = -sc[c] * v0;
+            }
+          }
         }
       }
       PK_LANES(l) {
-        float s = 0.f;
-        for (int r = l; r < K; r += 32) s = fmaf(Aw[r * L.ldw + k], zb[r], s);
-        part[l] = s;
+        const float z0 = (l < K) ? zb[l] : 0.f;
+        const float z1 = (l + 32 < K) ? zb[l + 32] : 0.f;
+        part[l] = fmaf(ak0[l], z0, ak1[l] * z1);
       }
       const float ztk = zt[k];
       const float s = fmaf(v0, ztk, lane_sum(part)) * tau;
       PK_WSYNC();
       PK_LANES(l) {
-        for (int r = l; r < K; r += 32) zb[r] = fmaf(-s, Aw[r * L.ldw + k], zb[r]);
+        if (l < K) zb[l] = fmaf(-s, ak0[l], zb[l]);
+        if (l + 32 < K) zb[l + 32] = fmaf(-s, ak1[l], zb[l + 32]);
         if (l == 0) {
           zt[k] = fmaf(-s, v0, ztk);
           Rd[k] = rdk;
@@ -157,23 +185,32 @@ struct TreeStep {
       }
     }
     PK_WSYNC();
-    // R ys = -zt
-    for (int kk = 0; kk < nf; ++kk) {
-      const int k = nf - 1 - kk;
-      LaneVar<float> part;
+    // R ys = -zt by columns: lane j owns the running sum of row j (two slots); each
+    // solved component is broadcast from its owner and folded into the rows above it.
+    {
+      LaneVar<float> acc0, acc1, sol0, sol1;
       PK_LANES(l) {
-        float s = 0.f;
-        for (int j = k + 1 + l; j < nf; j += 32) s = fmaf(Ru[k * L.ldw + j], ys[j], s);
-        part[l] = s;
+        acc0[l] = (l < nf) ? -zt[l] : 0.f;
+        acc1[l] = (l + 32 < nf) ? -zt[l + 32] : 0.f;
+        sol0[l] = 0.f;
+        sol1[l] = 0.f;
       }
-      const float rd = Rd[k];
-      const float yk = (rd != 0.f) ? (-zt[k] - lane_sum(part)) / rd : 0.f;
-      PK_WSYNC();
-      PK_LANES(l) {
-        if (l == 0) {
-          ys[k] = yk;
-          y[idx[k]] = yk;
+      for (int kk = 0; kk < nf; ++kk) {
+        const int k = nf - 1 - kk;
+        const float rd = Rd[k];
+        const float num = (k < 32) ? lane_bcast(acc0, k) : lane_bcast(acc1, k - 32);
+        const float yk = (rd != 0.f) ? num / rd : 0.f;
+        PK_LANES(l) {
+          if (l < k) acc0[l] = fmaf(-Ru[l * L.ldw + k], yk, acc0[l]);
+          if (l + 32 < k) acc1[l] = fmaf(-Ru[(l + 32) * L.ldw + k], yk, acc1[l]);
+          if (l == (k & 31)) {
+            if (k < 32) sol0[l] = yk; else sol1[l] = yk;
+          }
         }
+      }
+      PK_LANES(l) {
+        if (l < nf) y[idx[l]] = sol0[l];
+        if (l + 32 < nf) y[idx[l + 32]] = sol1[l];
       }
       PK_WSYNC();
     }
@@ -264,6 +301,30 @@ struct TreeStep {
         lane_argmin(sv, si, step, blk);
       }
       if (blk != 0x7fffffff) {
+        if (it < kMultiChange) {
+          // early iterations: clamp EVERY free coordinate that the Newton point pushes
+          // past a bound (primal-dual style; halves the number of factorisations on
+          // the humanoid workloads).  Later iterations take the classical single
+          // blocking step, which guarantees termination.
+          LaneVar<uint64_t> mh, ml;
+          PK_LANES(l) {
+            uint64_t h = 0ull, m = 0ull;
+            for (int i = l; i < n; i += 32) {
+              if (!((act >> i) & 1ull)) {
+                const float yi = y[i];
+                if (yi > hi[i]) { h |= (1ull << i); x[i] = hi[i]; }
+                else if (yi < lo[i]) { m |= (1ull << i); x[i] = lo[i]; }
+                else x[i] = yi;
+              }
+            }
+            mh[l] = h;
+            ml[l] = m;
+          }
+          at_hi |= lane_or64(mh);
+          at_lo |= lane_or64(ml);
+          PK_WSYNC();
+          continue;
+        }
         step = fmaxf(step, 0.f);
         const bool blk_hi = y[blk] > hi[blk];
         PK_WSYNC();
@@ -286,10 +347,15 @@ struct TreeStep {
       PK_WSYNC();
       // multipliers from the factored gradient: rho = A x + b (row-parallel) ...
       PK_LANES(l) {
-        for (int r = l; r < K; r += 32) {
-          float s = bv[r];
-          for (int j = 0; j < n; ++j) s = fmaf(A[r * L.lda + j], x[j], s);
-          rho[r] = s;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = l + 32 * h;
+          if (r < K) {
+            const float* Ar = A + r * L.lda;
+            float s = bv[r];
+            for (int j = 0; j < n; ++j) s = fmaf(Ar[j], x[j], s);
+            rho[r] = s;
+          }
         }
       }
       PK_WSYNC();
@@ -330,7 +396,7 @@ struct TreeStep {
         neg = lane_or64(nm);
       }
       if (neg == 0ull) break;
-      const uint64_t drop = (it == 0) ? neg : (1ull << rel);
+      const uint64_t drop = (it < kMultiChange) ? neg : (1ull << rel);
       at_hi &= ~drop;
       at_lo &= ~drop;
     }

@@ -61,6 +61,10 @@ __device__ __forceinline__ uint64_t lane_or64(const LaneVar<uint64_t>& a) {
 __device__ __forceinline__ int lane_or(const LaneVar<int>& a) {
   return __reduce_or_sync(0xffffffffu, a.v);
 }
+// value held by lane `src`, on every lane
+__device__ __forceinline__ float lane_bcast(const LaneVar<float>& a, int src) {
+  return __shfl_sync(0xffffffffu, a.v, src);
+}
 
 #else  // host emulation: one "warp" = a loop over 32 lanes
 
@@ -101,6 +105,7 @@ inline int lane_or(const LaneVar<int>& a) {
   for (int l = 0; l < 32; ++l) s |= a.v[l];
   return s;
 }
+inline float lane_bcast(const LaneVar<float>& a, int src) { return a.v[src]; }
 
 #endif
 

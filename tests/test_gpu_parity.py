@@ -260,3 +260,39 @@ def test_tree_kernel_on_gpu_agrees_with_general_path_body(name, kw):
     np.testing.assert_array_equal(st & 1, st_g & 1)
     ok = helpers.within_tolerance(v, v_g.astype(np.float64), atol=1e-3, rtol=5e-3)
     assert ok.mean() >= 0.98
+
+
+def test_fused_rollout_equals_step_by_step_loop():
+    """pk_rollout_prepared (K steps in one launch, q in registers) against the same
+    closed loop made of separate solve + integrate calls, and against the oracle."""
+    sc = helpers.ur5_scenario(4096, "reachable", out_of_limits=3)
+    ik = pink_b200.BatchedIK(sc.model, sc.tasks, sc.dt, damping=sc.damping, batch_size=sc.B)
+    prob, targets, _ = sc.problem()
+    q0 = torch.as_tensor(sc.q32, device="cuda")
+    t_d = torch.as_tensor(targets, device="cuda")
+    K = 12
+    q_f, v_f, st_f = ik.rollout(q0, t_d, K)
+    q = q0.clone()
+    eng = ik.engine
+    st_or = torch.zeros(sc.B, dtype=torch.int32, device="cuda")
+    for _ in range(K):
+        v, st = ik.solve(q, t_d)
+        failed = (st_or & 3) != 0
+        v = torch.where(failed[:, None], torch.zeros_like(v), v)
+        st_or |= torch.where(failed, torch.zeros_like(st), st)
+        q = eng.integrate(q, v, sc.dt)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(st_f.cpu().numpy() & 3, st_or.cpu().numpy() & 3)
+    np.testing.assert_allclose(q_f.cpu().numpy(), q.cpu().numpy(), atol=2e-5)
+    # oracle closed loop on a few instances
+    from oracle import kinematics as okin2
+
+    n = 24
+    q_o = sc.q64[:n].copy()
+    alive = np.ones(n, dtype=bool)
+    for _ in range(K):
+        tasks = [oik._slice_task_range(t, 0, n) for t in sc.oracle_tasks]
+        v_o, st_o = oik.solve_ik_batch(sc.table, q_o, tasks, sc.dt, sc.damping)
+        alive &= st_o == 0
+        q_o = np.where(alive[:, None], okin2.integrate(sc.table, q_o, v_o * sc.dt), q_o)
+    np.testing.assert_allclose(q_f.cpu().numpy()[:n], q_o, atol=2e-4)

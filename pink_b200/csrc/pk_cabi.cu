@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(64) ik_generic_kernel(const DevModel M, const 
 
 // Tree kernel: one instance per warp, per-instance state in the warp's slice of
 // dynamic shared memory (pk_tree.cuh).
-constexpr int kTreeWarpsPerBlock = 4;
+constexpr int kTreeWarpsPerBlock = 2;
 __global__ void __launch_bounds__(32 * kTreeWarpsPerBlock)
     ik_tree_kernel(const DevModel M, const __grid_constant__ DevProblem P, const __grid_constant__ TreePlan L,
                    const float* __restrict__ q, const float* __restrict__ targets, float* __restrict__ v,

@@ -210,32 +210,41 @@ inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok
   L.K = K;
   L.lda = L.nv | 1;
   L.ldw = L.nv | 1;
+  // Layout: persistent QP data first; then one region that is used twice - by the
+  // assembly phase (q, targets, joint transforms, per-task blocks, body CoMs) and,
+  // once A / b / box are built, by the QR scratch (compacted columns, R, right-hand
+  // sides).  Overlaying the two and packing R roughly halves the footprint, which is
+  // what bounds the number of resident warps per SM.
   int off = 0;
-  auto take = [&](int words) { const int at = off; off += (words + 3) / 4 * 4; return at; };
-  L.o_q = take(L.nq);
-  L.o_t = take(L.stride);
-  L.o_tw = take(kTwStride * (L.nj > 0 ? L.nj : 1));
-  L.o_root = take(12);
-  L.o_tf = take(kTreeTaskWords * (P.ntasks > 0 ? P.ntasks : 1));
-  L.o_A = take((K > 0 ? K : 1) * L.lda);
-  L.o_b = take(K);
-  L.o_d = take(L.nv);
-  L.o_beta = take(L.nv);
-  L.o_lo = take(L.nv);
-  L.o_hi = take(L.nv);
-  L.o_x = take(L.nv);
-  L.o_y = take(L.nv);
-  L.o_g = take(L.nv);
-  L.o_aw = take((K > 0 ? K : 1) * L.ldw);
-  L.o_ru = take(L.nv * L.ldw);
-  L.o_rd = take(L.nv);
-  L.o_zt = take(L.nv);
-  L.o_zb = take(K);
-  L.o_rho = take(K);
-  L.o_ys = take(L.nv);
-  L.o_idx = take(L.nv);
-  L.o_cw = take(3 * (L.nj + 1));
-  L.words = off;
+  auto take = [&](int& cursor, int words) { const int at = cursor; cursor += (words + 3) / 4 * 4; return at; };
+  const int Kp = K > 0 ? K : 1;
+  L.o_A = take(off, Kp * L.lda);
+  L.o_b = take(off, K);
+  L.o_d = take(off, L.nv);
+  L.o_beta = take(off, L.nv);
+  L.o_lo = take(off, L.nv);
+  L.o_hi = take(off, L.nv);
+  L.o_x = take(off, L.nv);
+  L.o_y = take(off, L.nv);
+  L.o_g = off;  // unused
+  const int shared_base = off;
+  int a = shared_base;  // assembly view
+  L.o_q = take(a, L.nq);
+  L.o_t = take(a, L.stride);
+  L.o_tw = take(a, kTwStride * (L.nj > 0 ? L.nj : 1));
+  L.o_root = take(a, 12);
+  L.o_tf = take(a, kTreeTaskWords * (P.ntasks > 0 ? P.ntasks : 1));
+  L.o_cw = take(a, 3 * (L.nj + 1));
+  int b2 = shared_base;  // QP view
+  L.o_aw = take(b2, Kp * L.ldw);
+  L.o_ru = take(b2, L.nv * (L.nv - 1) / 2 + 1);
+  L.o_rd = take(b2, L.nv);
+  L.o_zt = take(b2, L.nv);
+  L.o_zb = take(b2, K);
+  L.o_rho = take(b2, K);
+  L.o_ys = b2;  // unused
+  L.o_idx = take(b2, L.nv);
+  L.words = a > b2 ? a : b2;
   *ok = m.njoints >= 1 && m.njoints <= kTreeMaxJoints && m.nv <= 64 && P.ntasks <= 32 && K <= 64 && (size_t)L.words * 4 <= 48 * 1024;
   return L;
 }

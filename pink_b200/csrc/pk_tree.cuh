@@ -67,6 +67,9 @@ struct TreeStep {
     }
   }
 
+  // strict upper triangle of R, packed by rows: entry (k, j), j > k
+  static PK_HD int ru(const TreePlan& L, int k, int j) { return k * L.nv - k * (k + 1) / 2 + (j - k - 1); }
+
   // ---- least squares on the free set (cooperative Householder QR) -------------------
   // Rows of Aw are owned by lanes (r = l, l + 32, ...).  y receives the full solution.
   static PK_HD bool eqp(float* W, const TreePlan& L, uint64_t act) {
@@ -77,7 +80,6 @@ struct TreeStep {
     float* Rd = W + L.o_rd;
     float* zt = W + L.o_zt;
     float* zb = W + L.o_zb;
-    float* ys = W + L.o_ys;
     int* idx = reinterpret_cast<int*>(W + L.o_idx);
     const float* x = W + L.o_x;
     float* y = W + L.o_y;
@@ -154,15 +156,16 @@ struct TreeStep {
           }
         }
         float sc[4];
+        lane_sum4(p, sc);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) sc[c] = lane_sum(p[c]) * tau;
+        for (int c = 0; c < 4; ++c) sc[c] *= tau;
         PK_LANES(l) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (j + c < nf) {
               if (l < K) Aw[l * L.ldw + j + c] = fmaf(-sc[c], ak0[l], c0[c][l]);
               if (l + 32 < K) Aw[(l + 32) * L.ldw + j + c] = fmaf(-sc[c], ak1[l], c1[c][l]);
-              if (l == 0) Ru[k * L.ldw + j + c] = -sc[c] * v0;
+              if (l == 0) Ru[ru(L, k, j + c)] = -sc[c] * v0;
             }
           }
         }
@@ -201,8 +204,8 @@ struct TreeStep {
         const float num = (k < 32) ? lane_bcast(acc0, k) : lane_bcast(acc1, k - 32);
         const float yk = (rd != 0.f) ? num / rd : 0.f;
         PK_LANES(l) {
-          if (l < k) acc0[l] = fmaf(-Ru[l * L.ldw + k], yk, acc0[l]);
-          if (l + 32 < k) acc1[l] = fmaf(-Ru[(l + 32) * L.ldw + k], yk, acc1[l]);
+          if (l < k) acc0[l] = fmaf(-Ru[ru(L, l, k)], yk, acc0[l]);
+          if (l + 32 < k) acc1[l] = fmaf(-Ru[ru(L, l + 32, k)], yk, acc1[l]);
           if (l == (k & 31)) {
             if (k < 32) sol0[l] = yk; else sol1[l] = yk;
           }
@@ -243,14 +246,24 @@ struct TreeStep {
       PK_WSYNC();
       if (lane_or(bad)) return PK_STATUS_NO_SOLUTION;
     }
-    if (!eqp(W, L, 0ull)) status |= PK_STATUS_NOT_POSDEF;
+    // Start: a diagonally scaled gradient step x_i = -c_i / H_ii, clamped, guesses the
+    // active set.  With tight velocity limits most coordinates end on a bound, so this
+    // replaces the most expensive factorisation (all n columns free) by small ones; the
+    // loop below only stops at a point that passes the KKT test, whatever the start.
     uint64_t at_hi, at_lo;
     {
       LaneVar<uint64_t> mh, ml;
       PK_LANES(l) {
         uint64_t h = 0ull, m = 0ull;
         for (int i = l; i < n; i += 32) {
-          const float yi = y[i];
+          float ci = dv[i] * beta[i];
+          float hii = dv[i] * dv[i];
+          for (int r = 0; r < K; ++r) {
+            const float a = A[r * L.lda + i];
+            ci = fmaf(a, bv[r], ci);
+            hii = fmaf(a, a, hii);
+          }
+          const float yi = (hii > 0.f) ? -ci / hii : 0.f;
           if (yi > hi[i]) { h |= (1ull << i); x[i] = hi[i]; }
           else if (yi < lo[i]) { m |= (1ull << i); x[i] = lo[i]; }
           else x[i] = yi;
@@ -262,8 +275,6 @@ struct TreeStep {
       at_lo = lane_or64(ml);
       PK_WSYNC();
     }
-    if ((at_hi | at_lo) == 0ull) return status;
-
     const uint64_t all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
     const int max_iter = 4 * n + 16;
     for (int it = 0;; ++it) {
@@ -274,8 +285,8 @@ struct TreeStep {
           for (int i = l; i < n; i += 32) y[i] = x[i];
         }
         PK_WSYNC();
-      } else {
-        eqp(W, L, act);
+      } else if (!eqp(W, L, act)) {
+        status |= PK_STATUS_NOT_POSDEF;
       }
       // longest feasible step from x towards y
       float step;

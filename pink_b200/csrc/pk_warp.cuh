@@ -38,6 +38,31 @@ __device__ __forceinline__ float lane_sum(const LaneVar<float>& a) {
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   return s;
 }
+// Four sums at once with 10 shuffles instead of 20: after each of the first two
+// butterfly stages a lane keeps only half of the values (the other half travels to
+// its partner), the last three stages run on a single value, and the four results
+// are broadcast from the lane groups that own them.  Same pairing as lane_sum.
+__device__ __forceinline__ void lane_sum4(const LaneVar<float> (&p)[4], float (&out)[4]) {
+  const unsigned lane = threadIdx.x & 31u;
+  const bool h16 = lane & 16u;
+  float k0 = h16 ? p[2].v : p[0].v;
+  float k1 = h16 ? p[3].v : p[1].v;
+  const float s0 = h16 ? p[0].v : p[2].v;
+  const float s1 = h16 ? p[1].v : p[3].v;
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  const bool h8 = lane & 8u;
+  float k = h8 ? k1 : k0;
+  const float s = h8 ? k0 : k1;
+  k += __shfl_xor_sync(0xffffffffu, s, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  out[0] = __shfl_sync(0xffffffffu, k, 0);
+  out[1] = __shfl_sync(0xffffffffu, k, 8);
+  out[2] = __shfl_sync(0xffffffffu, k, 16);
+  out[3] = __shfl_sync(0xffffffffu, k, 24);
+}
 // smallest value and the index that carries it (ties: smallest index)
 __device__ __forceinline__ void lane_argmin(const LaneVar<float>& val, const LaneVar<int>& idx, float& best,
                                             int& best_idx) {
@@ -88,6 +113,9 @@ inline float lane_sum(const LaneVar<float>& a) {
     for (int l = 0; l < 32; ++l) t[l] = n[l];
   }
   return t[0];
+}
+inline void lane_sum4(const LaneVar<float> (&p)[4], float (&out)[4]) {
+  for (int c = 0; c < 4; ++c) out[c] = lane_sum(p[c]);
 }
 inline void lane_argmin(const LaneVar<float>& val, const LaneVar<int>& idx, float& best, int& best_idx) {
   best = val.v[0];

@@ -155,3 +155,59 @@ def within_tolerance(v, v_ref, atol=V_ATOL, rtol=V_RTOL):
     """Per-instance boolean: every coordinate within atol + rtol |v_ref|."""
     err = np.abs(np.asarray(v, dtype=np.float64) - v_ref)
     return (err <= atol + rtol * np.abs(v_ref)).all(axis=-1)
+
+
+def random_chain_model(nj, rng, prismatic=(), name="chain"):
+    """Fixed-base serial chain with random placements / axes, a tool frame on the last
+    joint and an elbow frame mid-chain (exercises NJ = 2..7, prismatic joints, two
+    frame tasks and the zero columns of a mid-chain frame)."""
+    from pink_b200.model import Model, SE3
+    from oracle import lie
+
+    model = Model(name)
+    parent = 0
+    for j in range(nj):
+        R, _ = lie.exp6(np.concatenate([np.zeros(3), rng.normal(size=3) * 0.8]))
+        T = SE3(R, rng.uniform(-0.3, 0.3, size=3))
+        kind = "prismatic" if j in prismatic else "revolute"
+        lim = 0.4 if kind == "prismatic" else 2.5
+        parent = model.add_joint(f"j{j}", parent, T, rng.normal(size=3), kind=kind, lower=-lim, upper=lim,
+                                 velocity=2.0 + j)
+        model.append_inertia(parent, 1.0 + 0.1 * j, rng.uniform(-0.1, 0.1, size=3))
+    model.add_frame("tool", parent, SE3(np.eye(3), np.array([0.05, 0.0, 0.1])))
+    model.add_frame("elbow", max(1, nj // 2), SE3(np.eye(3), np.array([0.0, 0.02, 0.0])))
+    return model
+
+
+def chain_scenario(nj, B, seed=1, prismatic=(), two_tasks=False, shared_target=False):
+    rng = np.random.default_rng(seed)
+    model = random_chain_model(nj, rng, prismatic)
+    table = model.table()
+    q = workloads.sample_configurations(table, B, rng)
+    qt = workloads.perturb_configurations(table, q, rng, sigma=0.2)
+    tasks, otasks = [], []
+    frames = [("tool", 1.0, 0.7)] + ([("elbow", [0.5, 0.0, 2.0], 0.3)] if two_tasks else [])
+    for frame, pc, oc in frames:
+        T = frame_targets(table, qt, frame)
+        t = FrameTask(frame, position_cost=pc, orientation_cost=oc, lm_damping=0.1, gain=0.9)
+        if shared_target:
+            from pink_b200.model import SE3
+
+            T = np.broadcast_to(T[:1], T.shape).copy()
+            t.set_target(SE3(T[0].astype(np.float64)))
+        else:
+            t.set_target(torch.as_tensor(T))
+        tasks.append(t)
+        T64 = T.astype(np.float64)
+        otasks.append({"type": "frame", "frame": table.frame_names.index(frame), "cost": np.array(t.cost),
+                       "gain": 0.9, "lm_damping": 0.1, "target": (T64[:, :, :3], T64[:, :, 3])})
+    q_ref = np.zeros(nj)
+    pt = PostureTask(cost=0.05, gain=0.5)
+    pt.set_target(q_ref)
+    tasks.append(pt)
+    otasks.append({"type": "posture", "cost": 0.05, "gain": 0.5, "lm_damping": 0.0, "target": q_ref})
+
+    class _R:
+        data = None
+
+    return Scenario(f"chain{nj}", _R(), model, table, q, tasks, otasks, 0.01, 1e-8)

@@ -296,3 +296,43 @@ def test_fused_rollout_equals_step_by_step_loop():
         alive &= st_o == 0
         q_o = np.where(alive[:, None], okin2.integrate(sc.table, q_o, v_o * sc.dt), q_o)
     np.testing.assert_allclose(q_f.cpu().numpy()[:n], q_o, atol=2e-4)
+
+
+@pytest.mark.parametrize("nj,kw", [
+    (2, {}), (3, {"prismatic": (1,)}), (4, {"two_tasks": True}), (5, {"shared_target": True}),
+    (7, {"two_tasks": True, "prismatic": (2,)}), (7, {}),
+])
+def test_chain_kernel_instantiations_on_gpu(nj, kw):
+    """Every <NJ, NFT> instantiation (compaction, dynamic shared memory sizes, ragged
+    batch that does not fill the last CTA) against the oracle."""
+    sc = helpers.chain_scenario(nj, 1000 + nj, seed=nj, **kw)
+    cfg = pink_b200.Configuration(sc.model, None, torch.as_tensor(sc.q32, device="cuda"))
+    v, st = pink_b200.solve_ik(cfg, sc.tasks, sc.dt, solver="quadprog", damping=sc.damping, return_status=True)
+    torch.cuda.synchronize()
+    v, st = v.cpu().numpy(), st.cpu().numpy()
+    v_ref, st_ref = sc.oracle_solve(200)
+    np.testing.assert_array_equal(st[:200] & 3, st_ref)
+    assert helpers.within_tolerance(v[:200], v_ref, atol=5e-4, rtol=5e-3).mean() >= 0.97
+    from tests.hostsim import HostSim
+
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v_h, st_h = hs.solve_ik(prob, sc.q32, targets)
+    np.testing.assert_array_equal(st, st_h)
+    np.testing.assert_allclose(v, v_h, atol=5e-4, rtol=5e-3)
+
+
+def test_empty_and_tiny_batches():
+    sc = helpers.ur5_scenario(5, "reachable")
+    ik = pink_b200.BatchedIK(sc.model, sc.tasks, sc.dt, damping=sc.damping, batch_size=5)
+    prob, targets, _ = sc.problem()
+    q_d = torch.as_tensor(sc.q32, device="cuda")
+    t_d = torch.as_tensor(targets, device="cuda")
+    v5, s5 = ik.solve(q_d, t_d)
+    v1, s1 = ik.solve(q_d[:1].contiguous(), t_d[:1].contiguous())
+    v0, s0 = ik.solve(q_d[:0].contiguous(), t_d[:0].contiguous())
+    torch.cuda.synchronize()
+    assert v0.shape == (0, 6) and s0.shape == (0,)
+    assert torch.equal(v1[0], v5[0])
+    v_ref, _ = sc.oracle_solve()
+    assert helpers.within_tolerance(v5.cpu().numpy(), v_ref).all()

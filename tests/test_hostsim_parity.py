@@ -186,3 +186,26 @@ def test_tree_kernel_is_selected_for_humanoids_and_handles_limits():
     prob, targets, _ = sc.problem()
     v, st = hs.solve_ik(prob, q, targets)
     assert st[3] == 2 and np.abs(v[3]).max() == 0.0 and (st[np.arange(16) != 3] == 0).all()
+
+
+@pytest.mark.parametrize("nj,kw", [
+    (2, {}), (3, {"prismatic": (1,)}), (4, {"two_tasks": True}), (5, {"shared_target": True}),
+    (7, {"two_tasks": True, "prismatic": (2,)}), (7, {}),
+])
+def test_chain_kernel_instantiations(nj, kw):
+    """Every <NJ, NFT> instantiation of the register-resident kernel, prismatic joints,
+    mid-chain frames and shared targets, against the oracle and the general path."""
+    sc = helpers.chain_scenario(nj, 96, seed=nj, **kw)
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v, st = hs.solve_ik(prob, sc.q32, targets)
+    assert hs.used_chain
+    v_g, st_g = hs.solve_ik(prob, sc.q32, targets, path=1)
+    np.testing.assert_array_equal(st, st_g)
+    np.testing.assert_allclose(v, v_g, atol=5e-4, rtol=5e-3)
+    v_ref, st_ref = sc.oracle_solve()
+    np.testing.assert_array_equal(st & 3, st_ref)
+    assert helpers.within_tolerance(v, v_ref, atol=5e-4, rtol=5e-3).mean() >= 0.97
+    # the tree kernel body handles fixed-base chains too
+    v_t, st_t = hs.solve_ik(prob, sc.q32, targets, path=2)
+    np.testing.assert_allclose(v_t, v_g, atol=5e-4, rtol=5e-3)

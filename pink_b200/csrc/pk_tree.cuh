@@ -88,8 +88,10 @@ struct TreeStep {
     const float* beta = W + L.o_beta;
     // free index list
     int nf = 0;
+    #pragma unroll 1
     for (int j = 0; j < n; ++j) nf += ((act >> j) & 1ull) ? 0 : 1;
     PK_LANES(l) {
+      #pragma unroll 1
       for (int i = l; i < n; i += 32) {
         y[i] = x[i];
         if (!((act >> i) & 1ull)) {
@@ -114,9 +116,11 @@ struct TreeStep {
           const float* Ar = A + r * L.lda;
           float* Awr = Aw + r * L.ldw;
           float s = bv[r];
+          #pragma unroll 1
           for (int j = 0; j < n; ++j)
             if ((act >> j) & 1ull) s = fmaf(Ar[j], x[j], s);
           zb[r] = s;
+          #pragma unroll 1
           for (int c = 0; c < nf; ++c) Awr[c] = Ar[idx[c]];
         }
       }
@@ -126,6 +130,7 @@ struct TreeStep {
     // Householder sweep.  K <= 64: every lane owns at most two rows (l and l + 32),
     // kept in registers for column k; four columns j are reflected per pass so that
     // the four shuffle reductions overlap.
+    #pragma unroll 1
     for (int k = 0; k < nf; ++k) {
       LaneVar<float> ak0, ak1, part;
       PK_LANES(l) {
@@ -142,6 +147,7 @@ struct TreeStep {
       const float v0 = alpha + norm;
       const float tau = (sigma > 0.f) ? 1.f / (norm * v0) : 0.f;
       const float rdk = (sigma > 0.f) ? -norm : alpha;
+      #pragma unroll 1
       for (int j = k + 1; j < nf; j += 4) {
         LaneVar<float> c0[4], c1[4], p[4];
         PK_LANES(l) {
@@ -198,6 +204,7 @@ struct TreeStep {
         sol0[l] = 0.f;
         sol1[l] = 0.f;
       }
+      #pragma unroll 1
       for (int kk = 0; kk < nf; ++kk) {
         const int k = nf - 1 - kk;
         const float rd = Rd[k];
@@ -237,6 +244,7 @@ struct TreeStep {
       LaneVar<int> bad;
       PK_LANES(l) {
         int f = 0;
+        #pragma unroll 1
         for (int i = l; i < n; i += 32) {
           x[i] = 0.f;
           if (lo[i] > hi[i]) f = 1;
@@ -255,9 +263,11 @@ struct TreeStep {
       LaneVar<uint64_t> mh, ml;
       PK_LANES(l) {
         uint64_t h = 0ull, m = 0ull;
+        #pragma unroll 1
         for (int i = l; i < n; i += 32) {
           float ci = dv[i] * beta[i];
           float hii = dv[i] * dv[i];
+          #pragma unroll 1
           for (int r = 0; r < K; ++r) {
             const float a = A[r * L.lda + i];
             ci = fmaf(a, bv[r], ci);
@@ -282,6 +292,7 @@ struct TreeStep {
       const uint64_t act = at_hi | at_lo;
       if (act == all) {
         PK_LANES(l) {
+          #pragma unroll 1
           for (int i = l; i < n; i += 32) y[i] = x[i];
         }
         PK_WSYNC();
@@ -297,6 +308,7 @@ struct TreeStep {
         PK_LANES(l) {
           float best = 1.f;
           int bi = 0x7fffffff;
+          #pragma unroll 1
           for (int i = l; i < n; i += 32) {
             if (!((act >> i) & 1ull)) {
               const float yi = y[i], xi = x[i];
@@ -320,6 +332,7 @@ struct TreeStep {
           LaneVar<uint64_t> mh, ml;
           PK_LANES(l) {
             uint64_t h = 0ull, m = 0ull;
+            #pragma unroll 1
             for (int i = l; i < n; i += 32) {
               if (!((act >> i) & 1ull)) {
                 const float yi = y[i];
@@ -340,6 +353,7 @@ struct TreeStep {
         const bool blk_hi = y[blk] > hi[blk];
         PK_WSYNC();
         PK_LANES(l) {
+          #pragma unroll 1
           for (int i = l; i < n; i += 32) {
             if (!((act >> i) & 1ull)) {
               float xi = fmaf(step, y[i] - x[i], x[i]);
@@ -353,6 +367,7 @@ struct TreeStep {
         continue;
       }
       PK_LANES(l) {
+        #pragma unroll 1
         for (int i = l; i < n; i += 32) x[i] = y[i];
       }
       PK_WSYNC();
@@ -364,6 +379,7 @@ struct TreeStep {
           if (r < K) {
             const float* Ar = A + r * L.lda;
             float s = bv[r];
+            #pragma unroll 1
             for (int j = 0; j < n; ++j) s = fmaf(Ar[j], x[j], s);
             rho[r] = s;
           }
@@ -382,11 +398,13 @@ struct TreeStep {
           float best = 0.f;
           int bi = 0x7fffffff;
           uint64_t m = 0ull;
+          #pragma unroll 1
           for (int i = l; i < n; i += 32) {
             if ((act >> i) & 1ull) {
               const float rt = fmaf(dv[i], x[i], beta[i]);
               float g = dv[i] * rt;
               float gabs = fabsf(g);
+              #pragma unroll 1
               for (int r = 0; r < K; ++r) {
                 const float a = A[r * L.lda + i];
                 g = fmaf(a, rho[r], g);
@@ -426,9 +444,12 @@ struct TreeStep {
     {
       LaneVar<int> bad;
       PK_LANES(l) {
+        #pragma unroll 1
         for (int i = l; i < L.nq; i += 32) qs[i] = qg[i];
+        #pragma unroll 1
         for (int i = l; i < L.stride; i += 32) ts[i] = tg[i];
         int f = 0;
+        #pragma unroll 1
         for (int i = rv + l; i < nv; i += 32) {
           const float qi = qg[i + rq - rv];
           if (qi < P.chk_lo[i] || qi > P.chk_hi[i]) f = 1;
@@ -440,6 +461,7 @@ struct TreeStep {
     }
     if (status && P.safety_break) {
       PK_LANES(l) {
+        #pragma unroll 1
         for (int i = l; i < nv; i += 32) vg[i] = 0.f;
         if (l == 0 && status_out) *status_out = status;
       }
@@ -487,6 +509,7 @@ struct TreeStep {
     }
     // world CoM of every body (only if a CoM task exists)
     bool has_com = false;
+    #pragma unroll 1
     for (int t = 0; t < P.ntasks; ++t) has_com = has_com || (P.tasks[t].type == PK_TASK_COM);
     if (has_com) {
       PK_LANES(l) {
@@ -550,6 +573,7 @@ struct TreeStep {
     PK_WSYNC();
     // ---- rows of A (column-parallel), b, diagonal terms -----------------------------------
     float diag = P.damping;
+    #pragma unroll 1
     for (int t = 0; t < P.ntasks; ++t) {
       const DevTask& Kt = P.tasks[t];
       const float* F = W + L.o_tf + kTreeTaskWords * t;
@@ -559,6 +583,7 @@ struct TreeStep {
         LaneVar<float> part;
         PK_LANES(l) {
           float s = 0.f;
+          #pragma unroll 1
           for (int i = rv + l; i < nv; i += 32) {
             const float e = qs[i + rq - rv] - tgt[i + rq - rv];
             s = fmaf(e, e, s);
@@ -570,6 +595,7 @@ struct TreeStep {
       }
       const int k = (Kt.type == PK_TASK_COM) ? 3 : 6;
       float mu = 0.f;
+      #pragma unroll 1
       for (int r = 0; r < k; ++r) {
         const float ew = Kt.cost[r] * Kt.gain * F[30 + r];
         mu = fmaf(ew, ew, mu);
@@ -581,9 +607,11 @@ struct TreeStep {
         // b entries of this task (rows with non-zero cost are packed in order)
         if (l == 0) {
           int row = base;
+          #pragma unroll 1
           for (int r = 0; r < k; ++r)
             if (Kt.cost[r] != 0.f) W[L.o_b + row++] = Kt.cost[r] * Kt.gain * F[30 + r];
         }
+        #pragma unroll 1
         for (int i = l; i < nv; i += 32) {
           float col[6];
           if (Kt.type == PK_TASK_COM) {
@@ -636,6 +664,7 @@ struct TreeStep {
             col[0] = tl.x; col[1] = tl.y; col[2] = tl.z; col[3] = ta.x; col[4] = ta.y; col[5] = ta.z;
           }
           int row = base;
+          #pragma unroll 1
           for (int r = 0; r < k; ++r)
             if (Kt.cost[r] != 0.f) A[(row++) * L.lda + i] = Kt.cost[r] * col[r];
         }
@@ -643,9 +672,11 @@ struct TreeStep {
     }
     // diagonal terms (posture tasks), box
     PK_LANES(l) {
+      #pragma unroll 1
       for (int i = l; i < nv; i += 32) {
         float pw2 = 0.f, pc = 0.f;
         const float qi = (i >= rv) ? qs[i + rq - rv] : 0.f;
+        #pragma unroll 1
         for (int t = 0; t < P.ntasks; ++t) {
           const DevTask& Kt = P.tasks[t];
           if (Kt.type == PK_TASK_POSTURE && i >= rv) {
@@ -667,6 +698,7 @@ struct TreeStep {
     // ---- QP -------------------------------------------------------------------------------
     status |= solve_qp(W, L);
     PK_LANES(l) {
+      #pragma unroll 1
       for (int i = l; i < nv; i += 32) vg[i] = W[L.o_x + i] * P.inv_dt;
       if (l == 0 && status_out) *status_out = status;
     }

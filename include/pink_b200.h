@@ -62,6 +62,7 @@ extern "C" {
 #define PK_TASK_RELATIVE_FRAME 1
 #define PK_TASK_POSTURE 2
 #define PK_TASK_COM 3
+#define PK_TASK_JOINT_VELOCITY 4 /* pink/tasks/joint_velocity_task.py, damping_task.py: e = target (nv - root_nv floats), J = I[root_nv:] */
 
 /* bodies: -2 universe, -1 root body (floating base if free_flyer, else the
  * universe), j >= 0 the body moved by 1-dof joint j                        */
@@ -89,9 +90,10 @@ typedef struct PkTaskDesc {
   int32_t target_offset; /* float offset of the target: inside one row of
                             `targets` (per instance) or inside
                             PkProblemDesc.shared (target_shared = 1).
-                            frame: 12 floats [R|p]; posture: nq; com: 3   */
+                            frame: 12 floats [R|p]; posture: nq; com: 3;
+                            joint velocity: nv - root_nv (dq_ref)       */
   int32_t target_shared;
-  float cost[6];         /* frame: [pos(3), ori(3)]; com: [3]; posture: cost[0] */
+  float cost[6];         /* frame: [pos(3), ori(3)]; com: [3]; posture / joint velocity: cost[0] */
   float gain;            /* Task.gain   (pink/tasks/task.py:146)          */
   float lm_damping;      /* Task.lm_damping (pink/tasks/task.py:160)      */
 } PkTaskDesc;

@@ -98,6 +98,14 @@ def task_error_jacobian(m, q, fk, task):
         return e, J
     if t == "com":
         return com_task_error(m, fk, task), com_task_jacobian(m, fk, task)
+    if t == "joint_velocity":
+        # e = dq_ref (zeros for the damping task), J = I[root_nv:, :]
+        # (pink/tasks/joint_velocity_task.py:59-110, damping_task.py:33-43)
+        _, rv = kin.root_dims(m)
+        batch = np.asarray(q).shape[:-1]
+        e = np.broadcast_to(np.asarray(task["target"], dtype=np.float64), batch + (m.nv - rv,))
+        J = np.broadcast_to(np.eye(m.nv)[rv:, :], batch + (m.nv - rv, m.nv))
+        return e, J
     raise ValueError(f"unknown task type {t!r}")
 
 

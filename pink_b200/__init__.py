@@ -13,7 +13,7 @@ from .exceptions import PinkError
 from .model import JointModelFreeFlyer, Model, RobotWrapper, load_urdf
 from .solve_ik import Problem, build_ik, solve_ik
 from .spatial import SE3
-from .tasks import ComTask, FrameTask, PostureTask, RelativeFrameTask, Task
+from .tasks import ComTask, DampingTask, FrameTask, JointVelocityTask, PostureTask, RelativeFrameTask, Task
 from .utils import custom_configuration_vector
 
 __version__ = "0.1.0"
@@ -22,8 +22,10 @@ __all__ = [
     "BatchedIK",
     "ComTask",
     "Configuration",
+    "DampingTask",
     "FrameTask",
     "JointModelFreeFlyer",
+    "JointVelocityTask",
     "Model",
     "PinkError",
     "PostureTask",

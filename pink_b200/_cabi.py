@@ -24,7 +24,7 @@ PK_STATUS_OUT_OF_LIMITS = 2
 PK_STATUS_NOT_POSDEF = 4
 PK_STATUS_ITER_LIMIT = 8
 
-PK_TASK_FRAME, PK_TASK_RELATIVE_FRAME, PK_TASK_POSTURE, PK_TASK_COM = 0, 1, 2, 3
+PK_TASK_FRAME, PK_TASK_RELATIVE_FRAME, PK_TASK_POSTURE, PK_TASK_COM, PK_TASK_JOINT_VELOCITY = 0, 1, 2, 3, 4
 
 _LIB_NAME = "libpink_b200.so"
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)

@@ -965,7 +965,7 @@ extern "C" int pk_task_terms_batched(const PkModel* m, const PkProblemDesc* prob
   A.J = J;
   A.task_index = task_index;
   const int type = P.tasks[task_index].type;
-  A.task_k = type == PK_TASK_COM ? 3 : (type == PK_TASK_POSTURE ? m->nv - (m->free_flyer ? 6 : 0) : 6);
+  A.task_k = type == PK_TASK_COM ? 3 : (pk::is_diag_task(type) ? m->nv - (m->free_flyer ? 6 : 0) : 6);
   // H must be accumulated for the task loop to run; give the kernel no v/H outputs
   // but keep ntasks > 0 so the loop executes
   return launch_generic(m, P, A, B, (cudaStream_t)stream);

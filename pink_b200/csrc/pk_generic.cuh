@@ -49,6 +49,15 @@ struct DevProblem {
   float shared[PK_MAX_SHARED];
 };
 
+// Tasks whose Jacobian is I[root_nv:, :] (they only touch the diagonal terms).
+PK_HD bool is_diag_task(int type) { return type == PK_TASK_POSTURE || type == PK_TASK_JOINT_VELOCITY; }
+// Error of such a task on tangent coordinate i >= rv: posture q_i - q*_i
+// (pink/tasks/posture_task.py:100-107), joint velocity dq_ref,i
+// (pink/tasks/joint_velocity_task.py:59-80; zeros for DampingTask).
+PK_HD float diag_task_error(int type, const float* q, const float* tgt, int i, int rq, int rv) {
+  return type == PK_TASK_POSTURE ? q[i + rq - rv] - tgt[i + rq - rv] : tgt[i - rv];
+}
+
 // Optional per-instance outputs of the export entry points (nullptr = skip).
 struct GenericOut {
   float* v;        // [nv]
@@ -200,12 +209,12 @@ struct Generic {
       const DevTask& Kt = P.tasks[t];
       const float* tgt = Kt.tgt_shared ? (P.shared + Kt.tgt_off) : (trow + Kt.tgt_off);
       const bool want = (out.e != nullptr || out.J != nullptr) && out.task_index == t;
-      if (Kt.type == PK_TASK_POSTURE) {
-        // e = (q (-) q*)[root_nv:], J = I[root_nv:, :]
+      if (is_diag_task(Kt.type)) {
+        // J = I[root_nv:, :]; e = (q (-) q*)[root_nv:] or dq_ref
         const float w2 = Kt.cost[0] * Kt.cost[0];
         float se = 0.f;
         for (int i = rv; i < nv; ++i) {
-          const float e = q[i + rq - rv] - tgt[i + rq - rv];
+          const float e = diag_task_error(Kt.type, q, tgt, i, rq, rv);
           se = fmaf(e, e, se);
           pw2[i] += w2;
           pc[i] = fmaf(Kt.gain * w2, e, pc[i]);

@@ -99,6 +99,7 @@ inline int target_size(const HostModel& m, const PkTaskDesc& t) {
     case PK_TASK_FRAME:
     case PK_TASK_RELATIVE_FRAME: return 12;
     case PK_TASK_POSTURE: return m.nq;
+    case PK_TASK_JOINT_VELOCITY: return m.nv - (m.free_flyer ? 6 : 0);
     case PK_TASK_COM: return 3;
     default: return -1;
   }
@@ -198,7 +199,7 @@ inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok
   for (int t = 0; t < PK_MAX_TASKS; ++t) L.row_base[t] = -1;
   for (int t = 0; t < P.ntasks; ++t) {
     const DevTask& d = P.tasks[t];
-    if (d.type == PK_TASK_POSTURE) continue;
+    if (is_diag_task(d.type)) continue;
     const int k = d.type == PK_TASK_COM ? 3 : 6;
     int rows = 0;
     for (int r = 0; r < k; ++r) rows += d.cost[r] != 0.f ? 1 : 0;
@@ -244,6 +245,7 @@ inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok
   L.o_rho = take(b2, K);
   L.o_ys = b2;  // unused
   L.o_idx = take(b2, L.nv);
+  L.o_xa = take(b2, L.nv);
   L.words = a > b2 ? a : b2;
   *ok = m.njoints >= 1 && m.njoints <= kTreeMaxJoints && m.nv <= 64 && P.ntasks <= 32 && K <= 64 && (size_t)L.words * 4 <= 48 * 1024;
   return L;

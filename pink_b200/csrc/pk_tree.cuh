@@ -23,7 +23,7 @@ struct TreePlan {
   int nj, nq, nv, rq, rv, K, ntasks, stride, lda, ldw, maxdepth;
   int row_base[PK_MAX_TASKS];  // first row of A of each task (-1: none)
   int o_q, o_t, o_tw, o_root, o_tf, o_A, o_b, o_d, o_beta, o_lo, o_hi, o_x, o_y, o_g, o_aw, o_ru, o_rd, o_zt, o_zb,
-      o_rho, o_ys, o_idx, o_cw, words;
+      o_rho, o_ys, o_idx, o_cw, o_xa, words;
 };
 
 constexpr int kTwStride = 13;     // 12 floats per joint transform, padded against bank conflicts
@@ -87,13 +87,17 @@ struct TreeStep {
     const float* dv = W + L.o_d;
     const float* beta = W + L.o_beta;
     // free index list
-    int nf = 0;
-    #pragma unroll 1
-    for (int j = 0; j < n; ++j) nf += ((act >> j) & 1ull) ? 0 : 1;
+#if defined(__CUDA_ARCH__)
+    const int nf = n - __popcll(act);
+#else
+    const int nf = n - __builtin_popcountll(act);
+#endif
+    float* xa = W + L.o_xa;  // x with the free entries zeroed
     PK_LANES(l) {
       #pragma unroll 1
       for (int i = l; i < n; i += 32) {
         y[i] = x[i];
+        xa[i] = ((act >> i) & 1ull) ? x[i] : 0.f;
         if (!((act >> i) & 1ull)) {
           const uint64_t below = (i == 0) ? 0ull : (~act & ((1ull << i) - 1ull));
 #if defined(__CUDA_ARCH__)
@@ -116,11 +120,10 @@ struct TreeStep {
           const float* Ar = A + r * L.lda;
           float* Awr = Aw + r * L.ldw;
           float s = bv[r];
-          #pragma unroll 1
-          for (int j = 0; j < n; ++j)
-            if ((act >> j) & 1ull) s = fmaf(Ar[j], x[j], s);
+#pragma unroll 4
+          for (int j = 0; j < n; ++j) s = fmaf(Ar[j], xa[j], s);
           zb[r] = s;
-          #pragma unroll 1
+#pragma unroll 4
           for (int c = 0; c < nf; ++c) Awr[c] = Ar[idx[c]];
         }
       }
@@ -379,7 +382,7 @@ struct TreeStep {
           if (r < K) {
             const float* Ar = A + r * L.lda;
             float s = bv[r];
-            #pragma unroll 1
+#pragma unroll 4
             for (int j = 0; j < n; ++j) s = fmaf(Ar[j], x[j], s);
             rho[r] = s;
           }
@@ -404,7 +407,7 @@ struct TreeStep {
               const float rt = fmaf(dv[i], x[i], beta[i]);
               float g = dv[i] * rt;
               float gabs = fabsf(g);
-              #pragma unroll 1
+#pragma unroll 4
               for (int r = 0; r < K; ++r) {
                 const float a = A[r * L.lda + i];
                 g = fmaf(a, rho[r], g);
@@ -577,7 +580,7 @@ struct TreeStep {
     for (int t = 0; t < P.ntasks; ++t) {
       const DevTask& Kt = P.tasks[t];
       const float* F = W + L.o_tf + kTreeTaskWords * t;
-      if (Kt.type == PK_TASK_POSTURE) {
+      if (is_diag_task(Kt.type)) {
         const float* tgt = Kt.tgt_shared ? (P.shared + Kt.tgt_off) : (ts + Kt.tgt_off);
         const float w2 = Kt.cost[0] * Kt.cost[0];
         LaneVar<float> part;
@@ -585,7 +588,7 @@ struct TreeStep {
           float s = 0.f;
           #pragma unroll 1
           for (int i = rv + l; i < nv; i += 32) {
-            const float e = qs[i + rq - rv] - tgt[i + rq - rv];
+            const float e = diag_task_error(Kt.type, qs, tgt, i, rq, rv);
             s = fmaf(e, e, s);
           }
           part[l] = s;
@@ -679,11 +682,11 @@ struct TreeStep {
         #pragma unroll 1
         for (int t = 0; t < P.ntasks; ++t) {
           const DevTask& Kt = P.tasks[t];
-          if (Kt.type == PK_TASK_POSTURE && i >= rv) {
+          if (is_diag_task(Kt.type) && i >= rv) {
             const float* tgt = Kt.tgt_shared ? (P.shared + Kt.tgt_off) : (ts + Kt.tgt_off);
             const float w2 = Kt.cost[0] * Kt.cost[0];
             pw2 += w2;
-            pc = fmaf(Kt.gain * w2, qi - tgt[i + rq - rv], pc);
+            pc = fmaf(Kt.gain * w2, diag_task_error(Kt.type, qs, tgt, i, rq, rv), pc);
           }
         }
         const float dd = sqrtf(pw2 + diag);

@@ -1,15 +1,25 @@
 """Kinematic tasks (``/root/reference/pink/tasks/__init__.py``).
 
 On the hot path (BASELINE north_star): :class:`FrameTask`,
-:class:`PostureTask`, :class:`ComTask`, :class:`RelativeFrameTask`.  The
-constant-Jacobian tasks (``JointCouplingTask``, ``DampingTask``, ...) are
-SURVEY section 8(f) "next" rows and are not provided yet.
+:class:`PostureTask`, :class:`ComTask`, :class:`RelativeFrameTask`; from the
+"next" rows :class:`JointVelocityTask` and :class:`DampingTask`.
+``JointCouplingTask`` / ``LinearHolonomicTask`` / ``LowAccelerationTask`` are not
+provided yet.
 """
 
 from .com_task import ComTask
 from .frame_task import FrameTask
+from .joint_velocity_task import DampingTask, JointVelocityTask
 from .posture_task import PostureTask
 from .relative_frame_task import RelativeFrameTask
 from .task import Task
 
-__all__ = ["ComTask", "FrameTask", "PostureTask", "RelativeFrameTask", "Task"]
+__all__ = [
+    "ComTask",
+    "DampingTask",
+    "FrameTask",
+    "JointVelocityTask",
+    "PostureTask",
+    "RelativeFrameTask",
+    "Task",
+]

@@ -137,7 +137,7 @@ int hs_task_terms(void* model, const PkProblemDesc* prob, int task_index, const 
   Args A{};
   A.q = q; A.targets = targets; A.e = eo; A.J = J; A.task_index = task_index;
   const int type = P.tasks[task_index].type;
-  A.task_k = type == PK_TASK_COM ? 3 : (type == PK_TASK_POSTURE ? hm.nv - (hm.free_flyer ? 6 : 0) : 6);
+  A.task_k = type == PK_TASK_COM ? 3 : (pk::is_diag_task(type) ? hm.nv - (hm.free_flyer ? 6 : 0) : 6);
   run_generic(hm, P, A, B);
   return 0;
 }

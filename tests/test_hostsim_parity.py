@@ -209,3 +209,32 @@ def test_chain_kernel_instantiations(nj, kw):
     # the tree kernel body handles fixed-base chains too
     v_t, st_t = hs.solve_ik(prob, sc.q32, targets, path=2)
     np.testing.assert_allclose(v_t, v_g, atol=5e-4, rtol=5e-3)
+
+
+def test_joint_velocity_and_damping_tasks():
+    """JointVelocityTask / DampingTask (diagonal-only tasks)."""
+    from pink_b200 import DampingTask, JointVelocityTask
+
+    for name in ["ur5_description", "draco3_description"]:
+        sc = helpers.ur5_scenario(64, "reachable") if name.startswith("ur5") else helpers.humanoid_scenario(name, 16)
+        rv = 6 if sc.table.free_flyer else 0
+        rng = np.random.default_rng(0)
+        v_ref = rng.normal(size=sc.model.nv - rv) * 0.3
+        jv = JointVelocityTask(cost=0.7)
+        jv.set_target(v_ref, sc.dt)
+        damp = DampingTask(cost=0.2)
+        sc.tasks = sc.tasks + [jv, damp]
+        sc.oracle_tasks = sc.oracle_tasks + [
+            {"type": "joint_velocity", "cost": 0.7, "gain": 1.0, "lm_damping": 0.0, "target": v_ref * sc.dt},
+            {"type": "joint_velocity", "cost": 0.2, "gain": 1.0, "lm_damping": 0.0, "target": np.zeros(sc.model.nv - rv)},
+        ]
+        hs = HostSim(sc.model)
+        prob, targets, descs = sc.problem()
+        v, st = hs.solve_ik(prob, sc.q32, targets)
+        assert hs.used_tree  # diagonal-only extras are handled by the tree kernel body
+        H, c, h4 = hs.build_ik(prob, sc.q32, targets)
+        H_ref, c_ref, _, _ = sc.oracle_build()
+        np.testing.assert_allclose(H, H_ref, atol=2e-5 * np.abs(H_ref).max(), rtol=1e-4)
+        np.testing.assert_allclose(c, c_ref, atol=2e-5 * np.abs(c_ref).max(), rtol=1e-4)
+        v_ref_o, st_ref = sc.oracle_solve()
+        assert helpers.within_tolerance(v, v_ref_o, atol=5e-4, rtol=5e-3).mean() >= 0.97

@@ -226,6 +226,20 @@ struct SlotIO {
     }
     at(sm, NT + 3 * NJ, slot) = S.gtol;
   }
+  static __device__ __forceinline__ void store_box(float* sm, int slot, const BoxState<NJ>& S) {
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      at(sm, NT + NJ + k, slot) = S.lo[k];
+      at(sm, NT + 2 * NJ + k, slot) = S.hi[k];
+    }
+  }
+  static __device__ __forceinline__ void load_box(float* sm, int slot, BoxState<NJ>& S) {
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      S.lo[k] = at(sm, NT + NJ + k, slot);
+      S.hi[k] = at(sm, NT + 2 * NJ + k, slot);
+    }
+  }
   static __device__ __forceinline__ void load_const(float* sm, int slot, BoxState<NJ>& S) {
 #pragma unroll
     for (int k = 0; k < NT; ++k) S.H[k] = at(sm, k, slot);
@@ -313,7 +327,7 @@ __global__ void __launch_bounds__(ChainSlots<NJ, NFT>::BLOCK, 2)
   using State = BoxState<NJ>;
   extern __shared__ __align__(16) float sm[];
   __shared__ int list[BLOCK];
-  __shared__ signed char phase[BLOCK];  // 0 done, 1 needs a round, 2 needs the polish
+  __shared__ signed char phase[BLOCK];  // 0 done, 1 rounds, 2 polish, 3 Gram matrix then rounds
   __shared__ int wcount[NW];
 
   const int tid = threadIdx.x;
@@ -358,18 +372,12 @@ __global__ void __launch_bounds__(ChainSlots<NJ, NFT>::BLOCK, 2)
       State S;
       st = C.assemble(P, qi, targets + i * (int64_t)P.target_stride, skip);
       if (!skip) {
-        bool more = QP::init(C.A, C.b, C.d, C.beta, C.lo, C.hi, S);
-        // cheap exits in place: every coordinate clamped => one multiplier check
-        if (more && (S.at_hi | S.at_lo) == QP::ALL) {
-          more = QP::round(S);
-          if (!more) more = QP::polish(C.A, C.b, C.d, C.beta, S);
-          ph = more ? 1 : 0;
-        } else {
-          // interior and well-conditioned => nothing left; otherwise park
-          ph = more ? 1 : (((S.at_hi | S.at_lo) == 0u && S.cond <= 1e3f) ? 0 : 2);
-        }
-        if (ph != 0) {
-          IO::store_const(sm, tid, S);
+        // corner start + KKT test in place: most instances end here with no Gram
+        // matrix and no factorisation; the others park their objective and box
+        const typename QP::ArrayObjective O{C.A, C.b, C.d, C.beta};
+        if (QP::corner_start(O, C.lo, C.hi, S)) {
+          ph = 3;
+          IO::store_box(sm, tid, S);
           IO::store_var(sm, tid, S);
           IO::store_obj(sm, tid, C);
         } else {
@@ -402,13 +410,22 @@ __global__ void __launch_bounds__(ChainSlots<NJ, NFT>::BLOCK, 2)
       if (tid < total) {
         const int slot = list[tid];
         State T;
-        IO::load_const(sm, slot, T);
-        IO::load_var(sm, slot, T);
-        // one barrier interval: up to `steps_per_sync` active-set rounds, or the polish.
-        // (Keeping the two in separate intervals lets the polish hold A in registers
-        // without spilling the round's Cholesky state: measured 24.2 us vs 29.2 us.)
+        // one barrier interval: (Gram matrix, then) up to `steps_per_sync` active-set
+        // rounds, or the polish.  (Keeping rounds and polish in separate intervals lets
+        // the polish hold A in registers without spilling the round's Cholesky state.)
         int next;
-        if (phase[slot] == 1) {
+        const int ph_slot = phase[slot];
+        if (ph_slot == 3) {
+          IO::load_box(sm, slot, T);
+          IO::load_var(sm, slot, T);
+          const typename IO::SlotObjective O{sm, slot};
+          QP::gram(O, T);
+          IO::store_const(sm, slot, T);
+        } else {
+          IO::load_const(sm, slot, T);
+          IO::load_var(sm, slot, T);
+        }
+        if (ph_slot != 2) {
           next = QP::round(T) ? 1 : 2;
           for (int r = 1; r < steps_per_sync && next == 1; ++r) next = QP::round(T) ? 1 : 2;
         } else {

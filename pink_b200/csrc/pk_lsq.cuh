@@ -352,6 +352,101 @@ struct BoxLSQChol {
     }
   }
 
+  // Cheap start.  Every coordinate is put on the bound the gradient at the origin
+  // points to (c_i < 0 -> upper, c_i > 0 -> lower) and the KKT conditions are tested
+  // there with the factored gradient.  On the UR5 benchmark 78 % of the instances are
+  // optimal at that corner (the velocity box is tight), which the clamp of the
+  // unconstrained minimiser only guessed for 42 % - and this start needs neither the
+  // Gram matrix nor a factorisation.  Returns false if x is optimal (or the box is
+  // empty); true if rounds are needed (wrong-signed bounds are already released).
+  template <class Obj>
+  static PK_HD bool corner_start(const Obj& O, const float (&lo)[N], const float (&hi)[N], State& S) {
+    S.status = 0;
+    S.rounds = 0;
+    S.at_hi = S.at_lo = 0u;
+    S.cond = 1.f;
+    S.gtol = 0.f;
+    bool infeasible = false;
+    float c[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      S.lo[i] = lo[i];
+      S.hi[i] = hi[i];
+      S.x[i] = 0.f;
+      infeasible = infeasible || (lo[i] > hi[i]);
+      c[i] = O.diag(i) * O.lin(i);
+    }
+    if (infeasible) {  // empty box <=> quadprog reports no solution
+      S.status = PK_STATUS_NO_SOLUTION;
+      return false;
+    }
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      float a[N], br;
+      O.row(r, a, br);
+#pragma unroll
+      for (int i = 0; i < N; ++i) c[i] = fmaf(a[i], br, c[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (c[i] < 0.f && hi[i] < 3.0e38f) { S.at_hi |= (1u << i); S.x[i] = hi[i]; }
+      else if (c[i] > 0.f && lo[i] > -3.0e38f) { S.at_lo |= (1u << i); S.x[i] = lo[i]; }
+      else S.x[i] = fminf(fmaxf(0.f, lo[i]), hi[i]);
+    }
+    const uint32_t act = S.at_hi | S.at_lo;
+    float g[N], gabs[N];
+    gradient_factored(O, S.x, g, gabs);
+    uint32_t neg = 0u;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if ((act >> i) & 1u) {
+        const float lam = ((S.at_hi >> i) & 1u) ? -g[i] : g[i];
+        if (lam < -4e-6f * gabs[i]) neg |= (1u << i);
+      }
+    }
+    if (act == ALL && neg == 0u) return false;
+    S.at_hi &= ~neg;
+    S.at_lo &= ~neg;
+    return true;
+  }
+
+  // Gram matrix H = A^T A + diag(d^2), c = A^T b + d beta and the tolerance of the
+  // rounds, for the instances that need them.
+  template <class Obj>
+  static PK_HD void gram(const Obj& O, State& S) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float di = O.diag(i);
+#pragma unroll
+      for (int j = 0; j <= i; ++j) S.H[tri(i, j)] = (i == j) ? di * di : 0.f;
+      S.c[i] = di * O.lin(i);
+    }
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      float a[N], br;
+      O.row(r, a, br);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) S.H[tri(i, j)] = fmaf(a[i], a[j], S.H[tri(i, j)]);
+        S.c[i] = fmaf(a[i], br, S.c[i]);
+      }
+    }
+    // rounding scale of H x + c over the box
+    float gs = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float s = fabsf(S.c[i]);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const float xm = fmaxf(fabsf(S.x[j]), fminf(fmaxf(fabsf(S.lo[j]), fabsf(S.hi[j])), 1e3f));
+        s = fmaf(fabsf(S.H[tri(i, j)]), xm, s);
+      }
+      gs = fmaxf(gs, s);
+    }
+    S.gtol = 4e-6f * gs;
+  }
+
   // Gram matrix, unconstrained minimiser, clamp.  Returns true if rounds are needed.
   static PK_HD bool init(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N],
                          const float (&beta)[N], const float (&lo)[N], const float (&hi)[N], State& S) {
@@ -534,11 +629,15 @@ struct BoxLSQChol {
   static PK_HD int run(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N], const float (&beta)[N],
                        const float (&lo)[N], const float (&hi)[N], float (&x)[N]) {
     State S;
-    bool more = init(A, b, d, beta, lo, hi, S);
-    for (;;) {
-      while (more) more = round(S);
-      more = polish(A, b, d, beta, S);
-      if (!more) break;
+    const ArrayObjective O{A, b, d, beta};
+    if (corner_start(O, lo, hi, S)) {
+      gram(O, S);
+      bool more = true;
+      for (;;) {
+        while (more) more = round(S);
+        more = polish(O, S);
+        if (!more) break;
+      }
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = S.x[i];

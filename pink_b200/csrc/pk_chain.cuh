@@ -28,6 +28,10 @@ struct ChainJoint {
   float X[12];  // placement in the parent joint frame, row-major [R | p]
   float ax, ay, az;
   int type;  // PK_JOINT_*
+  // X.R Rot(a, q) = X.R + sin q (X.R [a]x) + (1 - cos q) (X.R (a a^T - I)): the two
+  // constant matrices, and X.R a for prismatic joints, are folded on the host
+  float M1[9], M2[9];
+  float Xa[3];
 };
 
 struct ChainFrameTask {
@@ -96,11 +100,13 @@ struct ChainStep {
     if (Jn.type == PK_JOINT_REVOLUTE) {
       float s, c;
       sincos_f(q[j], &s, &c);
-      Tl.R = mul(X.R, rot_axis(axis, s, c));
+      const float t = 1.f - c;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Tl.R.m[k] = fmaf(s, Jn.M1[k], fmaf(t, Jn.M2[k], X.R.m[k]));
       Tl.p = X.p;
     } else {
       Tl.R = X.R;
-      Tl.p = X.p + mul(X.R, q[j] * axis);
+      Tl.p = X.p + q[j] * v3(Jn.Xa[0], Jn.Xa[1], Jn.Xa[2]);
     }
     T = compose(T, Tl);
     pj[j] = T.p;

@@ -602,18 +602,27 @@ struct BoxLSQChol {
       return true;
     }
     if (act != ALL && S.cond > 1e3f) {
-      // ill-conditioned free block: two refinement steps with the factored gradient
+      // ill-conditioned free block: iterative refinement with the factored gradient
+      // (corrected semi-normal equations) until the correction stalls, 4 steps at most
       float L[NT], inv[N], y[N];
       factor(S.H, act, L, inv);
 #pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
+      for (int pass = 0; pass < 4; ++pass) {
+        float dmax = 0.f, xmax = 0.f;
 #pragma unroll
         for (int i = 0; i < N; ++i) y[i] = ((act >> i) & 1u) ? 0.f : -g[i];
         solve(L, inv, y);
 #pragma unroll
-        for (int i = 0; i < N; ++i)
-          if (!((act >> i) & 1u)) S.x[i] = fminf(fmaxf(S.x[i] + y[i], S.lo[i]), S.hi[i]);
-        if (pass == 0) gradient_factored(O, S.x, g, gabs);
+        for (int i = 0; i < N; ++i) {
+          if (!((act >> i) & 1u)) {
+            const float xn = fminf(fmaxf(S.x[i] + y[i], S.lo[i]), S.hi[i]);
+            dmax = fmaxf(dmax, fabsf(xn - S.x[i]));
+            xmax = fmaxf(xmax, fabsf(xn));
+            S.x[i] = xn;
+          }
+        }
+        if (dmax <= 2e-7f * xmax) break;
+        gradient_factored(O, S.x, g, gabs);
       }
     }
     return false;

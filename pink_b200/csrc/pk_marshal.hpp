@@ -261,6 +261,29 @@ void make_chain_params(const HostModel& m, const DevProblem& P, ChainParams<NJ>*
     C.joint[j].ay = m.axis[3 * j + 1];
     C.joint[j].az = m.axis[3 * j + 2];
     C.joint[j].type = m.jtype[j];
+    {
+      // fold the constant factors of X.R Rot(a, q) in double precision
+      const float* X = &m.jX[12 * j];
+      const double a[3] = {m.axis[3 * j], m.axis[3 * j + 1], m.axis[3 * j + 2]};
+      const double Kx[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+      double R[9];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) R[3 * r + c] = X[4 * r + c];
+      for (int r = 0; r < 3; ++r) {
+        double xa = 0.0;
+        for (int c = 0; c < 3; ++c) {
+          double m1 = 0.0, m2 = 0.0;
+          for (int k = 0; k < 3; ++k) {
+            m1 += R[3 * r + k] * Kx[3 * k + c];
+            m2 += R[3 * r + k] * (a[k] * a[c] - (k == c ? 1.0 : 0.0));
+          }
+          C.joint[j].M1[3 * r + c] = (float)m1;
+          C.joint[j].M2[3 * r + c] = (float)m2;
+          xa += R[3 * r + c] * a[c];
+        }
+        C.joint[j].Xa[r] = (float)xa;
+      }
+    }
     C.cfg_lo[j] = P.cfg_lo[j];
     C.cfg_hi[j] = P.cfg_hi[j];
     C.vel[j] = P.vel[j];

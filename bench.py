@@ -28,6 +28,16 @@ BYTES_PER_STEP = 96  # q 24 B + frame target 48 B read, v 24 B written (BASELINE
 L2_BYTES = 126 * 1024 * 1024
 
 
+def committed_traffic():
+    """dram bytes per launch of the dominant kernel, from the committed ncu --set full
+    capture (profiles/traffic.json names the capture); None when absent."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -387,7 +397,7 @@ def run_gpu_arm(args):
             "clocks": clocks.summary(),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_kind": peak_kind,
+                "traffic": committed_traffic(), "peak_kind": peak_kind,
                 "kernel": "pk::ik_chain_kernel<6>", "kernel_ms": kern_ms,
                 "timing": "CUDA graph replay of %d launches" % NBUF if g_ms is not None else "eager launches",
                 "algorithmic_bytes_per_launch": B * BYTES_PER_STEP,

@@ -45,6 +45,8 @@ extern "C" {
 #define PK_MAX_FRAMES 256
 #define PK_MAX_TASKS 12
 #define PK_MAX_SHARED 192 /* floats of targets shared by all instances     */
+#define PK_MAX_INEQ_ROWS 24 /* dense inequality rows per instance (barriers, floating-base velocity limit) */
+#define PK_MAX_EQ_ROWS 12   /* equality rows per instance (solve_ik(..., constraints=...)) */
 
 /* per-instance status bits written by the solve entry points */
 #define PK_STATUS_OK 0

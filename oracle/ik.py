@@ -14,6 +14,7 @@ Follows ``pink/solve_ik.py`` line by line: ``H = damping I + sum H_t``,
 
 import numpy as np
 
+from . import barriers as bar
 from . import kinematics as kin
 from . import limits as lim
 from . import qp
@@ -71,6 +72,8 @@ def _slice_task(task, i):
     """Task with the per-instance target of row ``i`` (targets may be shared)."""
     tgt = task.get("target")
     t = dict(task)
+    if task["type"] == "linear":
+        return t
     if task["type"] in ("frame", "relative_frame"):
         R, p = np.asarray(tgt[0]), np.asarray(tgt[1])
         t["target"] = (R[i] if R.ndim == 3 else R, p[i] if p.ndim == 2 else p)
@@ -84,6 +87,8 @@ def _slice_task_range(task, lo, hi):
     """Task restricted to instances ``[lo, hi)`` (shared targets untouched)."""
     tgt = task.get("target")
     t = dict(task)
+    if task["type"] == "linear":
+        return t
     if task["type"] in ("frame", "relative_frame"):
         R, p = np.asarray(tgt[0]), np.asarray(tgt[1])
         t["target"] = (R[lo:hi] if R.ndim == 3 else R, p[lo:hi] if p.ndim == 2 else p)
@@ -93,7 +98,69 @@ def _slice_task_range(task, lo, hi):
     return t
 
 
-def solve_ik(m, q, tasks, dt, damping=1e-12, limits=None, safety_break=True):
+def assemble(m, q, tasks, dt, damping=1e-12, limits=None, barriers=None, constraints=None):
+    """Full QP of ONE instance, ``(H, c, G, h, A, b)``, in the reference's order
+    (``pink/solve_ik.py:20-149``): tasks then barriers in the objective; limits
+    then barriers in the inequalities; ``constraints`` (tasks) as equalities
+    ``J dq = -gain e``.
+
+    ``limits`` entries: ``("configuration", gain)``, ``("velocity", v_max)``,
+    ``("floating_base", frame, twist_max)``, ``("acceleration", a_max, dq_prev)``.
+    """
+    q = np.asarray(q, dtype=np.float64)
+    fk = kin.forward_kinematics(m, q)
+    H, c = qp_objective(m, q, fk, tasks, damping)
+    for b_ in barriers or []:
+        H_b, c_b = bar.barrier_qp_objective(m, q, fk, b_)
+        H = H + H_b
+        c = c + c_b
+    if limits is None:
+        limits = [("configuration", 0.5), ("velocity", None)]
+    G_list, h_list = [], []
+    for entry in limits:
+        kind = entry[0]
+        if kind == "configuration":
+            rows = lim.configuration_limit_rows(m, q, entry[1])
+        elif kind == "velocity":
+            rows = lim.velocity_limit_rows(m, dt, entry[1])
+        elif kind == "floating_base":
+            rows = lim.floating_base_velocity_rows(m, fk, entry[1], entry[2], dt)
+        elif kind == "acceleration":
+            rows = lim.acceleration_limit_rows(m, q, entry[1], entry[2], dt)
+        else:
+            raise ValueError(kind)
+        if rows is not None:
+            G_list.append(rows[0])
+            h_list.append(rows[1])
+    for b_ in barriers or []:
+        G_b, h_b = bar.barrier_qp_inequalities(m, q, fk, b_, dt)
+        G_list.append(G_b)
+        h_list.append(h_b)
+    G = np.vstack(G_list) if G_list else None
+    h = np.concatenate(h_list) if h_list else None
+    A_list, b_list = [], []
+    for task in constraints or []:
+        e, J = tk.task_error_jacobian(m, q, fk, task)
+        A_list.append(J)
+        b_list.append(-task.get("gain", 1.0) * e)
+    A = np.vstack(A_list) if A_list else None
+    b = np.concatenate(b_list) if b_list else None
+    return H, c, G, h, A, b
+
+
+def _slice_limits(limits, i):
+    if limits is None:
+        return None
+    out = []
+    for entry in limits:
+        if entry[0] == "acceleration" and entry[2] is not None and np.asarray(entry[2]).ndim == 2:
+            out.append((entry[0], entry[1], np.asarray(entry[2])[i]))
+        else:
+            out.append(entry)
+    return out
+
+
+def solve_ik(m, q, tasks, dt, damping=1e-12, limits=None, safety_break=True, barriers=None, constraints=None):
     """One IK step of one instance: ``(v, status)``.
 
     ``status``: 0 ok, 1 no QP solution (``NoSolutionFound``,
@@ -102,14 +169,16 @@ def solve_ik(m, q, tasks, dt, damping=1e-12, limits=None, safety_break=True):
     q = np.asarray(q, dtype=np.float64)
     if safety_break and bool(lim.check_limits(m, q)):
         return np.zeros(m.nv), 2
-    H, c, G, h = build_ik(m, q, tasks, dt, damping, limits)
-    res = qp.solve_qp(H, c, G, h)
+    H, c, G, h, A, b = assemble(m, q, tasks, dt, damping, limits, barriers, constraints)
+    if h is not None and not np.all(np.isfinite(h)):
+        return np.zeros(m.nv), 1
+    res = qp.solve_qp(H, c, G, h, A, b)
     if not res.found:
         return np.zeros(m.nv), 1
     return res.x / dt, 0
 
 
-def solve_ik_batch(m, q, tasks, dt, damping=1e-12, limits=None, safety_break=True):
+def solve_ik_batch(m, q, tasks, dt, damping=1e-12, limits=None, safety_break=True, barriers=None, constraints=None):
     """Loop of ``solve_ik`` over the leading dimension of ``q``."""
     q = np.asarray(q, dtype=np.float64)
     B = q.shape[0]
@@ -117,7 +186,8 @@ def solve_ik_batch(m, q, tasks, dt, damping=1e-12, limits=None, safety_break=Tru
     status = np.zeros(B, dtype=np.int32)
     for i in range(B):
         v[i], status[i] = solve_ik(
-            m, q[i], [_slice_task(t, i) for t in tasks], dt, damping, limits, safety_break
+            m, q[i], [_slice_task(t, i) for t in tasks], dt, damping, _slice_limits(limits, i), safety_break,
+            barriers, [_slice_task(t, i) for t in constraints or []],
         )
     return v, status
 

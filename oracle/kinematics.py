@@ -247,3 +247,49 @@ def neutral(m):
     if m.free_flyer:
         q[6] = 1.0
     return q
+
+
+def d_difference_arg1(m, q0, q1):
+    """``pin.dDifference(model, q0, q1, ARG1)``: Jacobian of ``q1 (-) q0`` with
+    respect to a LOCAL perturbation of ``q1``
+    (``pink/tasks/linear_holonomic_task.py:186-192``): identity on 1-dof joints,
+    ``Jlog6(M0^-1 M1)`` on the free-flyer block."""
+    q0 = np.asarray(q0, dtype=np.float64)
+    q1 = np.asarray(q1, dtype=np.float64)
+    batch = np.broadcast_shapes(q0.shape[:-1], q1.shape[:-1])
+    D = np.broadcast_to(np.eye(m.nv), batch + (m.nv, m.nv)).copy()
+    if m.free_flyer:
+        R0 = lie.quat_to_matrix(q0[..., 3:7])
+        R1 = lie.quat_to_matrix(q1[..., 3:7])
+        Rd, pd = lie.se3_act_inv(R0, q0[..., 0:3], R1, q1[..., 0:3])
+        D[..., 0:6, 0:6] = lie.jlog6(Rd, pd)
+    return D
+
+
+def point_jacobian_world(m, fk, body, x):
+    """Linear velocity (world axes) of the point ``x`` (world coordinates) rigidly
+    attached to ``body``, as a ``(..., 3, nv)`` Jacobian.  This is
+    ``J_p + skew(x - p_joint)^T J_w`` of ``pin.getJointJacobian(...,
+    LOCAL_WORLD_ALIGNED)`` (``pink/barriers/self_collision_barrier.py:205-217``)."""
+    R_root, p_root, R, p = fk
+    x = np.asarray(x, dtype=np.float64)
+    batch = x.shape[:-1]
+    J = np.zeros(batch + (3, m.nv))
+    _, rv = root_dims(m)
+    if m.free_flyer and body != -2:
+        # base twist is expressed in the base frame: v_world = R (v + w x (R^T (x - p)))
+        xl = np.einsum("...ji,...j->...i", R_root, x - p_root)
+        for k in range(3):
+            ek = np.zeros(3)
+            ek[k] = 1.0
+            J[..., :, k] = R_root[..., :, k]
+            J[..., :, 3 + k] = np.einsum("...ij,...j->...i", R_root, np.cross(ek, xl))
+    for j in range(m.njoints):
+        if body < 0 or not supports(m, j, body):
+            continue
+        axis_w = np.einsum("...ij,j->...i", R[..., j, :, :], np.asarray(m.axis[j], dtype=np.float64))
+        if int(m.jtype[j]) == 0:
+            J[..., :, rv + j] = np.cross(axis_w, x - p[..., j, :])
+        else:
+            J[..., :, rv + j] = axis_w
+    return J

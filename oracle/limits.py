@@ -82,3 +82,63 @@ def check_limits(m, q, tol=1e-6):
             continue
         bad |= (q[..., i] < q_min[i] - tol) | (q[..., i] > q_max[i] + tol)
     return bad
+
+
+def floating_base_velocity_rows(m, fk, frame, twist_max, dt):
+    """``FloatingBaseVelocityLimit.compute_qp_inequalities``
+    (``pink/limits/floating_base_velocity_limit.py:118-148``): rows of the LOCAL
+    Jacobian of a frame attached to the root joint, root columns only, for the
+    finite entries of ``twist_max = [linear_max; angular_max]``."""
+    twist_max = np.asarray(twist_max, dtype=np.float64)
+    finite = np.isfinite(twist_max)
+    if not finite.any():
+        return None
+    J = kin.frame_jacobian_local(m, fk, frame).copy()
+    J[..., :, 6:] = 0.0
+    rows = J[finite, :]
+    bounds = dt * twist_max[finite]
+    return np.vstack([rows, -rows]), np.concatenate([bounds, bounds])
+
+
+def acceleration_limit_indices(m, a_max):
+    """Tangent indices with ``1e-10 < a_max < 1e20``
+    (``pink/limits/acceleration_limit.py:60-72``); the free-flyer qualifies only
+    if all of its six coordinates do."""
+    a_max = np.asarray(a_max, dtype=np.float64)
+    ok = np.logical_and(a_max < 1e20, a_max > 1e-10)
+    _, rv = kin.root_dims(m)
+    idx = []
+    if m.free_flyer and ok[0:6].all():
+        idx.extend(range(6))
+    idx.extend(rv + j for j in range(m.njoints) if ok[rv + j])
+    return np.array(idx, dtype=np.int64)
+
+
+def acceleration_limit_rows(m, q, a_max, dq_prev, dt):
+    """``AccelerationLimit.compute_qp_inequalities``
+    (``pink/limits/acceleration_limit.py:119-200``): finite-difference
+    acceleration bound and braking distance to the configuration limits."""
+    idx = acceleration_limit_indices(m, a_max)
+    if idx.size == 0:
+        return None
+    rq, rv = kin.root_dims(m)
+    q = np.asarray(q, dtype=np.float64)
+    a = np.asarray(a_max, dtype=np.float64)[idx]
+    has_cfg = np.isin(idx, configuration_limit_indices(m))
+    q_min = np.asarray(m.q_min, dtype=np.float64)
+    q_max = np.asarray(m.q_max, dtype=np.float64)
+    dq_max = np.full(idx.shape, np.inf)
+    dq_min = np.full(idx.shape, np.inf)
+    for k, i in enumerate(idx):
+        if has_cfg[k]:
+            dq_max[k] = q_max[rq + i - rv] - q[rq + i - rv]
+            dq_min[k] = q[rq + i - rv] - q_min[rq + i - rv]
+    dq_prev = np.zeros(m.nv) if dq_prev is None else np.asarray(dq_prev, dtype=np.float64)
+    prev = dq_prev[idx]
+    P = np.eye(m.nv)[idx]
+    with np.errstate(invalid="ignore"):
+        h = np.concatenate([
+            np.minimum(a * dt * dt + prev, dt * np.sqrt(2.0 * a * dq_max)),
+            np.minimum(a * dt * dt - prev, dt * np.sqrt(2.0 * a * dq_min)),
+        ])
+    return np.vstack([P, -P]), h

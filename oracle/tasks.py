@@ -9,6 +9,8 @@ A task is a plain dict (so that tests can build them without product classes):
 ``{"type": "relative_frame", "frame": f, "root": r, ... "target": (R, p)}``
 ``{"type": "posture", "cost": w, "gain": a, "lm_damping": l, "target": q*[..., nq]}``
 ``{"type": "com", "cost": [3], ..., "target": c*[..., 3]}``
+``{"type": "joint_velocity", "cost": w, ..., "target": dq_ref[..., nv - root_nv]}``
+``{"type": "linear", "A": [p, nv], "b": [p], "q0": [nq] | None, "cost": [p], ...}``
 """
 
 import numpy as np
@@ -105,6 +107,15 @@ def task_error_jacobian(m, q, fk, task):
         batch = np.asarray(q).shape[:-1]
         e = np.broadcast_to(np.asarray(task["target"], dtype=np.float64), batch + (m.nv - rv,))
         J = np.broadcast_to(np.eye(m.nv)[rv:, :], batch + (m.nv - rv, m.nv))
+        return e, J
+    if t == "linear":
+        # e = A (q (-) q_0) - b, J = A dDifference(q_0, q, ARG1)
+        # (pink/tasks/linear_holonomic_task.py:148-192; JointCouplingTask is the
+        # one-row case with q_0 = neutral, joint_coupling_task.py:82-100)
+        A = np.asarray(task["A"], dtype=np.float64)
+        q0 = kin.neutral(m) if task.get("q0") is None else np.asarray(task["q0"], dtype=np.float64)
+        e = np.einsum("pn,...n->...p", A, kin.difference(m, q0, q)) - np.asarray(task["b"], dtype=np.float64)
+        J = A @ kin.d_difference_arg1(m, q0, q)
         return e, J
     raise ValueError(f"unknown task type {t!r}")
 

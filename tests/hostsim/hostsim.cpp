@@ -10,6 +10,7 @@
 
 #include "../../include/pink_b200.h"
 #include "../../pink_b200/csrc/pk_marshal.hpp"
+#include "../../pink_b200/csrc/pk_dualqp.cuh"
 
 namespace {
 thread_local std::string g_err;
@@ -163,5 +164,24 @@ int hs_frame_jacobian(void* model, int frame, const float* q, float* J, int64_t 
   A.q = q; A.Jf = J; A.jac_frame = frame; A.task_index = -1;
   run_generic(hm, P, A, B);
   return 0;
+}
+
+// Direct access to the dual active-set QP (pk_dualqp.cuh) for unit tests:
+//   min 1/2 |A x + b|^2 + 1/2 sum (d_i x_i + beta_i)^2,  lo <= x <= hi,  G x <= h,  E x = f
+// A[K][n], G[p][n], E[meq][n] row-major; returns the solver's status bits.
+int hs_dual_qp(int K, int n, int p, int meq, const float* A, const float* b, const float* d, const float* beta,
+               const float* lo, const float* hi, const float* G, const float* h, const float* E, const float* f,
+               float* x) {
+  using QP = pk::DualQP<pk::kGenericMaxRows, PK_MAX_NV, PK_MAX_INEQ_ROWS, PK_MAX_EQ_ROWS>;
+  if (K > pk::kGenericMaxRows || n > PK_MAX_NV || p > PK_MAX_INEQ_ROWS || meq > PK_MAX_EQ_ROWS) return -1;
+  static thread_local float Aa[pk::kGenericMaxRows][PK_MAX_NV], Ga[PK_MAX_INEQ_ROWS][PK_MAX_NV], Ea[PK_MAX_EQ_ROWS][PK_MAX_NV];
+  for (int r = 0; r < K; ++r) for (int c = 0; c < n; ++c) Aa[r][c] = A[r * n + c];
+  for (int r = 0; r < p; ++r) for (int c = 0; c < n; ++c) Ga[r][c] = G[r * n + c];
+  for (int r = 0; r < meq; ++r) for (int c = 0; c < n; ++c) Ea[r][c] = E[r * n + c];
+  QP::Problem P{Aa, b, d, beta, lo, hi, Ga, h, Ea, f, K, n, p, meq};
+  float xs[PK_MAX_NV];
+  const int st = QP::run(P, xs);
+  for (int i = 0; i < n; ++i) x[i] = xs[i];
+  return st;
 }
 }

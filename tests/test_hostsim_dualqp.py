@@ -1,0 +1,132 @@
+"""Dual active-set QP of the general path (pk_dualqp.cuh, fp32, host build) against
+the oracle's fp64 Goldfarb-Idnani solver and brute-force KKT enumeration."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import qp as oqp
+from tests import hostsim
+
+STATUS_NO_SOLUTION = 1
+
+
+def dual_qp(A, b, d, beta, lo, hi, G=None, h=None, E=None, f=None):
+    K, n = A.shape
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    G = np.zeros((0, n)) if G is None else G
+    h = np.zeros(0) if h is None else h
+    E = np.zeros((0, n)) if E is None else E
+    f = np.zeros(0) if f is None else f
+    args = [f32(a) for a in (A, b, d, beta, lo, hi, G, h, E, f)]
+    x = np.zeros(n, dtype=np.float32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    st = hostsim.lib().hs_dual_qp(K, n, G.shape[0], E.shape[0], *[ptr(a) for a in args], ptr(x))
+    return x.astype(np.float64), st
+
+
+def reference(A, b, d, beta, lo, hi, G=None, h=None, E=None, f=None):
+    n = A.shape[1]
+    H = A.T @ A + np.diag(d * d)
+    c = A.T @ b + d * beta
+    rows, rhs = [], []
+    fin = np.isfinite(hi)
+    rows.append(np.eye(n)[fin]); rhs.append(hi[fin])
+    fin = np.isfinite(lo)
+    rows.append(-np.eye(n)[fin]); rhs.append(-lo[fin])
+    if G is not None and len(G):
+        rows.append(G); rhs.append(h)
+    res = oqp.solve_qp(H, c, np.vstack(rows), np.concatenate(rhs), E, f)
+    return res
+
+
+def random_problem(rng, n, K, p, meq, tight=0.3, cond=1.0):
+    A = rng.normal(size=(K, n)) * np.exp(rng.uniform(-cond, cond, size=(K, 1)))
+    b = rng.normal(size=K)
+    d = np.exp(rng.uniform(-3, 0, size=n))
+    beta = rng.normal(size=n) * 0.1
+    lo = -np.abs(rng.normal(size=n)) * tight
+    hi = np.abs(rng.normal(size=n)) * tight
+    G = rng.normal(size=(p, n))
+    h = np.abs(rng.normal(size=p)) * tight
+    E = rng.normal(size=(meq, n))
+    f = rng.normal(size=meq) * 0.05
+    return A, b, d, beta, lo, hi, G, h, E, f
+
+
+@pytest.mark.parametrize("n,K,p,meq", [(6, 6, 0, 0), (6, 6, 3, 0), (6, 6, 2, 1), (12, 9, 5, 2), (33, 30, 6, 0),
+                                       (35, 33, 8, 3), (64, 48, 24, 12)])
+def test_matches_oracle(n, K, p, meq):
+    rng = np.random.default_rng(100 * n + p + meq)
+    worst = 0.0
+    solved = 0
+    for _ in range(40 if n <= 12 else 8):
+        prob = random_problem(rng, n, K, p, meq)
+        ref = reference(*prob)
+        x, st = dual_qp(*prob)
+        if not ref.found:
+            assert st & STATUS_NO_SOLUTION
+            continue
+        assert st == 0, st
+        solved += 1
+        scale = np.abs(ref.x).max() + 1e-3
+        worst = max(worst, np.abs(x - ref.x).max() / scale)
+    assert solved > 0
+    assert worst < 2e-4, worst
+
+
+def test_bruteforce_small():
+    rng = np.random.default_rng(7)
+    for _ in range(30):
+        A, b, d, beta, lo, hi, G, h, _, _ = random_problem(rng, 4, 4, 2, 0)
+        H = A.T @ A + np.diag(d * d)
+        c = A.T @ b + d * beta
+        Gall = np.vstack([np.eye(4), -np.eye(4), G])
+        hall = np.concatenate([hi, -lo, h])
+        xb = oqp.solve_qp_bruteforce(H, c, Gall, hall)
+        x, st = dual_qp(A, b, d, beta, lo, hi, G, h)
+        assert st == 0
+        assert np.abs(x - xb).max() < 1e-4 * (1 + np.abs(xb).max())
+
+
+def test_infeasible_and_unbounded_rows():
+    n = 5
+    rng = np.random.default_rng(3)
+    A, b, d, beta, lo, hi, _, _, _, _ = random_problem(rng, n, 5, 0, 0)
+    # contradictory general rows: x0 <= -1 and -x0 <= -1
+    G = np.zeros((2, n)); G[0, 0] = 1.0; G[1, 0] = -1.0
+    x, st = dual_qp(A, b, d, beta, np.full(n, -np.inf), np.full(n, np.inf), G, np.array([-1.0, -1.0]))
+    assert st & STATUS_NO_SOLUTION
+    # box that excludes the general row
+    G = np.ones((1, n))
+    x, st = dual_qp(A, b, d, beta, np.full(n, 0.1), np.full(n, 0.2), G, np.array([0.0]))
+    assert st & STATUS_NO_SOLUTION
+    # infinite bounds + feasible general row
+    x, st = dual_qp(A, b, d, beta, np.full(n, -np.inf), np.full(n, np.inf), G, np.array([0.0]))
+    ref = reference(A, b, d, beta, np.full(n, -np.inf), np.full(n, np.inf), G, np.array([0.0]))
+    assert st == 0 and np.abs(x - ref.x).max() < 1e-4
+
+
+def test_ill_conditioned_humanoid_like():
+    """cond(H) ~ 1e6 (CoM cost 200 next to posture cost 0.1): the square-root form
+    keeps fp32 within the parity tolerance."""
+    rng = np.random.default_rng(11)
+    n, K = 35, 33
+    worst = 0.0
+    for _ in range(6):
+        A = rng.normal(size=(K, n))
+        A[:3] *= 200.0
+        A[3:] *= rng.choice([2.0, 4.0, 10.0], size=(K - 3, 1))
+        b = A @ rng.normal(size=n) * 0.01
+        d = np.full(n, np.sqrt(0.01 + 0.01))
+        beta = rng.normal(size=n) * 0.01
+        lo, hi = np.full(n, -0.02), np.full(n, 0.02)
+        G = rng.normal(size=(6, n))
+        h = np.abs(rng.normal(size=6)) * 0.02
+        ref = reference(A, b, d, beta, lo, hi, G, h)
+        x, st = dual_qp(A, b, d, beta, lo, hi, G, h)
+        assert ref.found and st == 0
+        worst = max(worst, np.abs(x - ref.x).max())
+    # |x| <= 0.02; 2e-4 rad/s at dt = 5 ms is 1e-6 in x
+    assert worst < 2e-6, worst

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PK_ABI_VERSION 1
+#define PK_ABI_VERSION 2
 
 #define PK_MAX_JOINTS 58  /* 1-dof joints (free-flyer excluded)            */
 #define PK_MAX_NV 64      /* PK_MAX_JOINTS + 6 (active sets are 64-bit masks) */
@@ -65,6 +65,19 @@ extern "C" {
 #define PK_TASK_POSTURE 2
 #define PK_TASK_COM 3
 #define PK_TASK_JOINT_VELOCITY 4 /* pink/tasks/joint_velocity_task.py, damping_task.py: e = target (nv - root_nv floats), J = I[root_nv:] */
+#define PK_TASK_LINEAR 5         /* pink/tasks/linear_holonomic_task.py:148-192 (JointCouplingTask: joint_coupling_task.py:82-100):
+                                    e = A (q (-) q_0) - b, J = A, with A zero on the root columns; `rows` <= 6;
+                                    extra[data_offset ...] = A[rows][nv], b[rows], q_0[nq]                      */
+
+/* barriers (pink/barriers/*.py) */
+#define PK_MAX_BARRIERS 8
+#define PK_MAX_CONSTRAINTS 4
+#define PK_MAX_PAIRS 256
+#define PK_BARRIER_POSITION 0       /* position_barrier.py:95-153        */
+#define PK_BARRIER_BODY_SPHERICAL 1 /* body_spherical_barrier.py:73-143  */
+#define PK_BARRIER_SELF_COLLISION 2 /* self_collision_barrier.py:85-224, sphere-sphere pairs */
+#define PK_GAINFN_IDENTITY 0        /* barrier.py:75-77                  */
+#define PK_GAINFN_SATURATING 1      /* h / (1 + |h|), body_spherical_barrier.py:65 */
 
 /* bodies: -2 universe, -1 root body (floating base if free_flyer, else the
  * universe), j >= 0 the body moved by 1-dof joint j                        */
@@ -98,7 +111,31 @@ typedef struct PkTaskDesc {
   float cost[6];         /* frame: [pos(3), ori(3)]; com: [3]; posture / joint velocity: cost[0] */
   float gain;            /* Task.gain   (pink/tasks/task.py:146)          */
   float lm_damping;      /* Task.lm_damping (pink/tasks/task.py:160)      */
+  int32_t rows;          /* LINEAR: number of rows p (cost[0..p))         */
+  int32_t data_offset;   /* LINEAR: float offset into PkProblemDesc.extra */
 } PkTaskDesc;
+
+/* One barrier h(q) >= 0 (pink/barriers/barrier.py): rows  -J_h / dt dq <= gain_i alpha(h_i)
+ * (barrier.py:246-252) and, if safe_displacement_gain > 1e-6, the objective term
+ * safe_displacement_gain / |J_h|_F^2 * I (barrier.py:193-203, zero safe displacement). */
+typedef struct PkBarrierDesc {
+  int32_t type;            /* PK_BARRIER_*                                 */
+  int32_t frame;           /* POSITION: monitored frame; BODY_SPHERICAL: first frame */
+  int32_t frame2;          /* BODY_SPHERICAL: second frame                 */
+  int32_t dim;             /* rows: POSITION nidx * (has_min + has_max); BODY_SPHERICAL 1;
+                              SELF_COLLISION the n closest pairs           */
+  int32_t nidx;            /* POSITION: number of monitored coordinates    */
+  int32_t indices[3];      /* POSITION: 0..2 = x..z                         */
+  int32_t has_min, has_max;
+  float p_min[3], p_max[3];/* POSITION: bounds, by position in `indices`   */
+  float gain[6];           /* POSITION: per row; otherwise gain[0]         */
+  float d_min;             /* BODY_SPHERICAL / SELF_COLLISION              */
+  float safe_displacement_gain;
+  int32_t gain_function;   /* PK_GAINFN_*                                  */
+  int32_t npairs;          /* SELF_COLLISION: collision pairs ...          */
+  int32_t pair_offset;     /* ... pairs[2 (pair_offset + k)] = the frames of the two sphere centres */
+  int32_t data_offset;     /* ... extra[data_offset + 2 k] = their radii   */
+} PkBarrierDesc;
 
 typedef struct PkProblemDesc {
   int32_t ntasks;
@@ -123,11 +160,44 @@ typedef struct PkProblemDesc {
   float chk_lo[PK_MAX_NV];
   float chk_hi[PK_MAX_NV];
   float shared[PK_MAX_SHARED];
+  /* ---- ABI 2: barriers, equality constraints, opt-in limits (all optional, zero = absent) ---- */
+  int32_t nbarriers;
+  PkBarrierDesc barriers[PK_MAX_BARRIERS];
+  /* solve_ik(..., constraints=[tasks]) (pink/solve_ik.py:125-149): J dq = -gain e;
+   * FRAME, RELATIVE_FRAME, COM and LINEAR tasks                             */
+  int32_t nconstraints;
+  PkTaskDesc constraints[PK_MAX_CONSTRAINTS];
+  /* FloatingBaseVelocityLimit (pink/limits/floating_base_velocity_limit.py:118-148):
+   * +-J_frame[:, root] dq <= dt fb_max, rows with infinite fb_max dropped   */
+  int32_t fb_enabled;
+  int32_t fb_frame;
+  float fb_max[6];        /* [linear(3); angular(3)]                        */
+  /* AccelerationLimit (pink/limits/acceleration_limit.py:119-200), per tangent index:
+   *   +dq_i <= min(a dt^2 + dq_prev_i, dt sqrt(2 a (acc_qhi_i - q_i)))
+   *   -dq_i <= min(a dt^2 - dq_prev_i, dt sqrt(2 a (q_i - acc_qlo_i)))
+   * acc_max = INFINITY: no row; acc_qlo/acc_qhi = -+INFINITY: no braking term.
+   * dq_prev = v_prev * dt: nv floats at acc_prev_offset of the targets row
+   * (of `shared` if acc_prev_shared); acc_prev_offset < 0: zeros            */
+  int32_t acc_enabled;
+  int32_t acc_prev_offset;
+  int32_t acc_prev_shared;
+  float acc_max[PK_MAX_NV];
+  float acc_qlo[PK_MAX_NV];
+  float acc_qhi[PK_MAX_NV];
+  /* constant data referenced by LINEAR tasks and SELF_COLLISION barriers (host
+   * pointers, copied at pk_problem_create / at every pk_solve_ik_batched call) */
+  const float* extra;
+  int32_t n_extra;
+  const int32_t* pairs;   /* [n_pairs][2] frame indices                     */
+  int32_t n_pairs;
 } PkProblemDesc;
 
 typedef struct PkModel PkModel; /* opaque; immutable after creation */
 
 int pk_abi_version(void);
+/* sizeof of the descriptor structs as compiled (0 PkModelDesc, 1 PkTaskDesc,
+ * 2 PkBarrierDesc, 3 PkProblemDesc): lets a binding verify its own layout.   */
+int pk_struct_size(int which);
 const char* pk_last_error(void); /* thread-local */
 
 /* Build device-resident constant tables of a model on CUDA device `device`. */
@@ -180,6 +250,17 @@ int pk_solve_ik_batched_host(PkModel* model, const PkProblemDesc* prob,
 int pk_build_ik_batched(const PkModel* model, const PkProblemDesc* prob,
                         const float* q, const float* targets, float* H,
                         float* c, float* h, int64_t B, void* stream);
+
+/* The dense rows of the same QP that pk_build_ik_batched leaves out:
+ *   G[B][PK_MAX_INEQ_ROWS][nv], hG[B][PK_MAX_INEQ_ROWS]  (floating-base limit rows, then
+ *   barrier rows in list order; unused rows are zero with hG = +INFINITY),
+ *   E[B][PK_MAX_EQ_ROWS][nv], f[B][PK_MAX_EQ_ROWS]       (equality constraints; unused: 0),
+ *   lo[B][nv], hi[B][nv]  the box  lo <= dq <= hi  of all +-e_i rows (configuration,
+ *   velocity and acceleration limits).  Any output may be NULL.              */
+int pk_constraint_rows_batched(const PkModel* model, const PkProblemDesc* prob,
+                               const float* q, const float* targets, float* G,
+                               float* hG, float* E, float* f, float* lo,
+                               float* hi, int64_t B, void* stream);
 
 /* Task.compute_error / compute_jacobian of task `task_index`
  * (pink/tasks/task.py:66-113): e[B][k], J[B][k][nv]; k = 6 frame tasks,

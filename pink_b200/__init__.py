@@ -7,13 +7,16 @@ runs in hand-written CUDA kernels behind the C-ABI of ``include/pink_b200.h``;
 there is no CPU fallback.
 """
 
+from . import barriers, limits, tasks
 from .batched import BatchedIK
+from .collision import SphereCollisionModel
 from .configuration import Configuration
 from .exceptions import PinkError
 from .model import JointModelFreeFlyer, Model, RobotWrapper, load_urdf
 from .solve_ik import Problem, build_ik, solve_ik
 from .spatial import SE3
-from .tasks import ComTask, DampingTask, FrameTask, JointVelocityTask, PostureTask, RelativeFrameTask, Task
+from .tasks import (ComTask, DampingTask, FrameTask, JointCouplingTask, JointVelocityTask, LinearHolonomicTask,
+                    LowAccelerationTask, PostureTask, RelativeFrameTask, Task)
 from .utils import custom_configuration_vector
 
 __version__ = "0.1.0"
@@ -24,8 +27,11 @@ __all__ = [
     "Configuration",
     "DampingTask",
     "FrameTask",
+    "JointCouplingTask",
     "JointModelFreeFlyer",
     "JointVelocityTask",
+    "LinearHolonomicTask",
+    "LowAccelerationTask",
     "Model",
     "PinkError",
     "PostureTask",
@@ -33,6 +39,7 @@ __all__ = [
     "RelativeFrameTask",
     "RobotWrapper",
     "SE3",
+    "SphereCollisionModel",
     "Task",
     "build_ik",
     "custom_configuration_vector",

@@ -18,13 +18,21 @@ PK_MAX_NV = 64
 PK_MAX_FRAMES = 256
 PK_MAX_TASKS = 12
 PK_MAX_SHARED = 192
+PK_MAX_INEQ_ROWS = 24
+PK_MAX_EQ_ROWS = 12
+PK_MAX_BARRIERS = 8
+PK_MAX_CONSTRAINTS = 4
+PK_MAX_PAIRS = 256
+PK_ABI_VERSION = 2
 
 PK_STATUS_NO_SOLUTION = 1
 PK_STATUS_OUT_OF_LIMITS = 2
 PK_STATUS_NOT_POSDEF = 4
 PK_STATUS_ITER_LIMIT = 8
 
-PK_TASK_FRAME, PK_TASK_RELATIVE_FRAME, PK_TASK_POSTURE, PK_TASK_COM, PK_TASK_JOINT_VELOCITY = 0, 1, 2, 3, 4
+PK_TASK_FRAME, PK_TASK_RELATIVE_FRAME, PK_TASK_POSTURE, PK_TASK_COM, PK_TASK_JOINT_VELOCITY, PK_TASK_LINEAR = 0, 1, 2, 3, 4, 5
+PK_BARRIER_POSITION, PK_BARRIER_BODY_SPHERICAL, PK_BARRIER_SELF_COLLISION = 0, 1, 2
+PK_GAINFN_IDENTITY, PK_GAINFN_SATURATING = 0, 1
 
 _LIB_NAME = "libpink_b200.so"
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
@@ -58,6 +66,30 @@ class PkTaskDesc(C.Structure):
         ("cost", C.c_float * 6),
         ("gain", C.c_float),
         ("lm_damping", C.c_float),
+        ("rows", C.c_int32),
+        ("data_offset", C.c_int32),
+    ]
+
+
+class PkBarrierDesc(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32),
+        ("frame", C.c_int32),
+        ("frame2", C.c_int32),
+        ("dim", C.c_int32),
+        ("nidx", C.c_int32),
+        ("indices", C.c_int32 * 3),
+        ("has_min", C.c_int32),
+        ("has_max", C.c_int32),
+        ("p_min", C.c_float * 3),
+        ("p_max", C.c_float * 3),
+        ("gain", C.c_float * 6),
+        ("d_min", C.c_float),
+        ("safe_displacement_gain", C.c_float),
+        ("gain_function", C.c_int32),
+        ("npairs", C.c_int32),
+        ("pair_offset", C.c_int32),
+        ("data_offset", C.c_int32),
     ]
 
 
@@ -76,6 +108,23 @@ class PkProblemDesc(C.Structure):
         ("chk_lo", C.c_float * PK_MAX_NV),
         ("chk_hi", C.c_float * PK_MAX_NV),
         ("shared", C.c_float * PK_MAX_SHARED),
+        ("nbarriers", C.c_int32),
+        ("barriers", PkBarrierDesc * PK_MAX_BARRIERS),
+        ("nconstraints", C.c_int32),
+        ("constraints", PkTaskDesc * PK_MAX_CONSTRAINTS),
+        ("fb_enabled", C.c_int32),
+        ("fb_frame", C.c_int32),
+        ("fb_max", C.c_float * 6),
+        ("acc_enabled", C.c_int32),
+        ("acc_prev_offset", C.c_int32),
+        ("acc_prev_shared", C.c_int32),
+        ("acc_max", C.c_float * PK_MAX_NV),
+        ("acc_qlo", C.c_float * PK_MAX_NV),
+        ("acc_qhi", C.c_float * PK_MAX_NV),
+        ("extra", C.POINTER(C.c_float)),
+        ("n_extra", C.c_int32),
+        ("pairs", C.POINTER(C.c_int32)),
+        ("n_pairs", C.c_int32),
     ]
 
 
@@ -140,6 +189,7 @@ def declare(lib: C.CDLL, prefix: str = "pk_") -> None:
     lib.pk_solve_ik_prepared_host.argtypes = [C.c_void_p, C.c_void_p, _FP, _FP, _FP, _FP, C.c_int64, C.c_void_p]
     lib.pk_rollout_prepared.argtypes = [C.c_void_p, C.c_void_p, _FP, _FP, C.c_int32, _FP, _FP, _FP, C.c_int64, C.c_void_p]
     lib.pk_build_ik_batched.argtypes = [C.c_void_p, C.POINTER(PkProblemDesc), _FP, _FP, _FP, _FP, _FP, C.c_int64, C.c_void_p]
+    lib.pk_constraint_rows_batched.argtypes = [C.c_void_p, C.POINTER(PkProblemDesc), _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_int64, C.c_void_p]
     lib.pk_task_terms_batched.argtypes = [C.c_void_p, C.POINTER(PkProblemDesc), C.c_int32, _FP, _FP, _FP, _FP, C.c_int64, C.c_void_p]
     lib.pk_forward_kinematics_batched.argtypes = [C.c_void_p, _FP, _FP, _FP, C.c_int64, C.c_void_p]
     lib.pk_frame_jacobian_batched.argtypes = [C.c_void_p, C.c_int32, _FP, _FP, C.c_int64, C.c_void_p]
@@ -148,6 +198,7 @@ def declare(lib: C.CDLL, prefix: str = "pk_") -> None:
 
 EXPORTED_SYMBOLS = [
     "pk_abi_version",
+    "pk_struct_size",
     "pk_last_error",
     "pk_launch_count",
     "pk_model_create",
@@ -160,6 +211,7 @@ EXPORTED_SYMBOLS = [
     "pk_solve_ik_prepared_host",
     "pk_rollout_prepared",
     "pk_build_ik_batched",
+    "pk_constraint_rows_batched",
     "pk_task_terms_batched",
     "pk_forward_kinematics_batched",
     "pk_frame_jacobian_batched",
@@ -183,8 +235,11 @@ def load() -> C.CDLL:
             )
         lib = C.CDLL(_LIB_PATH)
         declare(lib)
-        if lib.pk_abi_version() != 1:
+        if lib.pk_abi_version() != PK_ABI_VERSION:
             raise RuntimeError("libpink_b200.so ABI version mismatch; rebuild")
+        for which, struct in enumerate((PkModelDesc, PkTaskDesc, PkBarrierDesc, PkProblemDesc)):
+            if lib.pk_struct_size(which) != C.sizeof(struct):
+                raise RuntimeError(f"libpink_b200.so: layout of {struct.__name__} differs from the binding; rebuild")
         _lib = lib
     return _lib
 

@@ -1,0 +1,13 @@
+"""Control Barrier Functions (``/root/reference/pink/barriers/__init__.py``)."""
+
+from .barrier import Barrier
+from .body_spherical_barrier import BodySphericalBarrier
+from .position_barrier import PositionBarrier
+from .self_collision_barrier import SelfCollisionBarrier
+
+__all__ = [
+    "Barrier",
+    "PositionBarrier",
+    "BodySphericalBarrier",
+    "SelfCollisionBarrier",
+]

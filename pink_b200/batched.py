@@ -18,7 +18,7 @@ import torch
 
 from . import _cabi
 from .engine import _addr, _stream, get_engine
-from .solve_ik import _reject_unsupported, describe_problem
+from .solve_ik import describe_problem
 
 
 class BatchedIK:
@@ -31,8 +31,7 @@ class BatchedIK:
 
     def __init__(self, model, tasks: Iterable, dt: float, damping: float = 1e-12, limits=None,
                  barriers=None, constraints=None, safety_break: bool = True, device=None,
-                 batch_size: Optional[int] = None):
-        _reject_unsupported(barriers, constraints)
+                 batch_size: Optional[int] = None, collision_model=None):
         from .configuration import Configuration  # attaches the default limits to the model
         import numpy as np
 
@@ -45,7 +44,8 @@ class BatchedIK:
             sizes = [d.shape[0] for d in (t._pk_describe(model)["target"] for t in tasks) if isinstance(d, torch.Tensor)]
             batch_size = sizes[0] if sizes else 1
         self.engine = get_engine(model, device)
-        self.prob, parts, descs = describe_problem(model, batch_size, tasks, dt, damping, list(limits), safety_break)
+        self.prob, parts, descs = describe_problem(model, batch_size, tasks, dt, damping, list(limits), safety_break,
+                                                   barriers, constraints, collision_model)
         self.target_stride = int(self.prob.target_stride)
         self.target_layout = [
             (k, int(self.prob.tasks[k].target_offset), int(d["target"].shape[1]))

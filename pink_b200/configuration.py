@@ -40,11 +40,8 @@ class Configuration:
         collision_data=None,
         device=None,
     ):
-        if collision_model is not None:
-            raise NotImplementedError(
-                "collision models (self-collision barriers) are outside the "
-                "scope of this engine"
-            )
+        if collision_model is not None and collision_model.model is not model:
+            raise ValueError("the collision model was built for another robot model")
         # per-model defaults cached on the model object (configuration.py:101-108)
         if not hasattr(model, "tangent"):
             model.tangent = VectorSpace(model.nv)
@@ -59,7 +56,9 @@ class Configuration:
             data = model.createData()
         self.data = data.copy() if copy_data else data
         self.tangent = model.tangent
-        self.collision_model = None
+        # sphere collision model (pink_b200.collision.SphereCollisionModel); distances are
+        # evaluated inside the kernels, there is no host-side collision data
+        self.collision_model = collision_model
         self.collision_data = None
         self._device = device
         self._set_q(q)

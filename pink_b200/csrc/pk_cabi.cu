@@ -70,6 +70,15 @@ size_t align_up(size_t off) {
 }  // namespace
 
 extern "C" int pk_abi_version(void) { return PK_ABI_VERSION; }
+extern "C" int pk_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(PkModelDesc);
+    case 1: return (int)sizeof(PkTaskDesc);
+    case 2: return (int)sizeof(PkBarrierDesc);
+    case 3: return (int)sizeof(PkProblemDesc);
+    default: return -1;
+  }
+}
 extern "C" const char* pk_last_error(void) { return g_error.c_str(); }
 extern "C" int64_t pk_launch_count(void) { return g_launches.load(); }
 
@@ -525,6 +534,12 @@ struct GenericArgs {
   float* com;
   float* Jf;
   int jac_frame;
+  float* G;
+  float* hG;
+  float* E;
+  float* f;
+  float* lo;
+  float* hi;
 };
 
 template <int NJMAX, int NVMAX>
@@ -546,6 +561,12 @@ __global__ void __launch_bounds__(64) ik_generic_kernel(const DevModel M, const 
   out.com = A.com ? A.com + i * 3 : nullptr;
   out.Jf = A.Jf ? A.Jf + i * 6 * nv : nullptr;
   out.jac_frame = A.jac_frame;
+  out.G = A.G ? A.G + i * PK_MAX_INEQ_ROWS * nv : nullptr;
+  out.hG = A.hG ? A.hG + i * PK_MAX_INEQ_ROWS : nullptr;
+  out.E = A.E ? A.E + i * PK_MAX_EQ_ROWS * nv : nullptr;
+  out.f = A.f ? A.f + i * PK_MAX_EQ_ROWS : nullptr;
+  out.lo = A.lo ? A.lo + i * nv : nullptr;
+  out.hi = A.hi ? A.hi + i * nv : nullptr;
   Generic<NJMAX, NVMAX> G;
   G.step(M, P, A.q + i * M.nq, A.targets ? A.targets + i * (int64_t)P.target_stride : nullptr, out);
 }
@@ -679,6 +700,10 @@ int launch_generic(const PkModel* m, const pk::DevProblem& P, const pk::GenericA
 // per-call host cost is one kernel launch.
 struct PkProblem {
   pk::DevProblem P;
+  void* dev_ext = nullptr;  // DevExtras + extra floats + pair indices (one allocation)
+  ~PkProblem() {
+    if (dev_ext) cudaFree(dev_ext);
+  }
   bool chain = false;
   bool tree = false;
   pk::TreePlan plan;
@@ -694,17 +719,47 @@ void fill_chain(const PkModel* m, PkProblem* pr) {
   pk::make_chain_params<NJ>(m->hm, pr->P, reinterpret_cast<pk::ChainParams<NJ>*>(pr->chain_params));
 }
 
-int prepare_problem(const PkModel* m, const PkProblemDesc* desc, PkProblem* pr) {
+// Device image of the optional problem parts: [DevExtras | extra | pairs] in one buffer.
+// With `stream` the allocation and copies are stream-ordered (temporary problems of the
+// un-prepared entry points, released with cudaFreeAsync after the launch).
+int upload_extras(pk::HostExtras& hx, cudaStream_t stream, bool async, void** out) {
+  const size_t o_extra = (sizeof(pk::DevExtras) + 15) & ~size_t(15);
+  const size_t o_pairs = (o_extra + sizeof(float) * hx.extra.size() + 15) & ~size_t(15);
+  const size_t total = o_pairs + sizeof(int) * hx.pairs.size() + 16;
+  unsigned char* dev = nullptr;
+  if (async) PK_CUDA(cudaMallocAsync((void**)&dev, total, stream));
+  else PK_CUDA(cudaMalloc((void**)&dev, total));
+  std::vector<unsigned char> img(total, 0);
+  pk::DevExtras X = hx.X;
+  X.extra = reinterpret_cast<const float*>(dev + o_extra);
+  X.pairs = reinterpret_cast<const int*>(dev + o_pairs);
+  memcpy(img.data(), &X, sizeof(X));
+  if (!hx.extra.empty()) memcpy(img.data() + o_extra, hx.extra.data(), sizeof(float) * hx.extra.size());
+  if (!hx.pairs.empty()) memcpy(img.data() + o_pairs, hx.pairs.data(), sizeof(int) * hx.pairs.size());
+  // pageable source: the copy is staged before the call returns
+  if (async) PK_CUDA(cudaMemcpyAsync(dev, img.data(), total, cudaMemcpyHostToDevice, stream));
+  else PK_CUDA(cudaMemcpy(dev, img.data(), total, cudaMemcpyHostToDevice));
+  *out = dev;
+  return 0;
+}
+
+int prepare_problem(const PkModel* m, const PkProblemDesc* desc, PkProblem* pr, cudaStream_t stream = nullptr,
+                    bool async = false) {
   if (!m) return fail("null model");
-  const std::string perr = pk::make_dev_problem(m->hm, desc, &pr->P);
+  pk::HostExtras hx;
+  const std::string perr = pk::make_dev_problem(m->hm, desc, &pr->P, &hx);
   if (!perr.empty()) return fail(perr);
+  if (hx.present) {
+    if (upload_extras(hx, stream, async, &pr->dev_ext)) return 1;
+    pr->P.ext = reinterpret_cast<const pk::DevExtras*>(pr->dev_ext);
+  }
   static const int force_generic = env_int("PK_FORCE_GENERIC", 0);
-  pr->chain = !force_generic && pk::chain_eligible(m->hm, pr->P);
+  pr->chain = !force_generic && pk::chain_eligible(m->hm, pr->P, hx.present);
   pr->nj = m->njoints;
   static const int use_tree = env_int("PK_TREE", 1);
   bool tree_ok = false;
   pr->plan = pk::make_tree_plan(m->hm, pr->P, &tree_ok);
-  pr->tree = !force_generic && use_tree && !pr->chain && tree_ok;
+  pr->tree = !force_generic && use_tree && !pr->chain && tree_ok && !hx.present;
   if (pr->chain) {
     switch (m->njoints) {
       case 2: fill_chain<2>(m, pr); break;
@@ -947,11 +1002,9 @@ static int solve_host_impl(PkModel* m, const PkProblem& pr, const float* q_host,
 extern "C" int pk_build_ik_batched(const PkModel* m, const PkProblemDesc* prob, const float* q,
                                    const float* targets, float* H, float* c, float* h, int64_t B, void* stream) {
   if (check_common(m, q, B)) return 1;
-  pk::DevProblem P;
-  {
-    const std::string perr = pk::make_dev_problem(m->hm, prob, &P);
-    if (!perr.empty()) return fail(perr);
-  }
+  PkProblem pr;
+  if (prepare_problem(m, prob, &pr)) return 1;
+  const pk::DevProblem& P = pr.P;
   if (B == 0) return 0;
   if (!H) return fail("null H");
   pk::GenericArgs A{};
@@ -964,15 +1017,36 @@ extern "C" int pk_build_ik_batched(const PkModel* m, const PkProblemDesc* prob, 
   return launch_generic(m, P, A, B, (cudaStream_t)stream);
 }
 
+extern "C" int pk_constraint_rows_batched(const PkModel* m, const PkProblemDesc* prob, const float* q,
+                                          const float* targets, float* G, float* hG, float* E, float* f, float* lo,
+                                          float* hi, int64_t B, void* stream) {
+  if (check_common(m, q, B)) return 1;
+  PkProblem pr;
+  if (prepare_problem(m, prob, &pr)) return 1;
+  if ((G == nullptr) != (hG == nullptr) || (E == nullptr) != (f == nullptr) || (lo == nullptr) != (hi == nullptr))
+    return fail("G/hG, E/f and lo/hi come in pairs");
+  if (B == 0) return 0;
+  if (pr.P.target_stride > 0 && !targets) return fail("null targets");
+  pk::GenericArgs A{};
+  A.q = q;
+  A.targets = targets;
+  A.G = G;
+  A.hG = hG;
+  A.E = E;
+  A.f = f;
+  A.lo = lo;
+  A.hi = hi;
+  A.task_index = -1;
+  return launch_generic(m, pr.P, A, B, (cudaStream_t)stream);
+}
+
 extern "C" int pk_task_terms_batched(const PkModel* m, const PkProblemDesc* prob, int32_t task_index,
                                      const float* q, const float* targets, float* e, float* J, int64_t B,
                                      void* stream) {
   if (check_common(m, q, B)) return 1;
-  pk::DevProblem P;
-  {
-    const std::string perr = pk::make_dev_problem(m->hm, prob, &P);
-    if (!perr.empty()) return fail(perr);
-  }
+  PkProblem pr;
+  if (prepare_problem(m, prob, &pr)) return 1;
+  const pk::DevProblem& P = pr.P;
   if (task_index < 0 || task_index >= P.ntasks) return fail("task_index out of range");
   if (B == 0) return 0;
   pk::GenericArgs A{};
@@ -982,7 +1056,9 @@ extern "C" int pk_task_terms_batched(const PkModel* m, const PkProblemDesc* prob
   A.J = J;
   A.task_index = task_index;
   const int type = P.tasks[task_index].type;
-  A.task_k = type == PK_TASK_COM ? 3 : (pk::is_diag_task(type) ? m->nv - (m->free_flyer ? 6 : 0) : 6);
+  A.task_k = type == PK_TASK_COM ? 3
+             : type == PK_TASK_LINEAR ? P.tasks[task_index].rows
+                                      : (pk::is_diag_task(type) ? m->nv - (m->free_flyer ? 6 : 0) : 6);
   // H must be accumulated for the task loop to run; give the kernel no v/H outputs
   // but keep ntasks > 0 so the loop executes
   return launch_generic(m, P, A, B, (cudaStream_t)stream);

@@ -33,6 +33,10 @@
 
 #include "../../include/pink_b200.h"
 
+#ifndef PK_DUALQP_POLISH
+#define PK_DUALQP_POLISH 3
+#endif
+
 namespace pk {
 
 template <int KMAX, int N, int MG, int ME>
@@ -170,195 +174,275 @@ struct DualQP {
     float Ra[NT];            // triangular factor of the active normals (J^T N = [Ra; 0])
     float u[N + 1];          // multipliers of the active constraints (+ the entering one)
     float dv[N], z[N], r[N];
-    short act[N + 1];        // active constraint ids
-    float asg[N + 1];        // sign the normal was added with (equalities may be flipped)
+    short act[N + 1] = {};   // active constraint ids
+    float asg[N + 1] = {};   // sign the normal was added with (equalities may be flipped)
     int iq = 0;
     // membership of the active set: one bit per general/equality row, two words for the box rows
     uint64_t in_hi = 0ull, in_lo = 0ull, in_gen = 0ull;
     const int max_iter = 4 * (n + P.p + P.meq) + 32;
     int iter = 0;
-    for (;; ++iter) {
-      if (iter >= max_iter) { status |= PK_STATUS_ITER_LIMIT; break; }
-      // step 1: most violated constraint (normalised by the row norm, as quadprog)
-      int ip = -1;
-      float worst = 0.f, sgn = 1.f;
-      for (int id = 0; id < m; ++id) {
-        float scale, rhs;
-        if (id < P.meq + P.p) {
-          if ((in_gen >> id) & 1ull) continue;
-          const float* row = (id < P.meq) ? P.E[id] : P.G[id - P.meq];
-          float nn = 0.f;
-          for (int k = 0; k < n; ++k) nn = fmaf(row[k], row[k], nn);
-          if (!(nn > 0.f)) {
-            // empty row: 0 <= h (or 0 = f) either holds or never will
-            const float s0 = (id < P.meq) ? -fabsf(P.f[id]) : P.h[id - P.meq];
-            if (s0 < 0.f) status |= PK_STATUS_NO_SOLUTION;
-            continue;
-          }
-          scale = rsqrtf(nn);
-          rhs = (id < P.meq) ? P.f[id] : P.h[id - P.meq];
-        } else {
-          const int bid = id - P.meq - P.p;
-          const int i = bid >> 1;
-          if ((bid & 1) ? ((in_lo >> i) & 1ull) : ((in_hi >> i) & 1ull)) continue;
-          rhs = (bid & 1) ? P.lo[i] : P.hi[i];
-          if (!(fabsf(rhs) < 3.0e38f)) continue;  // infinite bound: no row
-          scale = 1.f;
-        }
-        float s = value(P, id, x);
-        float sg = 1.f;
-        if (id < P.meq) { sg = (s > 0.f) ? -1.f : 1.f; s = -fabsf(s); }
-        s *= scale;
-        const float tol = 1e-6f * fabsf(rhs) * scale + 1e-9f;
-        if (s < -tol && s < worst) { worst = s; ip = id; sgn = sg; }
+    // x is carried in fp64: slacks are then exact functions of the fp32 data, so that
+    // after a polish (below) violations far below the fp32 resolution of x are seen
+    double xd[N];
+    for (int i = 0; i < n; ++i) xd[i] = (double)x[i];
+
+    auto slack = [&](int id) -> double {  // s(x) >= 0 form; equalities: E x - f
+      if (id < P.meq) {
+        double sv = -(double)P.f[id];
+        for (int c = 0; c < n; ++c) sv += (double)P.E[id][c] * xd[c];
+        return sv;
       }
-      if (status & PK_STATUS_NO_SOLUTION) break;
-      if (ip < 0) break;
-      u[iq] = 0.f;
-      bool added = false;
-      for (int inner = 0; inner <= n + P.p + P.meq + 2 && !added; ++inner) {
-        // step 2a: d = J^T n+, z = J2 d2, r = Ra^-1 d1
-        normal_times_J(P, J, ip, sgn, dv);
-        float dd = 0.f, d2 = 0.f;
+      if (id < P.meq + P.p) {
+        double sv = (double)P.h[id - P.meq];
+        for (int c = 0; c < n; ++c) sv -= (double)P.G[id - P.meq][c] * xd[c];
+        return sv;
+      }
+      const int bid = id - P.meq - P.p;
+      const int c = bid >> 1;
+      return (bid & 1) ? xd[c] - (double)P.lo[c] : (double)P.hi[c] - xd[c];
+    };
+    auto set_member = [&](int id, bool on) {
+      uint64_t* word;
+      int bit;
+      if (id < P.meq + P.p) { word = &in_gen; bit = id; }
+      else {
+        const int bid = id - P.meq - P.p;
+        word = (bid & 1) ? &in_lo : &in_hi;
+        bit = bid >> 1;
+      }
+      if (on) *word |= (1ull << bit); else *word &= ~(1ull << bit);
+    };
+    // remove active constraint l: column l of Ra goes, the Hessenberg part below it is
+    // rotated back to triangular (same rotations on the columns of J)
+    auto drop = [&](int l) {
+      set_member(act[l], false);
+      for (int i = 0; i < l; ++i)
+        for (int k = l; k < iq - 1; ++k) Ra[ut(i, k)] = Ra[ut(i, k + 1)];
+      for (int j = l; j < iq - 1; ++j) {
+        const float a = Ra[ut(j, j + 1)], bb = Ra[ut(j + 1, j + 1)];
+        const float hh = hypotf(a, bb);
+        const float c = (hh > 0.f) ? a / hh : 1.f, sn = (hh > 0.f) ? bb / hh : 0.f;
+        for (int k = j; k < iq - 1; ++k) {
+          const float ra = Ra[ut(j, k + 1)], rb = Ra[ut(j + 1, k + 1)];
+          Ra[ut(j, k)] = fmaf(c, ra, sn * rb);
+          Ra[ut(j + 1, k + 1)] = fmaf(-sn, ra, c * rb);
+        }
+        for (int k = 0; k < n; ++k) {
+          const float ja = J[k][j], jb = J[k][j + 1];
+          J[k][j] = fmaf(c, ja, sn * jb);
+          J[k][j + 1] = fmaf(-sn, ja, c * jb);
+        }
+      }
+      for (int c = l; c < iq - 1; ++c) { act[c] = act[c + 1]; asg[c] = asg[c + 1]; u[c] = u[c + 1]; }
+      u[iq - 1] = u[iq];
+      --iq;
+    };
+    // Projected Newton steps on the current active manifold with J as the (fp32-accurate)
+    // inverse-Hessian factor and everything accumulated in fp64; refreshes the multipliers
+    // from the gradient, u = Ra^-1 J1^T grad f.  Along weakly curved directions of the
+    // reduced Hessian (posture cost 0.1 next to CoM cost 200) fp32 steps leave errors
+    // far above the parity tolerance; this removes them.
+    auto polish = [&]() {
+      double w[N], gd[N], rho[KA], ud[N + 1];
+      for (int k = 0; k < iq; ++k) ud[k] = (double)u[k];
+      for (int pass = 0; pass < PK_DUALQP_POLISH; ++pass) {
+        // back onto the active constraints: N_a^T delta = -s, delta = J1 w, Ra^T w = -s
+        for (int k = 0; k < iq; ++k) {
+          double sv = slack(act[k]);
+          if (act[k] < P.meq) sv *= (double)asg[k];
+          double ww = -sv;
+          for (int i = 0; i < k; ++i) ww -= (double)Ra[ut(i, k)] * w[i];
+          w[k] = ww / (double)Ra[ut(k, k)];
+        }
         for (int i = 0; i < n; ++i) {
-          dd = fmaf(dv[i], dv[i], dd);
-          if (i >= iq) d2 = fmaf(dv[i], dv[i], d2);
+          double sacc = xd[i];
+          for (int k = 0; k < iq; ++k) sacc += (double)J[i][k] * w[k];
+          xd[i] = sacc;
         }
-        const bool dependent = !(d2 > 1e-10f * dd);
+        // stationarity residual  grad f(x) - N_a u  (normals = gradients of s_k >= 0)
+        for (int rr = 0; rr < K; ++rr) {
+          double sacc = (double)P.b[rr];
+          for (int j = 0; j < n; ++j) sacc += (double)P.A[rr][j] * xd[j];
+          rho[rr] = sacc;
+        }
         for (int i = 0; i < n; ++i) {
-          float s = 0.f;
-          for (int k = iq; k < n; ++k) s = fmaf(J[i][k], dv[k], s);
-          z[i] = s;
+          double g = (double)P.d[i] * ((double)P.d[i] * xd[i] + (double)P.beta[i]);
+          for (int rr = 0; rr < K; ++rr) g += (double)P.A[rr][i] * rho[rr];
+          gd[i] = g;
         }
-        for (int i = iq - 1; i >= 0; --i) {
-          float s = dv[i];
-          for (int k = i + 1; k < iq; ++k) s = fmaf(-Ra[ut(i, k)], r[k], s);
-          r[i] = s / Ra[ut(i, i)];
-        }
-        // step 2b: step lengths
-        float t1 = 3.0e38f;
-        int l = -1;
-        for (int k = 0; k < iq; ++k)
-          if (act[k] >= P.meq && r[k] > 0.f) {
-            const float t = fmaxf(u[k], 0.f) / r[k];
-            if (t < t1) { t1 = t; l = k; }
+        for (int k = 0; k < iq; ++k) {
+          const int id = act[k];
+          if (id < P.meq) {
+            for (int c = 0; c < n; ++c) gd[c] -= ud[k] * (double)asg[k] * (double)P.E[id][c];
+          } else if (id < P.meq + P.p) {
+            for (int c = 0; c < n; ++c) gd[c] += ud[k] * (double)P.G[id - P.meq][c];
+          } else {
+            const int bid = id - P.meq - P.p;
+            gd[bid >> 1] -= (bid & 1) ? ud[k] : -ud[k];
           }
-        float t2 = 3.0e38f;
-        if (!dependent) {
-          const float zn = normal_dot(P, ip, sgn, z);
-          float sp = value(P, ip, x);
-          if (ip < P.meq) sp *= sgn;
-          if (zn > 0.f) t2 = fmaxf(-sp, 0.f) / zn;
         }
-        const float t = fminf(t1, t2);
-        if (!(t < 3.0e38f)) { status |= PK_STATUS_NO_SOLUTION; break; }
-        if (t2 < 3.0e38f)
-          for (int k = 0; k < n; ++k) x[k] = fmaf(t, z[k], x[k]);
-        for (int k = 0; k < iq; ++k) u[k] = fmaf(-t, r[k], u[k]);
-        u[iq] += t;
-        if (t2 <= t1) {
-          // full step: the constraint enters.  Givens rotations on columns iq.. of J zero d[iq+1..]
-          for (int j = n - 1; j > iq; --j) {
-            const float a = dv[j - 1], bb = dv[j];
-            if (bb == 0.f) continue;
-            const float hh = sqrtf(fmaf(a, a, bb * bb));
-            const float c = a / hh, s = bb / hh;
-            dv[j - 1] = hh;
-            dv[j] = 0.f;
-            for (int k = 0; k < n; ++k) {
-              const float ja = J[k][j - 1], jb = J[k][j];
-              J[k][j - 1] = fmaf(c, ja, s * jb);
-              J[k][j] = fmaf(-s, ja, c * jb);
+        // w <- J^T residual: the first iq entries correct the multipliers (Ra du = w1),
+        // the rest is the null-space Newton step.  Working on the residual (not on the
+        // gradient) keeps the fixed point exact when J2 has drifted off N_a by fp32
+        // rounding: multipliers of 1e3..1e4 would otherwise leak into the step.
+        for (int k = 0; k < n; ++k) {
+          double sacc = 0.0;
+          for (int i = 0; i < n; ++i) sacc += (double)J[i][k] * gd[i];
+          w[k] = sacc;
+        }
+        for (int i = 0; i < n; ++i) {
+          double sacc = xd[i];
+          for (int k = iq; k < n; ++k) sacc -= (double)J[i][k] * w[k];
+          xd[i] = sacc;
+        }
+        for (int k = iq - 1; k >= 0; --k) {
+          double sacc = w[k];
+          for (int c = k + 1; c < iq; ++c) sacc -= (double)Ra[ut(k, c)] * w[c];
+          w[k] = sacc / (double)Ra[ut(k, k)];
+          ud[k] += w[k];
+        }
+      }
+      for (int k = 0; k < iq; ++k) u[k] = (float)ud[k];
+      for (int i = 0; i < n; ++i) x[i] = (float)xd[i];
+    };
+
+    // Rounds: dual iteration in fp32 -> polish -> drop wrong-signed multipliers -> look
+    // again for violations, now resolved far below fp32; done when a polish leaves nothing.
+    float vtol = 1e-6f;
+    for (int round = 0; round < 6 && !(status & (PK_STATUS_NO_SOLUTION | PK_STATUS_ITER_LIMIT)); ++round) {
+      int changed = 0;
+      for (;; ++iter) {
+        if (iter >= max_iter) { status |= PK_STATUS_ITER_LIMIT; break; }
+        // step 1: most violated constraint (normalised by the row norm, as quadprog)
+        int ip = -1;
+        float worst = 0.f, sgn = 1.f;
+        for (int id = 0; id < m; ++id) {
+          float scale, rhs;
+          if (id < P.meq + P.p) {
+            if ((in_gen >> id) & 1ull) continue;
+            const float* row = (id < P.meq) ? P.E[id] : P.G[id - P.meq];
+            float nn = 0.f;
+            for (int k = 0; k < n; ++k) nn = fmaf(row[k], row[k], nn);
+            if (!(nn > 0.f)) {
+              // empty row: 0 <= h (or 0 = f) either holds or never will
+              const float s0 = (id < P.meq) ? -fabsf(P.f[id]) : P.h[id - P.meq];
+              if (s0 < 0.f) status |= PK_STATUS_NO_SOLUTION;
+              continue;
             }
+            scale = rsqrtf(nn);
+            rhs = (id < P.meq) ? P.f[id] : P.h[id - P.meq];
+          } else {
+            const int bid = id - P.meq - P.p;
+            const int i = bid >> 1;
+            if ((bid & 1) ? ((in_lo >> i) & 1ull) : ((in_hi >> i) & 1ull)) continue;
+            rhs = (bid & 1) ? P.lo[i] : P.hi[i];
+            if (!(fabsf(rhs) < 3.0e38f)) continue;  // infinite bound: no row
+            scale = 1.f;
           }
-          for (int k = 0; k <= iq; ++k) Ra[ut(k, iq)] = dv[k];
-          act[iq] = (short)ip;
-          asg[iq] = sgn;
-          if (ip < P.meq + P.p) in_gen |= (1ull << ip);
-          else {
-            const int bid = ip - P.meq - P.p;
-            if (bid & 1) in_lo |= (1ull << (bid >> 1)); else in_hi |= (1ull << (bid >> 1));
-          }
-          ++iq;
-          added = true;
-          break;
+          float s = (float)slack(id);
+          float sg = 1.f;
+          if (id < P.meq) { sg = (s > 0.f) ? -1.f : 1.f; s = -fabsf(s); }
+          s *= scale;
+          const float tol = vtol * (fabsf(rhs) * scale + 1e-3f);
+          if (s < -tol && s < worst) { worst = s; ip = id; sgn = sg; }
         }
-        // partial step: constraint l leaves the active set
-        {
-          const int idl = act[l];
-          if (idl < P.meq + P.p) in_gen &= ~(1ull << idl);
-          else {
-            const int bid = idl - P.meq - P.p;
-            if (bid & 1) in_lo &= ~(1ull << (bid >> 1)); else in_hi &= ~(1ull << (bid >> 1));
+        if (status & PK_STATUS_NO_SOLUTION) break;
+        if (ip < 0) break;
+        ++changed;
+        u[iq] = 0.f;
+        bool added = false;
+        for (int inner = 0; inner <= n + P.p + P.meq + 2 && !added; ++inner) {
+          // step 2a: d = J^T n+, z = J2 d2, r = Ra^-1 d1
+          normal_times_J(P, J, ip, sgn, dv);
+          float dd = 0.f, d2 = 0.f;
+          for (int i = 0; i < n; ++i) {
+            dd = fmaf(dv[i], dv[i], dd);
+            if (i >= iq) d2 = fmaf(dv[i], dv[i], d2);
           }
+          const bool dependent = !(d2 > 1e-10f * dd);
+          for (int i = 0; i < n; ++i) {
+            float sacc = 0.f;
+            for (int k = iq; k < n; ++k) sacc = fmaf(J[i][k], dv[k], sacc);
+            z[i] = sacc;
+          }
+          for (int i = iq - 1; i >= 0; --i) {
+            float sacc = dv[i];
+            for (int k = i + 1; k < iq; ++k) sacc = fmaf(-Ra[ut(i, k)], r[k], sacc);
+            r[i] = sacc / Ra[ut(i, i)];
+          }
+          // step 2b: step lengths
+          float t1 = 3.0e38f;
+          int l = -1;
+          for (int k = 0; k < iq; ++k)
+            if (act[k] >= P.meq && r[k] > 0.f) {
+              const float t = fmaxf(u[k], 0.f) / r[k];
+              if (t < t1) { t1 = t; l = k; }
+            }
+          float t2 = 3.0e38f;
+          if (!dependent) {
+            const float zn = normal_dot(P, ip, sgn, z);
+            float sp = (float)slack(ip);
+            if (ip < P.meq) sp *= sgn;
+            if (zn > 0.f) t2 = fmaxf(-sp, 0.f) / zn;
+          }
+          const float t = fminf(t1, t2);
+#ifdef PK_DUALQP_TRACE
+          printf("round %d iter %d ip %d sgn %g iq %d dd %g d2 %g dep %d t1 %g (l %d) t2 %g viol %g\n", round, iter, ip, sgn,
+                 iq, dd, d2, (int)dependent, t1, l, t2, worst);
+#endif
+          if (!(t < 3.0e38f)) { status |= PK_STATUS_NO_SOLUTION; break; }
+          if (t2 < 3.0e38f)
+            for (int k = 0; k < n; ++k) xd[k] += (double)t * (double)z[k];
+          for (int k = 0; k < iq; ++k) u[k] = fmaf(-t, r[k], u[k]);
+          u[iq] += t;
+          if (t2 <= t1) {
+            // full step: the constraint enters.  Givens rotations on columns iq.. of J zero d[iq+1..]
+            for (int j = n - 1; j > iq; --j) {
+              const float a = dv[j - 1], bb = dv[j];
+              if (bb == 0.f) continue;
+              const float hh = hypotf(a, bb);  // no underflow of the squares: entries of d can be ~1e-25
+              if (!(hh > 0.f)) continue;
+              const float c = a / hh, sn = bb / hh;
+              dv[j - 1] = hh;
+              dv[j] = 0.f;
+              for (int k = 0; k < n; ++k) {
+                const float ja = J[k][j - 1], jb = J[k][j];
+                J[k][j - 1] = fmaf(c, ja, sn * jb);
+                J[k][j] = fmaf(-sn, ja, c * jb);
+              }
+            }
+            for (int k = 0; k <= iq; ++k) Ra[ut(k, iq)] = dv[k];
+            act[iq] = (short)ip;
+            asg[iq] = sgn;
+            set_member(ip, true);
+            ++iq;
+            added = true;
+            break;
+          }
+          drop(l);  // partial step: constraint l leaves the active set
         }
-        // remove column l of Ra: rows above l shift left, the Hessenberg part below is
-        // rotated back to triangular (same rotations on the columns of J)
-        for (int i = 0; i < l; ++i)
-          for (int k = l; k < iq - 1; ++k) Ra[ut(i, k)] = Ra[ut(i, k + 1)];
-        for (int j = l; j < iq - 1; ++j) {
-          const float a = Ra[ut(j, j + 1)], bb = Ra[ut(j + 1, j + 1)];
-          const float hh = sqrtf(fmaf(a, a, bb * bb));
-          const float c = (hh > 0.f) ? a / hh : 1.f, s = (hh > 0.f) ? bb / hh : 0.f;
-          for (int k = j; k < iq - 1; ++k) {
-            const float ra = Ra[ut(j, k + 1)], rb = Ra[ut(j + 1, k + 1)];
-            Ra[ut(j, k)] = fmaf(c, ra, s * rb);
-            Ra[ut(j + 1, k + 1)] = fmaf(-s, ra, c * rb);
-          }
-          for (int k = 0; k < n; ++k) {
-            const float ja = J[k][j], jb = J[k][j + 1];
-            J[k][j] = fmaf(c, ja, s * jb);
-            J[k][j + 1] = fmaf(-s, ja, c * jb);
-          }
-        }
-        for (int c = l; c < iq - 1; ++c) { act[c] = act[c + 1]; asg[c] = asg[c + 1]; u[c] = u[c + 1]; }
-        u[iq - 1] = u[iq];
-        --iq;
+        if (status & PK_STATUS_NO_SOLUTION) break;
+        if (!added) { status |= PK_STATUS_ITER_LIMIT; break; }
       }
-      if (status & PK_STATUS_NO_SOLUTION) break;
-      if (!added) { status |= PK_STATUS_ITER_LIMIT; break; }
+      if (status & (PK_STATUS_NO_SOLUTION | PK_STATUS_ITER_LIMIT)) break;
+      if (round > 0 && !changed) break;  // a polished point without violations: done
+      // polish; release inequality multipliers that the accurate gradient shows negative
+      for (int rel = 0; rel <= n; ++rel) {
+        polish();
+        float umax = 0.f, umin = 0.f;
+        int l = -1;
+        for (int k = 0; k < iq; ++k) {
+          umax = fmaxf(umax, fabsf(u[k]));
+          if (act[k] >= P.meq && u[k] < umin) { umin = u[k]; l = k; }
+        }
+        if (l < 0 || umin >= -1e-6f * umax) break;
+        u[iq] = 0.f;
+        drop(l);
+        ++changed;
+      }
+      vtol = 1e-9f;
     }
     if (status & PK_STATUS_NO_SOLUTION) return status;
-
-    // ---- polish on the final active set ----
-    for (int pass = 0; pass < 2 && iq < n + 1; ++pass) {
-      // back onto the active constraints: N_a^T delta = -rho, delta = J1 w, Ra^T w = -rho
-      for (int k = 0; k < iq; ++k) {
-        float s = value(P, act[k], x);
-        if (act[k] < P.meq) s *= asg[k];
-        float w = -s;
-        for (int i = 0; i < k; ++i) w = fmaf(-Ra[ut(i, k)], r[i], w);
-        r[k] = w / Ra[ut(k, k)];
-      }
-      for (int i = 0; i < n; ++i) {
-        float s = x[i];
-        for (int k = 0; k < iq; ++k) s = fmaf(J[i][k], r[k], s);
-        x[i] = s;
-      }
-      if (iq >= n) break;
-      // projected Newton step with the factored gradient
-      float rho[KA];
-      for (int rr = 0; rr < K; ++rr) {
-        float s = P.b[rr];
-        for (int j = 0; j < n; ++j) s = fmaf(P.A[rr][j], x[j], s);
-        rho[rr] = s;
-      }
-      for (int i = 0; i < n; ++i) {
-        float g = P.d[i] * fmaf(P.d[i], x[i], P.beta[i]);
-        for (int rr = 0; rr < K; ++rr) g = fmaf(P.A[rr][i], rho[rr], g);
-        z[i] = g;
-      }
-      for (int k = iq; k < n; ++k) {
-        float s = 0.f;
-        for (int i = 0; i < n; ++i) s = fmaf(J[i][k], z[i], s);
-        dv[k] = s;
-      }
-      for (int i = 0; i < n; ++i) {
-        float s = x[i];
-        for (int k = iq; k < n; ++k) s = fmaf(-J[i][k], dv[k], s);
-        x[i] = s;
-      }
-    }
     // coordinates on a bound sit exactly on it
     for (int i = 0; i < n; ++i) {
       if ((in_hi >> i) & 1ull) x[i] = P.hi[i];

@@ -13,6 +13,7 @@
 
 #include "pk_math.cuh"
 #include "pk_lsq.cuh"
+#include "pk_dualqp.cuh"
 
 namespace pk {
 
@@ -37,6 +38,29 @@ struct DevTask {
   int type, frame, root, tgt_off, tgt_shared, body, root_body;
   float cost[6];
   float gain, lm;
+  int rows, data_off;  // PK_TASK_LINEAR
+};
+
+struct DevBarrier {
+  int type, frame, frame2, body, body2, dim, nidx, idx[3], has_min, has_max;
+  float p_min[3], p_max[3], gain[6], d_min, safe_gain;
+  int gain_fn, npairs, pair_off, data_off;
+};
+
+// Optional parts of a problem (barriers, equality constraints, opt-in limits, constant
+// data of LINEAR tasks); lives in device memory, reached through DevProblem::ext.
+struct DevExtras {
+  int nbarriers;
+  DevBarrier barriers[PK_MAX_BARRIERS];
+  int nconstraints;
+  DevTask constraints[PK_MAX_CONSTRAINTS];
+  int fb_enabled, fb_frame, fb_body;
+  float fb_max[6];
+  int acc_enabled, acc_prev_off, acc_prev_shared;
+  float acc_max[PK_MAX_NV], acc_qlo[PK_MAX_NV], acc_qhi[PK_MAX_NV];
+  const float* extra;
+  const int* pairs;
+  int n_ineq_rows, n_eq_rows;  // totals (validated against PK_MAX_*_ROWS on the host)
 };
 
 // Problem description as the kernels read it (filled from PkProblemDesc).
@@ -47,6 +71,7 @@ struct DevProblem {
   int target_stride, safety_break;
   float cfg_lo[PK_MAX_NV], cfg_hi[PK_MAX_NV], vel[PK_MAX_NV], chk_lo[PK_MAX_NV], chk_hi[PK_MAX_NV];
   float shared[PK_MAX_SHARED];
+  const DevExtras* ext;  // nullptr: tasks + box limits only
 };
 
 // Tasks whose Jacobian is I[root_nv:, :] (they only touch the diagonal terms).
@@ -72,6 +97,12 @@ struct GenericOut {
   float* com;      // [3]
   float* Jf;       // [6][nv] LOCAL Jacobian of frame `jac_frame`
   int jac_frame;
+  float* G;        // [PK_MAX_INEQ_ROWS][nv] dense inequality rows
+  float* hG;       // [PK_MAX_INEQ_ROWS]
+  float* E;        // [PK_MAX_EQ_ROWS][nv] equality rows
+  float* f;        // [PK_MAX_EQ_ROWS]
+  float* lo;       // [nv] box
+  float* hi;       // [nv]
 };
 
 constexpr int kGenericMaxRows = 48;  // stacked task rows (6 per frame task, 3 per CoM task)
@@ -155,6 +186,192 @@ struct Generic {
     return (1.f / M.total_mass) * acc;
   }
 
+  // Error e[k] and Jacobian Jw[k][nv] of one (non-diagonal) task; returns k.
+  // FrameTask pink/tasks/frame_task.py:178-227, RelativeFrameTask
+  // relative_frame_task.py:173-246, ComTask com_task.py:120-148, LinearHolonomicTask
+  // linear_holonomic_task.py:148-192.
+  PK_HD int task_rows(const DevModel& M, const DevProblem& P, const DevTask& Kt, const float* q, const float* tgt,
+                      float (&e)[6], float (&Jw)[6][NVMAX]) const {
+    const int nv = M.nv;
+    const int rq = M.free_flyer ? 7 : 0;
+    const int rv = M.free_flyer ? 6 : 0;
+    if (Kt.type == PK_TASK_LINEAR) {
+      const float* A = P.ext->extra + Kt.data_off;
+      const float* bb = A + Kt.rows * nv;
+      const float* q0 = bb + Kt.rows;
+      for (int r = 0; r < Kt.rows; ++r) {
+        float s = -bb[r];
+        for (int i = 0; i < nv; ++i) {
+          Jw[r][i] = A[r * nv + i];
+          if (i >= rv) s = fmaf(A[r * nv + i], q[i + rq - rv] - q0[i + rq - rv], s);
+        }
+        e[r] = s;
+      }
+      for (int r = Kt.rows; r < 6; ++r) e[r] = 0.f;
+      return Kt.rows;
+    }
+    if (Kt.type == PK_TASK_COM) {
+      const V3 cm = center_of_mass(M);
+      e[0] = cm.x - tgt[0]; e[1] = cm.y - tgt[1]; e[2] = cm.z - tgt[2];
+      e[3] = e[4] = e[5] = 0.f;
+      // subtree masses and first moments, leaves to root
+      float sm[NJMAX];
+      V3 smc[NJMAX];
+      for (int j = 0; j < M.njoints; ++j) {
+        const V3 cl = v3(M.com[3 * (j + 1)], M.com[3 * (j + 1) + 1], M.com[3 * (j + 1) + 2]);
+        sm[j] = M.mass[j + 1];
+        smc[j] = sm[j] * (mul(Tw[j].R, cl) + Tw[j].p);
+      }
+      for (int j = M.njoints - 1; j >= 0; --j) {
+        const int par = M.parent[j];
+        if (par >= 0) { sm[par] += sm[j]; smc[par] = smc[par] + smc[j]; }
+      }
+      const float invM = 1.f / M.total_mass;
+      for (int i = 0; i < nv; ++i) {
+        V3 col = v3(0.f, 0.f, 0.f);
+        if (i < rv) {
+          const V3 ek = v3(i % 3 == 0 ? 1.f : 0.f, i % 3 == 1 ? 1.f : 0.f, i % 3 == 2 ? 1.f : 0.f);
+          if (i < 3) col = mul(root.R, ek);
+          else col = mul(root.R, cross(ek, mulT(root.R, cm - root.p)));
+        } else {
+          const int j = i - rv;
+          if (sm[j] > 0.f) {
+            const V3 axis = v3(M.axis[3 * j], M.axis[3 * j + 1], M.axis[3 * j + 2]);
+            const V3 aw = mul(Tw[j].R, axis);
+            if (M.jtype[j] == PK_JOINT_REVOLUTE)
+              col = (sm[j] * invM) * cross(aw, (1.f / sm[j]) * smc[j] - Tw[j].p);
+            else
+              col = (sm[j] * invM) * aw;
+          }
+        }
+        Jw[0][i] = col.x; Jw[1][i] = col.y; Jw[2][i] = col.z;
+      }
+      return 3;
+    }
+    const SE3f Tf = compose(body_placement(Kt.body), load_se3(M.fX + 12 * Kt.frame));
+    const SE3f Tt = load_se3(tgt);
+    M3 Am, Bm;
+    float sign;
+    SE3f Trf;  // relative task: frame in root-frame coordinates
+    SE3f Tr;
+    if (Kt.type == PK_TASK_FRAME) {
+      const SE3f Tbt = act_inv(Tf, Tt);
+      Log3 L = log3(Tbt.R);
+      log6(Tbt, L, e);
+      SE3f Ttb;
+      for (int a = 0; a < 3; ++a)
+        for (int c2 = 0; c2 < 3; ++c2) Ttb.R.m[3 * a + c2] = Tbt.R.m[3 * c2 + a];
+      Ttb.p = -1.f * mul(Ttb.R, Tbt.p);
+      L.w = -1.f * L.w;
+      jlog6(Ttb, L, Am, Bm);
+      sign = -1.f;
+      Trf = identity_se3();
+      Tr = identity_se3();
+    } else {
+      Tr = compose(body_placement(Kt.root_body), load_se3(M.fX + 12 * Kt.root));
+      Trf = act_inv(Tr, Tf);
+      const SE3f Ttf = act_inv(Tt, Trf);
+      const Log3 L = log3(Ttf.R);
+      log6(Ttf, L, e);
+      jlog6(Ttf, L, Am, Bm);
+      sign = 1.f;
+    }
+    for (int i = 0; i < nv; ++i) {
+      V3 lin, ang;
+      frame_jac_col(M, Kt.body, Tf, i, lin, ang);
+      if (Kt.type == PK_TASK_RELATIVE_FRAME) {
+        V3 rl, ra;
+        frame_jac_col(M, Kt.root_body, Tr, i, rl, ra);
+        // Ad_{T_rf^-1} [rl; ra] = [R^T (rl - p x ra); R^T ra]
+        lin = lin - mulT(Trf.R, rl - cross(Trf.p, ra));
+        ang = ang - mulT(Trf.R, ra);
+      }
+      const V3 tl = sign * (mul(Am, lin) + mul(Bm, ang));
+      const V3 ta = sign * mul(Am, ang);
+      Jw[0][i] = tl.x; Jw[1][i] = tl.y; Jw[2][i] = tl.z;
+      Jw[3][i] = ta.x; Jw[4][i] = ta.y; Jw[5][i] = ta.z;
+    }
+    return 6;
+  }
+
+  // World-frame velocity of the origin of a frame placed at Tf on `body`, per unit of
+  // tangent coordinate i: R_f J_f[:3, i] (pink/barriers/position_barrier.py:139-146).
+  PK_HD V3 point_jac_col(const DevModel& M, int body, const SE3f& Tf, int i) const {
+    V3 lin, ang;
+    frame_jac_col(M, body, Tf, i, lin, ang);
+    return mul(Tf.R, lin);
+  }
+
+  PK_HD static float barrier_gain_fn(int fn, float h) { return fn == PK_GAINFN_SATURATING ? h / (1.f + fabsf(h)) : h; }
+
+  // Rows of one barrier: Jh[dim][nv] = dh/dq and hv[dim] = h(q).
+  PK_HD void barrier_rows(const DevModel& M, const DevExtras& X, const DevBarrier& Bd, float (*Jh)[NVMAX],
+                          float* hv) const {
+    const int nv = M.nv;
+    if (Bd.type == PK_BARRIER_POSITION) {
+      const SE3f Tf = compose(body_placement(Bd.body), load_se3(M.fX + 12 * Bd.frame));
+      const float pw[3] = {Tf.p.x, Tf.p.y, Tf.p.z};
+      int r = 0;
+      if (Bd.has_min)
+        for (int k = 0; k < Bd.nidx; ++k) hv[r++] = pw[Bd.idx[k]] - Bd.p_min[k];
+      if (Bd.has_max)
+        for (int k = 0; k < Bd.nidx; ++k) hv[r++] = Bd.p_max[k] - pw[Bd.idx[k]];
+      for (int i = 0; i < nv; ++i) {
+        const V3 c = point_jac_col(M, Bd.body, Tf, i);
+        const float cw[3] = {c.x, c.y, c.z};
+        int rr = 0;
+        if (Bd.has_min)
+          for (int k = 0; k < Bd.nidx; ++k) Jh[rr++][i] = cw[Bd.idx[k]];
+        if (Bd.has_max)
+          for (int k = 0; k < Bd.nidx; ++k) Jh[rr++][i] = -cw[Bd.idx[k]];
+      }
+      return;
+    }
+    if (Bd.type == PK_BARRIER_BODY_SPHERICAL) {
+      const SE3f T1 = compose(body_placement(Bd.body), load_se3(M.fX + 12 * Bd.frame));
+      const SE3f T2 = compose(body_placement(Bd.body2), load_se3(M.fX + 12 * Bd.frame2));
+      const V3 dp = T1.p - T2.p;
+      hv[0] = dot(dp, dp) - Bd.d_min * Bd.d_min;
+      for (int i = 0; i < nv; ++i)
+        Jh[0][i] = 2.f * dot(dp, point_jac_col(M, Bd.body, T1, i) - point_jac_col(M, Bd.body2, T2, i));
+      return;
+    }
+    // SELF_COLLISION on sphere pairs: the `dim` smallest distances
+    // (pink/barriers/self_collision_barrier.py:108-127, 169-224)
+    float dist[PK_MAX_PAIRS];
+    const int* pr = X.pairs + 2 * Bd.pair_off;
+    const float* rad = X.extra + Bd.data_off;
+    for (int k = 0; k < Bd.npairs; ++k) {
+      const int fa = pr[2 * k], fb = pr[2 * k + 1];
+      const SE3f Ta = body_placement(M.frame_body[fa]);
+      const SE3f Tb = body_placement(M.frame_body[fb]);
+      const V3 ca = mul(Ta.R, v3(M.fX[12 * fa + 3], M.fX[12 * fa + 7], M.fX[12 * fa + 11])) + Ta.p;
+      const V3 cb = mul(Tb.R, v3(M.fX[12 * fb + 3], M.fX[12 * fb + 7], M.fX[12 * fb + 11])) + Tb.p;
+      const V3 dp = ca - cb;
+      dist[k] = sqrtf(dot(dp, dp)) - rad[2 * k] - rad[2 * k + 1];
+    }
+    for (int r = 0; r < Bd.dim; ++r) {
+      int best = -1;
+      float bd = 3.0e38f;
+      for (int k = 0; k < Bd.npairs; ++k)
+        if (dist[k] < bd) { bd = dist[k]; best = k; }
+      hv[r] = bd - Bd.d_min;
+      for (int i = 0; i < nv; ++i) Jh[r][i] = 0.f;
+      if (best < 0) continue;
+      dist[best] = 3.0e38f;  // taken
+      const int fa = pr[2 * best], fb = pr[2 * best + 1];
+      const SE3f Ta = compose(body_placement(M.frame_body[fa]), load_se3(M.fX + 12 * fa));
+      const SE3f Tb = compose(body_placement(M.frame_body[fb]), load_se3(M.fX + 12 * fb));
+      const V3 dp = Ta.p - Tb.p;
+      const float gap = sqrtf(dot(dp, dp));
+      // nearest points w1 - w2 = (gap - ra - rb) u: coincident -> zero row (:198-199)
+      if (!(gap > 0.f) || fabsf(bd) <= 1e-8f) continue;
+      const V3 n = ((bd < 0.f ? -1.f : 1.f) / gap) * dp;
+      for (int i = 0; i < nv; ++i)
+        Jh[r][i] = dot(n, point_jac_col(M, M.frame_body[fa], Ta, i) - point_jac_col(M, M.frame_body[fb], Tb, i));
+    }
+  }
+
   // One step. `q` [nq], `trow` per-instance targets.
   PK_HD void step(const DevModel& M, const DevProblem& P, const float* q, const float* trow, const GenericOut& out) {
     const int nv = M.nv;
@@ -190,7 +407,7 @@ struct Generic {
         out.Jf[3 * nv + i] = ang.x; out.Jf[4 * nv + i] = ang.y; out.Jf[5 * nv + i] = ang.z;
       }
     }
-    if (!P.ntasks && !out.v && !out.H) {
+    if (!P.ntasks && !out.v && !out.H && !out.G && !out.E && !out.lo) {
       if (out.status) *out.status = status;
       return;
     }
@@ -226,90 +443,8 @@ struct Generic {
             for (int i = 0; i < nv; ++i) out.J[r * nv + i] = (i == r + rv) ? 1.f : 0.f;
         continue;
       }
-      int k = 6;
       float e[6];
-      if (Kt.type == PK_TASK_COM) {
-        k = 3;
-        const V3 cm = center_of_mass(M);
-        e[0] = cm.x - tgt[0]; e[1] = cm.y - tgt[1]; e[2] = cm.z - tgt[2];
-        e[3] = e[4] = e[5] = 0.f;
-        // subtree masses and first moments, leaves to root
-        float sm[NJMAX];
-        V3 smc[NJMAX];
-        for (int j = 0; j < M.njoints; ++j) {
-          const V3 cl = v3(M.com[3 * (j + 1)], M.com[3 * (j + 1) + 1], M.com[3 * (j + 1) + 2]);
-          sm[j] = M.mass[j + 1];
-          smc[j] = sm[j] * (mul(Tw[j].R, cl) + Tw[j].p);
-        }
-        for (int j = M.njoints - 1; j >= 0; --j) {
-          const int par = M.parent[j];
-          if (par >= 0) { sm[par] += sm[j]; smc[par] = smc[par] + smc[j]; }
-        }
-        const float invM = 1.f / M.total_mass;
-        for (int i = 0; i < nv; ++i) {
-          V3 col = v3(0.f, 0.f, 0.f);
-          if (i < rv) {
-            const V3 ek = v3(i % 3 == 0 ? 1.f : 0.f, i % 3 == 1 ? 1.f : 0.f, i % 3 == 2 ? 1.f : 0.f);
-            if (i < 3) col = mul(root.R, ek);
-            else col = mul(root.R, cross(ek, mulT(root.R, cm - root.p)));
-          } else {
-            const int j = i - rv;
-            if (sm[j] > 0.f) {
-              const V3 axis = v3(M.axis[3 * j], M.axis[3 * j + 1], M.axis[3 * j + 2]);
-              const V3 aw = mul(Tw[j].R, axis);
-              if (M.jtype[j] == PK_JOINT_REVOLUTE)
-                col = (sm[j] * invM) * cross(aw, (1.f / sm[j]) * smc[j] - Tw[j].p);
-              else
-                col = (sm[j] * invM) * aw;
-            }
-          }
-          Jw[0][i] = col.x; Jw[1][i] = col.y; Jw[2][i] = col.z;
-        }
-      } else {
-        const SE3f Tf = compose(body_placement(Kt.body), load_se3(M.fX + 12 * Kt.frame));
-        const SE3f Tt = load_se3(tgt);
-        M3 Am, Bm;
-        float sign;
-        SE3f Trf;  // relative task: frame in root-frame coordinates
-        SE3f Tr;
-        if (Kt.type == PK_TASK_FRAME) {
-          const SE3f Tbt = act_inv(Tf, Tt);
-          Log3 L = log3(Tbt.R);
-          log6(Tbt, L, e);
-          SE3f Ttb;
-          for (int a = 0; a < 3; ++a)
-            for (int c2 = 0; c2 < 3; ++c2) Ttb.R.m[3 * a + c2] = Tbt.R.m[3 * c2 + a];
-          Ttb.p = -1.f * mul(Ttb.R, Tbt.p);
-          L.w = -1.f * L.w;
-          jlog6(Ttb, L, Am, Bm);
-          sign = -1.f;
-          Trf = identity_se3();
-          Tr = identity_se3();
-        } else {
-          Tr = compose(body_placement(Kt.root_body), load_se3(M.fX + 12 * Kt.root));
-          Trf = act_inv(Tr, Tf);
-          const SE3f Ttf = act_inv(Tt, Trf);
-          const Log3 L = log3(Ttf.R);
-          log6(Ttf, L, e);
-          jlog6(Ttf, L, Am, Bm);
-          sign = 1.f;
-        }
-        for (int i = 0; i < nv; ++i) {
-          V3 lin, ang;
-          frame_jac_col(M, Kt.body, Tf, i, lin, ang);
-          if (Kt.type == PK_TASK_RELATIVE_FRAME) {
-            V3 rl, ra;
-            frame_jac_col(M, Kt.root_body, Tr, i, rl, ra);
-            // Ad_{T_rf^-1} [rl; ra] = [R^T (rl - p x ra); R^T ra]
-            lin = lin - mulT(Trf.R, rl - cross(Trf.p, ra));
-            ang = ang - mulT(Trf.R, ra);
-          }
-          const V3 tl = sign * (mul(Am, lin) + mul(Bm, ang));
-          const V3 ta = sign * mul(Am, ang);
-          Jw[0][i] = tl.x; Jw[1][i] = tl.y; Jw[2][i] = tl.z;
-          Jw[3][i] = ta.x; Jw[4][i] = ta.y; Jw[5][i] = ta.z;
-        }
-      }
+      const int k = task_rows(M, P, Kt, q, tgt, e, Jw);
       if (want) {
         if (out.e)
           for (int r = 0; r < k; ++r) out.e[r] = e[r];
@@ -331,12 +466,8 @@ struct Generic {
       diag = fmaf(Kt.lm, mu, diag);
     }
     if (K > kGenericMaxRows) { status |= PK_STATUS_NOT_POSDEF; K = kGenericMaxRows; }
-    for (int i = 0; i < nv; ++i) {
-      const float dd = sqrtf(pw2[i] + diag);
-      d[i] = dd;
-      beta[i] = dd > 0.f ? pc[i] / dd : 0.f;
-    }
 
+    // box of all +-e_i rows: configuration and velocity limits ...
     float lo[NVMAX], hi[NVMAX];
     for (int i = 0; i < nv; ++i) {
       const float qi = (i >= rv) ? q[i + rq - rv] : 0.f;
@@ -352,6 +483,124 @@ struct Generic {
         out.h[3 * nv + i] = vb;
       }
     }
+
+    // ---- optional parts: dense inequality rows, equality rows, acceleration box ----
+    constexpr int MG = PK_MAX_INEQ_ROWS, ME = PK_MAX_EQ_ROWS;
+    int p = 0, meq = 0;
+    if (P.ext) {
+      const DevExtras& X = *P.ext;
+      float Gg[MG][NVMAX], hg[MG], Eq[ME][NVMAX], fe[ME];
+      if (X.acc_enabled) {
+        // ... and AccelerationLimit (pink/limits/acceleration_limit.py:119-200)
+        const float* prev = X.acc_prev_off < 0 ? nullptr
+                                                : (X.acc_prev_shared ? P.shared + X.acc_prev_off : trow + X.acc_prev_off);
+        const float dt2 = P.dt * P.dt;
+        for (int i = 0; i < nv; ++i) {
+          const float a = X.acc_max[i];
+          if (!(a < 3.0e38f)) continue;
+          const float pv = prev ? prev[i] : 0.f;
+          const float qi = (i >= rv) ? q[i + rq - rv] : 0.f;
+          const float up = X.acc_qhi[i] - qi, dn = qi - X.acc_qlo[i];
+          if (up < 0.f || dn < 0.f) status |= PK_STATUS_NO_SOLUTION;  // sqrt of a negative margin: NaN rows
+          const float hu = fminf(fmaf(a, dt2, pv), (up < 3.0e38f) ? P.dt * sqrtf(2.f * a * fmaxf(up, 0.f)) : INFINITY);
+          const float hl = fminf(fmaf(a, dt2, -pv), (dn < 3.0e38f) ? P.dt * sqrtf(2.f * a * fmaxf(dn, 0.f)) : INFINITY);
+          hi[i] = fminf(hi[i], hu);
+          lo[i] = fmaxf(lo[i], -hl);
+        }
+      }
+      if (X.fb_enabled) {
+        // FloatingBaseVelocityLimit (pink/limits/floating_base_velocity_limit.py:118-148)
+        const SE3f Tf = compose(body_placement(X.fb_body), load_se3(M.fX + 12 * X.fb_frame));
+        const int p0 = p;
+        int nfin = 0;
+        for (int r = 0; r < 6; ++r) nfin += (X.fb_max[r] < 3.0e38f) ? 1 : 0;
+        for (int i = 0; i < nv; ++i) {
+          V3 lin = v3(0.f, 0.f, 0.f), ang = v3(0.f, 0.f, 0.f);
+          if (i < rv) frame_jac_col(M, X.fb_body, Tf, i, lin, ang);
+          const float col[6] = {lin.x, lin.y, lin.z, ang.x, ang.y, ang.z};
+          int rr = 0;
+          for (int r = 0; r < 6; ++r)
+            if (X.fb_max[r] < 3.0e38f) {
+              Gg[p0 + rr][i] = col[r];
+              Gg[p0 + nfin + rr][i] = -col[r];
+              ++rr;
+            }
+        }
+        int rr = 0;
+        for (int r = 0; r < 6; ++r)
+          if (X.fb_max[r] < 3.0e38f) {
+            hg[p0 + rr] = hg[p0 + nfin + rr] = P.dt * X.fb_max[r];
+            ++rr;
+          }
+        p += 2 * nfin;
+      }
+      for (int bi = 0; bi < X.nbarriers; ++bi) {
+        const DevBarrier& Bd = X.barriers[bi];
+        barrier_rows(M, X, Bd, &Gg[p], &hg[p]);
+        float fro = 0.f;
+        for (int r = 0; r < Bd.dim; ++r) {
+          const float g = Bd.gain[Bd.type == PK_BARRIER_POSITION ? r : 0];
+          hg[p + r] = g * barrier_gain_fn(Bd.gain_fn, hg[p + r]);
+          for (int i = 0; i < nv; ++i) {
+            fro = fmaf(Gg[p + r][i], Gg[p + r][i], fro);
+            Gg[p + r][i] *= -P.inv_dt;  // G = -J_h / dt (pink/barriers/barrier.py:246)
+          }
+        }
+        if (Bd.safe_gain > 1e-6f) diag += Bd.safe_gain / fro;  // barrier.py:193-203
+        p += Bd.dim;
+      }
+      for (int ci = 0; ci < X.nconstraints; ++ci) {
+        // J dq = -gain e (pink/solve_ik.py:143-148)
+        const DevTask& Kt = X.constraints[ci];
+        const float* tgt = Kt.tgt_shared ? (P.shared + Kt.tgt_off) : (trow + Kt.tgt_off);
+        float e[6];
+        const int k = task_rows(M, P, Kt, q, tgt, e, Jw);
+        for (int r = 0; r < k; ++r) {
+          fe[meq] = -Kt.gain * e[r];
+          for (int i = 0; i < nv; ++i) Eq[meq][i] = Jw[r][i];
+          ++meq;
+        }
+      }
+      if (out.G)
+        for (int r = 0; r < MG; ++r) {
+          out.hG[r] = r < p ? hg[r] : INFINITY;
+          for (int i = 0; i < nv; ++i) out.G[r * nv + i] = r < p ? Gg[r][i] : 0.f;
+        }
+      if (out.E)
+        for (int r = 0; r < ME; ++r) {
+          out.f[r] = r < meq ? fe[r] : 0.f;
+          for (int i = 0; i < nv; ++i) out.E[r * nv + i] = r < meq ? Eq[r][i] : 0.f;
+        }
+      finish(M, P, out, A, b, d, beta, pw2, pc, diag, lo, hi, K, status, skip, Gg, hg, p, Eq, fe, meq);
+      return;
+    }
+    if (out.G)
+      for (int r = 0; r < MG; ++r) {
+        out.hG[r] = INFINITY;
+        for (int i = 0; i < nv; ++i) out.G[r * nv + i] = 0.f;
+      }
+    if (out.E)
+      for (int r = 0; r < ME; ++r) {
+        out.f[r] = 0.f;
+        for (int i = 0; i < nv; ++i) out.E[r * nv + i] = 0.f;
+      }
+    finish(M, P, out, A, b, d, beta, pw2, pc, diag, lo, hi, K, status, skip, nullptr, nullptr, 0, nullptr, nullptr, 0);
+  }
+
+  // Diagonal terms, exports and the QP solve.
+  PK_HD void finish(const DevModel& M, const DevProblem& P, const GenericOut& out, const float (&A)[kGenericMaxRows][NVMAX],
+                    const float (&b)[kGenericMaxRows], float (&d)[NVMAX], float (&beta)[NVMAX], const float (&pw2)[NVMAX],
+                    const float (&pc)[NVMAX], float diag, const float (&lo)[NVMAX], const float (&hi)[NVMAX], int K,
+                    int status, bool skip, const float (*Gg)[NVMAX], const float* hg, int p, const float (*Eq)[NVMAX],
+                    const float* fe, int meq) {
+    const int nv = M.nv;
+    for (int i = 0; i < nv; ++i) {
+      const float dd = sqrtf(pw2[i] + diag);
+      d[i] = dd;
+      beta[i] = dd > 0.f ? pc[i] / dd : 0.f;
+    }
+    if (out.lo)
+      for (int i = 0; i < nv; ++i) { out.lo[i] = lo[i]; out.hi[i] = hi[i]; }
     if (out.H)
       for (int i = 0; i < nv; ++i)
         for (int j = 0; j < nv; ++j) {
@@ -368,10 +617,18 @@ struct Generic {
 
     if (out.v) {
       float x[NVMAX];
-      if (skip) {
+      if (skip || (status & PK_STATUS_NO_SOLUTION)) {
         for (int i = 0; i < nv; ++i) out.v[i] = 0.f;
       } else {
-        status |= BoxLSQ<kGenericMaxRows, NVMAX>::run(A, b, d, beta, lo, hi, K, nv, x);
+        if (p + meq == 0) {
+          status |= BoxLSQ<kGenericMaxRows, NVMAX>::run(A, b, d, beta, lo, hi, K, nv, x);
+        } else {
+          using QP = DualQP<kGenericMaxRows, NVMAX, PK_MAX_INEQ_ROWS, PK_MAX_EQ_ROWS>;
+          typename QP::Problem Q{A, b, d, beta, lo, hi, Gg, hg, Eq, fe, K, nv, p, meq};
+          status |= QP::run(Q, x);
+        }
+        if (status & PK_STATUS_NO_SOLUTION)
+          for (int i = 0; i < nv; ++i) x[i] = 0.f;
         for (int i = 0; i < nv; ++i) out.v[i] = x[i] * P.inv_dt;
       }
     }

@@ -101,11 +101,71 @@ inline int target_size(const HostModel& m, const PkTaskDesc& t) {
     case PK_TASK_POSTURE: return m.nq;
     case PK_TASK_JOINT_VELOCITY: return m.nv - (m.free_flyer ? 6 : 0);
     case PK_TASK_COM: return 3;
+    case PK_TASK_LINEAR: return 0;
     default: return -1;
   }
 }
 
-inline std::string make_dev_problem(const HostModel& m, const PkProblemDesc* p, DevProblem* out) {
+// Host image of the optional problem parts; `X.extra` / `X.pairs` point into the
+// vectors here until the C-ABI layer re-points them at device copies.
+struct HostExtras {
+  DevExtras X;
+  std::vector<float> extra;
+  std::vector<int> pairs;
+  bool present = false;
+};
+
+inline std::string fill_dev_task(const HostModel& m, const PkProblemDesc* p, const PkTaskDesc& s, DevTask& d,
+                                 bool as_constraint) {
+  const int ts = target_size(m, s);
+  if (ts < 0) return "unknown task type";
+  const int limit = s.target_shared ? PK_MAX_SHARED : p->target_stride;
+  if (ts > 0 && (s.target_offset < 0 || s.target_offset + ts > limit)) return "task target does not fit its buffer";
+  d.type = s.type;
+  d.frame = s.frame;
+  d.root = s.root;
+  d.tgt_off = s.target_offset;
+  d.tgt_shared = s.target_shared ? 1 : 0;
+  d.body = d.root_body = -2;
+  d.rows = 0;
+  d.data_off = 0;
+  if (s.type == PK_TASK_FRAME || s.type == PK_TASK_RELATIVE_FRAME) {
+    if (s.frame < 0 || s.frame >= m.nframes) return "task frame index out of range";
+    d.body = m.frame_body[s.frame];
+  }
+  if (s.type == PK_TASK_RELATIVE_FRAME) {
+    if (s.root < 0 || s.root >= m.nframes) return "task root frame index out of range";
+    d.root_body = m.frame_body[s.root];
+  }
+  if (s.type == PK_TASK_LINEAR) {
+    if (s.rows < 1 || s.rows > 6) return "linear task: rows must be in 1..6";
+    const int need = s.rows * m.nv + s.rows + m.nq;
+    if (s.data_offset < 0 || !p->extra || s.data_offset + need > p->n_extra) return "linear task data does not fit `extra`";
+    const int rv = m.free_flyer ? 6 : 0;
+    for (int r = 0; r < s.rows; ++r)
+      for (int i = 0; i < rv; ++i)
+        if (p->extra[s.data_offset + r * m.nv + i] != 0.f) return "linear task: root columns of A must be zero";
+    d.rows = s.rows;
+    d.data_off = s.data_offset;
+  }
+  if (as_constraint && is_diag_task(s.type)) return "posture / joint-velocity tasks cannot be equality constraints";
+  for (int k = 0; k < 6; ++k) {
+    if (s.cost[k] < 0.f) return "negative task cost";
+    d.cost[k] = s.cost[k];
+  }
+  d.gain = s.gain;
+  d.lm = s.lm_damping;
+  return "";
+}
+
+inline int task_row_count(const HostModel& m, const DevTask& d) {
+  if (d.type == PK_TASK_COM) return 3;
+  if (d.type == PK_TASK_LINEAR) return d.rows;
+  return 6;
+}
+
+inline std::string make_dev_problem(const HostModel& m, const PkProblemDesc* p, DevProblem* out,
+                                    HostExtras* hx = nullptr) {
   if (!p) return "null problem";
   if (p->ntasks < 0 || p->ntasks > PK_MAX_TASKS) return "ntasks out of range";
   if (!(p->dt > 0.f)) return "dt must be positive";
@@ -113,33 +173,11 @@ inline std::string make_dev_problem(const HostModel& m, const PkProblemDesc* p, 
   DevProblem& P = *out;
   memset(&P, 0, sizeof(P));
   P.ntasks = p->ntasks;
+  bool any_linear = false;
   for (int t = 0; t < p->ntasks; ++t) {
-    const PkTaskDesc& s = p->tasks[t];
-    DevTask& d = P.tasks[t];
-    const int ts = target_size(m, s);
-    if (ts < 0) return "unknown task type";
-    const int limit = s.target_shared ? PK_MAX_SHARED : p->target_stride;
-    if (s.target_offset < 0 || s.target_offset + ts > limit) return "task target does not fit its buffer";
-    d.type = s.type;
-    d.frame = s.frame;
-    d.root = s.root;
-    d.tgt_off = s.target_offset;
-    d.tgt_shared = s.target_shared ? 1 : 0;
-    d.body = d.root_body = -2;
-    if (s.type == PK_TASK_FRAME || s.type == PK_TASK_RELATIVE_FRAME) {
-      if (s.frame < 0 || s.frame >= m.nframes) return "task frame index out of range";
-      d.body = m.frame_body[s.frame];
-    }
-    if (s.type == PK_TASK_RELATIVE_FRAME) {
-      if (s.root < 0 || s.root >= m.nframes) return "task root frame index out of range";
-      d.root_body = m.frame_body[s.root];
-    }
-    for (int k = 0; k < 6; ++k) {
-      if (s.cost[k] < 0.f) return "negative task cost";
-      d.cost[k] = s.cost[k];
-    }
-    d.gain = s.gain;
-    d.lm = s.lm_damping;
+    const std::string e = fill_dev_task(m, p, p->tasks[t], P.tasks[t], false);
+    if (!e.empty()) return e;
+    any_linear = any_linear || p->tasks[t].type == PK_TASK_LINEAR;
   }
   P.dt = p->dt;
   P.inv_dt = 1.f / p->dt;
@@ -156,11 +194,129 @@ inline std::string make_dev_problem(const HostModel& m, const PkProblemDesc* p, 
     P.chk_hi[i] = in ? p->chk_hi[i] : INFINITY;
   }
   memcpy(P.shared, p->shared, sizeof(P.shared));
+  P.ext = nullptr;
+
+  // ---- optional parts (ABI 2) ----
+  const bool present = any_linear || p->nbarriers > 0 || p->nconstraints > 0 || p->fb_enabled || p->acc_enabled;
+  if (!present) {
+    if (hx) hx->present = false;
+    return "";
+  }
+  if (!hx) return "this entry point does not support barriers / constraints / opt-in limits";
+  hx->present = true;
+  DevExtras& X = hx->X;
+  memset(&X, 0, sizeof(X));
+  if (p->nbarriers < 0 || p->nbarriers > PK_MAX_BARRIERS) return "nbarriers out of range";
+  if (p->nconstraints < 0 || p->nconstraints > PK_MAX_CONSTRAINTS) return "nconstraints out of range";
+  if (p->n_extra < 0 || p->n_pairs < 0 || (p->n_extra > 0 && !p->extra) || (p->n_pairs > 0 && !p->pairs))
+    return "extra / pairs buffers inconsistent";
+  hx->extra.assign(p->extra, p->extra + p->n_extra);
+  hx->pairs.assign(p->pairs, p->pairs + 2 * (size_t)p->n_pairs);
+  int rows = 0;
+  if (p->fb_enabled) {
+    if (!m.free_flyer) return "FloatingBaseVelocityLimit requires a floating-base root joint";
+    if (p->fb_frame < 0 || p->fb_frame >= m.nframes) return "floating-base frame index out of range";
+    if (m.frame_body[p->fb_frame] != -1) return "floating-base frame is not attached to the root joint";
+    X.fb_enabled = 1;
+    X.fb_frame = p->fb_frame;
+    X.fb_body = -1;
+    int nfin = 0;
+    for (int r = 0; r < 6; ++r) {
+      if (!(p->fb_max[r] >= 0.f)) return "floating-base velocity bounds must be non-negative";
+      X.fb_max[r] = p->fb_max[r];
+      nfin += std::isfinite(p->fb_max[r]) ? 1 : 0;
+    }
+    if (nfin == 0) X.fb_enabled = 0;  // no finite bound: the limit contributes no row
+    rows += 2 * nfin;
+  }
+  X.nbarriers = p->nbarriers;
+  for (int b = 0; b < p->nbarriers; ++b) {
+    const PkBarrierDesc& s = p->barriers[b];
+    DevBarrier& d = X.barriers[b];
+    d.type = s.type;
+    d.frame = s.frame;
+    d.frame2 = s.frame2;
+    d.body = d.body2 = -2;
+    d.d_min = s.d_min;
+    d.safe_gain = s.safe_displacement_gain;
+    d.gain_fn = s.gain_function;
+    if (s.gain_function != PK_GAINFN_IDENTITY && s.gain_function != PK_GAINFN_SATURATING) return "unknown barrier gain function";
+    for (int k = 0; k < 6; ++k) d.gain[k] = s.gain[k];
+    if (s.type == PK_BARRIER_POSITION) {
+      if (s.frame < 0 || s.frame >= m.nframes) return "barrier frame index out of range";
+      if (s.nidx < 1 || s.nidx > 3) return "position barrier: 1..3 indices";
+      if (!s.has_min && !s.has_max) return "position barrier needs p_min or p_max";
+      d.body = m.frame_body[s.frame];
+      d.nidx = s.nidx;
+      d.has_min = s.has_min ? 1 : 0;
+      d.has_max = s.has_max ? 1 : 0;
+      for (int k = 0; k < s.nidx; ++k) {
+        if (s.indices[k] < 0 || s.indices[k] > 2) return "position barrier index out of range";
+        d.idx[k] = s.indices[k];
+        d.p_min[k] = s.p_min[k];
+        d.p_max[k] = s.p_max[k];
+      }
+      d.dim = s.nidx * (d.has_min + d.has_max);
+    } else if (s.type == PK_BARRIER_BODY_SPHERICAL) {
+      if (s.frame < 0 || s.frame >= m.nframes || s.frame2 < 0 || s.frame2 >= m.nframes) return "barrier frame index out of range";
+      if (s.d_min < 0.f) return "negative minimum distance";
+      d.body = m.frame_body[s.frame];
+      d.body2 = m.frame_body[s.frame2];
+      d.dim = 1;
+    } else if (s.type == PK_BARRIER_SELF_COLLISION) {
+      if (s.d_min < 0.f) return "negative minimum distance";
+      if (s.npairs < 0 || s.npairs > PK_MAX_PAIRS) return "self-collision barrier: too many pairs";
+      if (s.dim < 0 || s.dim > s.npairs) return "self-collision barrier: dim exceeds the number of collision pairs";
+      if (s.pair_offset < 0 || s.pair_offset + s.npairs > p->n_pairs) return "self-collision pairs out of range";
+      if (s.data_offset < 0 || s.data_offset + 2 * s.npairs > p->n_extra) return "self-collision radii out of range";
+      for (int k = 0; k < 2 * s.npairs; ++k) {
+        const int f = p->pairs[2 * s.pair_offset + k];
+        if (f < 0 || f >= m.nframes) return "self-collision frame index out of range";
+      }
+      d.dim = s.dim;
+      d.npairs = s.npairs;
+      d.pair_off = s.pair_offset;
+      d.data_off = s.data_offset;
+    } else {
+      return "unknown barrier type";
+    }
+    if (d.dim != s.dim) return "barrier dim does not match its definition";
+    rows += d.dim;
+  }
+  if (rows > PK_MAX_INEQ_ROWS) return "too many dense inequality rows (PK_MAX_INEQ_ROWS)";
+  X.n_ineq_rows = rows;
+  X.nconstraints = p->nconstraints;
+  int erows = 0;
+  for (int c = 0; c < p->nconstraints; ++c) {
+    const std::string e = fill_dev_task(m, p, p->constraints[c], X.constraints[c], true);
+    if (!e.empty()) return e;
+    erows += task_row_count(m, X.constraints[c]);
+  }
+  if (erows > PK_MAX_EQ_ROWS) return "too many equality rows (PK_MAX_EQ_ROWS)";
+  X.n_eq_rows = erows;
+  if (p->acc_enabled) {
+    X.acc_enabled = 1;
+    X.acc_prev_off = p->acc_prev_offset;
+    X.acc_prev_shared = p->acc_prev_shared ? 1 : 0;
+    if (p->acc_prev_offset >= 0) {
+      const int limit = p->acc_prev_shared ? PK_MAX_SHARED : p->target_stride;
+      if (p->acc_prev_offset + m.nv > limit) return "acceleration-limit dq_prev does not fit its buffer";
+    }
+    for (int i = 0; i < PK_MAX_NV; ++i) {
+      const bool in = i < m.nv;
+      X.acc_max[i] = in ? p->acc_max[i] : INFINITY;
+      X.acc_qlo[i] = in ? p->acc_qlo[i] : -INFINITY;
+      X.acc_qhi[i] = in ? p->acc_qhi[i] : INFINITY;
+    }
+  }
+  X.extra = hx->extra.data();
+  X.pairs = hx->pairs.data();
   return "";
 }
 
 // Does the register-resident chain kernel cover this (model, problem)?
-inline bool chain_eligible(const HostModel& m, const DevProblem& P) {
+inline bool chain_eligible(const HostModel& m, const DevProblem& P, bool has_extras = false) {
+  if (has_extras) return false;
   if (!m.serial_chain || m.njoints > 7 || m.njoints < 2) return false;
   int nf = 0, np = 0;
   for (int t = 0; t < P.ntasks; ++t) {
@@ -247,7 +403,10 @@ inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok
   L.o_idx = take(b2, L.nv);
   L.o_xa = take(b2, L.nv);
   L.words = a > b2 ? a : b2;
-  *ok = m.njoints >= 1 && m.njoints <= kTreeMaxJoints && m.nv <= 64 && P.ntasks <= 32 && K <= 64 && (size_t)L.words * 4 <= 48 * 1024;
+  bool plain = true;  // LINEAR tasks and the optional parts (DevExtras) run on the general path
+  for (int t = 0; t < P.ntasks; ++t) plain = plain && P.tasks[t].type != PK_TASK_LINEAR;
+  *ok = plain && m.njoints >= 1 && m.njoints <= kTreeMaxJoints && m.nv <= 64 && P.ntasks <= 32 && K <= 64 &&
+        (size_t)L.words * 4 <= 48 * 1024;
   return L;
 }
 

@@ -112,6 +112,20 @@ class Engine:
                 _stream(self.device)))
         return H, c, h
 
+    def constraint_rows(self, prob: _cabi.PkProblemDesc, q: torch.Tensor, targets: Optional[torch.Tensor]):
+        """Dense inequality rows ``(G, hG)``, equality rows ``(E, f)`` and the box
+        ``(lo, hi)`` of every instance (``pk_constraint_rows_batched``)."""
+        B, nv = q.shape[0], self.nv
+        mk = lambda *shape: torch.empty(shape, device=self.device, dtype=torch.float32)
+        G, hG = mk(B, _cabi.PK_MAX_INEQ_ROWS, nv), mk(B, _cabi.PK_MAX_INEQ_ROWS)
+        E, f = mk(B, _cabi.PK_MAX_EQ_ROWS, nv), mk(B, _cabi.PK_MAX_EQ_ROWS)
+        lo, hi = mk(B, nv), mk(B, nv)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.pk_constraint_rows_batched(
+                self.handle, C.byref(prob), _addr(q), _addr(targets), _addr(G), _addr(hG), _addr(E), _addr(f),
+                _addr(lo), _addr(hi), B, _stream(self.device)))
+        return G, hG, E, f, lo, hi
+
     def task_terms(self, prob: _cabi.PkProblemDesc, task_index: int, k: int, q: torch.Tensor,
                    targets: Optional[torch.Tensor]):
         B, nv = q.shape[0], self.nv

@@ -17,6 +17,18 @@ class FrameNotFound(PinkError):
         super().__init__(self.message)
 
 
+class InvalidCollisionPairs(PinkError):
+    """Exception raised when the number of collision pairs is invalid."""
+
+
+class NegativeMinimumDistance(PinkError):
+    """Exception raised when the minimum distance threshold is negative."""
+
+
+class NoPositionLimitProvided(PinkError):
+    """Exception raised when neither a minimum nor a maximum position limit is provided."""
+
+
 class NoSolutionFound(PinkError):
     """The QP solver did not find a solution to the differential IK problem.
 

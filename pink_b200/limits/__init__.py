@@ -1,12 +1,20 @@
 """Kinematic limits (``/root/reference/pink/limits/__init__.py``).
 
-On the hot path: :class:`ConfigurationLimit`, :class:`VelocityLimit`.
-``FloatingBaseVelocityLimit`` and ``AccelerationLimit`` are SURVEY section 8(f) "next"
-rows and are not provided yet.
+:class:`ConfigurationLimit`, :class:`VelocityLimit` and :class:`AccelerationLimit`
+produce ``+-e_i`` rows (a box on the displacement);
+:class:`FloatingBaseVelocityLimit` produces dense rows on the base twist.
 """
 
+from .acceleration_limit import AccelerationLimit
 from .configuration_limit import ConfigurationLimit
+from .floating_base_velocity_limit import FloatingBaseVelocityLimit
 from .limit import Limit
 from .velocity_limit import VelocityLimit
 
-__all__ = ["ConfigurationLimit", "Limit", "VelocityLimit"]
+__all__ = [
+    "AccelerationLimit",
+    "ConfigurationLimit",
+    "FloatingBaseVelocityLimit",
+    "Limit",
+    "VelocityLimit",
+]

@@ -9,6 +9,7 @@ solve all run inside one CUDA kernel launch per call.
 
 from __future__ import annotations
 
+import ctypes as C
 import logging
 from typing import Iterable, List, Optional, Sequence, Tuple
 
@@ -17,7 +18,7 @@ import torch
 
 from . import _cabi
 from .exceptions import NoSolutionFound, NotWithinConfigurationLimits, PinkError
-from .limits import ConfigurationLimit, Limit, VelocityLimit
+from .limits import AccelerationLimit, ConfigurationLimit, FloatingBaseVelocityLimit, Limit, VelocityLimit
 from .utils import get_root_joint_dim
 
 # The only QP back-end is the in-kernel active-set solver; the `solver`
@@ -56,21 +57,28 @@ def _default_limits(configuration, limits):
 
 
 def _fill_limits(prob: _cabi.PkProblemDesc, model, limits: Sequence[Limit], safety_break: bool,
-                 check_tol: float = 1e-6) -> Tuple[Optional[ConfigurationLimit], Optional[VelocityLimit]]:
+                 check_tol: float = 1e-6):
+    """Box limits (configuration / velocity / acceleration) and the floating-base
+    rows.  Returns the AccelerationLimit (its ``Delta_q_prev`` is a per-problem
+    input placed by the caller) or ``None``."""
     nv = model.nv
     cfg = [l for l in limits if isinstance(l, ConfigurationLimit)]
     vel = [l for l in limits if isinstance(l, VelocityLimit)]
-    other = [l for l in limits if not isinstance(l, (ConfigurationLimit, VelocityLimit))]
+    acc = [l for l in limits if isinstance(l, AccelerationLimit)]
+    fb = [l for l in limits if isinstance(l, FloatingBaseVelocityLimit)]
+    other = [l for l in limits if l is not None
+             and not isinstance(l, (ConfigurationLimit, VelocityLimit, AccelerationLimit, FloatingBaseVelocityLimit))]
     if other:
         raise NotImplementedError(
-            f"limits of type {[type(l).__name__ for l in other]} are not supported by the CUDA engine yet"
+            f"limits of type {[type(l).__name__ for l in other]} are not supported by the CUDA engine"
         )
-    if len(cfg) > 1 or len(vel) > 1:
-        raise NotImplementedError("at most one ConfigurationLimit and one VelocityLimit per solve")
+    if len(cfg) > 1 or len(vel) > 1 or len(acc) > 1 or len(fb) > 1:
+        raise NotImplementedError("at most one limit of each kind per solve")
     inf = float("inf")
     for i in range(_cabi.PK_MAX_NV):
         prob.cfg_lo[i], prob.cfg_hi[i], prob.vel[i] = -inf, inf, inf
         prob.chk_lo[i], prob.chk_hi[i] = -inf, inf
+        prob.acc_max[i], prob.acc_qlo[i], prob.acc_qhi[i] = inf, -inf, inf
     prob.cfg_gain = 0.5
     if cfg:
         lo, hi = cfg[0].box_bounds()
@@ -81,6 +89,19 @@ def _fill_limits(prob: _cabi.PkProblemDesc, model, limits: Sequence[Limit], safe
         v = vel[0].box_bounds()
         for i in range(nv):
             prob.vel[i] = float(v[i])
+    prob.acc_enabled = 0
+    prob.acc_prev_offset = -1
+    if acc and acc[0].projection_matrix is not None:
+        a, qlo, qhi = acc[0].box_arrays()
+        prob.acc_enabled = 1
+        for i in range(nv):
+            prob.acc_max[i], prob.acc_qlo[i], prob.acc_qhi[i] = float(a[i]), float(qlo[i]), float(qhi[i])
+    prob.fb_enabled = 0
+    if fb:
+        prob.fb_enabled = 1
+        prob.fb_frame = int(fb[0].frame_id)
+        for r in range(6):
+            prob.fb_max[r] = float(fb[0].twist_max[r])
     # Configuration.check_limits (configuration.py:181-201)
     root_nq, _ = get_root_joint_dim(model)
     shift = model.nq - nv
@@ -91,68 +112,166 @@ def _fill_limits(prob: _cabi.PkProblemDesc, model, limits: Sequence[Limit], safe
         prob.chk_lo[iq - shift] = float(q_min[iq] - check_tol)
         prob.chk_hi[iq - shift] = float(q_max[iq] + check_tol)
     prob.safety_break = 1 if safety_break else 0
-    return (cfg[0] if cfg else None), (vel[0] if vel else None)
+    return acc[0] if prob.acc_enabled else None
+
+
+class _TargetLayout:
+    """Places targets either in ``PkProblemDesc.shared`` (one value for all
+    instances) or in the per-instance ``targets`` row."""
+
+    def __init__(self, prob, batch_size: int):
+        self.prob, self.B = prob, batch_size
+        self.shared_off = 0
+        self.inst_off = 0
+        self.inst_parts: List[torch.Tensor] = []
+
+    def place(self, tgt, owner) -> Tuple[int, int]:
+        """-> (offset, shared flag)."""
+        if isinstance(tgt, torch.Tensor):
+            if tgt.shape[0] != self.B:
+                raise PinkError(
+                    f"{owner!r} has {tgt.shape[0]} per-instance targets but the configuration holds {self.B} instances"
+                )
+            off = self.inst_off
+            self.inst_parts.append(tgt)
+            self.inst_off += tgt.shape[1]
+            return off, 0
+        flat = np.asarray(tgt, dtype=np.float64).reshape(-1)
+        if self.shared_off + flat.size > _cabi.PK_MAX_SHARED:
+            raise PinkError("too many shared task targets for one solve")
+        off = self.shared_off
+        for i, x in enumerate(flat):
+            self.prob.shared[off + i] = float(x)
+        self.shared_off += flat.size
+        return off, 1
+
+
+def _fill_task(td, task, d, layout: _TargetLayout, extra: List[float]) -> None:
+    td.type, td.frame, td.root = d["type"], d["frame"], d["root"]
+    for i in range(6):
+        c = float(d["cost6"][i])
+        if c < 0.0:
+            raise PinkError(f"negative cost in {task!r}")
+        td.cost[i] = c
+    td.gain = float(task.gain)
+    td.lm_damping = float(task.lm_damping)
+    td.rows = int(d.get("rows", 0))
+    td.data_offset = 0
+    if "data" in d:
+        td.data_offset = len(extra)
+        extra.extend(float(x) for x in d["data"])
+    tgt = d["target"]
+    if isinstance(tgt, torch.Tensor) or np.size(tgt) > 0:
+        td.target_offset, td.target_shared = layout.place(tgt, task)
+    else:
+        td.target_offset, td.target_shared = 0, 1
+
+
+def _fill_barrier(bd, barrier, d, dt_gain: bool, extra: List[float], pairs: List[int]) -> None:
+    bd.type = d["type"]
+    bd.frame = int(d.get("frame", 0))
+    bd.frame2 = int(d.get("frame2", 0))
+    bd.dim = int(d["dim"])
+    bd.d_min = float(d.get("d_min", 0.0))
+    gain = np.asarray(d["gain"], dtype=np.float64).reshape(-1)
+    if bd.type == _cabi.PK_BARRIER_POSITION:
+        idx = d["indices"]
+        bd.nidx = len(idx)
+        for k, i in enumerate(idx):
+            bd.indices[k] = int(i)
+        bd.has_min = 0 if d["p_min"] is None else 1
+        bd.has_max = 0 if d["p_max"] is None else 1
+        for k in range(len(idx)):
+            bd.p_min[k] = 0.0 if d["p_min"] is None else float(d["p_min"][k])
+            bd.p_max[k] = 0.0 if d["p_max"] is None else float(d["p_max"][k])
+        if gain.size != bd.dim:
+            raise PinkError(f"{barrier!r}: gain has {gain.size} entries for {bd.dim} rows")
+        for k in range(bd.dim):
+            bd.gain[k] = float(gain[k]) if dt_gain else 1.0
+    else:
+        bd.gain[0] = float(gain[0]) if dt_gain else 1.0
+    bd.safe_displacement_gain = float(barrier.safe_displacement_gain) if dt_gain else 0.0
+    bd.gain_function = int(barrier.gain_function_id) if dt_gain else _cabi.PK_GAINFN_IDENTITY
+    if bd.type == _cabi.PK_BARRIER_SELF_COLLISION:
+        pr = np.asarray(d["pairs"], dtype=np.int32).reshape(-1, 2)
+        rd = np.asarray(d["radii"], dtype=np.float64).reshape(-1, 2)
+        if pr.shape[0] > _cabi.PK_MAX_PAIRS:
+            raise PinkError(f"at most {_cabi.PK_MAX_PAIRS} collision pairs, got {pr.shape[0]}")
+        bd.npairs = pr.shape[0]
+        bd.pair_offset = len(pairs) // 2
+        bd.data_offset = len(extra)
+        pairs.extend(int(x) for x in pr.reshape(-1))
+        extra.extend(float(x) for x in rd.reshape(-1))
 
 
 def describe_problem(model, batch_size: int, tasks: Iterable, dt: float, damping: float, limits,
-                     safety_break: bool):
-    """Fill a ``PkProblemDesc`` from reference-style task / limit objects.
+                     safety_break: bool, barriers=None, constraints=None, collision_model=None,
+                     raw_barriers: bool = False):
+    """Fill a ``PkProblemDesc`` from reference-style task / limit / barrier objects.
 
     Pure host code (no device access).  Returns ``(prob, parts, descs)`` where
     ``parts`` lists the per-instance target tensors in the order they must be
     concatenated along dim 1 to form the ``targets`` argument of the C-ABI.
-    ``limits`` must already be a list (see :func:`_default_limits`)."""
+    ``limits`` must already be a list (see :func:`_default_limits`).
+    ``raw_barriers`` describes barriers with unit gains, the identity class-K
+    function and no objective term (used to export ``h`` and ``J_h`` themselves)."""
     B = batch_size
     tasks = list(tasks)
+    barriers = list(barriers) if barriers else []
+    constraints = list(constraints) if constraints else []
     if len(tasks) > _cabi.PK_MAX_TASKS:
         raise PinkError(f"at most {_cabi.PK_MAX_TASKS} tasks per solve, got {len(tasks)}")
+    if len(barriers) > _cabi.PK_MAX_BARRIERS:
+        raise PinkError(f"at most {_cabi.PK_MAX_BARRIERS} barriers per solve, got {len(barriers)}")
+    if len(constraints) > _cabi.PK_MAX_CONSTRAINTS:
+        raise PinkError(f"at most {_cabi.PK_MAX_CONSTRAINTS} equality-constraint tasks per solve, got {len(constraints)}")
     prob = _cabi.PkProblemDesc()
     prob.ntasks = len(tasks)
     prob.dt = float(dt)
     prob.damping = float(damping)
+    layout = _TargetLayout(prob, B)
+    extra: List[float] = []
+    pairs: List[int] = []
     descs = [t._pk_describe(model) for t in tasks]
-    shared_off = 0
-    inst_parts: List[torch.Tensor] = []
-    inst_off = 0
     for k, (task, d) in enumerate(zip(tasks, descs)):
-        td = prob.tasks[k]
-        td.type, td.frame, td.root = d["type"], d["frame"], d["root"]
-        for i in range(6):
-            c = float(d["cost6"][i])
-            if c < 0.0:
-                raise PinkError(f"negative cost in {task!r}")
-            td.cost[i] = c
-        td.gain = float(task.gain)
-        td.lm_damping = float(task.lm_damping)
-        tgt = d["target"]
-        if isinstance(tgt, torch.Tensor):
-            if tgt.shape[0] != B:
-                raise PinkError(
-                    f"{task!r} has {tgt.shape[0]} per-instance targets but the configuration holds {B} instances"
-                )
-            td.target_shared = 0
-            td.target_offset = inst_off
-            inst_parts.append(tgt)
-            inst_off += tgt.shape[1]
-        else:
-            flat = np.asarray(tgt, dtype=np.float64).reshape(-1)
-            if shared_off + flat.size > _cabi.PK_MAX_SHARED:
-                raise PinkError("too many shared task targets for one solve")
-            td.target_shared = 1
-            td.target_offset = shared_off
-            for i, x in enumerate(flat):
-                prob.shared[shared_off + i] = float(x)
-            shared_off += flat.size
-    prob.target_stride = inst_off
-    _fill_limits(prob, model, limits, safety_break)
-    return prob, inst_parts, descs
+        _fill_task(prob.tasks[k], task, d, layout, extra)
+    prob.nconstraints = len(constraints)
+    for k, task in enumerate(constraints):
+        d = task._pk_describe(model)
+        if d["type"] in (_cabi.PK_TASK_POSTURE, _cabi.PK_TASK_JOINT_VELOCITY):
+            raise NotImplementedError(f"{task!r} cannot be used as an equality constraint on the CUDA engine")
+        _fill_task(prob.constraints[k], task, d, layout, extra)
+    prob.nbarriers = len(barriers)
+    for k, barrier in enumerate(barriers):
+        from .barriers import SelfCollisionBarrier
+
+        d = (barrier._pk_describe(model, collision_model) if isinstance(barrier, SelfCollisionBarrier)
+             else barrier._pk_describe(model))
+        _fill_barrier(prob.barriers[k], barrier, d, not raw_barriers, extra, pairs)
+    acc = _fill_limits(prob, model, limits, safety_break)
+    if acc is not None:
+        prev = acc.Delta_q_prev
+        if isinstance(prev, torch.Tensor) or np.any(np.asarray(prev) != 0.0):
+            prob.acc_prev_offset, prob.acc_prev_shared = layout.place(prev, acc)
+    prob.target_stride = layout.inst_off
+    # constant data referenced by pointer: keep the arrays alive with the descriptor
+    extra_np = np.ascontiguousarray(extra, dtype=np.float32)
+    pairs_np = np.ascontiguousarray(pairs, dtype=np.int32)
+    prob._keepalive = (extra_np, pairs_np)
+    prob.n_extra = int(extra_np.size)
+    prob.n_pairs = int(pairs_np.size // 2)
+    prob.extra = extra_np.ctypes.data_as(C.POINTER(C.c_float)) if extra_np.size else None
+    prob.pairs = pairs_np.ctypes.data_as(C.POINTER(C.c_int32)) if pairs_np.size else None
+    return prob, layout.inst_parts, descs
 
 
-def _pack_problem(configuration, tasks: Iterable, dt: float, damping: float, limits, safety_break: bool):
+def _pack_problem(configuration, tasks: Iterable, dt: float, damping: float, limits, safety_break: bool,
+                  barriers=None, constraints=None, raw_barriers: bool = False):
     """-> (PkProblemDesc, per-instance targets tensor on the device or None, task descriptions)."""
     prob, inst_parts, descs = describe_problem(
         configuration.model, configuration.batch_size, tasks, dt, damping,
-        _default_limits(configuration, limits), safety_break,
+        _default_limits(configuration, limits), safety_break, barriers, constraints,
+        getattr(configuration, "collision_model", None), raw_barriers,
     )
     targets = None
     if inst_parts:
@@ -161,13 +280,6 @@ def _pack_problem(configuration, tasks: Iterable, dt: float, damping: float, lim
         # a single per-instance target is used in place (no copy, no extra traffic)
         targets = parts[0].contiguous() if len(parts) == 1 else torch.cat(parts, dim=1).contiguous()
     return prob, targets, descs
-
-
-def _reject_unsupported(barriers, constraints) -> None:
-    if barriers:
-        raise NotImplementedError("barriers are outside the scope of this engine (SURVEY section 8: config 4 only)")
-    if constraints:
-        raise NotImplementedError("equality constraints are a SURVEY section 8(f) 'next' row, not provided yet")
 
 
 # ---------------------------------------------------------------------------
@@ -191,19 +303,67 @@ def _task_objective(configuration, task):
     return _unbatch(configuration, H), _unbatch(configuration, c)
 
 
-def _rows_from_h(configuration, limits: Sequence[Limit], h4: torch.Tensor):
-    """Stack ``(G, h)`` in list order from the kernel's per-coordinate rows."""
-    G_list, h_list = [], []
+def _acc_rows_for(configuration, limit: AccelerationLimit, dt: float):
+    """``h`` of one AccelerationLimit alone: its box, read back from the kernel."""
+    prob, targets, _ = _pack_problem(configuration, [], dt, 0.0, [limit], False)
+    _, _, _, _, lo, hi = configuration.engine.constraint_rows(prob, configuration.q_device, targets)
+    idx = torch.as_tensor(np.asarray(limit.indices), device=lo.device, dtype=torch.long)
+    return torch.cat([hi.index_select(1, idx), -lo.index_select(1, idx)], dim=1)
+
+
+def _stack_inequalities(configuration, limits: Sequence[Limit], barriers, dt: float, h4: torch.Tensor, rows):
+    """``(G, h)`` in the reference's order (``solve_ik.py:109-122``): limits in
+    list order, then barriers.  ``G`` is ``[m, nv]`` numpy when every row is the
+    same for all instances (box limits only), else a ``[B, m, nv]`` tensor."""
+    G_const, h_list, dense = [], [], []
+    Gd, hd = (rows[0], rows[1]) if rows is not None else (None, None)
+    cursor = 0
+    nv = configuration.model.nv
     for limit in limits:
+        if limit is None:
+            continue
+        if isinstance(limit, FloatingBaseVelocityLimit):
+            n = 2 * int(np.isfinite(limit.twist_max).sum())
+            if n == 0:
+                continue
+            dense.append((len(G_const), Gd[:, cursor:cursor + n]))
+            G_const.append(None)
+            h_list.append(hd[:, cursor:cursor + n])
+            cursor += n
+            continue
         if limit.projection_matrix is None:
             continue
         idx = torch.as_tensor(np.asarray(limit.indices), device=h4.device, dtype=torch.long)
-        base = 0 if isinstance(limit, ConfigurationLimit) else 2
-        G_list.append(np.vstack([limit.projection_matrix, -limit.projection_matrix]))
-        h_list.append(torch.cat([h4[:, base].index_select(1, idx), h4[:, base + 1].index_select(1, idx)], dim=1))
-    if not G_list:
+        G_const.append(np.vstack([limit.projection_matrix, -limit.projection_matrix]))
+        if isinstance(limit, AccelerationLimit):
+            h_list.append(_acc_rows_for(configuration, limit, dt))
+        else:
+            base = 0 if isinstance(limit, ConfigurationLimit) else 2
+            h_list.append(torch.cat([h4[:, base].index_select(1, idx), h4[:, base + 1].index_select(1, idx)], dim=1))
+    for barrier in barriers or []:
+        n = barrier.dim
+        dense.append((len(G_const), Gd[:, cursor:cursor + n]))
+        G_const.append(None)
+        h_list.append(hd[:, cursor:cursor + n])
+        cursor += n
+    if not G_const:
         return None, None
-    return np.vstack(G_list), torch.cat(h_list, dim=1)
+    h = torch.cat(h_list, dim=1)
+    if not dense:
+        return np.vstack(G_const), h
+    B = h.shape[0]
+    blocks = []
+    for k, g in enumerate(G_const):
+        if g is None:
+            blocks.append(dict(dense)[k])
+        else:
+            blocks.append(torch.as_tensor(g, device=h.device, dtype=torch.float32).unsqueeze(0).expand(B, -1, -1))
+    return torch.cat(blocks, dim=1), h
+
+
+def _rows_from_h(configuration, limits: Sequence[Limit], h4: torch.Tensor):
+    """Stack ``(G, h)`` of box limits in list order from the kernel's per-coordinate rows."""
+    return _stack_inequalities(configuration, limits, None, 1.0, h4, None)
 
 
 def _limit_rows(configuration, limits: Sequence[Limit], dt: float):
@@ -213,6 +373,31 @@ def _limit_rows(configuration, limits: Sequence[Limit], dt: float):
     if G is None:
         return None
     return G, _unbatch(configuration, h)
+
+
+def _acceleration_rows(configuration, limit: AccelerationLimit, dt: float):
+    G = np.vstack([limit.projection_matrix, -limit.projection_matrix])
+    return G, _unbatch(configuration, _acc_rows_for(configuration, limit, dt))
+
+
+def _dense_limit_rows(configuration, limit: FloatingBaseVelocityLimit, dt: float):
+    prob, targets, _ = _pack_problem(configuration, [], dt, 0.0, [limit], False)
+    G, hG, _, _, _, _ = configuration.engine.constraint_rows(prob, configuration.q_device, targets)
+    n = 2 * int(np.isfinite(limit.twist_max).sum())
+    return _unbatch(configuration, G[:, :n]), _unbatch(configuration, hG[:, :n])
+
+
+def _barrier_rows(configuration, barrier, raw: bool, dt: float = 1.0):
+    """``(G, h)`` of one barrier; ``raw``: ``(-J_h, h(q))`` (unit gains, dt = 1)."""
+    prob, targets, _ = _pack_problem(configuration, [], 1.0 if raw else dt, 0.0, [], False, [barrier], None, raw)
+    G, hG, _, _, _, _ = configuration.engine.constraint_rows(prob, configuration.q_device, targets)
+    return _unbatch(configuration, G[:, :barrier.dim]), _unbatch(configuration, hG[:, :barrier.dim])
+
+
+def _barrier_objective(configuration, barrier):
+    prob, targets, _ = _pack_problem(configuration, [], 1.0, 0.0, [], False, [barrier])
+    H, c, _ = configuration.engine.build_ik(prob, configuration.q_device, targets)
+    return _unbatch(configuration, H), _unbatch(configuration, c)
 
 
 # ---------------------------------------------------------------------------
@@ -231,21 +416,37 @@ def build_ik(
 ) -> Problem:
     r"""Build the quadratic program of every instance (``solve_ik.py:152-203``).
 
-    Returns ``Problem(P, q, G, h, None, None)``: ``P [B, nv, nv]``, ``q [B, nv]``
-    and ``h [B, m]`` are device tensors (numpy without the batch dimension for a
-    single configuration); ``G [m, nv]`` is the same for all instances.
-    ``G`` and ``h`` are ``None`` when there is no inequality (``:120-121``).
+    Returns ``Problem(P, q, G, h, A, b)``: ``P [B, nv, nv]``, ``q [B, nv]`` and
+    ``h [B, m]`` are device tensors (numpy without the batch dimension for a
+    single configuration).  ``G [m, nv]`` is one numpy matrix when all rows are
+    box rows (the same for every instance) and a ``[B, m, nv]`` tensor as soon as
+    barriers or a floating-base limit add instance-dependent rows.  ``A, b`` are the
+    equality rows of ``constraints`` (``None`` without).  ``G`` and ``h`` are
+    ``None`` when there is no inequality (``:120-121``).
     """
-    _reject_unsupported(barriers, constraints)
     lims = _default_limits(configuration, limits)
-    prob, targets, _ = _pack_problem(configuration, tasks, dt, damping, lims, False)
+    barriers = list(barriers) if barriers else []
+    constraints = list(constraints) if constraints else []
+    prob, targets, _ = _pack_problem(configuration, tasks, dt, damping, lims, False, barriers, constraints)
     H, c, h4 = configuration.engine.build_ik(prob, configuration.q_device, targets)
-    G, h = _rows_from_h(configuration, lims, h4)
+    rows = None
+    A = b = None
+    if barriers or constraints or any(isinstance(l, FloatingBaseVelocityLimit) for l in lims):
+        rows = configuration.engine.constraint_rows(prob, configuration.q_device, targets)
+        if constraints:
+            meq = sum(t._pk_describe(configuration.model)["k"] for t in constraints)
+            A = _unbatch(configuration, rows[2][:, :meq])
+            b = _unbatch(configuration, rows[3][:, :meq])
+    G, h = _stack_inequalities(configuration, lims, barriers, dt, h4, rows)
+    if isinstance(G, torch.Tensor):
+        G = _unbatch(configuration, G)
     return Problem(
         _unbatch(configuration, H),
         _unbatch(configuration, c),
         G,
         None if h is None else _unbatch(configuration, h),
+        A,
+        b,
     )
 
 
@@ -288,7 +489,9 @@ def solve_ik(
 
     Args:
         configuration: :class:`pink_b200.Configuration` holding ``B`` instances.
-        tasks, dt, damping, limits, safety_break: as in the reference.
+        tasks, dt, damping, limits, barriers, constraints, safety_break: as in the
+            reference (``barriers``: :mod:`pink_b200.barriers`; ``constraints``:
+            tasks enforced as equalities ``J dq = -gain e``).
         solver: accepted for signature compatibility; the QP is solved inside
             the CUDA kernel (parity target: ``"quadprog"``).
         return_status: batched extension. When true, return ``(v, status)``
@@ -302,8 +505,7 @@ def solve_ik(
         Velocity ``v = dq / dt``: ``[B, nv]`` device tensor, or ``[nv]`` numpy for
         a single (1-D) configuration.
     """
-    _reject_unsupported(barriers, constraints)
-    prob, targets, _ = _pack_problem(configuration, tasks, dt, damping, limits, safety_break)
+    prob, targets, _ = _pack_problem(configuration, tasks, dt, damping, limits, safety_break, barriers, constraints)
     v, status = configuration.engine.solve_ik(prob, configuration.q_device, targets, v=out)
     if return_status:
         return (v, status) if configuration.batched else (v[0], status[0])

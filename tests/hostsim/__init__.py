@@ -96,6 +96,21 @@ class HostSim:
         self._chk(lib().hs_build_ik(self.handle, C.byref(prob), _p(q), _p(t), _p(H), _p(c), _p(h), C.c_int64(B)))
         return H, c, h
 
+    def constraint_rows(self, prob, q, targets=None):
+        """(G, hG, E, f, lo, hi) of every instance (pk_constraint_rows_batched)."""
+        q = self._f32(q)
+        B = q.shape[0]
+        t = None if targets is None else self._f32(targets)
+        G = np.zeros((B, _cabi.PK_MAX_INEQ_ROWS, self.nv), dtype=np.float32)
+        hG = np.zeros((B, _cabi.PK_MAX_INEQ_ROWS), dtype=np.float32)
+        E = np.zeros((B, _cabi.PK_MAX_EQ_ROWS, self.nv), dtype=np.float32)
+        f = np.zeros((B, _cabi.PK_MAX_EQ_ROWS), dtype=np.float32)
+        lo = np.zeros((B, self.nv), dtype=np.float32)
+        hi = np.zeros((B, self.nv), dtype=np.float32)
+        self._chk(lib().hs_constraint_rows(self.handle, C.byref(prob), _p(q), _p(t), _p(G), _p(hG), _p(E), _p(f),
+                                           _p(lo), _p(hi), C.c_int64(B)))
+        return G, hG, E, f, lo, hi
+
     def task_terms(self, prob, task_index, k, q, targets=None):
         q = self._f32(q)
         B = q.shape[0]

@@ -39,7 +39,15 @@ void run_chain(const pk::HostModel& hm, const pk::DevProblem& P, const float* q,
 struct Args {
   const float* q; const float* targets; float* v; int32_t* status; float* H; float* c; float* h;
   float* e; float* J; int task_index; int task_k; float* oMf; float* com; float* Jf; int jac_frame;
+  float* G; float* hG; float* E; float* f; float* lo; float* hi;
 };
+
+// make_dev_problem + host image of the optional parts, wired through P.ext
+std::string make_problem(const pk::HostModel& hm, const PkProblemDesc* prob, pk::DevProblem* P, pk::HostExtras* hx) {
+  const std::string e = pk::make_dev_problem(hm, prob, P, hx);
+  if (e.empty() && hx->present) P->ext = &hx->X;
+  return e;
+}
 
 void run_generic(const pk::HostModel& hm, const pk::DevProblem& P, const Args& A, int64_t B) {
   const pk::DevModel M = hm.host_view();
@@ -59,6 +67,12 @@ void run_generic(const pk::HostModel& hm, const pk::DevProblem& P, const Args& A
     out.com = A.com ? A.com + i * 3 : nullptr;
     out.Jf = A.Jf ? A.Jf + i * 6 * nv : nullptr;
     out.jac_frame = A.jac_frame;
+    out.G = A.G ? A.G + i * PK_MAX_INEQ_ROWS * nv : nullptr;
+    out.hG = A.hG ? A.hG + i * PK_MAX_INEQ_ROWS : nullptr;
+    out.E = A.E ? A.E + i * PK_MAX_EQ_ROWS * nv : nullptr;
+    out.f = A.f ? A.f + i * PK_MAX_EQ_ROWS : nullptr;
+    out.lo = A.lo ? A.lo + i * nv : nullptr;
+    out.hi = A.hi ? A.hi + i * nv : nullptr;
     G.step(M, P, A.q + i * M.nq, A.targets ? A.targets + i * (int64_t)P.target_stride : nullptr, out);
   }
 }
@@ -82,9 +96,10 @@ int hs_solve_ik(void* model, const PkProblemDesc* prob, const float* q, const fl
                 int32_t* status, int64_t B, int path, int* used_chain) {
   const pk::HostModel& hm = *(pk::HostModel*)model;
   pk::DevProblem P;
-  const std::string e = pk::make_dev_problem(hm, prob, &P);
+  pk::HostExtras hx;
+  const std::string e = make_problem(hm, prob, &P, &hx);
   if (!e.empty()) return fail(e);
-  const bool chain = path == 0 && pk::chain_eligible(hm, P);
+  const bool chain = path == 0 && pk::chain_eligible(hm, P, hx.present);
   if (used_chain) *used_chain = chain ? 1 : 0;
   if (chain) {
     switch (hm.njoints) {
@@ -99,7 +114,7 @@ int hs_solve_ik(void* model, const PkProblemDesc* prob, const float* q, const fl
   if (path == 2 || (path == 0 && !chain)) {
     bool ok = false;
     const pk::TreePlan L = pk::make_tree_plan(hm, P, &ok);
-    if (ok) {
+    if (ok && !hx.present) {
       if (used_chain) *used_chain = 2;
       const pk::DevModel M = hm.host_view();
       std::vector<float> W(L.words);
@@ -120,10 +135,24 @@ int hs_build_ik(void* model, const PkProblemDesc* prob, const float* q, const fl
                 float* h, int64_t B) {
   const pk::HostModel& hm = *(pk::HostModel*)model;
   pk::DevProblem P;
-  const std::string e = pk::make_dev_problem(hm, prob, &P);
+  pk::HostExtras hx;
+  const std::string e = make_problem(hm, prob, &P, &hx);
   if (!e.empty()) return fail(e);
   Args A{};
   A.q = q; A.targets = targets; A.H = H; A.c = c; A.h = h; A.task_index = -1;
+  run_generic(hm, P, A, B);
+  return 0;
+}
+
+int hs_constraint_rows(void* model, const PkProblemDesc* prob, const float* q, const float* targets, float* G,
+                       float* hG, float* E, float* f, float* lo, float* hi, int64_t B) {
+  const pk::HostModel& hm = *(pk::HostModel*)model;
+  pk::DevProblem P;
+  pk::HostExtras hx;
+  const std::string e = make_problem(hm, prob, &P, &hx);
+  if (!e.empty()) return fail(e);
+  Args A{};
+  A.q = q; A.targets = targets; A.G = G; A.hG = hG; A.E = E; A.f = f; A.lo = lo; A.hi = hi; A.task_index = -1;
   run_generic(hm, P, A, B);
   return 0;
 }
@@ -132,13 +161,16 @@ int hs_task_terms(void* model, const PkProblemDesc* prob, int task_index, const 
                   float* eo, float* J, int64_t B) {
   const pk::HostModel& hm = *(pk::HostModel*)model;
   pk::DevProblem P;
-  const std::string e = pk::make_dev_problem(hm, prob, &P);
+  pk::HostExtras hx;
+  const std::string e = make_problem(hm, prob, &P, &hx);
   if (!e.empty()) return fail(e);
   if (task_index < 0 || task_index >= P.ntasks) return fail("task_index out of range");
   Args A{};
   A.q = q; A.targets = targets; A.e = eo; A.J = J; A.task_index = task_index;
   const int type = P.tasks[task_index].type;
-  A.task_k = type == PK_TASK_COM ? 3 : (pk::is_diag_task(type) ? hm.nv - (hm.free_flyer ? 6 : 0) : 6);
+  A.task_k = type == PK_TASK_COM ? 3
+             : type == PK_TASK_LINEAR ? P.tasks[task_index].rows
+                                      : (pk::is_diag_task(type) ? hm.nv - (hm.free_flyer ? 6 : 0) : 6);
   run_generic(hm, P, A, B);
   return 0;
 }

@@ -26,18 +26,24 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     lib.pk_abi_version.restype = ctypes.c_int
-    assert lib.pk_abi_version() == 1
+    assert lib.pk_abi_version() == _cabi.PK_ABI_VERSION == 2
 
 
 def test_struct_layouts_match_the_header_constants():
     with open(os.path.join(ROOT, "include", "pink_b200.h")) as fh:
         text = fh.read()
-    for name in ["PK_MAX_JOINTS", "PK_MAX_NV", "PK_MAX_FRAMES", "PK_MAX_TASKS", "PK_MAX_SHARED"]:
+    for name in ["PK_MAX_JOINTS", "PK_MAX_NV", "PK_MAX_FRAMES", "PK_MAX_TASKS", "PK_MAX_SHARED", "PK_MAX_INEQ_ROWS",
+                 "PK_MAX_EQ_ROWS", "PK_MAX_BARRIERS", "PK_MAX_CONSTRAINTS", "PK_MAX_PAIRS", "PK_ABI_VERSION"]:
         value = int(re.search(rf"#define {name} (\d+)", text).group(1))
         assert getattr(_cabi, name) == value
-    # sizeof(PkProblemDesc): 4 + 12*52 + 4*4 + 4 + 5*64*4 + 192*4
-    assert ctypes.sizeof(_cabi.PkTaskDesc) == 52
-    assert ctypes.sizeof(_cabi.PkProblemDesc) == 4 + 12 * 52 + 16 + 4 + 5 * 64 * 4 + 192 * 4
+    # the ctypes mirrors have the sizes the compiler gave the C structs
+    import __graft_entry__
+
+    __graft_entry__.build()
+    lib = ctypes.CDLL(_cabi.library_path())
+    for which, struct in enumerate((_cabi.PkModelDesc, _cabi.PkTaskDesc, _cabi.PkBarrierDesc, _cabi.PkProblemDesc)):
+        assert lib.pk_struct_size(which) == ctypes.sizeof(struct), struct.__name__
+    assert ctypes.sizeof(_cabi.PkTaskDesc) == 60
 
 
 def test_compute_without_gpu_fails_loudly():

@@ -1,0 +1,101 @@
+"""CPU suite: barriers, equality constraints, opt-in limits and constant-Jacobian
+tasks through the kernel body of the general path (fp32, host build) against the
+fp64 oracle."""
+
+import numpy as np
+
+from pink_b200 import _cabi
+from tests import extras, helpers
+from tests.hostsim import HostSim
+
+
+def _check_rows(sc, hs, prob, targets, n):
+    G, hG, E, f, lo, hi = hs.constraint_rows(prob, sc.q32[:n], None if targets is None else targets[:n])
+    H32, c32, _ = hs.build_ik(prob, sc.q32[:n], None if targets is None else targets[:n])
+    nv = sc.table.nv
+    for i in range(n):
+        H, c, Go, ho, A, b = sc.oracle_assemble(i)
+        # objective (barrier safe-displacement terms included)
+        assert np.abs(H32[i] - H).max() <= 2e-4 * np.abs(H).max()
+        assert np.abs(c32[i] - c).max() <= 2e-4 * (np.abs(c).max() + 1e-3)
+        # dense rows = the oracle rows that are not +-e_i, in order
+        dense = [r for r in range(Go.shape[0]) if np.count_nonzero(Go[r]) != 1 or abs(abs(Go[r]).max() - 1.0) > 1e-12]
+        p = len(dense)
+        if sc.obarriers and sc.obarriers[-1]["type"] == "self_collision":
+            # closest-pair rows may come in any order: compare as sorted by right-hand side
+            k = sc.obarriers[-1]["n_pairs"]
+            head, tail = dense[: p - k], dense[p - k:]
+            order_o = list(head) + [tail[j] for j in np.argsort(ho[tail], kind="stable")]
+            order_k = list(range(p - k)) + [p - k + j for j in np.argsort(hG[i, p - k:p], kind="stable")]
+        else:
+            order_o, order_k = dense, list(range(p))
+        assert np.isinf(hG[i, p:]).all() and not G[i, p:].any()
+        scale = np.abs(Go[order_o]).max() + 1e-9
+        assert np.abs(G[i, order_k] - Go[order_o]).max() <= 5e-4 * scale, i
+        assert np.abs(hG[i, order_k] - ho[order_o]).max() <= 5e-4 * (np.abs(ho[order_o]).max() + 1e-3), i
+        if A is not None:
+            m = A.shape[0]
+            assert np.abs(E[i, :m] - A).max() <= 1e-5 and np.abs(f[i, :m] - b).max() <= 1e-5
+        # box = intersection of all +-e_i rows
+        hi_o = np.full(nv, np.inf)
+        lo_o = np.full(nv, -np.inf)
+        for r in range(Go.shape[0]):
+            if r in dense:
+                continue
+            j = int(np.nonzero(Go[r])[0][0])
+            if Go[r, j] > 0:
+                hi_o[j] = min(hi_o[j], ho[r])
+            else:
+                lo_o[j] = max(lo_o[j], -ho[r])
+        fin = np.isfinite(hi_o)
+        assert np.abs(hi[i][fin] - hi_o[fin]).max() <= 1e-6 and np.abs(lo[i][fin] - lo_o[fin]).max() <= 1e-6
+
+
+def test_ur5_rows_match_oracle():
+    sc = extras.ur5_extras(24)
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    _check_rows(sc, hs, prob, targets, 24)
+
+
+def test_ur5_barriers_constraints_limits_match_oracle():
+    sc = extras.ur5_extras(300)
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v, st = hs.solve_ik(prob, sc.q32, targets)
+    assert not hs.used_chain and not hs.used_tree
+    v_ref, st_ref = sc.oracle_solve()
+    feasible = st_ref == 0
+    # infeasible QPs (barrier already violated and unreachable within the velocity box) are flagged alike
+    assert ((st & _cabi.PK_STATUS_NO_SOLUTION) != 0)[~feasible].all()
+    assert (st[feasible] == 0).all()
+    assert feasible.mean() > 0.5
+    ok = helpers.within_tolerance(v[feasible], v_ref[feasible])
+    assert ok.all(), f"{(~ok).sum()} of {feasible.sum()} off, worst {np.abs(v - v_ref)[feasible].max()}"
+    # the barrier rows matter: the same problem without them moves differently
+    sc2 = extras.ur5_extras(300, active=False)
+    v2_ref, _ = sc2.oracle_solve(60)
+    assert np.abs(v2_ref - v_ref[:60])[feasible[:60]].max() > 1e-2
+
+
+def test_g1_rows_match_oracle():
+    sc = extras.g1_extras(6)
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    _check_rows(sc, hs, prob, targets, 6)
+
+
+def test_g1_self_collision_barrier_config_matches_oracle():
+    """Config 4 of BASELINE.json: G1-class humanoid, CoM + frame tasks + sphere
+    self-collision barrier (+ floating-base limit and a joint coupling task)."""
+    sc = extras.g1_extras(40)
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v, st = hs.solve_ik(prob, sc.q32, targets)
+    assert not hs.used_tree
+    v_ref, st_ref = sc.oracle_solve()
+    feasible = st_ref == 0
+    assert feasible.mean() > 0.8
+    assert (st[feasible] == 0).all()
+    ok = helpers.within_tolerance(v[feasible], v_ref[feasible])
+    assert ok.all(), f"{(~ok).sum()} off, worst {np.abs(v - v_ref)[feasible].max()}"

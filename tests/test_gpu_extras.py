@@ -1,0 +1,144 @@
+"""GPU suite (`-m gpu`): barriers, equality constraints, the opt-in limits and the
+constant-Jacobian tasks through the public Python API and the C-ABI, against the
+fp64 oracle (the CPU twins are in test_hostsim_extras.py)."""
+
+import numpy as np
+import pytest
+import torch
+
+import pink_b200
+from oracle import barriers as obar
+from oracle import kinematics as okin
+from pink_b200 import _cabi
+from tests import extras, helpers
+
+pytestmark = pytest.mark.gpu
+
+DEVICE = "cuda"  # test_api_extras_host.py re-runs these bodies on the host build with DEVICE = "cpu"
+
+
+def _sync():
+    if DEVICE == "cuda":
+        torch.cuda.synchronize()
+
+
+def _cfg(sc):
+    return pink_b200.Configuration(sc.model, None, torch.as_tensor(sc.q32, device=DEVICE),
+                                   collision_model=sc.collision_model)
+
+
+def _solve(sc):
+    v, st = pink_b200.solve_ik(_cfg(sc), sc.tasks, sc.dt, solver="quadprog", damping=sc.damping, limits=sc.limits,
+                               barriers=sc.barriers, constraints=sc.constraints, safety_break=sc.safety_break,
+                               return_status=True)
+    _sync()
+    return v.cpu().numpy(), st.cpu().numpy()
+
+
+def test_ur5_barriers_constraints_limits_match_oracle():
+    sc = extras.ur5_extras(512)
+    v, st = _solve(sc)
+    v_ref, st_ref = sc.oracle_solve()
+    feasible = st_ref == 0
+    assert ((st & _cabi.PK_STATUS_NO_SOLUTION) != 0)[~feasible].all()
+    assert (st[feasible] == 0).all() and feasible.mean() > 0.5
+    ok = helpers.within_tolerance(v[feasible], v_ref[feasible])
+    assert ok.all(), f"{(~ok).sum()} off, worst {np.abs(v - v_ref)[feasible].max()}"
+    # the reference raises NoSolutionFound for the infeasible instances
+    with pytest.raises(pink_b200.exceptions.NoSolutionFound):
+        pink_b200.solve_ik(_cfg(sc), sc.tasks, sc.dt, damping=sc.damping, limits=sc.limits, barriers=sc.barriers,
+                           constraints=sc.constraints, safety_break=False)
+
+
+def test_g1_config4_self_collision_barrier_matches_oracle():
+    """BASELINE.json config 4: G1-class humanoid, ComTask + FrameTasks + self-collision
+    barrier (sphere pairs), plus floating-base limit and a joint coupling task."""
+    sc = extras.g1_extras(96)
+    v, st = _solve(sc)
+    v_ref, st_ref = sc.oracle_solve()
+    feasible = st_ref == 0
+    assert feasible.mean() > 0.8 and (st[feasible] == 0).all()
+    ok = helpers.within_tolerance(v[feasible], v_ref[feasible])
+    assert ok.all(), f"{(~ok).sum()} off, worst {np.abs(v - v_ref)[feasible].max()}"
+
+
+def test_gpu_agrees_with_host_build_on_the_dual_qp_path():
+    from tests.hostsim import HostSim
+
+    sc = extras.g1_extras(64)
+    v, st = _solve(sc)
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v_h, st_h = hs.solve_ik(prob, sc.q32, targets)
+    np.testing.assert_array_equal(st, st_h)
+    np.testing.assert_allclose(v, v_h, rtol=2e-3, atol=2e-4)
+
+
+def test_barrier_api_matches_oracle():
+    """Barrier.compute_barrier / compute_jacobian / compute_qp_objective /
+    compute_qp_inequalities (pink/barriers/barrier.py) and build_ik with barriers
+    and constraints (pink/solve_ik.py:152-203)."""
+    sc = extras.ur5_extras(16)
+    cfg = _cfg(sc)
+    dt = sc.dt
+    for barrier, ob in zip(sc.barriers, sc.obarriers):
+        h = barrier.compute_barrier(cfg).cpu().numpy()
+        J = barrier.compute_jacobian(cfg).cpu().numpy()
+        G, rhs = barrier.compute_qp_inequalities(cfg, dt)
+        H, c = barrier.compute_qp_objective(cfg)
+        G, rhs, H, c = (t.cpu().numpy() for t in (G, rhs, H, c))
+        for i in range(16):
+            fk = okin.forward_kinematics(sc.table, sc.q64[i])
+            h_o = obar.barrier_value(sc.table, sc.q64[i], fk, ob)
+            J_o = obar.barrier_jacobian(sc.table, sc.q64[i], fk, ob)
+            G_o, rhs_o = obar.barrier_qp_inequalities(sc.table, sc.q64[i], fk, ob, dt)
+            H_o, _ = obar.barrier_qp_objective(sc.table, sc.q64[i], fk, ob)
+            order, order_o = np.argsort(h[i], kind="stable"), np.argsort(h_o, kind="stable")
+            if ob["type"] != "self_collision":
+                order = order_o = np.arange(h_o.shape[0])
+            assert np.abs(h[i][order] - h_o[order_o]).max() < 2e-6
+            assert np.abs(J[i][order] - J_o[order_o]).max() < 1e-5
+            assert np.abs(G[i][order] - G_o[order_o]).max() < 5e-4 * (np.abs(G_o).max() + 1e-9)
+            assert np.abs(rhs[i][order] - rhs_o[order_o]).max() < 5e-5
+            assert np.abs(H[i] - H_o).max() < 2e-4 * (np.abs(H_o).max() + 1e-9) and not c[i].any()
+    problem = pink_b200.build_ik(cfg, sc.tasks, dt, damping=sc.damping, limits=sc.limits, barriers=sc.barriers,
+                                 constraints=sc.constraints)
+    P, q, G, h, A, b = (None if t is None else t.cpu().numpy() for t in problem.unpack()[:6])
+    for i in range(16):
+        H_o, c_o, G_o, h_o, A_o, b_o = sc.oracle_assemble(i)
+        assert G[i].shape == G_o.shape and h[i].shape == h_o.shape
+        nb = sum(bb.dim for bb in sc.barriers[:-1])
+        k = sc.barriers[-1].dim
+        fixed = G_o.shape[0] - k  # everything but the closest-pair rows has a fixed order
+        assert np.abs(G[i][:fixed] - G_o[:fixed]).max() < 5e-4 * np.abs(G_o).max()
+        assert np.abs(h[i][:fixed] - h_o[:fixed]).max() < 5e-5
+        assert np.abs(np.sort(h[i][fixed:]) - np.sort(h_o[fixed:])).max() < 5e-5
+        assert np.abs(A[i] - A_o).max() < 1e-5 and np.abs(b[i] - b_o).max() < 1e-5
+        assert np.abs(P[i] - H_o).max() < 2e-4 * np.abs(H_o).max()
+
+
+def test_opt_in_limits_api():
+    """FloatingBaseVelocityLimit / AccelerationLimit.compute_qp_inequalities."""
+    sc = extras.g1_extras(8)
+    cfg = _cfg(sc)
+    fb = sc.limits[2]
+    G, h = fb.compute_qp_inequalities(cfg, sc.dt)
+    G, h = G.cpu().numpy(), h.cpu().numpy()
+    assert G.shape == (8, 6, sc.table.nv) and not G[:, :, 6:].any()
+    assert np.allclose(h[0], sc.dt * np.array([0.4, 0.2, 1.0, 0.4, 0.2, 1.0]))
+    from oracle import limits as olim
+
+    for i in range(8):
+        fk = okin.forward_kinematics(sc.table, sc.q64[i])
+        G_o, h_o = olim.floating_base_velocity_rows(sc.table, fk, sc.table.frame_names.index("pelvis"),
+                                                    fb.twist_max, sc.dt)
+        assert np.abs(G[i] - G_o).max() < 1e-5
+    su = extras.ur5_extras(8)
+    cfg = _cfg(su)
+    acc = su.limits[2]
+    G, h = acc.compute_qp_inequalities(cfg, su.dt)
+    h = h.cpu().numpy()
+    for i in range(8):
+        G_o, h_o = olim.acceleration_limit_rows(su.table, su.q64[i], su.olimits[2][1], su.olimits[2][2][i], su.dt)
+        assert np.array_equal(G, G_o)
+        assert np.abs(h[i] - h_o).max() < 1e-6

@@ -108,7 +108,7 @@ class Configuration:
         """``[B, nq]`` fp32 tensor on the compute device."""
         if self._q_dev is None:
             eng = self.engine
-            self._q_dev = torch.as_tensor(self._q_host, dtype=torch.float32).to(eng.device)
+            self._q_dev = torch.tensor(self._q_host, dtype=torch.float32).to(eng.device)
             self._device = eng.device
         return self._q_dev
 

@@ -443,6 +443,14 @@ struct DualQP {
       vtol = 1e-9f;
     }
     if (status & PK_STATUS_NO_SOLUTION) return status;
+    // Inconsistent rows that fp32 data rounding has turned "consistent" meet at infinity:
+    // a displacement beyond 1e3 (rad or m, per step) on an unbounded coordinate (floating
+    // base) is reported as no solution, like the exactly inconsistent case; also traps NaN.
+    {
+      float xmax = 0.f;
+      for (int i = 0; i < n; ++i) xmax = fmaxf(xmax, fabsf(x[i]));
+      if (!(xmax < 1e3f)) return status | PK_STATUS_NO_SOLUTION;
+    }
     // coordinates on a bound sit exactly on it
     for (int i = 0; i < n; ++i) {
       if ((in_hi >> i) & 1ull) x[i] = P.hi[i];

@@ -88,7 +88,7 @@ def test_g1_rows_match_oracle():
 def test_g1_self_collision_barrier_config_matches_oracle():
     """Config 4 of BASELINE.json: G1-class humanoid, CoM + frame tasks + sphere
     self-collision barrier (+ floating-base limit and a joint coupling task)."""
-    sc = extras.g1_extras(40)
+    sc = extras.g1_extras(64)
     hs = HostSim(sc.model)
     prob, targets, _ = sc.problem()
     v, st = hs.solve_ik(prob, sc.q32, targets)
@@ -97,5 +97,7 @@ def test_g1_self_collision_barrier_config_matches_oracle():
     feasible = st_ref == 0
     assert feasible.mean() > 0.8
     assert (st[feasible] == 0).all()
+    # infeasible QPs (penetrating spheres that cannot separate within the limits) are flagged
+    assert ((st & _cabi.PK_STATUS_NO_SOLUTION) != 0)[~feasible].all() and not feasible.all()
     ok = helpers.within_tolerance(v[feasible], v_ref[feasible])
     assert ok.all(), f"{(~ok).sum()} off, worst {np.abs(v - v_ref)[feasible].max()}"

@@ -330,26 +330,43 @@ def run_gpu_arm(args):
         print(f"[bench] CUDA graph timing skipped: {exc}", file=sys.stderr)
 
     # ---- end to end through host buffers ("e2e") ---------------------------------
-    q_h = [torch.empty((B, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
-    t_h = [torch.empty((B, 12), dtype=torch.float32).pin_memory() for _ in range(2)]
-    v_h = [torch.empty((B, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
-    s_h = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
-    for i in range(2):
-        q_h[i].copy_(qs[i].cpu())
-        t_h[i].copy_(ts[i].cpu())
+    # Every step copies its inputs from pinned host memory and its results back, inside
+    # the timed region.  Steps are submitted round-robin on `--e2e-streams` CUDA streams
+    # with one pinned buffer set per stream (double buffering): step k+1's H2D overlaps
+    # step k's D2H on the full-duplex link; all streams are joined before the stop event.
+    NS = max(1, args.e2e_streams)
+    q_h = [torch.empty((B, 6), dtype=torch.float32).pin_memory() for _ in range(NS)]
+    t_h = [torch.empty((B, 12), dtype=torch.float32).pin_memory() for _ in range(NS)]
+    v_h = [torch.empty((B, 6), dtype=torch.float32).pin_memory() for _ in range(NS)]
+    s_h = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(NS)]
+    for i in range(NS):
+        q_h[i].copy_(qs[i % NBUF].cpu())
+        t_h[i].copy_(ts[i % NBUF].cpu())
+    e2e_streams = [torch.cuda.Stream(device=device) for _ in range(NS)] if NS > 1 else [torch.cuda.current_stream(device)]
 
     def e2e_step(k):
-        i = k % 2
-        ik.solve_host(q_h[i], t_h[i], v_h[i], s_h[i])
+        i = k % NS
+        with torch.cuda.stream(e2e_streams[i]):
+            ik.solve_host(q_h[i], t_h[i], v_h[i], s_h[i])
+
+    def e2e_join():
+        cur = torch.cuda.current_stream(device)
+        for st_ in e2e_streams:
+            if st_ is not cur:
+                cur.wait_stream(st_)
 
     for k in range(max(3, args.warmup)):
         e2e_step(k)
+    e2e_join()
     barrier()
     h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_steps = args.steps
     h0.record()
+    for st_ in e2e_streams:
+        st_.wait_event(h0)
     for k in range(e2e_steps):
         e2e_step(k)
+    e2e_join()
     h1.record()
     barrier()
     e2e_ms = h0.elapsed_time(h1)
@@ -406,7 +423,7 @@ def run_gpu_arm(args):
                 "value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": B * (6 + 12) * 4, "d2h_bytes_per_step": B * (6 + 1) * 4,
                 "ms_per_step": e2e_ms / e2e_steps, "bitwise_equal_to_device_path": e2e_ok,
-                "api": "BatchedIK.solve_host -> pk_solve_ik_prepared_host (pinned host buffers; mode %s)" % os.environ.get("PK_HOST_MODE", "0"),
+                "api": "BatchedIK.solve_host -> pk_solve_ik_prepared_host (pinned host buffers; mode %s; %d submission stream(s))" % (os.environ.get("PK_HOST_MODE", "0"), NS),
             },
             "nonzero_status": bad,
         }
@@ -428,6 +445,7 @@ def main():
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--nbuf", type=int, default=32)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-streams", type=int, default=1, help="CUDA streams the e2e steps are submitted on (double buffering)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -58,6 +58,10 @@ struct PkModel {
   cudaStream_t st_streams[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t st_fork = nullptr;
   cudaEvent_t st_join[3] = {nullptr, nullptr, nullptr};
+  bool st_busy = false;
+  static constexpr int kMaxChunks = 64;
+  cudaEvent_t st_in[kMaxChunks] = {};    // H2D of chunk k complete
+  cudaEvent_t st_kern[kMaxChunks] = {};  // kernel of chunk k complete
 };
 
 namespace {
@@ -177,6 +181,10 @@ extern "C" void pk_model_destroy(PkModel* m) {
     if (m->st_join[i]) cudaEventDestroy(m->st_join[i]);
   }
   if (m->st_fork) cudaEventDestroy(m->st_fork);
+  for (int i = 0; i < PkModel::kMaxChunks; ++i) {
+    if (m->st_in[i]) cudaEventDestroy(m->st_in[i]);
+    if (m->st_kern[i]) cudaEventDestroy(m->st_kern[i]);
+  }
   delete m;
 }
 
@@ -968,34 +976,82 @@ static int solve_host_impl(PkModel* m, const PkProblem& pr, const float* q_host,
       PK_CUDA(cudaEventCreateWithFlags(&m->st_join[i], cudaEventDisableTiming));
     }
   }
-  // chunks round-robin over three internal streams: the H2D of chunk k+1, the
-  // kernel of chunk k and the D2H of chunk k-1 overlap (PCIe is full duplex)
   static const int64_t chunk_env = env_int("PK_HOST_CHUNK", 32768);
-  const int64_t chunk = std::max<int64_t>(1024, chunk_env);
+  int64_t chunk = std::max<int64_t>(1024, chunk_env);
+  if ((B + chunk - 1) / chunk > PkModel::kMaxChunks) chunk = (B + PkModel::kMaxChunks - 1) / PkModel::kMaxChunks;
   const int64_t nchunks = (B + chunk - 1) / chunk;
-  const int nstreams = (int)std::min<int64_t>(3, nchunks);
+  // PK_HOST_DUPLEX=1: chunks round-robin over three internal streams, so that the H2D of
+  // chunk k+1, the kernel of chunk k and the D2H of chunk k-1 overlap.  Default (0): the
+  // two directions never overlap - all uploads on one stream, each kernel as soon as its
+  // chunk has landed (hidden behind the next upload), all downloads after the last upload.
+  // On the boxes measured, concurrent H2D + D2H run far below the sum of the one-way rates
+  // (4.7 MiB up with 1.8 MiB down: 290 us together, 125 us back to back;
+  // scripts/pcie_probe.py), so serialising the directions is the faster schedule.
+  static const int duplex = env_int("PK_HOST_DUPLEX", 0);
   PK_CUDA(cudaEventRecord(m->st_fork, stream));
-  for (int i = 0; i < nstreams; ++i) PK_CUDA(cudaStreamWaitEvent(m->st_streams[i], m->st_fork, 0));
+  if (duplex) {
+    const int nstreams = (int)std::min<int64_t>(3, nchunks);
+    for (int i = 0; i < nstreams; ++i) PK_CUDA(cudaStreamWaitEvent(m->st_streams[i], m->st_fork, 0));
+    for (int64_t k = 0; k < nchunks; ++k) {
+      cudaStream_t s = m->st_streams[k % nstreams];
+      const int64_t b0 = k * chunk;
+      const int64_t nb = std::min(chunk, B - b0);
+      PK_CUDA(cudaMemcpyAsync(m->st_q + b0 * m->nq, q_host + b0 * m->nq, sizeof(float) * nb * m->nq,
+                              cudaMemcpyHostToDevice, s));
+      if (ts > 0)
+        PK_CUDA(cudaMemcpyAsync(m->st_t + b0 * ts, targets_host + b0 * ts, sizeof(float) * nb * ts,
+                                cudaMemcpyHostToDevice, s));
+      if (solve_device(m, pr, m->st_q + b0 * m->nq, m->st_t + b0 * ts, m->st_v + b0 * m->nv, m->st_s + b0, nb, s))
+        return 1;
+      PK_CUDA(cudaMemcpyAsync(v_host + b0 * m->nv, m->st_v + b0 * m->nv, sizeof(float) * nb * m->nv,
+                              cudaMemcpyDeviceToHost, s));
+      if (status_host)
+        PK_CUDA(cudaMemcpyAsync(status_host + b0, m->st_s + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < nstreams; ++i) {
+      PK_CUDA(cudaEventRecord(m->st_join[i], m->st_streams[i]));
+      PK_CUDA(cudaStreamWaitEvent(stream, m->st_join[i], 0));
+    }
+    return 0;
+  }
+  cudaStream_t s_in = m->st_streams[0], s_k = m->st_streams[1], s_out = m->st_streams[2];
+  for (int i = 0; i < 3; ++i) PK_CUDA(cudaStreamWaitEvent(m->st_streams[i], m->st_fork, 0));
+  // calls submitted on different caller streams share the staging buffers: the next upload
+  // waits for the previous call's last download (a no-op for calls on one stream)
+  if (m->st_busy) PK_CUDA(cudaStreamWaitEvent(s_in, m->st_join[2], 0));
+  m->st_busy = true;
   for (int64_t k = 0; k < nchunks; ++k) {
-    cudaStream_t s = m->st_streams[k % nstreams];
+    if (!m->st_in[k]) {
+      PK_CUDA(cudaEventCreateWithFlags(&m->st_in[k], cudaEventDisableTiming));
+      PK_CUDA(cudaEventCreateWithFlags(&m->st_kern[k], cudaEventDisableTiming));
+    }
     const int64_t b0 = k * chunk;
     const int64_t nb = std::min(chunk, B - b0);
     PK_CUDA(cudaMemcpyAsync(m->st_q + b0 * m->nq, q_host + b0 * m->nq, sizeof(float) * nb * m->nq,
-                            cudaMemcpyHostToDevice, s));
+                            cudaMemcpyHostToDevice, s_in));
     if (ts > 0)
       PK_CUDA(cudaMemcpyAsync(m->st_t + b0 * ts, targets_host + b0 * ts, sizeof(float) * nb * ts,
-                              cudaMemcpyHostToDevice, s));
-    if (solve_device(m, pr, m->st_q + b0 * m->nq, m->st_t + b0 * ts, m->st_v + b0 * m->nv, m->st_s + b0, nb, s))
+                              cudaMemcpyHostToDevice, s_in));
+    PK_CUDA(cudaEventRecord(m->st_in[k], s_in));
+    PK_CUDA(cudaStreamWaitEvent(s_k, m->st_in[k], 0));
+    if (solve_device(m, pr, m->st_q + b0 * m->nq, m->st_t + b0 * ts, m->st_v + b0 * m->nv, m->st_s + b0, nb, s_k))
       return 1;
+    PK_CUDA(cudaEventRecord(m->st_kern[k], s_k));
+  }
+  // downloads start once the last upload is through (st_in[nchunks-1] on the in-order s_in)
+  PK_CUDA(cudaStreamWaitEvent(s_out, m->st_in[nchunks - 1], 0));
+  for (int64_t k = 0; k < nchunks; ++k) {
+    const int64_t b0 = k * chunk;
+    const int64_t nb = std::min(chunk, B - b0);
+    PK_CUDA(cudaStreamWaitEvent(s_out, m->st_kern[k], 0));
     PK_CUDA(cudaMemcpyAsync(v_host + b0 * m->nv, m->st_v + b0 * m->nv, sizeof(float) * nb * m->nv,
-                            cudaMemcpyDeviceToHost, s));
+                            cudaMemcpyDeviceToHost, s_out));
     if (status_host)
-      PK_CUDA(cudaMemcpyAsync(status_host + b0, m->st_s + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+      PK_CUDA(cudaMemcpyAsync(status_host + b0, m->st_s + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s_out));
   }
-  for (int i = 0; i < nstreams; ++i) {
-    PK_CUDA(cudaEventRecord(m->st_join[i], m->st_streams[i]));
-    PK_CUDA(cudaStreamWaitEvent(stream, m->st_join[i], 0));
-  }
+  // the caller's stream resumes when everything is back; s_in / s_k are ordered before s_out
+  PK_CUDA(cudaEventRecord(m->st_join[2], s_out));
+  PK_CUDA(cudaStreamWaitEvent(stream, m->st_join[2], 0));
   return 0;
 }
 

@@ -26,15 +26,21 @@ n = int(4.7 * 2**20 // 4)
 h1, h2 = (torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(2))
 d1, d2 = (torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2))
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(20):
-    with torch.cuda.stream(s1):
-        d1.copy_(h1, non_blocking=True)
-    with torch.cuda.stream(s2):
-        h2.copy_(d2, non_blocking=True)
-torch.cuda.synchronize()
-e1.record()
-torch.cuda.synchronize()
-print(f"duplex 4.7 MiB each way: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per pair")
+for mb_up, mb_dn in [(4.7, 4.7), (4.7, 1.8)]:
+    nu, nd = int(mb_up * 2**20 // 4), int(mb_dn * 2**20 // 4)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur = torch.cuda.current_stream()
+    e0.record()
+    s1.wait_event(e0)
+    s2.wait_event(e0)
+    for _ in range(20):
+        with torch.cuda.stream(s1):
+            d1[:nu].copy_(h1[:nu], non_blocking=True)
+        with torch.cuda.stream(s2):
+            h2[:nd].copy_(d2[:nd], non_blocking=True)
+    cur.wait_stream(s1)
+    cur.wait_stream(s2)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"duplex {mb_up} MiB up + {mb_dn} MiB down concurrently: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per pair")

@@ -307,7 +307,7 @@ def _acc_rows_for(configuration, limit: AccelerationLimit, dt: float):
     """``h`` of one AccelerationLimit alone: its box, read back from the kernel."""
     prob, targets, _ = _pack_problem(configuration, [], dt, 0.0, [limit], False)
     _, _, _, _, lo, hi = configuration.engine.constraint_rows(prob, configuration.q_device, targets)
-    idx = torch.as_tensor(np.asarray(limit.indices), device=lo.device, dtype=torch.long)
+    idx = torch.tensor(np.asarray(limit.indices), device=lo.device, dtype=torch.long)
     return torch.cat([hi.index_select(1, idx), -lo.index_select(1, idx)], dim=1)
 
 
@@ -333,7 +333,7 @@ def _stack_inequalities(configuration, limits: Sequence[Limit], barriers, dt: fl
             continue
         if limit.projection_matrix is None:
             continue
-        idx = torch.as_tensor(np.asarray(limit.indices), device=h4.device, dtype=torch.long)
+        idx = torch.tensor(np.asarray(limit.indices), device=h4.device, dtype=torch.long)
         G_const.append(np.vstack([limit.projection_matrix, -limit.projection_matrix]))
         if isinstance(limit, AccelerationLimit):
             h_list.append(_acc_rows_for(configuration, limit, dt))

@@ -27,3 +27,34 @@ def test_barrier_api_matches_oracle():
 
 def test_opt_in_limits_api():
     g.test_opt_in_limits_api()
+
+
+def test_barrier_fulfilled_and_violated_like_the_reference():
+    """tests/test_solve_ik.py:104-158 on the unbatched API: with the only task fulfilled
+    the velocity is zero when the position barrier holds with margin, and non-zero when
+    the barrier is violated (the QP must move the frame back)."""
+    import numpy as np
+
+    import pink_b200
+    from pink_b200.barriers import PositionBarrier
+    from pink_b200.model import JointModelFreeFlyer
+    from pink_b200.robots import load_robot_description
+
+    robot = load_robot_description("g1_description", root_joint=JointModelFreeFlyer())
+    configuration = pink_b200.Configuration(robot.model, robot.data, robot.q0)
+    frame = "left_ankle_roll_link"
+    task = pink_b200.FrameTask(frame, position_cost=1.0, orientation_cost=1.0)
+    task.set_target(configuration.get_transform_frame_to_world(frame))
+    p = configuration.get_transform_frame_to_world(frame).translation
+    barrier = PositionBarrier(frame, p_min=p - 0.1 * np.ones(3))
+    velocity = pink_b200.solve_ik(configuration, [task], dt=5e-3, solver="daqp", barriers=[barrier],
+                                  limits=[configuration.model.configuration_limit])
+    assert velocity.shape == (robot.model.nv,) and np.allclose(velocity, 0.0, atol=1e-5)
+    barrier = PositionBarrier(frame, p_min=p + 0.01 * np.ones(3))
+    velocity = pink_b200.solve_ik(configuration, [task], dt=5e-3, solver="daqp", barriers=[barrier],
+                                  limits=[configuration.model.configuration_limit])
+    assert not np.allclose(velocity, 0.0, atol=1e-3)
+    # the frame moves back inside: dh/dt + gain * h >= 0 with h = -0.01
+    J = barrier.compute_jacobian(configuration)
+    h = barrier.compute_barrier(configuration)
+    assert np.all(J @ velocity + 1.0 * h >= -1e-5)

@@ -281,32 +281,15 @@ def run_gpu_arm(args):
         ik.solve(qs[i], ts[i], vs[i], ss[i])
 
     # ---- device-resident throughput ("value") ---------------------------------
+    # The K timed steps are K launches of the fused kernel on rotating buffer sets.  They
+    # are submitted as replays of a CUDA graph holding NBUF consecutive steps (plus K mod
+    # NBUF direct launches), so that the figure measures the device, not how fast this
+    # host thread can issue 20 us kernels; `eager_ms_per_step` reports the direct-launch
+    # loop next to it.
     for k in range(args.warmup):
         step(k)
     barrier()
-    launches0 = _cabi.load().pk_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        barrier()
-        e0.record()
-        for k in range(args.steps):
-            step(k)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        # keep the GPU under the same load a little longer so the sampler sees it
-        t_end = time.time() + 0.6
-        k = 0
-        while time.time() < t_end:
-            step(k)
-            k += 1
-        torch.cuda.synchronize()
-    launches = _cabi.load().pk_launch_count() - launches0 - k
-    bad = int(sum(int((s != 0).sum().item()) for s in ss))
-
-    # same loop replayed from a CUDA graph: removes host launch latency from the
-    # per-kernel duration used for the roofline figure
-    g_ms = None
+    graph = None
     try:
         graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device)
@@ -316,18 +299,52 @@ def run_gpu_arm(args):
                 for k in range(NBUF):
                     step(k)
         torch.cuda.current_stream(device).wait_stream(side)
-        reps = max(1, args.steps // NBUF)
         graph.replay()
         barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
+    except Exception as exc:  # pragma: no cover - graph capture is an optimisation only
+        graph = None
+        print(f"[bench] CUDA graph submission unavailable, direct launches: {exc}", file=sys.stderr)
+
+    def run_steps(n):
+        """exactly n steps; returns the number of launches issued outside graphs"""
+        reps, tail = (n // NBUF, n % NBUF) if graph is not None else (0, n)
         for _ in range(reps):
             graph.replay()
-        g1.record()
+        for k in range(tail):
+            step(k)
+        return tail
+
+    launches0 = _cabi.load().pk_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
         barrier()
-        g_ms = g0.elapsed_time(g1) / (reps * NBUF)
-    except Exception as exc:  # pragma: no cover - graph capture is an optimisation only
-        print(f"[bench] CUDA graph timing skipped: {exc}", file=sys.stderr)
+        e0.record()
+        direct = run_steps(args.steps)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        # keep the GPU under the same load a little longer so the sampler sees it
+        t_end = time.time() + 0.6
+        while time.time() < t_end:
+            run_steps(NBUF)
+        torch.cuda.synchronize()
+    # launches inside the timed region: every step is one launch of the fused kernel
+    # (graph replays launch the captured kernels; pk_launch_count only sees direct calls)
+    launches = args.steps
+    assert _cabi.load().pk_launch_count() - launches0 >= direct
+    bad = int(sum(int((s != 0).sum().item()) for s in ss))
+
+    # direct-launch loop (host launch latency included), for reference
+    barrier()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_direct = min(args.steps, 2000)
+    d0.record()
+    for k in range(n_direct):
+        step(k)
+    d1.record()
+    barrier()
+    eager_ms = d0.elapsed_time(d1) / n_direct
+    g_ms = ms / args.steps if graph is not None else None
 
     # ---- end to end through host buffers ("e2e") ---------------------------------
     # Every step copies its inputs from pinned host memory and its results back, inside
@@ -417,6 +434,7 @@ def run_gpu_arm(args):
                 "traffic": committed_traffic(), "peak_kind": peak_kind,
                 "kernel": "pk::ik_chain_kernel<6>", "kernel_ms": kern_ms,
                 "timing": "CUDA graph replay of %d launches" % NBUF if g_ms is not None else "eager launches",
+                "eager_ms_per_step": eager_ms,
                 "algorithmic_bytes_per_launch": B * BYTES_PER_STEP,
             },
             "e2e": {

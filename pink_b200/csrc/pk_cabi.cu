@@ -194,309 +194,24 @@ extern "C" void pk_model_destroy(PkModel* m) {
 
 namespace pk {
 
-// Chain kernel: one instance per thread up to the QP data, then the data-dependent
-// active-set rounds run on warps COMPACTED across the CTA.
+// Chain kernel: one instance per thread, everything in registers - limit check, FK,
+// task rows, box, corner start with the closed-form first releases, and (for the few
+// instances that still need them) the Cholesky active-set rounds and the polish
+// (pk_chain.cuh, pk_lsq.cuh).  n_steps > 1: closed-loop rollout, q <- q (+) v dt after
+// every step with q kept in registers (pink/configuration.py:285-293 after
+// pink/solve_ik.py:274); an instance that fails a step (no solution / outside limits
+// with safety_break) is frozen.
 //
-// Why: on the UR5 benchmark a lane needs 0.93 active-set rounds on average but a
-// warp pays the maximum over its 32 lanes (3.65 on average); in the first captures
-// (profiles/r01a, r01b) 68-77 % of all issued instructions belonged to QP rounds
-// running with 6-12 of 32 lanes active.  So: every lane first tries the cheap
-// uniform exits in place (no bound active; or every coordinate clamped and all
-// multipliers of the right sign).  Lanes that still need work park their whole QP
-// (state + the factored objective A, b, beta, d) in shared memory, word-major, one
-// slot per thread, and keep nothing in registers.  Then, round after round, the
-// unfinished slots of the CTA are ranked with ballot + popc and the first `total`
-// threads each advance ONE slot by one step of its state machine (active-set round,
-// or the final polish): full warps instead of sparse ones.
-template <int NJ, int NFT>
-struct ChainSlots {
-  static constexpr int K = 6 * NFT;
-  static constexpr int NT = NJ * (NJ + 1) / 2;
-  static constexpr int kConst = NT + 3 * NJ + 1;  // H, c, lo, hi, gtol
-  static constexpr int kVar = NJ + 5;             // x, at_hi, at_lo, cond, status, rounds
-  static constexpr int kObj = K * NJ + K + NJ + 1;  // A, b, beta, d
-  static constexpr int kWords = kConst + kVar + kObj;
-  // CTA size: as many warps as fit ~96 KB of slots, at most 7 (2 CTAs/SM = 448
-  // threads/SM, which holds 65536 instances on 148 SMs in a single wave)
-  static constexpr int kFit = (96 * 1024 / (kWords * 4)) / 32 * 32;
-  static constexpr int BLOCK = kFit >= 224 ? 224 : (kFit >= 64 ? kFit : 64);
-  static constexpr size_t kSmemBytes = (size_t)kWords * BLOCK * 4;
-};
-
-template <int NJ, int NFT>
-struct SlotIO {
-  using L = ChainSlots<NJ, NFT>;
-  static constexpr int BLOCK = L::BLOCK;
-  static constexpr int K = L::K;
-  static constexpr int KA = K > 0 ? K : 1;
-  static constexpr int NT = L::NT;
-  static __device__ __forceinline__ float& at(float* sm, int word, int slot) { return sm[word * BLOCK + slot]; }
-
-  static __device__ __forceinline__ void store_const(float* sm, int slot, const BoxState<NJ>& S) {
-#pragma unroll
-    for (int k = 0; k < NT; ++k) at(sm, k, slot) = S.H[k];
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) {
-      at(sm, NT + k, slot) = S.c[k];
-      at(sm, NT + NJ + k, slot) = S.lo[k];
-      at(sm, NT + 2 * NJ + k, slot) = S.hi[k];
-    }
-    at(sm, NT + 3 * NJ, slot) = S.gtol;
-  }
-  static __device__ __forceinline__ void store_box(float* sm, int slot, const BoxState<NJ>& S) {
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) {
-      at(sm, NT + NJ + k, slot) = S.lo[k];
-      at(sm, NT + 2 * NJ + k, slot) = S.hi[k];
-    }
-  }
-  static __device__ __forceinline__ void load_box(float* sm, int slot, BoxState<NJ>& S) {
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) {
-      S.lo[k] = at(sm, NT + NJ + k, slot);
-      S.hi[k] = at(sm, NT + 2 * NJ + k, slot);
-    }
-  }
-  static __device__ __forceinline__ void load_const(float* sm, int slot, BoxState<NJ>& S) {
-#pragma unroll
-    for (int k = 0; k < NT; ++k) S.H[k] = at(sm, k, slot);
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) {
-      S.c[k] = at(sm, NT + k, slot);
-      S.lo[k] = at(sm, NT + NJ + k, slot);
-      S.hi[k] = at(sm, NT + 2 * NJ + k, slot);
-    }
-    S.gtol = at(sm, NT + 3 * NJ, slot);
-  }
-  static __device__ __forceinline__ void store_var(float* sm, int slot, const BoxState<NJ>& S) {
-    constexpr int base = L::kConst;
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) at(sm, base + k, slot) = S.x[k];
-    at(sm, base + NJ, slot) = __uint_as_float(S.at_hi);
-    at(sm, base + NJ + 1, slot) = __uint_as_float(S.at_lo);
-    at(sm, base + NJ + 2, slot) = S.cond;
-    at(sm, base + NJ + 3, slot) = __int_as_float(S.status);
-    at(sm, base + NJ + 4, slot) = __int_as_float(S.rounds);
-  }
-  static __device__ __forceinline__ void load_var(float* sm, int slot, BoxState<NJ>& S) {
-    constexpr int base = L::kConst;
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) S.x[k] = at(sm, base + k, slot);
-    S.at_hi = __float_as_uint(at(sm, base + NJ, slot));
-    S.at_lo = __float_as_uint(at(sm, base + NJ + 1, slot));
-    S.cond = at(sm, base + NJ + 2, slot);
-    S.status = __float_as_int(at(sm, base + NJ + 3, slot));
-    S.rounds = __float_as_int(at(sm, base + NJ + 4, slot));
-  }
-  static __device__ __forceinline__ void store_obj(float* sm, int slot, const ChainStep<NJ, NFT>& C) {
-    constexpr int base = L::kConst + L::kVar;
-#pragma unroll
-    for (int r = 0; r < K; ++r) {
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) at(sm, base + r * NJ + j, slot) = C.A[r][j];
-      at(sm, base + K * NJ + r, slot) = C.b[r];
-    }
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) at(sm, base + K * NJ + K + j, slot) = C.beta[j];
-    at(sm, base + K * NJ + K + NJ, slot) = C.d[0];
-  }
-  // Objective streamed from a slot (rows are read when needed, never all at once).
-  struct SlotObjective {
-    float* sm;
-    int slot;
-    __device__ __forceinline__ void row(int r, float (&a)[NJ], float& br) const {
-      constexpr int base = L::kConst + L::kVar;
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) a[j] = at(sm, base + r * NJ + j, slot);
-      br = at(sm, base + K * NJ + r, slot);
-    }
-    __device__ __forceinline__ float diag(int) const { return at(sm, L::kConst + L::kVar + K * NJ + K + NJ, slot); }
-    __device__ __forceinline__ float lin(int i) const { return at(sm, L::kConst + L::kVar + K * NJ + K + i, slot); }
-  };
-  static __device__ __forceinline__ void load_obj(float* sm, int slot, float (&A)[KA][NJ], float (&b)[KA],
-                                                  float (&d)[NJ], float (&beta)[NJ]) {
-    constexpr int base = L::kConst + L::kVar;
-#pragma unroll
-    for (int r = 0; r < K; ++r) {
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) A[r][j] = at(sm, base + r * NJ + j, slot);
-      b[r] = at(sm, base + K * NJ + r, slot);
-    }
-    const float dd = at(sm, base + K * NJ + K + NJ, slot);
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      beta[j] = at(sm, base + K * NJ + K + j, slot);
-      d[j] = dd;
-    }
-  }
-};
-
-template <int NJ, int NFT>
-__global__ void __launch_bounds__(ChainSlots<NJ, NFT>::BLOCK, 2)
-    ik_chain_kernel(const __grid_constant__ ChainParams<NJ> P, const float* __restrict__ q,
-                    const float* __restrict__ targets, float* __restrict__ v, int32_t* __restrict__ status,
-                    int64_t B, int steps_per_sync, int n_steps, float* __restrict__ q_out) {
-  using IO = SlotIO<NJ, NFT>;
-  constexpr int BLOCK = IO::BLOCK;
-  constexpr int NW = BLOCK / 32;
-  constexpr int KA = IO::KA;
-  using QP = BoxLSQChol<6 * NFT, NJ>;
-  using State = BoxState<NJ>;
-  extern __shared__ __align__(16) float sm[];
-  __shared__ int list[BLOCK];
-  __shared__ signed char phase[BLOCK];  // 0 done, 1 rounds, 2 polish, 3 Gram matrix then rounds
-  __shared__ int wcount[NW];
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const int64_t i = (int64_t)blockIdx.x * BLOCK + tid;
-  const bool valid = i < B;
-
-  float qi[NJ];
-#pragma unroll
-  for (int k = 0; k < NJ; ++k) qi[k] = 0.f;
-  if (valid) {
-    const float* qrow = q + i * NJ;
-    if constexpr (NJ % 2 == 0) {
-#pragma unroll
-      for (int k = 0; k < NJ / 2; ++k) {
-        const float2 t = __ldg(reinterpret_cast<const float2*>(qrow) + k);
-        qi[2 * k] = t.x;
-        qi[2 * k + 1] = t.y;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < NJ; ++k) qi[k] = __ldg(qrow + k);
-    }
-  }
-  // n_steps > 1: closed-loop rollout, q <- q (+) v dt after every step with q kept in
-  // registers (pink/configuration.py:285-293 after pink/solve_ik.py:274); an instance
-  // that fails a step (no solution / outside limits with safety_break) is frozen.
-  int st_all = 0;
-  float x[NJ];
-#pragma unroll
-  for (int k = 0; k < NJ; ++k) x[k] = 0.f;
-  for (int step_no = 0; step_no < n_steps; ++step_no) {
-    int st = 0;
-    bool skip = true;
-    int ph = 0;
-    const bool frozen =
-        (st_all & (PK_STATUS_NO_SOLUTION | PK_STATUS_NOT_POSDEF)) || ((st_all & PK_STATUS_OUT_OF_LIMITS) && P.safety_break);
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) x[k] = 0.f;
-    if (valid && !frozen) {
-      ChainStep<NJ, NFT> C;
-      State S;
-      st = C.assemble(P, qi, targets + i * (int64_t)P.target_stride, skip);
-      if (!skip) {
-        // corner start + KKT test in place: most instances end here with no Gram
-        // matrix and no factorisation; the others park their objective and box
-        const typename QP::ArrayObjective O{C.A, C.b, C.d, C.beta};
-        if (QP::corner_start(O, C.lo, C.hi, S)) {
-          ph = 3;
-          IO::store_box(sm, tid, S);
-          IO::store_var(sm, tid, S);
-          IO::store_obj(sm, tid, C);
-        } else {
-#pragma unroll
-          for (int k = 0; k < NJ; ++k) x[k] = S.x[k];
-          st |= S.status;
-        }
-      }
-    }
-    const bool parked = ph != 0;
-    phase[tid] = (signed char)ph;
-
-    // ---- compacted state machine ------------------------------------------------------
-    for (;;) {
-      __syncthreads();
-      const bool unfinished = phase[tid] != 0;
-      const unsigned ball = __ballot_sync(0xffffffffu, unfinished);
-      if (lane == 0) wcount[warp] = __popc(ball);
-      __syncthreads();
-      int base = 0, total = 0;
-#pragma unroll
-      for (int k = 0; k < NW; ++k) {
-        const int c = wcount[k];
-        if (k < warp) base += c;
-        total += c;
-      }
-      if (total == 0) break;
-      if (unfinished) list[base + __popc(ball & ((1u << lane) - 1u))] = tid;
-      __syncthreads();
-      if (tid < total) {
-        const int slot = list[tid];
-        State T;
-        // one barrier interval: (Gram matrix, then) up to `steps_per_sync` active-set
-        // rounds, or the polish.  (Keeping rounds and polish in separate intervals lets
-        // the polish hold A in registers without spilling the round's Cholesky state.)
-        int next;
-        const int ph_slot = phase[slot];
-        if (ph_slot == 3) {
-          IO::load_box(sm, slot, T);
-          IO::load_var(sm, slot, T);
-          const typename IO::SlotObjective O{sm, slot};
-          QP::gram(O, T);
-          IO::store_const(sm, slot, T);
-        } else {
-          IO::load_const(sm, slot, T);
-          IO::load_var(sm, slot, T);
-        }
-        if (ph_slot != 2) {
-          next = QP::round(T) ? 1 : 2;
-          for (int r = 1; r < steps_per_sync && next == 1; ++r) next = QP::round(T) ? 1 : 2;
-        } else {
-          float A[KA][NJ], b[KA], d[NJ], beta[NJ];
-          IO::load_obj(sm, slot, A, b, d, beta);
-          next = QP::polish(A, b, d, beta, T) ? 1 : 0;
-        }
-        IO::store_var(sm, slot, T);
-        phase[slot] = (signed char)next;
-      }
-    }
-
-    if (valid) {
-      if (parked) {
-        constexpr int base = ChainSlots<NJ, NFT>::kConst;
-#pragma unroll
-        for (int k = 0; k < NJ; ++k) x[k] = IO::at(sm, base + k, tid);
-        st |= __float_as_int(IO::at(sm, base + NJ + 3, tid));
-      }
-      st_all |= st & 0xff;
-      if (n_steps > 1 || q_out) {
-#pragma unroll
-        for (int k = 0; k < NJ; ++k) qi[k] += x[k];  // 1-dof joints: q (+) dq = q + dq
-      }
-    }
-    if (step_no + 1 < n_steps) __syncthreads();  // slots are reused by the next step
-  }
-
-  if (!valid) return;
-  float* vrow = v + i * NJ;
-  if constexpr (NJ % 2 == 0) {
-#pragma unroll
-    for (int k = 0; k < NJ / 2; ++k)
-      reinterpret_cast<float2*>(vrow)[k] = make_float2(x[2 * k] * P.inv_dt, x[2 * k + 1] * P.inv_dt);
-  } else {
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) vrow[k] = x[k] * P.inv_dt;
-  }
-  if (q_out) {
-    float* orow = q_out + i * NJ;
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) orow[k] = qi[k];
-  }
-  if (status) status[i] = st_all;
-}
-
-// Plain variant: the whole step, QP rounds included, in the owning thread (lanes of
-// a warp wait for the slowest QP).  Kept selectable (PK_CHAIN_MODE=0) so that the
-// compaction can be measured against it; see DESIGN.md "Kernels".
+// History (profiles/): an earlier version parked the unfinished QPs
+// of a CTA in shared memory and ran their rounds on compacted warps; once the corner
+// start and the closed-form releases settle 99.3 % of the benchmark instances in the
+// uniform part, that machinery (barriers, slot traffic) cost more than the sparse warps
+// it saved (21.6 us vs 18.4 us per 65536-instance launch) and was removed.
 template <int NJ, int NFT>
 __global__ void __launch_bounds__(128, 4)
-    ik_chain_kernel_plain(const __grid_constant__ ChainParams<NJ> P, const float* __restrict__ q,
-                          const float* __restrict__ targets, float* __restrict__ v, int32_t* __restrict__ status,
-                          int64_t B) {
+    ik_chain_kernel(const __grid_constant__ ChainParams<NJ> P, const float* __restrict__ q,
+                    const float* __restrict__ targets, float* __restrict__ v, int32_t* __restrict__ status,
+                    int64_t B, int flags, int n_steps, float* __restrict__ q_out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   float qi[NJ], vi[NJ];
@@ -512,8 +227,23 @@ __global__ void __launch_bounds__(128, 4)
 #pragma unroll
     for (int k = 0; k < NJ; ++k) qi[k] = __ldg(qrow + k);
   }
-  int st;
-  ik_step_chain<NJ, NFT>(P, qi, targets + i * (int64_t)P.target_stride, vi, st);
+  const float* trow = targets + i * (int64_t)P.target_stride;
+  int st_all = 0;
+#pragma unroll
+  for (int k = 0; k < NJ; ++k) vi[k] = 0.f;
+#pragma unroll 1
+  for (int step_no = 0; step_no < n_steps; ++step_no) {
+    const bool frozen =
+        (st_all & (PK_STATUS_NO_SOLUTION | PK_STATUS_NOT_POSDEF)) || ((st_all & PK_STATUS_OUT_OF_LIMITS) && P.safety_break);
+    if (frozen) break;
+    int st;
+    ik_step_chain<NJ, NFT>(P, qi, trow, vi, st, flags);
+    st_all |= st & 0xff;
+    if (n_steps > 1 || q_out) {
+#pragma unroll
+      for (int k = 0; k < NJ; ++k) qi[k] = fmaf(vi[k], P.dt, qi[k]);  // 1-dof joints: q (+) v dt = q + v dt
+    }
+  }
   float* vrow = v + i * NJ;
   if constexpr (NJ % 2 == 0) {
 #pragma unroll
@@ -522,7 +252,12 @@ __global__ void __launch_bounds__(128, 4)
 #pragma unroll
     for (int k = 0; k < NJ; ++k) vrow[k] = vi[k];
   }
-  if (status) status[i] = st & 0xff;
+  if (q_out) {
+    float* orow = q_out + i * NJ;
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) orow[k] = qi[k];
+  }
+  if (status) status[i] = st_all;
 }
 
 // General path: one instance per thread, per-thread arrays in local memory.
@@ -654,24 +389,11 @@ int env_int(const char* name, int dflt) {
 template <int NJ, int NFT>
 int launch_chain_nft(const pk::ChainParams<NJ>& C, const float* q, const float* targets, float* v, int32_t* status,
                      int64_t B, cudaStream_t stream, int n_steps, float* q_out) {
-  using L = pk::ChainSlots<NJ, NFT>;
-  static bool configured = false;  // opt in to > 48 KB of dynamic shared memory once per instantiation
-  if (!configured) {
-    PK_CUDA(cudaFuncSetAttribute(pk::ik_chain_kernel<NJ, NFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)L::kSmemBytes));
-    configured = true;
-  }
-  static const int mode = env_int("PK_CHAIN_MODE", 1);
-  if (mode == 0 && n_steps == 1 && !q_out) {
-    const int64_t grid0 = (B + 127) / 128;
-    pk::ik_chain_kernel_plain<NJ, NFT><<<(unsigned)grid0, 128, 0, stream>>>(C, q, targets, v, status, B);
-    g_launches.fetch_add(1);
-    PK_CUDA(cudaGetLastError());
-    return 0;
-  }
-  const int64_t grid = (B + L::BLOCK - 1) / L::BLOCK;
-  static const int rps = std::max(1, env_int("PK_STEPS_PER_SYNC", 8));
-  pk::ik_chain_kernel<NJ, NFT><<<(unsigned)grid, L::BLOCK, L::kSmemBytes, stream>>>(C, q, targets, v, status, B, rps, n_steps, q_out);
+  // A/B and probe switches (timing experiments; see scripts/ab.sh)
+  static const int flags = (env_int("PK_CLOSED_FORM", 1) ? 0 : 1) | (env_int("PK_PROBE_SKIP_ROUNDS", 0) ? 2 : 0);
+  static const int block = env_int("PK_CHAIN_BLOCK", 128);
+  const int64_t grid = (B + block - 1) / block;
+  pk::ik_chain_kernel<NJ, NFT><<<(unsigned)grid, block, 0, stream>>>(C, q, targets, v, status, B, flags, n_steps, q_out);
   g_launches.fetch_add(1);
   PK_CUDA(cudaGetLastError());
   return 0;

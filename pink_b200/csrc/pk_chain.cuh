@@ -64,8 +64,7 @@ struct ChainParams {
 //
 // ChainStep::assemble runs everything up to the QP data (limit check, FK, task
 // rows, box); the QP itself is BoxLSQChol (pk_lsq.cuh), either run to completion
-// in the same thread (ik_step_chain, used by the CPU harness and small batches) or
-// staged by the kernel so that its data-dependent rounds run on compacted warps.
+// in the same thread (ik_step_chain).
 template <int NJ, int NFT>
 struct ChainStep {
   static_assert(NFT >= 0 && NFT <= kChainMaxFrameTasks, "unsupported number of frame tasks");
@@ -88,9 +87,9 @@ struct ChainStep {
   // ---- forward kinematics: oMi[j] = oMi[j-1] X_j exp(S_j q_j) -----------------
   SE3f T = identity_se3();
   V3 pj[NJ], wj[NJ];  // world origin and world axis of every joint
-  SE3f Tf[NFT > 0 ? NFT : 1];
+  SE3f Tf[NFT > 0 ? NFT : 1], Tb[NFT > 0 ? NFT : 1];
 #pragma unroll
-  for (int t = 0; t < NFT; ++t) Tf[t] = load_se3(P.ft[t].X);  // frames fixed to the world body
+  for (int t = 0; t < NFT; ++t) Tb[t] = identity_se3();  // frames fixed to the world body
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     const ChainJoint& Jn = P.joint[j];
@@ -111,10 +110,20 @@ struct ChainStep {
     T = compose(T, Tl);
     pj[j] = T.p;
     wj[j] = mul(T.R, axis);
+    // remember the placement of the joint that carries each task frame (selects only;
+    // the frame offset is composed once, after the sweep)
 #pragma unroll
-    for (int t = 0; t < NFT; ++t)
-      if (P.ft[t].body == j) Tf[t] = compose(T, load_se3(P.ft[t].X));
+    for (int t = 0; t < NFT; ++t) {
+      const bool here = P.ft[t].body == j;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Tb[t].R.m[k] = here ? T.R.m[k] : Tb[t].R.m[k];
+      Tb[t].p.x = here ? T.p.x : Tb[t].p.x;
+      Tb[t].p.y = here ? T.p.y : Tb[t].p.y;
+      Tb[t].p.z = here ? T.p.z : Tb[t].p.z;
+    }
   }
+#pragma unroll
+  for (int t = 0; t < NFT; ++t) Tf[t] = compose(Tb[t], load_se3(P.ft[t].X));
 
   // ---- objective in square-root form: rows of A / b are W J and W alpha e ----------
   float diag = P.damping;  // damping + sum of Levenberg-Marquardt terms
@@ -210,14 +219,14 @@ struct ChainStep {
 
 template <int NJ, int NFT>
 PK_HD void ik_step_chain(const ChainParams<NJ>& P, const float (&q)[NJ], const float* __restrict__ trow,
-                         float (&v)[NJ], int& status_out) {
+                         float (&v)[NJ], int& status_out, int flags = 0) {
   ChainStep<NJ, NFT> C;
   bool skip;
   int status = C.assemble(P, q, trow, skip);
   float x[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) x[j] = 0.f;
-  if (!skip) status |= BoxLSQChol<6 * NFT, NJ>::run(C.A, C.b, C.d, C.beta, C.lo, C.hi, x);
+  if (!skip) status |= BoxLSQChol<6 * NFT, NJ>::run(C.A, C.b, C.d, C.beta, C.lo, C.hi, x, flags);
 #pragma unroll
   for (int j = 0; j < NJ; ++j) v[j] = x[j] * P.inv_dt;
   status_out = status;

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU session: tests, smoke, bench, ncu launch list + one full capture.
-# Usage (from the repo root on the GPU box): bash scripts/gpu_check.sh [tag] [quick]
+# Usage (from the repo root on the GPU box): bash scripts/gpu_check.sh [tag]
 TAG=${1:-run}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT

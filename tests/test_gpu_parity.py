@@ -303,8 +303,8 @@ def test_fused_rollout_equals_step_by_step_loop():
     (7, {"two_tasks": True, "prismatic": (2,)}), (7, {}),
 ])
 def test_chain_kernel_instantiations_on_gpu(nj, kw):
-    """Every <NJ, NFT> instantiation (compaction, dynamic shared memory sizes, ragged
-    batch that does not fill the last CTA) against the oracle."""
+    """Every <NJ, NFT> instantiation (ragged batch that does not fill the last CTA)
+    against the oracle."""
     sc = helpers.chain_scenario(nj, 1000 + nj, seed=nj, **kw)
     cfg = pink_b200.Configuration(sc.model, None, torch.as_tensor(sc.q32, device="cuda"))
     v, st = pink_b200.solve_ik(cfg, sc.tasks, sc.dt, solver="quadprog", damping=sc.damping, return_status=True)

@@ -143,7 +143,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def workload_config(args, cpu=False):
@@ -233,8 +233,15 @@ def run_gpu_arm(args):
         raise RuntimeError("bench.py needs a CUDA device; pink_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    real_stdout = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner on fd 1 at
+        # communicator creation (NCCL_DEBUG >= VERSION); everything written to fd 1 from here
+        # on goes to stderr, the JSON line is written to the saved descriptor at the end
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
+        os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
 
     # model constants: built on rank 0, broadcast over NCCL (north_star), then
@@ -295,7 +302,9 @@ def run_gpu_arm(args):
         side = torch.cuda.Stream(device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
-            with torch.cuda.graph(graph, stream=side):
+            # thread-local capture mode: the NCCL watchdog thread of a multi-rank run may
+            # issue CUDA calls (event queries) while this thread is capturing
+            with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
                 for k in range(NBUF):
                     step(k)
         torch.cuda.current_stream(device).wait_stream(side)
@@ -449,8 +458,16 @@ def run_gpu_arm(args):
             line["solve_plus_allgather"] = {"value": total_steps / (gather_ms * 1e-3), "unit": UNIT}
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline_block(B)
-        print(json.dumps(line))
+        if real_stdout is not None:
+            os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
+    # release the captured graph and the prepared problem before the process group goes
+    graph = None
+    ik = None
+    torch.cuda.synchronize()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -3,12 +3,14 @@
 N=${1:-2}
 OUT=gpurun_out/${2:-mgpu}
 mkdir -p $OUT
-for n in 1 $N; do
+export PYTHONFAULTHANDLER=1
+for n in ${ONLY_N-1} $N; do
   if [ $n -eq 1 ]; then
     timeout 600 python bench.py --gpus 1 --steps 5000 --warmup 20 --no-cpu > $OUT/bench_n1.json 2> $OUT/bench_n1.err
   else
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 \
-      bench.py --gpus $n --steps 5000 --warmup 20 > $OUT/bench_n$n.json 2> $OUT/bench_n$n.err
+      bench.py --gpus $n --steps 5000 --warmup 20 --no-cpu > $OUT/bench_n$n.json 2> $OUT/bench_n$n.err
+    echo "torchrun exit $?" >> $OUT/bench_n$n.err
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29534 \
       bench.py --impl reference --gpus $n --steps 5 --warmup 1 > $OUT/ref_n$n.json 2> $OUT/ref_n$n.err
   fi

@@ -12,6 +12,3 @@ PY
 run base
 run nocf PK_CLOSED_FORM=0
 run probe PK_PROBE_SKIP_ROUNDS=1
-run b64 PK_CHAIN_BLOCK=64
-run b256 PK_CHAIN_BLOCK=256
-run base2

@@ -113,6 +113,10 @@ struct HostExtras {
   std::vector<float> extra;
   std::vector<int> pairs;
   bool present = false;
+  // nothing but the constant data of LINEAR tasks: the tree kernel handles these problems
+  bool only_task_data() const {
+    return present && X.nbarriers == 0 && X.nconstraints == 0 && !X.fb_enabled && !X.acc_enabled;
+  }
 };
 
 inline std::string fill_dev_task(const HostModel& m, const PkProblemDesc* p, const PkTaskDesc& s, DevTask& d,
@@ -356,7 +360,7 @@ inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok
   for (int t = 0; t < P.ntasks; ++t) {
     const DevTask& d = P.tasks[t];
     if (is_diag_task(d.type)) continue;
-    const int k = d.type == PK_TASK_COM ? 3 : 6;
+    const int k = d.type == PK_TASK_COM ? 3 : (d.type == PK_TASK_LINEAR ? d.rows : 6);
     int rows = 0;
     for (int r = 0; r < k; ++r) rows += d.cost[r] != 0.f ? 1 : 0;
     if (rows) {
@@ -403,9 +407,7 @@ inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok
   L.o_idx = take(b2, L.nv);
   L.o_xa = take(b2, L.nv);
   L.words = a > b2 ? a : b2;
-  bool plain = true;  // LINEAR tasks and the optional parts (DevExtras) run on the general path
-  for (int t = 0; t < P.ntasks; ++t) plain = plain && P.tasks[t].type != PK_TASK_LINEAR;
-  *ok = plain && m.njoints >= 1 && m.njoints <= kTreeMaxJoints && m.nv <= 64 && P.ntasks <= 32 && K <= 64 &&
+  *ok = m.njoints >= 1 && m.njoints <= kTreeMaxJoints && m.nv <= 64 && P.ntasks <= 32 && K <= 64 &&
         (size_t)L.words * 4 <= 48 * 1024;
   return L;
 }

@@ -560,6 +560,21 @@ struct TreeStep {
           for (int k = 0; k < 6; ++k) F[30 + k] = e[k];
           store_se3(Tr, F + 36);
           store_se3(Trf, F + 48);
+        } else if (Kt.type == PK_TASK_LINEAR) {
+          // e = A (q - q_0) - b on the joint coordinates (pink/tasks/linear_holonomic_task.py:148-166)
+          const float* Al = P.ext->extra + Kt.data_off;
+          const float* bl = Al + Kt.rows * nv;
+          const float* q0 = bl + Kt.rows;
+          #pragma unroll 1
+          for (int r = 0; r < 6; ++r) {
+            float sacc = 0.f;
+            if (r < Kt.rows) {
+              sacc = -bl[r];
+              #pragma unroll 1
+              for (int i = rv; i < nv; ++i) sacc = fmaf(Al[r * nv + i], qs[i + rq - rv] - q0[i + rq - rv], sacc);
+            }
+            F[30 + r] = sacc;
+          }
         } else if (Kt.type == PK_TASK_COM) {
           V3 acc = v3(0.f, 0.f, 0.f);
           for (int b = 0; b <= nj; ++b) {
@@ -596,7 +611,7 @@ struct TreeStep {
         diag = fmaf(Kt.lm * Kt.gain * Kt.gain * w2, lane_sum(part), diag);
         continue;
       }
-      const int k = (Kt.type == PK_TASK_COM) ? 3 : 6;
+      const int k = (Kt.type == PK_TASK_COM) ? 3 : (Kt.type == PK_TASK_LINEAR ? Kt.rows : 6);
       float mu = 0.f;
       #pragma unroll 1
       for (int r = 0; r < k; ++r) {
@@ -617,7 +632,11 @@ struct TreeStep {
         #pragma unroll 1
         for (int i = l; i < nv; i += 32) {
           float col[6];
-          if (Kt.type == PK_TASK_COM) {
+          if (Kt.type == PK_TASK_LINEAR) {
+            const float* Al = P.ext->extra + Kt.data_off;
+            #pragma unroll 1
+            for (int r = 0; r < 6; ++r) col[r] = (r < Kt.rows) ? Al[r * nv + i] : 0.f;
+          } else if (Kt.type == PK_TASK_COM) {
             const V3 cm = v3(F[0], F[1], F[2]);
             V3 c = v3(0.f, 0.f, 0.f);
             if (i < rv) {

@@ -114,7 +114,7 @@ int hs_solve_ik(void* model, const PkProblemDesc* prob, const float* q, const fl
   if (path == 2 || (path == 0 && !chain)) {
     bool ok = false;
     const pk::TreePlan L = pk::make_tree_plan(hm, P, &ok);
-    if (ok && !hx.present) {
+    if (ok && (!hx.present || hx.only_task_data())) {
       if (used_chain) *used_chain = 2;
       const pk::DevModel M = hm.host_view();
       std::vector<float> W(L.words);

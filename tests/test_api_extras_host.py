@@ -58,3 +58,7 @@ def test_barrier_fulfilled_and_violated_like_the_reference():
     J = barrier.compute_jacobian(configuration)
     h = barrier.compute_barrier(configuration)
     assert np.all(J @ velocity + 1.0 * h >= -1e-5)
+
+
+def test_joint_coupling_tasks_on_the_tree_kernel():
+    g.test_joint_coupling_tasks_on_the_tree_kernel()

@@ -144,3 +144,32 @@ def test_opt_in_limits_api():
         G_o, h_o = olim.acceleration_limit_rows(su.table, su.q64[i], su.olimits[2][1], su.olimits[2][2][i], su.dt)
         assert np.array_equal(G, G_o)
         assert np.abs(h[i] - h_o).max() < 1e-6
+
+
+def test_joint_coupling_tasks_on_the_tree_kernel():
+    """examples/humanoid_draco3.py:94-107: JointCouplingTasks + frame + posture tasks
+    (warp-cooperative kernel with constant task data in device memory)."""
+    from oracle import ik as oik
+    from pink_b200 import JointCouplingTask
+
+    sc = helpers.humanoid_scenario("draco3_description", 256)
+    cfg = pink_b200.Configuration(sc.model, None, torch.as_tensor(sc.q32, device=DEVICE))
+    names = [n for n in sc.table.joint_names if "knee" in n or "hip_pitch" in n][:4]
+    jc1 = JointCouplingTask(names[:2], [1.0, -1.0], 100.0, cfg)
+    jc2 = JointCouplingTask(names[2:], [1.0, -0.5], 50.0, cfg, gain=0.7, lm_damping=1e-3)
+    otasks = sc.oracle_tasks + [
+        {"type": "linear", "A": jc1.A, "b": np.zeros(1), "q0": None, "cost": np.full(1, 100.0), "gain": 1.0, "lm_damping": 0.0},
+        {"type": "linear", "A": jc2.A, "b": np.zeros(1), "q0": None, "cost": np.full(1, 50.0), "gain": 0.7, "lm_damping": 1e-3},
+    ]
+    v, st = pink_b200.solve_ik(cfg, sc.tasks + [jc1, jc2], sc.dt, damping=sc.damping, safety_break=sc.safety_break,
+                               return_status=True)
+    _sync()
+    v, st = v.cpu().numpy(), st.cpu().numpy()
+    n = 96
+    v_ref, st_ref = oik.solve_ik_batch(sc.table, sc.q64[:n], [oik._slice_task_range(t, 0, n) for t in otasks], sc.dt,
+                                       sc.damping, sc.oracle_limits, sc.safety_break)
+    assert (st == 0).all() and (st_ref == 0).all()
+    assert helpers.within_tolerance(v[:n], v_ref).all(), np.abs(v[:n] - v_ref).max()
+    e, J = jc2.compute_error(cfg), jc2.compute_jacobian(cfg)
+    assert tuple(e.shape) == (256, 1) and tuple(J.shape) == (256, 1, sc.table.nv)
+    assert np.allclose(J[0].cpu().numpy(), jc2.A)

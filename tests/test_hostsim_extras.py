@@ -101,3 +101,43 @@ def test_g1_self_collision_barrier_config_matches_oracle():
     assert ((st & _cabi.PK_STATUS_NO_SOLUTION) != 0)[~feasible].all() and not feasible.all()
     ok = helpers.within_tolerance(v[feasible], v_ref[feasible])
     assert ok.all(), f"{(~ok).sum()} off, worst {np.abs(v - v_ref)[feasible].max()}"
+
+
+def test_joint_coupling_task_runs_on_the_tree_kernel_body():
+    """examples/humanoid_draco3.py:94-107: JointCouplingTasks next to frame and posture
+    tasks stay on the warp-cooperative kernel (no barriers / constraints involved)."""
+    import torch
+
+    from pink_b200 import JointCouplingTask
+
+    sc = helpers.humanoid_scenario("draco3_description", 48)
+
+    class _Cfg:
+        model = sc.model
+
+    names = [n for n in sc.table.joint_names if "knee" in n or "hip_pitch" in n][:4]
+    assert len(names) == 4
+    jc1 = JointCouplingTask(names[:2], [1.0, -1.0], 100.0, _Cfg())
+    jc2 = JointCouplingTask(names[2:], [1.0, -0.5], 50.0, _Cfg(), gain=0.7, lm_damping=1e-3)
+    tasks = sc.tasks + [jc1, jc2]
+    otasks = sc.oracle_tasks + [
+        {"type": "linear", "A": jc1.A, "b": np.zeros(1), "q0": None, "cost": np.full(1, 100.0), "gain": 1.0, "lm_damping": 0.0},
+        {"type": "linear", "A": jc2.A, "b": np.zeros(1), "q0": None, "cost": np.full(1, 50.0), "gain": 0.7, "lm_damping": 1e-3},
+    ]
+    from pink_b200.solve_ik import describe_problem
+    from oracle import ik as oik
+
+    prob, parts, _ = describe_problem(sc.model, sc.B, tasks, sc.dt, sc.damping, sc.limits, sc.safety_break)
+    targets = torch.cat([p.cpu().float() for p in parts], dim=1).numpy()
+    hs = HostSim(sc.model)
+    v, st = hs.solve_ik(prob, sc.q32, targets)
+    assert hs.used_tree
+    v_gen, st_gen = hs.solve_ik(prob, sc.q32, targets, path=1)
+    v_ref, st_ref = oik.solve_ik_batch(sc.table, sc.q64, otasks, sc.dt, sc.damping, sc.oracle_limits, sc.safety_break)
+    assert (st == 0).all() and (st_gen == 0).all() and (st_ref == 0).all()
+    assert helpers.within_tolerance(v, v_ref).all(), np.abs(v - v_ref).max()
+    assert helpers.within_tolerance(v_gen, v_ref).all(), np.abs(v_gen - v_ref).max()
+    # the coupling matters
+    v_plain, _ = oik.solve_ik_batch(sc.table, sc.q64[:8], [oik._slice_task_range(t, 0, 8) for t in sc.oracle_tasks],
+                                    sc.dt, sc.damping, sc.oracle_limits, sc.safety_break)
+    assert np.abs(v_plain - v_ref[:8]).max() > 1e-3

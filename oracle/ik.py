@@ -192,10 +192,13 @@ def solve_ik_batch(m, q, tasks, dt, damping=1e-12, limits=None, safety_break=Tru
     return v, status
 
 
-def kkt_check_batch(H, c, G, h, x):
+def kkt_check_batch(H, c, G, h, x, bound_tol=0.0):
     """Vectorised optimality certificate of ``x[B, nv]`` for the batch of QPs
     ``(H[B], c[B], G, h[B])`` whose rows are all ``+-e_i`` (box rows, as
     produced by the two default limits).
+
+    ``bound_tol``: extra absolute slack when deciding that a coordinate sits on a
+    bound (fp32 evaluates ``gain * (q_lim - q)`` with ~1e-7 absolute rounding).
 
     Returns per-instance ``(stationarity, primal_violation)`` where
     stationarity is the largest KKT violation given the best admissible
@@ -216,7 +219,7 @@ def kkt_check_batch(H, c, G, h, x):
             else:
                 lo[:, i] = np.maximum(lo[:, i], -h[:, r])
     prim = np.maximum(np.maximum(x - hi, lo - x), 0.0).max(axis=-1)
-    scale = 1e-9 + 1e-6 * np.abs(x)
+    scale = 1e-9 + 1e-6 * np.abs(x) + bound_tol
     at_hi = x >= hi - scale
     at_lo = x <= lo + scale
     # admissible: g<=0 at upper bound, g>=0 at lower bound, g=0 when free

@@ -62,3 +62,27 @@ def test_barrier_fulfilled_and_violated_like_the_reference():
 
 def test_joint_coupling_tasks_on_the_tree_kernel():
     g.test_joint_coupling_tasks_on_the_tree_kernel()
+
+
+def test_config4_feasibility_and_sample_parity_small(monkeypatch):
+    """Same body as the full-size GPU test, on a batch the host build finishes quickly."""
+    real = g.extras.g1_extras
+    monkeypatch.setattr(g.extras, "g1_extras", lambda B: real(96))
+    monkeypatch.setattr(g.np.random, "default_rng", lambda seed=0: _SmallChoice(real_rng(seed)))
+    g.test_config4_full_batch_feasibility_and_sample_parity()
+
+
+import numpy as _np
+
+real_rng = _np.random.default_rng
+
+
+class _SmallChoice:
+    def __init__(self, rng):
+        self.rng = rng
+
+    def choice(self, a, size, replace):
+        return self.rng.choice(a, size=min(size, 24), replace=replace)
+
+    def __getattr__(self, name):
+        return getattr(self.rng, name)

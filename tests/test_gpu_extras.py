@@ -173,3 +173,35 @@ def test_joint_coupling_tasks_on_the_tree_kernel():
     e, J = jc2.compute_error(cfg), jc2.compute_jacobian(cfg)
     assert tuple(e.shape) == (256, 1) and tuple(J.shape) == (256, 1, sc.table.nv)
     assert np.allclose(J[0].cpu().numpy(), jc2.A)
+
+
+def test_config4_full_batch_feasibility_and_sample_parity():
+    """BASELINE config 4 at full size (B = 16384, G1-class + sphere self-collision
+    barrier): every velocity flagged OK satisfies the dense rows and the box of its own
+    QP (rows exported by pk_constraint_rows_batched), infeasible instances are flagged with
+    zero velocity, and a random sample matches the oracle."""
+    sc = extras.g1_extras(16384)
+    v, st = _solve(sc)
+    ok = st == 0
+    assert ok.mean() > 0.95 and ((st[~ok] & _cabi.PK_STATUS_NO_SOLUTION) != 0).all() and not v[~ok].any()
+    cfg = _cfg(sc)
+    from pink_b200.solve_ik import _pack_problem
+
+    prob, targets, _ = _pack_problem(cfg, sc.tasks, sc.dt, sc.damping, sc.limits, sc.safety_break, sc.barriers,
+                                     sc.constraints)
+    G, hG, _, _, lo, hi = (t.cpu().numpy().astype(np.float64) for t in cfg.engine.constraint_rows(prob, cfg.q_device, targets))
+    x = v.astype(np.float64) * sc.dt
+    rows = np.isfinite(hG)
+    viol = np.where(rows, np.einsum("brn,bn->br", G, x) - hG, -np.inf).max(axis=1)
+    box = np.maximum(x - hi, lo - x).max(axis=1)
+    assert viol[ok].max() <= 2e-6 and box[ok].max() <= 1e-7
+    rng = np.random.default_rng(0)
+    pick = rng.choice(np.nonzero(ok)[0], size=48, replace=False)
+    from oracle import ik as oik
+
+    for i in pick:
+        tasks = [oik._slice_task(t, i) for t in sc.otasks]
+        v_ref, st_ref = oik.solve_ik(sc.table, sc.q64[i], tasks, sc.dt, sc.damping, oik._slice_limits(sc.olimits, i),
+                                     sc.safety_break, sc.obarriers, [])
+        assert st_ref == 0
+        assert helpers.within_tolerance(v[i][None], v_ref[None]).all(), (i, np.abs(v[i] - v_ref).max())

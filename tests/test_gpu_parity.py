@@ -336,3 +336,31 @@ def test_empty_and_tiny_batches():
     assert torch.equal(v1[0], v5[0])
     v_ref, _ = sc.oracle_solve()
     assert helpers.within_tolerance(v5.cpu().numpy(), v_ref).all()
+
+
+@pytest.mark.parametrize("name,B,kw", [
+    ("draco3_description", 32768, {}),
+    ("g1_description", 16384, {"with_com": True}),
+])
+def test_humanoid_full_batch_kkt_certificate(name, B, kw):
+    """BASELINE configs 3 and 4 (without the barrier) at their full batch sizes: the
+    fp32 velocities of the warp-cooperative kernel satisfy the fp64 KKT conditions of
+    their own QPs, checked in chunks; the stationarity scale accounts for cond(H) ~ 1e6."""
+    sc = helpers.humanoid_scenario(name, B, **kw)
+    v, st = _gpu_solve(sc)
+    assert (st == 0).all()
+    worst_prim, ratios = 0.0, []
+    for lo_i in range(0, B, 4096):
+        hi_i = min(B, lo_i + 4096)
+        tasks = [oik._slice_task_range(t, lo_i, hi_i) for t in sc.oracle_tasks]
+        H, c, G, h = oik.build_ik(sc.table, sc.q64[lo_i:hi_i], tasks, sc.dt, sc.damping, sc.oracle_limits)
+        x = v[lo_i:hi_i].astype(np.float64) * sc.dt
+        stat, prim, _, _ = oik.kkt_check_batch(H, c, G, h, x, bound_tol=3e-7)
+        worst_prim = max(worst_prim, prim.max())
+        # gradient rounding scale: |H| |x| + |c|
+        scale = np.einsum("bij,bj->bi", np.abs(H), np.abs(x)).max(axis=1) + np.abs(c).max(axis=1)
+        ratios.append(stat / scale)
+    ratios = np.concatenate(ratios)
+    assert worst_prim <= 1e-6
+    assert np.quantile(ratios, 0.999) <= 5e-5, np.quantile(ratios, 0.999)
+    assert ratios.max() <= 5e-4, ratios.max()

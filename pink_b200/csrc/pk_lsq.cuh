@@ -134,6 +134,9 @@ struct BoxLSQ {
 
     const uint64_t all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
     const int max_iter = 4 * n + 16;
+    // anti-cycling at degenerate vertices (multiplier ~ 0 in fp32): a bound that was
+    // released and blocks again at once, with a zero-length step, is not released again
+    uint64_t released = 0ull, tabu = 0ull;
     for (int it = 0;; ++it) {
       if (it >= max_iter) { status |= PK_STATUS_ITER_LIMIT; break; }
       const uint64_t act = at_hi | at_lo;
@@ -171,6 +174,7 @@ struct BoxLSQ {
           }
         }
         if (blk_hi) at_hi |= (1ull << blk); else at_lo |= (1ull << blk);
+        if (((released >> blk) & 1ull) && step <= 1e-6f) tabu |= (1ull << blk);
         continue;
       }
       for (int i = 0; i < n; ++i) x[i] = y[i];
@@ -185,7 +189,7 @@ struct BoxLSQ {
       int rel = -1;
       uint64_t neg = 0ull;
       for (int i = 0; i < n; ++i) {
-        if ((act >> i) & 1ull) {
+        if (((act & ~tabu) >> i) & 1ull) {
           const float rt = fmaf(d[i], x[i], beta[i]);
           float g = d[i] * rt;
           float gabs = fabsf(g);
@@ -204,6 +208,7 @@ struct BoxLSQ {
       if (rel < 0) break;
       // first pass: release every wrong-signed bound; afterwards one at a time
       const uint64_t drop = (it == 0) ? neg : (1ull << rel);
+      if (it > 0) released |= drop;
       at_hi &= ~drop;
       at_lo &= ~drop;
     }

@@ -290,6 +290,9 @@ struct TreeStep {
     }
     const uint64_t all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
     const int max_iter = 4 * n + 16;
+    // anti-cycling at degenerate vertices (multiplier ~ 0 in fp32): a bound that was
+    // released and blocks again at once, with a zero-length step, is not released again
+    uint64_t released = 0ull, tabu = 0ull;
     for (int it = 0;; ++it) {
       if (it >= max_iter) { status |= PK_STATUS_ITER_LIMIT; break; }
       const uint64_t act = at_hi | at_lo;
@@ -367,6 +370,7 @@ struct TreeStep {
         }
         PK_WSYNC();
         if (blk_hi) at_hi |= (1ull << blk); else at_lo |= (1ull << blk);
+        if (((released >> blk) & 1ull) && step <= 1e-6f) tabu |= (1ull << blk);
         continue;
       }
       PK_LANES(l) {
@@ -403,7 +407,7 @@ struct TreeStep {
           uint64_t m = 0ull;
           #pragma unroll 1
           for (int i = l; i < n; i += 32) {
-            if ((act >> i) & 1ull) {
+            if (((act & ~tabu) >> i) & 1ull) {
               const float rt = fmaf(dv[i], x[i], beta[i]);
               float g = dv[i] * rt;
               float gabs = fabsf(g);
@@ -429,6 +433,7 @@ struct TreeStep {
       }
       if (neg == 0ull) break;
       const uint64_t drop = (it < kMultiChange) ? neg : (1ull << rel);
+      if (it >= kMultiChange) released |= drop;
       at_hi &= ~drop;
       at_lo &= ~drop;
     }

@@ -444,9 +444,9 @@ struct PkProblem {
 namespace {
 
 template <int NJ>
-void fill_chain(const PkModel* m, PkProblem* pr) {
+void fill_chain(const PkModel* m, PkProblem* pr, const pk::DevExtras* X) {
   static_assert(sizeof(pk::ChainParams<NJ>) <= sizeof(pr->chain_params), "parameter block too small");
-  pk::make_chain_params<NJ>(m->hm, pr->P, reinterpret_cast<pk::ChainParams<NJ>*>(pr->chain_params));
+  pk::make_chain_params<NJ>(m->hm, pr->P, reinterpret_cast<pk::ChainParams<NJ>*>(pr->chain_params), X);
 }
 
 // Device image of the optional problem parts: [DevExtras | extra | pairs] in one buffer.
@@ -484,20 +484,20 @@ int prepare_problem(const PkModel* m, const PkProblemDesc* desc, PkProblem* pr, 
     pr->P.ext = reinterpret_cast<const pk::DevExtras*>(pr->dev_ext);
   }
   static const int force_generic = env_int("PK_FORCE_GENERIC", 0);
-  pr->chain = !force_generic && pk::chain_eligible(m->hm, pr->P, hx.present);
+  pr->chain = !force_generic && pk::chain_eligible(m->hm, pr->P, hx.present && !hx.box_only());
   pr->nj = m->njoints;
   static const int use_tree = env_int("PK_TREE", 1);
   bool tree_ok = false;
   pr->plan = pk::make_tree_plan(m->hm, pr->P, &tree_ok);
-  pr->tree = !force_generic && use_tree && !pr->chain && tree_ok && (!hx.present || hx.only_task_data());
+  pr->tree = !force_generic && use_tree && !pr->chain && tree_ok && (!hx.present || hx.box_only());
   if (pr->chain) {
     switch (m->njoints) {
-      case 2: fill_chain<2>(m, pr); break;
-      case 3: fill_chain<3>(m, pr); break;
-      case 4: fill_chain<4>(m, pr); break;
-      case 5: fill_chain<5>(m, pr); break;
-      case 6: fill_chain<6>(m, pr); break;
-      case 7: fill_chain<7>(m, pr); break;
+      case 2: fill_chain<2>(m, pr, hx.present ? &hx.X : nullptr); break;
+      case 3: fill_chain<3>(m, pr, hx.present ? &hx.X : nullptr); break;
+      case 4: fill_chain<4>(m, pr, hx.present ? &hx.X : nullptr); break;
+      case 5: fill_chain<5>(m, pr, hx.present ? &hx.X : nullptr); break;
+      case 6: fill_chain<6>(m, pr, hx.present ? &hx.X : nullptr); break;
+      case 7: fill_chain<7>(m, pr, hx.present ? &hx.X : nullptr); break;
       default: pr->chain = false;
     }
   }

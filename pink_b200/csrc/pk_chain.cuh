@@ -57,6 +57,9 @@ struct ChainParams {
   int target_stride;
   int safety_break;
   float shared[12 * kChainMaxFrameTasks + NJ];
+  // AccelerationLimit (pink/limits/acceleration_limit.py:119-200): a box as well
+  int acc_enabled, acc_prev_off;  // dq_prev per instance at acc_prev_off of the targets row (< 0: zeros)
+  float acc_max[NJ], acc_qlo[NJ], acc_qhi[NJ];
 };
 
 // NFT = number of FrameTasks (compile time, so that the stacked Jacobian has a
@@ -212,6 +215,22 @@ struct ChainStep {
     hi[j] = fminf(P.cfg_gain * (P.cfg_hi[j] - q[j]), vb);
     lo[j] = fmaxf(P.cfg_gain * (P.cfg_lo[j] - q[j]), -vb);
   }
+  if (P.acc_enabled) {
+    const float dt2 = P.dt * P.dt;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float a = P.acc_max[j];
+      if (a < 3.0e38f) {
+        const float pv = P.acc_prev_off >= 0 ? trow[P.acc_prev_off + j] : 0.f;
+        const float up = P.acc_qhi[j] - q[j], dn = q[j] - P.acc_qlo[j];
+        if (up < 0.f || dn < 0.f) status |= PK_STATUS_NO_SOLUTION;  // sqrt of a negative margin: NaN rows
+        const float hu = fminf(fmaf(a, dt2, pv), (up < 3.0e38f) ? P.dt * sqrtf(2.f * a * fmaxf(up, 0.f)) : INFINITY);
+        const float hl = fminf(fmaf(a, dt2, -pv), (dn < 3.0e38f) ? P.dt * sqrtf(2.f * a * fmaxf(dn, 0.f)) : INFINITY);
+        hi[j] = fminf(hi[j], hu);
+        lo[j] = fmaxf(lo[j], -hl);
+      }
+    }
+  }
 
   return status;
   }
@@ -226,7 +245,8 @@ PK_HD void ik_step_chain(const ChainParams<NJ>& P, const float (&q)[NJ], const f
   float x[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) x[j] = 0.f;
-  if (!skip) status |= BoxLSQChol<6 * NFT, NJ>::run(C.A, C.b, C.d, C.beta, C.lo, C.hi, x, flags);
+  if (!skip && !(status & PK_STATUS_NO_SOLUTION))
+    status |= BoxLSQChol<6 * NFT, NJ>::run(C.A, C.b, C.d, C.beta, C.lo, C.hi, x, flags);
 #pragma unroll
   for (int j = 0; j < NJ; ++j) v[j] = x[j] * P.inv_dt;
   status_out = status;

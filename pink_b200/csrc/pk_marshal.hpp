@@ -113,9 +113,12 @@ struct HostExtras {
   std::vector<float> extra;
   std::vector<int> pairs;
   bool present = false;
-  // nothing but the constant data of LINEAR tasks: the tree kernel handles these problems
-  bool only_task_data() const {
-    return present && X.nbarriers == 0 && X.nconstraints == 0 && !X.fb_enabled && !X.acc_enabled;
+  // no dense inequality rows and no equalities (only constant data of LINEAR tasks and / or an
+  // AccelerationLimit, which is a box): the chain and tree kernels handle these problems.  A
+  // shared (not per-instance) non-zero dq_prev stays on the general path.
+  bool box_only() const {
+    return present && X.nbarriers == 0 && X.nconstraints == 0 && !X.fb_enabled &&
+           !(X.acc_enabled && X.acc_prev_shared && X.acc_prev_off >= 0);
   }
 };
 
@@ -413,9 +416,19 @@ inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok
 }
 
 template <int NJ>
-void make_chain_params(const HostModel& m, const DevProblem& P, ChainParams<NJ>* out) {
+void make_chain_params(const HostModel& m, const DevProblem& P, ChainParams<NJ>* out, const DevExtras* X = nullptr) {
   ChainParams<NJ>& C = *out;
   memset(&C, 0, sizeof(C));
+  C.acc_prev_off = -1;
+  if (X && X->acc_enabled) {  // host image of the extras (P.ext may be a device pointer)
+    C.acc_enabled = 1;
+    C.acc_prev_off = X->acc_prev_shared ? -1 : X->acc_prev_off;
+    for (int j = 0; j < NJ; ++j) {
+      C.acc_max[j] = X->acc_max[j];
+      C.acc_qlo[j] = X->acc_qlo[j];
+      C.acc_qhi[j] = X->acc_qhi[j];
+    }
+  }
   for (int j = 0; j < NJ; ++j) {
     memcpy(C.joint[j].X, &m.jX[12 * j], sizeof(float) * 12);
     C.joint[j].ax = m.axis[3 * j];

@@ -717,8 +717,23 @@ struct TreeStep {
         W[L.o_d + i] = dd;
         W[L.o_beta + i] = dd > 0.f ? pc / dd : 0.f;
         const float vb = P.dt * P.vel[i];
-        W[L.o_hi + i] = fminf(P.cfg_gain * (P.cfg_hi[i] - qi), vb);
-        W[L.o_lo + i] = fmaxf(P.cfg_gain * (P.cfg_lo[i] - qi), -vb);
+        float hb = fminf(P.cfg_gain * (P.cfg_hi[i] - qi), vb);
+        float lb = fmaxf(P.cfg_gain * (P.cfg_lo[i] - qi), -vb);
+        if (P.ext && P.ext->acc_enabled) {
+          // AccelerationLimit (pink/limits/acceleration_limit.py:119-200): a box as well
+          const DevExtras& X = *P.ext;
+          const float a = X.acc_max[i];
+          if (a < 3.0e38f) {
+            const float pv = X.acc_prev_off >= 0 ? ts[X.acc_prev_off + i] : 0.f;
+            const float up = X.acc_qhi[i] - qi, dn = qi - X.acc_qlo[i];
+            if (up < 0.f || dn < 0.f) hb = -INFINITY;  // NaN rows in the reference: empty box -> no solution
+            const float dt2 = P.dt * P.dt;
+            hb = fminf(hb, fminf(fmaf(a, dt2, pv), (up < 3.0e38f) ? P.dt * sqrtf(2.f * a * fmaxf(up, 0.f)) : INFINITY));
+            lb = fmaxf(lb, -fminf(fmaf(a, dt2, -pv), (dn < 3.0e38f) ? P.dt * sqrtf(2.f * a * fmaxf(dn, 0.f)) : INFINITY));
+          }
+        }
+        W[L.o_hi + i] = hb;
+        W[L.o_lo + i] = lb;
       }
     }
     PK_WSYNC();

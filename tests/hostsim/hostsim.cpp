@@ -20,7 +20,7 @@ template <int NJ>
 void run_chain(const pk::HostModel& hm, const pk::DevProblem& P, const float* q, const float* targets, float* v,
                int32_t* status, int64_t B) {
   pk::ChainParams<NJ> C;
-  pk::make_chain_params<NJ>(hm, P, &C);
+  pk::make_chain_params<NJ>(hm, P, &C, P.ext);
   for (int64_t i = 0; i < B; ++i) {
     float qi[NJ], vi[NJ];
     for (int k = 0; k < NJ; ++k) qi[k] = q[i * NJ + k];
@@ -99,7 +99,7 @@ int hs_solve_ik(void* model, const PkProblemDesc* prob, const float* q, const fl
   pk::HostExtras hx;
   const std::string e = make_problem(hm, prob, &P, &hx);
   if (!e.empty()) return fail(e);
-  const bool chain = path == 0 && pk::chain_eligible(hm, P, hx.present);
+  const bool chain = path == 0 && pk::chain_eligible(hm, P, hx.present && !hx.box_only());
   if (used_chain) *used_chain = chain ? 1 : 0;
   if (chain) {
     switch (hm.njoints) {
@@ -114,7 +114,7 @@ int hs_solve_ik(void* model, const PkProblemDesc* prob, const float* q, const fl
   if (path == 2 || (path == 0 && !chain)) {
     bool ok = false;
     const pk::TreePlan L = pk::make_tree_plan(hm, P, &ok);
-    if (ok && (!hx.present || hx.only_task_data())) {
+    if (ok && (!hx.present || hx.box_only())) {
       if (used_chain) *used_chain = 2;
       const pk::DevModel M = hm.host_view();
       std::vector<float> W(L.words);

@@ -141,3 +141,48 @@ def test_joint_coupling_task_runs_on_the_tree_kernel_body():
     v_plain, _ = oik.solve_ik_batch(sc.table, sc.q64[:8], [oik._slice_task_range(t, 0, 8) for t in sc.oracle_tasks],
                                     sc.dt, sc.damping, sc.oracle_limits, sc.safety_break)
     assert np.abs(v_plain - v_ref[:8]).max() > 1e-3
+
+
+def test_acceleration_limit_stays_on_the_chain_and_tree_kernels():
+    """AccelerationLimit is a box (pink/limits/acceleration_limit.py:119-200): with
+    per-instance previous velocities it runs inside the chain kernel (UR5) and the tree
+    kernel (G1-class), and all three paths agree with the oracle."""
+    import torch
+
+    from pink_b200.limits import AccelerationLimit, ConfigurationLimit, VelocityLimit
+    from pink_b200.solve_ik import describe_problem
+    from oracle import ik as oik
+
+    for name, B in [("ur5", 200), ("g1", 24)]:
+        if name == "ur5":
+            sc = helpers.ur5_scenario(B, "reachable")
+            a_max = np.array([40.0, 40.0, 60.0, np.inf, 80.0, 80.0])
+        else:
+            sc = helpers.humanoid_scenario("g1_description", B, with_com=True)
+            a_max = np.concatenate([np.full(6, np.inf), np.full(sc.table.nv - 6, 150.0)])
+        rng = np.random.default_rng(1)
+        v_prev = (rng.normal(size=(B, sc.table.nv)) * 0.3).astype(np.float32)
+        acc = AccelerationLimit(sc.model, a_max)
+        acc.set_last_integration(torch.as_tensor(v_prev), sc.dt)
+        limits = [ConfigurationLimit(sc.model), VelocityLimit(sc.model), acc]
+        prob, parts, _ = describe_problem(sc.model, B, sc.tasks, sc.dt, sc.damping, limits, sc.safety_break)
+        targets = torch.cat([p.cpu().float() for p in parts], dim=1).numpy()
+        hs = HostSim(sc.model)
+        v, st = hs.solve_ik(prob, sc.q32, targets)
+        assert hs.used_chain if name == "ur5" else hs.used_tree
+        v_gen, st_gen = hs.solve_ik(prob, sc.q32, targets, path=1)
+        dq_prev = (torch.as_tensor(v_prev) * sc.dt).numpy().astype(np.float64)
+        v_ref, st_ref = oik.solve_ik_batch(sc.table, sc.q64, sc.oracle_tasks, sc.dt, sc.damping,
+                                           [("configuration", 0.5), ("velocity", None), ("acceleration", a_max, dq_prev)],
+                                           sc.safety_break)
+        feasible = st_ref == 0
+        assert feasible.mean() > 0.7
+        assert (st[feasible] == 0).all() and (st_gen[feasible] == 0).all()
+        assert ((st[~feasible] & _cabi.PK_STATUS_NO_SOLUTION) != 0).all()
+        tol = dict(atol=5e-4, rtol=5e-3) if name == "g1" else {}
+        assert helpers.within_tolerance(v[feasible], v_ref[feasible], **tol).all(), np.abs(v - v_ref)[feasible].max()
+        assert helpers.within_tolerance(v_gen[feasible], v_ref[feasible], **tol).all()
+        # the limit matters
+        v_plain, _ = oik.solve_ik_batch(sc.table, sc.q64[:16], [oik._slice_task_range(t, 0, 16) for t in sc.oracle_tasks],
+                                        sc.dt, sc.damping, None, sc.safety_break)
+        assert np.abs(v_plain - v_ref[:16])[feasible[:16]].max() > 1e-2

@@ -30,5 +30,7 @@ network.  The oracle is therefore pinned only by the model-independent
 invariants the reference's own tests assert (finite-difference Jacobians,
 at-target identities, unit-cost ``H == J^T J``, ...; see
 ``tests/test_oracle_*.py``) plus independent numerical cross-checks
-(``scipy.linalg.logm``, brute-force KKT enumeration, SLSQP).
+(``scipy.linalg.logm``, brute-force KKT enumeration, SLSQP).  The vectors under
+``tests/golden/`` are frozen outputs of THIS oracle (``scripts/make_golden.py``), a
+drift guard and a GPU-side fixture - not reference outputs.
 """

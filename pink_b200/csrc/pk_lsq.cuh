@@ -609,65 +609,6 @@ struct BoxLSQChol {
     S.gtol = 4e-6f * gs;
   }
 
-  // Gram matrix, unconstrained minimiser, clamp.  Returns true if rounds are needed.
-  static PK_HD bool init(const float (&A)[KA][N], const float (&b)[KA], const float (&d)[N],
-                         const float (&beta)[N], const float (&lo)[N], const float (&hi)[N], State& S) {
-    S.status = 0;
-    S.rounds = 0;
-    S.at_hi = S.at_lo = 0u;
-    S.cond = 1.f;
-    S.gtol = 0.f;
-    bool infeasible = false;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      S.lo[i] = lo[i];
-      S.hi[i] = hi[i];
-      S.x[i] = 0.f;
-      infeasible = infeasible || (lo[i] > hi[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-#pragma unroll
-      for (int j = 0; j <= i; ++j) {
-        float s = (i == j) ? d[i] * d[i] : 0.f;
-#pragma unroll
-        for (int r = 0; r < K; ++r) s = fmaf(A[r][i], A[r][j], s);
-        S.H[tri(i, j)] = s;
-      }
-      float s = d[i] * beta[i];
-#pragma unroll
-      for (int r = 0; r < K; ++r) s = fmaf(A[r][i], b[r], s);
-      S.c[i] = s;
-    }
-    if (infeasible) {  // empty box <=> quadprog reports no solution
-      S.status = PK_STATUS_NO_SOLUTION;
-      return false;
-    }
-    float L[NT], inv[N], y[N];
-    S.cond = factor(S.H, 0u, L, inv);
-    if (!(S.cond > 0.f)) S.status |= PK_STATUS_NOT_POSDEF;
-#pragma unroll
-    for (int i = 0; i < N; ++i) y[i] = -S.c[i];
-    solve(L, inv, y);
-    float gs = 0.f;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      if (y[i] > hi[i]) { S.at_hi |= (1u << i); S.x[i] = hi[i]; }
-      else if (y[i] < lo[i]) { S.at_lo |= (1u << i); S.x[i] = lo[i]; }
-      else S.x[i] = y[i];
-    }
-    // rounding scale of H x + c over the box reachable from here
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      float s = fabsf(S.c[i]);
-#pragma unroll
-      for (int j = 0; j < N; ++j) s = fmaf(fabsf(S.H[tri(i, j)]), fabsf(S.x[j]), s);
-      gs = fmaxf(gs, s);
-    }
-    S.gtol = 4e-6f * gs;
-    return (S.at_hi | S.at_lo) != 0u;
-  }
-
   // One active-set round: Newton step on the free set (with blocking), then release
   // of wrong-signed bounds.  Returns true if another round is needed.
   static PK_HD bool round(State& S) {
@@ -783,6 +724,9 @@ struct BoxLSQChol {
             S.x[i] = xn;
           }
         }
+#ifdef PK_COUNT_ITERS
+        pk_count_nfree(100 + pass, -1);
+#endif
         if (dmax <= 2e-7f * xmax) break;
         gradient_factored(O, S.x, g, gabs);
       }

@@ -736,6 +736,46 @@ static int solve_host_impl(PkModel* m, const PkProblem& pr, const float* q_host,
     }
     return 0;
   }
+  // PK_HOST_MODE=2: uploads staged as below, but the kernels write v / status straight into
+  // the caller's pinned host buffers (posted PCIe writes, no download phase)
+  if (host_mode == 2) {
+    auto dev_ptr = [](const void* ptr) -> void* {
+      if (!ptr) return nullptr;
+      cudaPointerAttributes a{};
+      if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess || a.type != cudaMemoryTypeHost) return nullptr;
+      return a.devicePointer;
+    };
+    float* v_dev = static_cast<float*>(dev_ptr(v_host));
+    int32_t* s_dev = static_cast<int32_t*>(dev_ptr(status_host));
+    cudaGetLastError();
+    if (v_dev && (s_dev || !status_host)) {
+      cudaStream_t s_in = m->st_streams[0], s_k = m->st_streams[1];
+      for (int i = 0; i < 2; ++i) PK_CUDA(cudaStreamWaitEvent(m->st_streams[i], m->st_fork, 0));
+      if (m->st_busy) PK_CUDA(cudaStreamWaitEvent(s_in, m->st_join[2], 0));
+      m->st_busy = true;
+      for (int64_t k = 0; k < nchunks; ++k) {
+        if (!m->st_in[k]) {
+          PK_CUDA(cudaEventCreateWithFlags(&m->st_in[k], cudaEventDisableTiming));
+          PK_CUDA(cudaEventCreateWithFlags(&m->st_kern[k], cudaEventDisableTiming));
+        }
+        const int64_t b0 = k * chunk;
+        const int64_t nb = std::min(chunk, B - b0);
+        PK_CUDA(cudaMemcpyAsync(m->st_q + b0 * m->nq, q_host + b0 * m->nq, sizeof(float) * nb * m->nq,
+                                cudaMemcpyHostToDevice, s_in));
+        if (ts > 0)
+          PK_CUDA(cudaMemcpyAsync(m->st_t + b0 * ts, targets_host + b0 * ts, sizeof(float) * nb * ts,
+                                  cudaMemcpyHostToDevice, s_in));
+        PK_CUDA(cudaEventRecord(m->st_in[k], s_in));
+        PK_CUDA(cudaStreamWaitEvent(s_k, m->st_in[k], 0));
+        if (solve_device(m, pr, m->st_q + b0 * m->nq, m->st_t + b0 * ts, v_dev + b0 * m->nv, s_dev ? s_dev + b0 : nullptr,
+                         nb, s_k))
+          return 1;
+      }
+      PK_CUDA(cudaEventRecord(m->st_join[2], s_k));
+      PK_CUDA(cudaStreamWaitEvent(stream, m->st_join[2], 0));
+      return 0;
+    }
+  }
   cudaStream_t s_in = m->st_streams[0], s_k = m->st_streams[1], s_out = m->st_streams[2];
   for (int i = 0; i < 3; ++i) PK_CUDA(cudaStreamWaitEvent(m->st_streams[i], m->st_fork, 0));
   // calls submitted on different caller streams share the staging buffers: the next upload

@@ -211,3 +211,61 @@ def chain_scenario(nj, B, seed=1, prismatic=(), two_tasks=False, shared_target=F
         data = None
 
     return Scenario(f"chain{nj}", _R(), model, table, q, tasks, otasks, 0.01, 1e-8)
+
+
+def random_tree_model(nj, rng, free_flyer=False, name="tree"):
+    """Random joint tree (each joint hangs under a random earlier joint, or the root),
+    optional free-flyer root, a few frames on leaves: exercises models beyond the
+    32-joint warp kernel up to the C-ABI maximum (58 joints, nv = 64)."""
+    from pink_b200.model import Model, SE3
+    from oracle import lie
+
+    model = Model(name, free_flyer=free_flyer)
+    root = model.root_body  # property: Pinocchio id of the root body (1 with a free-flyer)
+    ids = []
+    for j in range(nj):
+        parent = root if (j == 0 or rng.random() < 0.15) else ids[int(rng.integers(max(0, j - 6), j))]
+        R, _ = lie.exp6(np.concatenate([np.zeros(3), rng.normal(size=3) * 0.8]))
+        T = SE3(R, rng.uniform(-0.15, 0.15, size=3))
+        kind = "prismatic" if rng.random() < 0.1 else "revolute"
+        lim = 0.3 if kind == "prismatic" else 2.0
+        jid = model.add_joint(f"j{j}", parent, T, rng.normal(size=3), kind=kind, lower=-lim, upper=lim, velocity=3.0)
+        model.append_inertia(jid, 0.5 + 0.05 * j, rng.uniform(-0.05, 0.05, size=3))
+        ids.append(jid)
+    for k, jid in enumerate(ids[-4:]):
+        model.add_frame(f"tip{k}", jid, SE3(np.eye(3), rng.uniform(-0.1, 0.1, size=3)))
+    return model
+
+
+def tree_scenario(nj, B, free_flyer=False, seed=3):
+    """Frame tasks on the four tip frames + relative frame + posture (+ CoM) on a random tree."""
+    rng = np.random.default_rng(seed)
+    model = random_tree_model(nj, rng, free_flyer)
+    table = model.table()
+    q = workloads.sample_configurations(table, B, rng)
+    qt = workloads.perturb_configurations(table, q, rng, sigma=0.2)
+    tasks, otasks = [], []
+    for k, (pc, oc) in enumerate([(1.0, 1.0), (2.0, 0.0), ([1.0, 0.0, 3.0], 0.5)]):
+        frame = f"tip{k}"
+        T = frame_targets(table, qt, frame)
+        t = FrameTask(frame, position_cost=pc, orientation_cost=oc, lm_damping=0.05)
+        t.set_target(torch.as_tensor(T))
+        tasks.append(t)
+        T64 = T.astype(np.float64)
+        otasks.append({"type": "frame", "frame": table.frame_names.index(frame), "cost": np.array(t.cost), "gain": 1.0,
+                       "lm_damping": 0.05, "target": (T64[:, :, :3], T64[:, :, 3])})
+    q_ref = q[0].copy()
+    pt = PostureTask(cost=0.05)
+    pt.set_target(q_ref)
+    tasks.append(pt)
+    otasks.append({"type": "posture", "cost": 0.05, "gain": 1.0, "lm_damping": 0.0, "target": q_ref})
+    com = okin.center_of_mass(table, okin.forward_kinematics(table, qt)).astype(np.float32)
+    ct = ComTask(cost=5.0)
+    ct.set_target(torch.as_tensor(com))
+    tasks.append(ct)
+    otasks.append({"type": "com", "cost": np.full(3, 5.0), "gain": 1.0, "lm_damping": 0.0, "target": com.astype(np.float64)})
+
+    class _R:
+        data = None
+
+    return Scenario(f"tree{nj}", _R(), model, table, q, tasks, otasks, 0.01, 1e-6, safety_break=False)

@@ -364,3 +364,20 @@ def test_humanoid_full_batch_kkt_certificate(name, B, kw):
     assert worst_prim <= 1e-6
     assert np.quantile(ratios, 0.999) <= 5e-5, np.quantile(ratios, 0.999)
     assert ratios.max() <= 5e-4, ratios.max()
+
+
+@pytest.mark.parametrize("nj,free_flyer", [(40, False), (58, True)])
+def test_models_up_to_the_abi_maximum_on_gpu(nj, free_flyer):
+    """ik_generic_kernel<58, 64>: more than 32 joints, up to PK_MAX_JOINTS = 58 with a
+    free-flyer (nv = 64), against the oracle; FK / CoM exports on the same model."""
+    sc = helpers.tree_scenario(nj, 96, free_flyer)
+    cfg = pink_b200.Configuration(sc.model, None, torch.as_tensor(sc.q32, device="cuda"))
+    v, st = pink_b200.solve_ik(cfg, sc.tasks, sc.dt, damping=sc.damping, safety_break=False, return_status=True)
+    torch.cuda.synchronize()
+    v, st = v.cpu().numpy(), st.cpu().numpy()
+    v_ref, st_ref = sc.oracle_solve(48)
+    assert (st == 0).all() and (st_ref == 0).all()
+    assert helpers.within_tolerance(v[:48], v_ref, atol=5e-4, rtol=5e-3).all(), np.abs(v[:48] - v_ref).max()
+    com = cfg.get_center_of_mass().cpu().numpy()
+    com_ref = okin.center_of_mass(sc.table, okin.forward_kinematics(sc.table, sc.q64))
+    np.testing.assert_allclose(com, com_ref, atol=2e-6)

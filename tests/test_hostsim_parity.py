@@ -239,3 +239,28 @@ def test_joint_velocity_and_damping_tasks():
         np.testing.assert_allclose(c, c_ref, atol=2e-5 * np.abs(c_ref).max(), rtol=1e-4)
         v_ref_o, st_ref = sc.oracle_solve()
         assert helpers.within_tolerance(v, v_ref_o, atol=5e-4, rtol=5e-3).mean() >= 0.97
+
+
+@pytest.mark.parametrize("nj,free_flyer", [(40, False), (58, True)])
+def test_models_beyond_the_warp_kernel_up_to_the_abi_maximum(nj, free_flyer):
+    """Random joint trees with more than 32 joints (general path), up to the C-ABI
+    maximum PK_MAX_JOINTS = 58 with a free-flyer (nv = PK_MAX_NV = 64)."""
+    sc = helpers.tree_scenario(nj, 24, free_flyer)
+    assert sc.table.nv == (nj + 6 if free_flyer else nj)
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v, st = hs.solve_ik(prob, sc.q32, targets)
+    assert not hs.used_tree and not hs.used_chain
+    v_ref, st_ref = sc.oracle_solve()
+    assert (st == 0).all() and (st_ref == 0).all()
+    assert helpers.within_tolerance(v, v_ref, atol=5e-4, rtol=5e-3).all(), np.abs(v - v_ref).max()
+
+
+def test_model_larger_than_the_abi_maximum_is_rejected():
+    import pink_b200
+    from tests import hostsim as hsmod
+
+    rng = np.random.default_rng(0)
+    model = helpers.random_tree_model(59, rng, free_flyer=True)
+    with pytest.raises(RuntimeError):
+        HostSim(model)

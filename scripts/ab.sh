@@ -9,9 +9,7 @@ try:
 except Exception as e: print("$name", "ERR", e); print(open("$OUT/$name.err").read()[-800:])
 PY
 }
-run mode0 PK_HOST_MODE=0
-run mode2 PK_HOST_MODE=2
-run mode2_c16 PK_HOST_MODE=2 PK_HOST_CHUNK=16384
-run mode2_c64 PK_HOST_MODE=2 PK_HOST_CHUNK=65536
-run mode0b PK_HOST_MODE=0
-run mode2b PK_HOST_MODE=2
+run base
+run probe PK_PROBE_SKIP_ROUNDS=1
+run base2
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_golden.py -m gpu -q -x 2>&1 | tail -3

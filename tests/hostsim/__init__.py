@@ -59,8 +59,12 @@ class HostSim:
         self.nq, self.nv, self.nframes = self.table.nq, self.table.nv, self.table.nframes
 
     def __del__(self):
-        if getattr(self, "handle", None):
-            lib().hs_model_destroy(self.handle)
+        try:
+            if getattr(self, "handle", None):
+                lib().hs_model_destroy(self.handle)
+                self.handle = None
+        except Exception:  # interpreter shutdown
+            pass
 
     def _chk(self, rc):
         if rc:

@@ -186,3 +186,41 @@ def test_acceleration_limit_stays_on_the_chain_and_tree_kernels():
         v_plain, _ = oik.solve_ik_batch(sc.table, sc.q64[:16], [oik._slice_task_range(t, 0, 16) for t in sc.oracle_tasks],
                                         sc.dt, sc.damping, None, sc.safety_break)
         assert np.abs(v_plain - v_ref[:16])[feasible[:16]].max() > 1e-2
+
+
+def test_frame_and_com_tasks_as_equality_constraints():
+    """solve_ik(..., constraints=[FrameTask, ComTask]) (pink/solve_ik.py:125-149): nine
+    equality rows J dq = -gain e on the G1-class model, next to the other tasks."""
+    import torch
+
+    from oracle import ik as oik
+    from pink_b200.solve_ik import describe_problem
+
+    sc = helpers.humanoid_scenario("g1_description", 24, with_com=True)
+    # constraints: left foot (frame task, gain 0.5) and the CoM task; the rest stays in the objective
+    foot = [i for i, t in enumerate(sc.tasks) if getattr(t, "frame", "") == "left_ankle_roll_link"][0]
+    com = [i for i, t in enumerate(sc.tasks) if type(t).__name__ == "ComTask"][0]
+    sc.tasks[foot].gain = 0.05
+    sc.oracle_tasks[foot]["gain"] = 0.05
+    sc.tasks[com].gain = 0.05
+    sc.oracle_tasks[com]["gain"] = 0.05
+    cons, ocons = [sc.tasks[foot], sc.tasks[com]], [sc.oracle_tasks[foot], sc.oracle_tasks[com]]
+    tasks = [t for i, t in enumerate(sc.tasks) if i not in (foot, com)]
+    otasks = [t for i, t in enumerate(sc.oracle_tasks) if i not in (foot, com)]
+    prob, parts, _ = describe_problem(sc.model, sc.B, tasks, sc.dt, sc.damping, sc.limits, sc.safety_break, None, cons)
+    targets = torch.cat([p.cpu().float() for p in parts], dim=1).numpy()
+    hs = HostSim(sc.model)
+    v, st = hs.solve_ik(prob, sc.q32, targets)
+    assert not hs.used_tree
+    v_ref, st_ref = oik.solve_ik_batch(sc.table, sc.q64, otasks, sc.dt, sc.damping, sc.oracle_limits, sc.safety_break,
+                                       None, ocons)
+    feasible = st_ref == 0
+    assert feasible.mean() > 0.5 and (st[feasible] == 0).all()
+    assert ((st[~feasible] & _cabi.PK_STATUS_NO_SOLUTION) != 0).all()
+    assert helpers.within_tolerance(v[feasible], v_ref[feasible], atol=5e-4, rtol=5e-3).all(), \
+        np.abs(v - v_ref)[feasible].max()
+    # the equalities hold in the exported rows: E dq = f
+    _, _, E, f, _, _ = hs.constraint_rows(prob, sc.q32, targets)
+    x = v.astype(np.float64) * sc.dt
+    res = np.abs(np.einsum("brn,bn->br", E[:, :9].astype(np.float64), x) - f[:, :9])
+    assert res[feasible].max() < 2e-6

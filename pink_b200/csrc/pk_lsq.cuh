@@ -530,27 +530,41 @@ struct BoxLSQChol {
           hi2 = fmaf(m2[j], fminf(hi[j], 3.0e38f), hi2);
         }
         float d2;
+        bool solved;  // the released block was well-conditioned
         if (flipped) {
           d2 = -fmaf(h12, d1, g2) / h22;
-          ok = h22 > 0.f;
+          solved = h22 > 0.f;
         } else {
           const float det = fmaf(h11, h22, -h12 * h12);
           const float inv = 1.f / det;
           d1 = (h12 * g2 - h22 * g1) * inv;
           d2 = (h12 * g1 - h11 * g2) * inv;
-          ok = det > 1e-6f * h11 * h22;  // well-conditioned 2 x 2 block; otherwise the rounds decide
-          ok = ok && (x1 + d1) >= lo1 && (x1 + d1) <= hi1;
+          solved = det > 1e-6f * h11 * h22;  // otherwise the rounds decide
         }
-        ok = ok && (x2 + d2) >= lo2 && (x2 + d2) <= hi2;
+        // longest feasible step towards the minimiser of the released block
+        float alpha = 1.f;
+        uint32_t blk = 0u;
+        bool blk_hi = false;
+        if (!flipped) {
+          if (x1 + d1 > hi1) { const float a = (hi1 - x1) / d1; if (a < alpha) { alpha = a; blk = n1; blk_hi = true; } }
+          else if (x1 + d1 < lo1) { const float a = (lo1 - x1) / d1; if (a < alpha) { alpha = a; blk = n1; blk_hi = false; } }
+        }
+        if (x2 + d2 > hi2) { const float a = (hi2 - x2) / d2; if (a < alpha) { alpha = a; blk = n2; blk_hi = true; } }
+        else if (x2 + d2 < lo2) { const float a = (lo2 - x2) / d2; if (a < alpha) { alpha = a; blk = n2; blk_hi = false; } }
+        alpha = fmaxf(alpha, 0.f);
         const uint32_t freed = flipped ? n2 : (n1 | n2);
+        // multipliers of the others at the block minimiser
+        float worst3 = 0.f;
+        uint32_t n3 = 0u;
 #pragma unroll
         for (int j = 0; j < N; ++j) {
           if (!((freed >> j) & 1u)) {
             const float gj = fmaf(h1[j], d1, fmaf(h2[j], d2, g[j]));
             const float lam = ((hi1m >> j) & 1u) ? -gj : gj;
-            ok = ok && !(lam < -4e-6f * gabs[j]);
+            if (lam < -4e-6f * gabs[j] && lam < worst3) { worst3 = lam; n3 = 1u << j; }
           }
         }
+        ok = solved && blk == 0u && n3 == 0u;
 #ifdef PK_COUNT_ITERS
         pk_count_nfree(ok ? (flipped ? 4 : 2) : (flipped ? 14 : 12), -1);
 #endif
@@ -564,11 +578,26 @@ struct BoxLSQChol {
           S.at_lo = lo1m & ~n2;
           return false;
         }
-        // Not settled: hand the rounds the state after the first closed-form step (i1 at
-        // its 1-D minimiser or on its opposite bound) with i2 released, rather than the
-        // corner with every wrong-signed bound released: same total number of rounds on the
-        // benchmark, but the longest chain drops from 9 rounds to 5, and the kernel ends
-        // when the slowest instance does.
+        // Not settled: hand the rounds the furthest state reached here rather than the corner
+        // with every wrong-signed bound released.  The kernel ends when the slowest instance
+        // does, and this cuts the longest chain on the benchmark from 9 rounds to 5 (state
+        // after the first closed-form step) and further (state after the second one).
+        if (solved) {
+          // (a) a released coordinate reaches a bound on the way: stop there, it becomes active;
+          // (b) the block minimiser is feasible but another multiplier is negative: release it
+          const float e1 = flipped ? d1 : alpha * d1;  // the flipped coordinate is already placed
+          const float e2 = alpha * d2;
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            S.x[j] = fmaf(m1[j], e1, fmaf(m2[j], e2, S.x[j]));
+            if (flipped && ((n1 >> j) & 1u)) S.x[j] = flip_hi ? hi[j] : lo[j];
+            if ((blk >> j) & 1u) S.x[j] = blk_hi ? hi[j] : lo[j];
+          }
+          S.at_hi = (hi1m & ~n2) | (blk_hi ? blk : 0u);
+          S.at_lo = (lo1m & ~n2) | (blk_hi ? 0u : blk);
+          if (blk == 0u) { S.at_hi &= ~n3; S.at_lo &= ~n3; }
+          return true;
+        }
         {
           const float d1s = flipped ? d1 : -g1 / h11;
 #pragma unroll

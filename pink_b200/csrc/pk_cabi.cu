@@ -488,8 +488,8 @@ int prepare_problem(const PkModel* m, const PkProblemDesc* desc, PkProblem* pr, 
   pr->nj = m->njoints;
   static const int use_tree = env_int("PK_TREE", 1);
   bool tree_ok = false;
-  pr->plan = pk::make_tree_plan(m->hm, pr->P, &tree_ok);
-  pr->tree = !force_generic && use_tree && !pr->chain && tree_ok && (!hx.present || hx.box_only());
+  pr->plan = pk::make_tree_plan(m->hm, pr->P, &tree_ok, hx.present ? &hx.X : nullptr);
+  pr->tree = !force_generic && use_tree && !pr->chain && tree_ok;
   if (pr->chain) {
     switch (m->njoints) {
       case 2: fill_chain<2>(m, pr, hx.present ? &hx.X : nullptr); break;

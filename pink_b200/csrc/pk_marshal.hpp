@@ -13,6 +13,7 @@
 #include "pk_chain.cuh"
 #include "pk_generic.cuh"
 #include "pk_tree.cuh"
+#include "pk_treedual.cuh"
 
 namespace pk {
 
@@ -347,9 +348,79 @@ inline bool chain_eligible(const HostModel& m, const DevProblem& P, bool has_ext
 
 // Workspace layout of the warp-cooperative tree kernel; `ok` false if the problem
 // does not fit it (then the general path is used).
-inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok) {
+// Workspace layout of one instance (offsets in floats) from L.nj / nq / nv / K / p / npairs.
+inline void tree_layout(TreePlan& L, int ntasks, int stride) {
+  int off = 0;
+  auto take = [&](int& cursor, int words) { const int at = cursor; cursor += (words + 3) / 4 * 4; return at; };
+  const int K = L.K;
+  const int Kp = K > 0 ? K : 1;
+  L.lda = L.nv | 1;
+  L.ldw = L.nv | 1;
+  L.ldj = L.nv | 1;
+  L.o_A = take(off, Kp * L.lda);
+  L.o_b = take(off, K);
+  L.o_d = take(off, L.nv);
+  L.o_beta = take(off, L.nv);
+  L.o_lo = take(off, L.nv);
+  L.o_hi = take(off, L.nv);
+  L.o_x = take(off, L.nv);
+  L.o_y = take(off, L.nv);
+  L.o_g = off;  // unused
+  if (L.p > 0) {
+    // dense rows and dual-method state: persistent (not overlaid with the assembly scratch)
+    L.o_G = take(off, L.p * L.lda);
+    L.o_hg = take(off, L.p);
+    L.o_gn = take(off, L.p);
+    L.o_J = take(off, L.nv * L.ldj);
+    L.o_RA = take(off, L.nv * L.ldj);
+    L.o_dv = take(off, L.nv);
+    L.o_z = take(off, L.nv);
+    L.o_r = take(off, L.nv + 1);
+    L.o_u = take(off, L.nv + 1);
+    L.o_act = take(off, L.nv + 1);
+    L.o_xd = take(off, 2 * L.nv);
+    L.o_wd = take(off, 2 * (L.nv + 1));
+    L.o_gd = take(off, 2 * L.nv);
+    L.o_rhod = take(off, 2 * Kp);
+    L.o_ud = take(off, 2 * (L.nv + 1));
+    L.o_dist = take(off, L.npairs > 0 ? L.npairs : 1);
+  }
+  // Then one region that is used twice - by the assembly phase (q, targets, joint
+  // transforms, per-task blocks, body CoMs) and, once A / b / box are built, by the QR
+  // scratch (compacted columns, R, right-hand sides).  Overlaying the two and packing R
+  // roughly halves the footprint, which is what bounds the number of resident warps per SM.
+  const int shared_base = off;
+  int a = shared_base;  // assembly view
+  L.o_q = take(a, L.nq);
+  L.o_t = take(a, stride);
+  L.o_tw = take(a, kTwStride * (L.nj > 0 ? L.nj : 1));
+  L.o_root = take(a, 12);
+  L.o_tf = take(a, kTreeTaskWords * (ntasks > 0 ? ntasks : 1));
+  L.o_cw = take(a, 3 * (L.nj + 1));
+  int b2 = shared_base;  // QP view
+  L.o_aw = take(b2, Kp * L.ldw);
+  L.o_ru = take(b2, L.nv * (L.nv - 1) / 2 + 1);
+  L.o_rd = take(b2, L.nv);
+  L.o_zt = take(b2, L.nv);
+  L.o_zb = take(b2, K);
+  L.o_rho = take(b2, K);
+  L.o_ys = b2;  // unused
+  L.o_idx = take(b2, L.nv);
+  L.o_xa = take(b2, L.nv);
+  L.words = a > b2 ? a : b2;
+}
+
+// `X` (host image of the extras): barriers become the dense rows of the warp-cooperative
+// dual method; equality constraints and the floating-base limit stay on the general path.
+inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok, const DevExtras* X = nullptr) {
   TreePlan L;
   memset(&L, 0, sizeof(L));
+  if (X) {
+    for (int b = 0; b < X->nbarriers; ++b) {
+      L.p += X->barriers[b].dim;
+      if (X->barriers[b].type == PK_BARRIER_SELF_COLLISION) L.npairs = std::max(L.npairs, X->barriers[b].npairs);
+    }
+  }
   L.nj = m.njoints;
   L.nq = m.nq;
   L.nv = m.nv;
@@ -379,38 +450,10 @@ inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok
   // once A / b / box are built, by the QR scratch (compacted columns, R, right-hand
   // sides).  Overlaying the two and packing R roughly halves the footprint, which is
   // what bounds the number of resident warps per SM.
-  int off = 0;
-  auto take = [&](int& cursor, int words) { const int at = cursor; cursor += (words + 3) / 4 * 4; return at; };
-  const int Kp = K > 0 ? K : 1;
-  L.o_A = take(off, Kp * L.lda);
-  L.o_b = take(off, K);
-  L.o_d = take(off, L.nv);
-  L.o_beta = take(off, L.nv);
-  L.o_lo = take(off, L.nv);
-  L.o_hi = take(off, L.nv);
-  L.o_x = take(off, L.nv);
-  L.o_y = take(off, L.nv);
-  L.o_g = off;  // unused
-  const int shared_base = off;
-  int a = shared_base;  // assembly view
-  L.o_q = take(a, L.nq);
-  L.o_t = take(a, L.stride);
-  L.o_tw = take(a, kTwStride * (L.nj > 0 ? L.nj : 1));
-  L.o_root = take(a, 12);
-  L.o_tf = take(a, kTreeTaskWords * (P.ntasks > 0 ? P.ntasks : 1));
-  L.o_cw = take(a, 3 * (L.nj + 1));
-  int b2 = shared_base;  // QP view
-  L.o_aw = take(b2, Kp * L.ldw);
-  L.o_ru = take(b2, L.nv * (L.nv - 1) / 2 + 1);
-  L.o_rd = take(b2, L.nv);
-  L.o_zt = take(b2, L.nv);
-  L.o_zb = take(b2, K);
-  L.o_rho = take(b2, K);
-  L.o_ys = b2;  // unused
-  L.o_idx = take(b2, L.nv);
-  L.o_xa = take(b2, L.nv);
-  L.words = a > b2 ? a : b2;
-  *ok = m.njoints >= 1 && m.njoints <= kTreeMaxJoints && m.nv <= 64 && P.ntasks <= 32 && K <= 64 &&
+  tree_layout(L, P.ntasks, L.stride);
+  const bool dense_ok = !X || (X->nconstraints == 0 && !X->fb_enabled && L.p <= 32 &&
+                               !(X->acc_enabled && X->acc_prev_shared && X->acc_prev_off >= 0));
+  *ok = dense_ok && m.njoints >= 1 && m.njoints <= kTreeMaxJoints && m.nv <= 64 && P.ntasks <= 32 && K <= 64 &&
         (size_t)L.words * 4 <= 48 * 1024;
   return L;
 }

@@ -24,7 +24,13 @@ struct TreePlan {
   int row_base[PK_MAX_TASKS];  // first row of A of each task (-1: none)
   int o_q, o_t, o_tw, o_root, o_tf, o_A, o_b, o_d, o_beta, o_lo, o_hi, o_x, o_y, o_g, o_aw, o_ru, o_rd, o_zt, o_zb,
       o_rho, o_ys, o_idx, o_cw, o_xa, words;
+  // dense inequality rows (barriers) and the state of the dual method (pk_treedual.cuh); p = 0: none
+  int p, ldj, npairs;
+  int o_G, o_hg, o_gn, o_J, o_RA, o_dv, o_z, o_r, o_u, o_act, o_xd, o_wd, o_gd, o_rhod, o_ud, o_dist;
 };
+
+// defined in pk_treedual.cuh
+PK_HD int tree_dual_solve(float* W, const TreePlan& L);
 
 constexpr int kTwStride = 13;     // 12 floats per joint transform, padded against bank conflicts
 constexpr int kMultiChange = 12;  // iterations with multi-add / multi-release before single steps
@@ -697,6 +703,146 @@ struct TreeStep {
         }
       }
     }
+    // ---- dense inequality rows of the barriers (pink/barriers/*.py), column-parallel ------
+    // G = -J_h / dt, h = gain * alpha(h(q)) (barrier.py:246-252); the safe-displacement
+    // term adds safe_gain / |J_h|_F^2 to the diagonal (barrier.py:193-203).  Same
+    // arithmetic as Generic::barrier_rows.
+    if (L.p > 0) {
+      const DevExtras& X = *P.ext;
+      int prow = 0;
+      #pragma unroll 1
+      for (int bi = 0; bi < X.nbarriers; ++bi) {
+        const DevBarrier& Bd = X.barriers[bi];
+        float* Gb = W + L.o_G + prow * L.lda;
+        float* hb = W + L.o_hg + prow;
+        LaneVar<float> fro;
+        PK_LANES(l) { fro[l] = 0.f; }
+        if (Bd.type == PK_BARRIER_POSITION) {
+          const SE3f Tf = compose(load_tw(W, L, Bd.body), load_se3(M.fX + 12 * Bd.frame));
+          PK_LANES(l) {
+            const float pw[3] = {Tf.p.x, Tf.p.y, Tf.p.z};
+            if (l == 0) {
+              int r = 0;
+              if (Bd.has_min)
+                for (int k = 0; k < Bd.nidx; ++k, ++r)
+                  hb[r] = Bd.gain[r] * Generic<1, 1>::barrier_gain_fn(Bd.gain_fn, pw[Bd.idx[k]] - Bd.p_min[k]);
+              if (Bd.has_max)
+                for (int k = 0; k < Bd.nidx; ++k, ++r)
+                  hb[r] = Bd.gain[r] * Generic<1, 1>::barrier_gain_fn(Bd.gain_fn, Bd.p_max[k] - pw[Bd.idx[k]]);
+            }
+            float f = 0.f;
+            #pragma unroll 1
+            for (int i = l; i < nv; i += 32) {
+              V3 lin, ang;
+              jac_col(M, W, L, Bd.body, Tf, i, lin, ang);
+              const V3 c = mul(Tf.R, lin);
+              const float cw[3] = {c.x, c.y, c.z};
+              int r = 0;
+              if (Bd.has_min)
+                for (int k = 0; k < Bd.nidx; ++k, ++r) { Gb[r * L.lda + i] = -cw[Bd.idx[k]] * P.inv_dt; f = fmaf(cw[Bd.idx[k]], cw[Bd.idx[k]], f); }
+              if (Bd.has_max)
+                for (int k = 0; k < Bd.nidx; ++k, ++r) { Gb[r * L.lda + i] = cw[Bd.idx[k]] * P.inv_dt; f = fmaf(cw[Bd.idx[k]], cw[Bd.idx[k]], f); }
+            }
+            fro[l] = f;
+          }
+        } else if (Bd.type == PK_BARRIER_BODY_SPHERICAL) {
+          const SE3f T1 = compose(load_tw(W, L, Bd.body), load_se3(M.fX + 12 * Bd.frame));
+          const SE3f T2 = compose(load_tw(W, L, Bd.body2), load_se3(M.fX + 12 * Bd.frame2));
+          const V3 dp = T1.p - T2.p;
+          PK_LANES(l) {
+            if (l == 0) hb[0] = Bd.gain[0] * Generic<1, 1>::barrier_gain_fn(Bd.gain_fn, dot(dp, dp) - Bd.d_min * Bd.d_min);
+            float f = 0.f;
+            #pragma unroll 1
+            for (int i = l; i < nv; i += 32) {
+              V3 l1, a1, l2, a2;
+              jac_col(M, W, L, Bd.body, T1, i, l1, a1);
+              jac_col(M, W, L, Bd.body2, T2, i, l2, a2);
+              const float jh = 2.f * dot(dp, mul(T1.R, l1) - mul(T2.R, l2));
+              Gb[i] = -jh * P.inv_dt;
+              f = fmaf(jh, jh, f);
+            }
+            fro[l] = f;
+          }
+        } else {
+          // SELF_COLLISION on sphere pairs: the `dim` smallest distances
+          float* dist = W + L.o_dist;
+          const int* pr = X.pairs + 2 * Bd.pair_off;
+          const float* rad = X.extra + Bd.data_off;
+          PK_LANES(l) {
+            #pragma unroll 1
+            for (int k = l; k < Bd.npairs; k += 32) {
+              const int fa = pr[2 * k], fb = pr[2 * k + 1];
+              const SE3f Ta = load_tw(W, L, M.frame_body[fa]);
+              const SE3f Tb = load_tw(W, L, M.frame_body[fb]);
+              const V3 ca = mul(Ta.R, v3(M.fX[12 * fa + 3], M.fX[12 * fa + 7], M.fX[12 * fa + 11])) + Ta.p;
+              const V3 cb = mul(Tb.R, v3(M.fX[12 * fb + 3], M.fX[12 * fb + 7], M.fX[12 * fb + 11])) + Tb.p;
+              const V3 dp = ca - cb;
+              dist[k] = sqrtf(dot(dp, dp)) - rad[2 * k] - rad[2 * k + 1];
+            }
+          }
+          PK_WSYNC();
+          #pragma unroll 1
+          for (int r = 0; r < Bd.dim; ++r) {
+            float bd;
+            int best;
+            {
+              LaneVar<float> dvl;
+              LaneVar<int> dil;
+              PK_LANES(l) {
+                float b0 = 3.0e38f;
+                int bi0 = 0x7fffffff;
+                #pragma unroll 1
+                for (int k = l; k < Bd.npairs; k += 32)
+                  if (dist[k] < b0) { b0 = dist[k]; bi0 = k; }
+                dvl[l] = b0;
+                dil[l] = bi0;
+              }
+              lane_argmin(dvl, dil, bd, best);
+            }
+            const bool have = best != 0x7fffffff;
+            SE3f Ta = identity_se3(), Tb = identity_se3();
+            int ba = -2, bb = -2;
+            if (have) {
+              const int fa = pr[2 * best], fb = pr[2 * best + 1];
+              ba = M.frame_body[fa];
+              bb = M.frame_body[fb];
+              Ta = compose(load_tw(W, L, ba), load_se3(M.fX + 12 * fa));
+              Tb = compose(load_tw(W, L, bb), load_se3(M.fX + 12 * fb));
+            }
+            const V3 dp = Ta.p - Tb.p;
+            const float gap = sqrtf(dot(dp, dp));
+            const bool zero = !have || !(gap > 0.f) || fabsf(bd) <= 1e-8f;
+            const V3 nrm = zero ? v3(0.f, 0.f, 0.f) : ((bd < 0.f ? -1.f : 1.f) / gap) * dp;
+            PK_WSYNC();
+            PK_LANES(l) {
+              if (l == 0) {
+                hb[r] = Bd.gain[0] * Generic<1, 1>::barrier_gain_fn(Bd.gain_fn, bd - Bd.d_min);
+                if (have) dist[best] = 3.0e38f;  // taken
+              }
+              float f = fro[l];
+              #pragma unroll 1
+              for (int i = l; i < nv; i += 32) {
+                float jh = 0.f;
+                if (!zero) {
+                  V3 l1, a1, l2, a2;
+                  jac_col(M, W, L, ba, Ta, i, l1, a1);
+                  jac_col(M, W, L, bb, Tb, i, l2, a2);
+                  jh = dot(nrm, mul(Ta.R, l1) - mul(Tb.R, l2));
+                }
+                Gb[r * L.lda + i] = -jh * P.inv_dt;
+                f = fmaf(jh, jh, f);
+              }
+              fro[l] = f;
+            }
+            PK_WSYNC();
+          }
+        }
+        const float fr = lane_sum(fro);
+        if (Bd.safe_gain > 1e-6f) diag += Bd.safe_gain / fr;
+        prow += Bd.dim;
+        PK_WSYNC();
+      }
+    }
     // diagonal terms (posture tasks), box
     PK_LANES(l) {
       #pragma unroll 1
@@ -738,7 +884,7 @@ struct TreeStep {
     }
     PK_WSYNC();
     // ---- QP -------------------------------------------------------------------------------
-    status |= solve_qp(W, L);
+    status |= (L.p > 0) ? tree_dual_solve(W, L) : solve_qp(W, L);
     PK_LANES(l) {
       #pragma unroll 1
       for (int i = l; i < nv; i += 32) vg[i] = W[L.o_x + i] * P.inv_dt;

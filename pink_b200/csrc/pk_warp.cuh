@@ -90,6 +90,12 @@ __device__ __forceinline__ int lane_or(const LaneVar<int>& a) {
 __device__ __forceinline__ float lane_bcast(const LaneVar<float>& a, int src) {
   return __shfl_sync(0xffffffffu, a.v, src);
 }
+__device__ __forceinline__ double lane_sum_d(const LaneVar<double>& a) {
+  double s = a.v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
 
 #else  // host emulation: one "warp" = a loop over 32 lanes
 
@@ -134,6 +140,16 @@ inline int lane_or(const LaneVar<int>& a) {
   return s;
 }
 inline float lane_bcast(const LaneVar<float>& a, int src) { return a.v[src]; }
+inline double lane_sum_d(const LaneVar<double>& a) {
+  double t[32];
+  for (int l = 0; l < 32; ++l) t[l] = a.v[l];
+  for (int o = 16; o > 0; o >>= 1) {
+    double n[32];
+    for (int l = 0; l < 32; ++l) n[l] = t[l] + t[l ^ o];
+    for (int l = 0; l < 32; ++l) t[l] = n[l];
+  }
+  return t[0];
+}
 
 #endif
 

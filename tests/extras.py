@@ -127,7 +127,7 @@ def ur5_extras(B, seed=3, active=True):
                          [lc], [olc], dt, workloads.UR5_DT and 1e-12, cm, safety_break=True)
 
 
-def g1_extras(B, seed=5):
+def g1_extras(B, seed=5, floating_base_limit=True):
     """G1-class humanoid (config 4 of BASELINE.json): CoM + feet + pelvis + wrist
     tasks, posture, a knee coupling task, default limits + floating-base velocity
     limit, sphere self-collision barrier (gain 20, safe displacement gain 1,
@@ -175,6 +175,8 @@ def g1_extras(B, seed=5):
     limits = [ConfigurationLimit(model), VelocityLimit(model), fb]
     olimits = [("configuration", 0.5), ("velocity", None),
                ("floating_base", table.frame_names.index("pelvis"), np.array([0.4, 0.2, np.inf, np.inf, np.inf, 1.0]))]
+    if not floating_base_limit:  # barriers only: the warp-cooperative kernel takes the problem
+        limits, olimits = limits[:2], olimits[:2]
     cb = SelfCollisionBarrier(n_collision_pairs=8, gain=20.0, safe_displacement_gain=1.0, d_min=0.05)
     pf, pr = cm.pair_frames(), cm.pair_radii().astype(np.float64)
     ocb = {"type": "self_collision", "pairs": [(int(a), int(b), float(ra), float(rb)) for (a, b), (ra, rb) in zip(pf, pr)],

@@ -113,13 +113,15 @@ int hs_solve_ik(void* model, const PkProblemDesc* prob, const float* q, const fl
   }
   if (path == 2 || (path == 0 && !chain)) {
     bool ok = false;
-    const pk::TreePlan L = pk::make_tree_plan(hm, P, &ok);
-    if (ok && (!hx.present || hx.box_only())) {
+    const pk::TreePlan L = pk::make_tree_plan(hm, P, &ok, hx.present ? &hx.X : nullptr);
+    if (ok) {
       if (used_chain) *used_chain = 2;
       const pk::DevModel M = hm.host_view();
-      std::vector<float> W(L.words);
+      std::vector<float> W(L.words + 8);
+      float* Wp = W.data();
+      if (((uintptr_t)Wp & 7) != 0) ++Wp;  // the dual method keeps doubles in the workspace
       for (int64_t i = 0; i < B; ++i)
-        pk::TreeStep::run(M, P, L, q + i * L.nq, targets ? targets + i * (int64_t)L.stride : nullptr, W.data(),
+        pk::TreeStep::run(M, P, L, q + i * L.nq, targets ? targets + i * (int64_t)L.stride : nullptr, Wp,
                           v + i * L.nv, status ? status + i : nullptr);
       return 0;
     }
@@ -214,6 +216,33 @@ int hs_dual_qp(int K, int n, int p, int meq, const float* A, const float* b, con
   float xs[PK_MAX_NV];
   const int st = QP::run(P, xs);
   for (int i = 0; i < n; ++i) x[i] = xs[i];
+  return st;
+}
+
+// Direct access to the warp-cooperative dual QP (pk_treedual.cuh) for unit tests; same
+// problem as hs_dual_qp without equalities.
+int hs_tree_dual_qp(int K, int n, int p, const float* A, const float* b, const float* d, const float* beta,
+                    const float* lo, const float* hi, const float* G, const float* h, float* x) {
+  pk::TreePlan L;
+  memset(&L, 0, sizeof(L));
+  L.nj = 1; L.nq = n; L.nv = n; L.K = K; L.p = p; L.npairs = 0;
+  pk::tree_layout(L, 1, 0);
+  std::vector<float> W(L.words + 8, 0.f);
+  float* Wp = W.data();
+  if (((uintptr_t)Wp & 7) != 0) ++Wp;  // doubles in the workspace
+  for (int r = 0; r < K; ++r) {
+    for (int c = 0; c < n; ++c) Wp[L.o_A + r * L.lda + c] = A[r * n + c];
+    Wp[L.o_b + r] = b[r];
+  }
+  for (int r = 0; r < p; ++r) {
+    for (int c = 0; c < n; ++c) Wp[L.o_G + r * L.lda + c] = G[r * n + c];
+    Wp[L.o_hg + r] = h[r];
+  }
+  for (int i = 0; i < n; ++i) {
+    Wp[L.o_d + i] = d[i]; Wp[L.o_beta + i] = beta[i]; Wp[L.o_lo + i] = lo[i]; Wp[L.o_hi + i] = hi[i];
+  }
+  const int st = pk::TreeDual::solve(Wp, L);
+  for (int i = 0; i < n; ++i) x[i] = Wp[L.o_x + i];
   return st;
 }
 }

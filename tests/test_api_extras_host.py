@@ -67,9 +67,10 @@ def test_joint_coupling_tasks_on_the_tree_kernel():
 def test_config4_feasibility_and_sample_parity_small(monkeypatch):
     """Same body as the full-size GPU test, on a batch the host build finishes quickly."""
     real = g.extras.g1_extras
-    monkeypatch.setattr(g.extras, "g1_extras", lambda B: real(96))
+    monkeypatch.setattr(g.extras, "g1_extras", lambda B, floating_base_limit=True: real(96, floating_base_limit=floating_base_limit))
     monkeypatch.setattr(g.np.random, "default_rng", lambda seed=0: _SmallChoice(real_rng(seed)))
-    g.test_config4_full_batch_feasibility_and_sample_parity()
+    g.test_config4_full_batch_feasibility_and_sample_parity(False)
+    g.test_config4_full_batch_feasibility_and_sample_parity(True)
 
 
 import numpy as _np

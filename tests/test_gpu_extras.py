@@ -63,14 +63,16 @@ def test_g1_config4_self_collision_barrier_matches_oracle():
     assert ok.all(), f"{(~ok).sum()} off, worst {np.abs(v - v_ref)[feasible].max()}"
 
 
-def test_gpu_agrees_with_host_build_on_the_dual_qp_path():
+@pytest.mark.parametrize("floating_base_limit", [False, True])
+def test_gpu_agrees_with_host_build_on_the_dual_qp_path(floating_base_limit):
     from tests.hostsim import HostSim
 
-    sc = extras.g1_extras(64)
+    sc = extras.g1_extras(64, floating_base_limit=floating_base_limit)
     v, st = _solve(sc)
     hs = HostSim(sc.model)
     prob, targets, _ = sc.problem()
     v_h, st_h = hs.solve_ik(prob, sc.q32, targets)
+    assert hs.used_tree == (not floating_base_limit)
     np.testing.assert_array_equal(st, st_h)
     assert (st != 0).any() and (v[st != 0] == 0).all()  # infeasible instances: flagged, zero velocity
     np.testing.assert_allclose(v[st == 0], v_h[st == 0], rtol=2e-3, atol=2e-4)
@@ -175,12 +177,15 @@ def test_joint_coupling_tasks_on_the_tree_kernel():
     assert np.allclose(J[0].cpu().numpy(), jc2.A)
 
 
-def test_config4_full_batch_feasibility_and_sample_parity():
+@pytest.mark.parametrize("floating_base_limit", [False, True])
+def test_config4_full_batch_feasibility_and_sample_parity(floating_base_limit):
     """BASELINE config 4 at full size (B = 16384, G1-class + sphere self-collision
     barrier): every velocity flagged OK satisfies the dense rows and the box of its own
     QP (rows exported by pk_constraint_rows_batched), infeasible instances are flagged with
-    zero velocity, and a random sample matches the oracle."""
-    sc = extras.g1_extras(16384)
+    zero velocity, and a random sample matches the oracle.  Without the floating-base
+    limit the warp-cooperative kernel runs (dual QP in shared memory), with it the
+    general path."""
+    sc = extras.g1_extras(16384, floating_base_limit=floating_base_limit)
     v, st = _solve(sc)
     ok = st == 0
     assert ok.mean() > 0.95 and ((st[~ok] & _cabi.PK_STATUS_NO_SOLUTION) != 0).all() and not v[~ok].any()

@@ -130,3 +130,67 @@ def test_ill_conditioned_humanoid_like():
         worst = max(worst, np.abs(x - ref.x).max())
     # |x| <= 0.02; 2e-4 rad/s at dt = 5 ms is 1e-6 in x
     assert worst < 2e-6, worst
+
+
+# ---- the warp-cooperative variant used by the tree kernel (pk_treedual.cuh) ------------
+
+
+def tree_dual_qp(A, b, d, beta, lo, hi, G, h):
+    K, n = A.shape
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    args = [f32(a) for a in (A, b, d, beta, lo, hi, G, h)]
+    x = np.zeros(n, dtype=np.float32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    st = hostsim.lib().hs_tree_dual_qp(K, n, G.shape[0], *[ptr(a) for a in args], ptr(x))
+    return x.astype(np.float64), st
+
+
+@pytest.mark.parametrize("n,K,p", [(6, 6, 3), (12, 9, 5), (33, 30, 6), (35, 33, 8), (40, 45, 24), (64, 60, 16)])
+def test_warp_cooperative_variant_matches_oracle(n, K, p):
+    rng = np.random.default_rng(1000 * n + p)
+    worst, solved, infeasible = 0.0, 0, 0
+    for _ in range(30 if n <= 12 else 8):
+        A, b, d, beta, lo, hi, G, h, _, _ = random_problem(rng, n, K, p, 0)
+        ref = reference(A, b, d, beta, lo, hi, G, h)
+        x, st = tree_dual_qp(A, b, d, beta, lo, hi, G, h)
+        if not ref.found:
+            assert st & STATUS_NO_SOLUTION
+            infeasible += 1
+            continue
+        assert st == 0, st
+        solved += 1
+        worst = max(worst, np.abs(x - ref.x).max() / (np.abs(ref.x).max() + 1e-3))
+    assert solved > 0
+    assert worst < 2e-4, worst
+
+
+def test_warp_cooperative_variant_ill_conditioned_and_infeasible():
+    rng = np.random.default_rng(11)
+    n, K = 35, 33
+    worst = 0.0
+    for _ in range(6):
+        A = rng.normal(size=(K, n))
+        A[:3] *= 200.0
+        A[3:] *= rng.choice([2.0, 4.0, 10.0], size=(K - 3, 1))
+        b = A @ rng.normal(size=n) * 0.01
+        d = np.full(n, np.sqrt(0.02))
+        beta = rng.normal(size=n) * 0.01
+        lo, hi = np.full(n, -0.02), np.full(n, 0.02)
+        G = rng.normal(size=(6, n))
+        h = np.abs(rng.normal(size=6)) * 0.02
+        ref = reference(A, b, d, beta, lo, hi, G, h)
+        x, st = tree_dual_qp(A, b, d, beta, lo, hi, G, h)
+        assert ref.found and st == 0
+        worst = max(worst, np.abs(x - ref.x).max())
+    assert worst < 2e-6, worst
+    # contradictory rows; a box that excludes a row; unbounded coordinates
+    A, b, d, beta, lo, hi, _, _, _, _ = random_problem(rng, 5, 5, 0, 0)
+    G = np.zeros((2, 5)); G[0, 0] = 1.0; G[1, 0] = -1.0
+    _, st = tree_dual_qp(A, b, d, beta, np.full(5, -np.inf), np.full(5, np.inf), G, np.array([-1.0, -1.0]))
+    assert st & STATUS_NO_SOLUTION
+    G = np.ones((1, 5))
+    _, st = tree_dual_qp(A, b, d, beta, np.full(5, 0.1), np.full(5, 0.2), G, np.array([0.0]))
+    assert st & STATUS_NO_SOLUTION
+    x, st = tree_dual_qp(A, b, d, beta, np.full(5, -np.inf), np.full(5, np.inf), G, np.array([0.0]))
+    ref = reference(A, b, d, beta, np.full(5, -np.inf), np.full(5, np.inf), G, np.array([0.0]))
+    assert st == 0 and np.abs(x - ref.x).max() < 1e-4

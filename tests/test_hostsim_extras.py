@@ -224,3 +224,42 @@ def test_frame_and_com_tasks_as_equality_constraints():
     x = v.astype(np.float64) * sc.dt
     res = np.abs(np.einsum("brn,bn->br", E[:, :9].astype(np.float64), x) - f[:, :9])
     assert res[feasible].max() < 2e-6
+
+
+def test_barriers_run_on_the_tree_kernel_body():
+    """Barriers without equality constraints / floating-base limit stay on the
+    warp-cooperative kernel (dual active-set QP in shared memory, pk_treedual.cuh):
+    config 4 of BASELINE.json, and a UR5 with position + distance barriers."""
+    import torch
+
+    from oracle import ik as oik
+    from pink_b200.solve_ik import describe_problem
+
+    sc = extras.g1_extras(64, floating_base_limit=False)
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v, st = hs.solve_ik(prob, sc.q32, targets)
+    assert hs.used_tree
+    v_ref, st_ref = sc.oracle_solve()
+    feasible = st_ref == 0
+    assert feasible.mean() > 0.8 and not feasible.all()
+    assert (st[feasible] == 0).all() and ((st[~feasible] & _cabi.PK_STATUS_NO_SOLUTION) != 0).all()
+    assert not v[~feasible].any()
+    assert helpers.within_tolerance(v[feasible], v_ref[feasible]).all(), np.abs(v - v_ref)[feasible].max()
+    v_gen, st_gen = hs.solve_ik(prob, sc.q32, targets, path=1)
+    np.testing.assert_array_equal(st, st_gen)
+    np.testing.assert_allclose(v[feasible], v_gen[feasible], rtol=2e-3, atol=2e-4)
+
+    su = extras.ur5_extras(200)
+    prob, parts, _ = describe_problem(su.model, su.B, su.tasks, su.dt, su.damping, su.limits, su.safety_break,
+                                      su.barriers, None, su.collision_model)
+    targets = torch.cat([p.cpu().float() for p in parts], dim=1).numpy()
+    hs = HostSim(su.model)
+    v, st = hs.solve_ik(prob, su.q32, targets)
+    assert hs.used_tree and not hs.used_chain
+    v_ref, st_ref = oik.solve_ik_batch(su.table, su.q64, su.otasks, su.dt, su.damping, su.olimits, su.safety_break,
+                                       su.obarriers, [])
+    feasible = st_ref == 0
+    assert feasible.mean() > 0.5
+    assert (st[feasible] == 0).all() and ((st[~feasible] & _cabi.PK_STATUS_NO_SOLUTION) != 0).all()
+    assert helpers.within_tolerance(v[feasible], v_ref[feasible]).all(), np.abs(v - v_ref)[feasible].max()

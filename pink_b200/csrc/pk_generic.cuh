@@ -302,6 +302,20 @@ struct Generic {
     return mul(Tf.R, lin);
   }
 
+  // Distance-type barriers between two bodies of the same robot do not depend on
+  // coordinates that move both bodies rigidly: the floating base and every joint that
+  // supports both.  Analytically those Jacobian columns are exactly zero; computed as a
+  // difference of two point Jacobians in fp32 they come out as ~1e-7 |J| / dt of
+  // cancellation noise, which an active barrier row with a large multiplier turns into
+  // visible motion of the unbounded base.  true -> the column is zero by construction.
+  PK_HD static bool rigid_for_both(const DevModel& M, int body_a, int body_b, int i) {
+    if (body_a == -2 || body_b == -2) return false;
+    const int rv = M.free_flyer ? 6 : 0;
+    if (i < rv) return true;
+    const uint64_t common = M.anc[body_a + 2] & M.anc[body_b + 2];
+    return (common >> (i - rv)) & 1ull;
+  }
+
   PK_HD static float barrier_gain_fn(int fn, float h) { return fn == PK_GAINFN_SATURATING ? h / (1.f + fabsf(h)) : h; }
 
   // Rows of one barrier: Jh[dim][nv] = dh/dq and hv[dim] = h(q).
@@ -333,7 +347,9 @@ struct Generic {
       const V3 dp = T1.p - T2.p;
       hv[0] = dot(dp, dp) - Bd.d_min * Bd.d_min;
       for (int i = 0; i < nv; ++i)
-        Jh[0][i] = 2.f * dot(dp, point_jac_col(M, Bd.body, T1, i) - point_jac_col(M, Bd.body2, T2, i));
+        Jh[0][i] = rigid_for_both(M, Bd.body, Bd.body2, i)
+                       ? 0.f
+                       : 2.f * dot(dp, point_jac_col(M, Bd.body, T1, i) - point_jac_col(M, Bd.body2, T2, i));
       return;
     }
     // SELF_COLLISION on sphere pairs: the `dim` smallest distances
@@ -368,7 +384,9 @@ struct Generic {
       if (!(gap > 0.f) || fabsf(bd) <= 1e-8f) continue;
       const V3 n = ((bd < 0.f ? -1.f : 1.f) / gap) * dp;
       for (int i = 0; i < nv; ++i)
-        Jh[r][i] = dot(n, point_jac_col(M, M.frame_body[fa], Ta, i) - point_jac_col(M, M.frame_body[fb], Tb, i));
+        Jh[r][i] = rigid_for_both(M, M.frame_body[fa], M.frame_body[fb], i)
+                       ? 0.f
+                       : dot(n, point_jac_col(M, M.frame_body[fa], Ta, i) - point_jac_col(M, M.frame_body[fb], Tb, i));
     }
   }
 

@@ -757,7 +757,9 @@ struct TreeStep {
               V3 l1, a1, l2, a2;
               jac_col(M, W, L, Bd.body, T1, i, l1, a1);
               jac_col(M, W, L, Bd.body2, T2, i, l2, a2);
-              const float jh = 2.f * dot(dp, mul(T1.R, l1) - mul(T2.R, l2));
+              const float jh = Generic<1, 1>::rigid_for_both(M, Bd.body, Bd.body2, i)
+                                   ? 0.f
+                                   : 2.f * dot(dp, mul(T1.R, l1) - mul(T2.R, l2));
               Gb[i] = -jh * P.inv_dt;
               f = fmaf(jh, jh, f);
             }
@@ -823,7 +825,7 @@ struct TreeStep {
               #pragma unroll 1
               for (int i = l; i < nv; i += 32) {
                 float jh = 0.f;
-                if (!zero) {
+                if (!zero && !Generic<1, 1>::rigid_for_both(M, ba, bb, i)) {
                   V3 l1, a1, l2, a2;
                   jac_col(M, W, L, ba, Ta, i, l1, a1);
                   jac_col(M, W, L, bb, Tb, i, l2, a2);

@@ -443,6 +443,28 @@ struct DualQP {
       vtol = 1e-9f;
     }
     if (status & PK_STATUS_NO_SOLUTION) return status;
+    if (!(status & PK_STATUS_ITER_LIMIT)) {
+      // the rounds may run out on inconsistent rows that fp32 keeps "almost consistent":
+      // a point that still violates a constraint (active or not) is not a solution
+      for (int id = 0; id < m; ++id) {
+        float scale = 1.f, rhs;
+        if (id < P.meq + P.p) {
+          const float* row = (id < P.meq) ? P.E[id] : P.G[id - P.meq];
+          float nn = 0.f;
+          for (int k = 0; k < n; ++k) nn = fmaf(row[k], row[k], nn);
+          if (!(nn > 0.f)) continue;
+          scale = rsqrtf(nn);
+          rhs = (id < P.meq) ? P.f[id] : P.h[id - P.meq];
+        } else {
+          const int bid = id - P.meq - P.p;
+          rhs = (bid & 1) ? P.lo[bid >> 1] : P.hi[bid >> 1];
+          if (!(fabsf(rhs) < 3.0e38f)) continue;
+        }
+        float sv = (float)slack(id);
+        if (id < P.meq) sv = -fabsf(sv);
+        if (sv * scale < -1e-4f * (fabsf(rhs) * scale + 1e-3f)) return status | PK_STATUS_NO_SOLUTION;
+      }
+    }
     // Inconsistent rows that fp32 data rounding has turned "consistent" meet at infinity:
     // a displacement beyond 1e3 (rad or m, per step) on an unbounded coordinate (floating
     // base) is reported as no solution, like the exactly inconsistent case; also traps NaN.

@@ -268,15 +268,9 @@ struct TreeDual {
       PK_WSYNC();
     };
 
-    #pragma unroll 1
-    for (int round = 0; round < 6 && !(status & (PK_STATUS_NO_SOLUTION | PK_STATUS_ITER_LIMIT)); ++round) {
-      int changed = 0;
-      #pragma unroll 1
-      for (;; ++iter) {
-        if (iter >= max_iter) { status |= PK_STATUS_ITER_LIMIT; break; }
-        // step 1: most violated constraint (dense rows normalised by their norm)
-        int ip;
-        float worst;
+    // most violated constraint at xd (dense rows normalised by their norm); ip = 0x7fffffff:
+    // none beyond the tolerance, ip = -1: an empty row that can never hold
+    auto most_violated = [&](float tol_rel, int& ip, float& worst, bool all = false) {
         {
           LaneVar<float> bv_, dummy;
           LaneVar<int> bi;
@@ -286,28 +280,39 @@ struct TreeDual {
             int bid = 0x7fffffff;
             #pragma unroll 1
             for (int i = l; i < n; i += 32) {
-              if (!((in_hi >> i) & 1ull) && hi[i] < 3.0e38f) {
+              if ((all || !((in_hi >> i) & 1ull)) && hi[i] < 3.0e38f) {
                 const float s = (float)((double)hi[i] - xd[i]);
-                if (s < -vtol * (fabsf(hi[i]) + 1e-3f) && s < best) { best = s; bid = p + 2 * i; }
+                if (s < -tol_rel * (fabsf(hi[i]) + 1e-3f) && s < best) { best = s; bid = p + 2 * i; }
               }
-              if (!((in_lo >> i) & 1ull) && lo[i] > -3.0e38f) {
+              if ((all || !((in_lo >> i) & 1ull)) && lo[i] > -3.0e38f) {
                 const float s = (float)(xd[i] - (double)lo[i]);
-                if (s < -vtol * (fabsf(lo[i]) + 1e-3f) && s < best) { best = s; bid = p + 2 * i + 1; }
+                if (s < -tol_rel * (fabsf(lo[i]) + 1e-3f) && s < best) { best = s; bid = p + 2 * i + 1; }
               }
             }
-            if (l < p && !((in_gen >> l) & 1u)) {
+            if (l < p && (all || !((in_gen >> l) & 1u))) {
               double sacc = (double)hg[l];
               #pragma unroll 1
               for (int k = 0; k < n; ++k) sacc -= (double)G[l * L.lda + k] * xd[k];
               const float s = (float)sacc * gn[l];
               if (gn[l] == 0.f) { if (hg[l] < 0.f) { best = -3.0e38f; bid = -1; } }
-              else if (s < -vtol * (fabsf(hg[l]) * gn[l] + 1e-3f) && s < best) { best = s; bid = l; }
+              else if (s < -tol_rel * (fabsf(hg[l]) * gn[l] + 1e-3f) && s < best) { best = s; bid = l; }
             }
             bv_[l] = best;
             bi[l] = bid;
           }
           lane_argmin(bv_, bi, worst, ip);
         }
+    };
+    #pragma unroll 1
+    for (int round = 0; round < 6 && !(status & (PK_STATUS_NO_SOLUTION | PK_STATUS_ITER_LIMIT)); ++round) {
+      int changed = 0;
+      #pragma unroll 1
+      for (;; ++iter) {
+        if (iter >= max_iter) { status |= PK_STATUS_ITER_LIMIT; break; }
+        // step 1: most violated constraint (dense rows normalised by their norm)
+        int ip;
+        float worst;
+        most_violated(vtol, ip, worst);
         if (ip == -1) { status |= PK_STATUS_NO_SOLUTION; break; }  // empty row with h < 0
         if (ip == 0x7fffffff) break;
         ++changed;
@@ -495,6 +500,14 @@ struct TreeDual {
         ++changed;
       }
       vtol = 1e-9f;
+    }
+    if (!(status & (PK_STATUS_NO_SOLUTION | PK_STATUS_ITER_LIMIT))) {
+      // the rounds may run out on inconsistent rows that fp32 keeps "almost consistent":
+      // a point that still violates a constraint is not a solution
+      int ipf;
+      float wf;
+      most_violated(1e-4f, ipf, wf, true);
+      if (ipf != 0x7fffffff) status |= PK_STATUS_NO_SOLUTION;
     }
     if (status & PK_STATUS_NO_SOLUTION) {
       PK_LANES(l) {

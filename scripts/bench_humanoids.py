@@ -64,7 +64,7 @@ def main():
         ms = e0.elapsed_time(e1) / steps
         ach = B * BYTES[name] / (ms * 1e-3) / 1e9
         print(json.dumps({
-            "config": name + (" (synthetic) + self-collision barrier (36 sphere pairs, 8 closest), dual-QP general path"
+            "config": name + (" (synthetic) + self-collision barrier (36 sphere pairs, 8 closest), tree kernel with the warp-cooperative dual QP"
                               if config4 else " (synthetic), tree kernel"), "batch": B, "nv": model.nv, "ms_per_step": ms,
             "ik_steps_per_s": B / (ms * 1e-3), "hbm_gbs_algorithmic": ach, "hbm_frac_of_measured": ach / peak,
             "status_counts": {int(k): int(c) for k, c in zip(*np.unique(st.cpu().numpy(), return_counts=True))},

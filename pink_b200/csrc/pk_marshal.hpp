@@ -372,7 +372,6 @@ inline void tree_layout(TreePlan& L, int ntasks, int stride) {
     L.o_hg = take(off, L.p);
     L.o_gn = take(off, L.p);
     L.o_J = take(off, L.nv * L.ldj);
-    L.o_RA = take(off, L.nv * L.ldj);
     L.o_dv = take(off, L.nv);
     L.o_z = take(off, L.nv);
     L.o_r = take(off, L.nv + 1);
@@ -408,6 +407,14 @@ inline void tree_layout(TreePlan& L, int ntasks, int stride) {
   L.o_idx = take(b2, L.nv);
   L.o_xa = take(b2, L.nv);
   L.words = a > b2 ? a : b2;
+  if (L.p > 0) {
+    // third use of the region: once J = R^-1 is built the QR scratch is dead, and the
+    // triangular factor of the active normals (written from the first entering constraint
+    // on) takes its place
+    int c3 = shared_base;
+    L.o_RA = take(c3, L.nv * L.ldj);
+    L.words = c3 > L.words ? c3 : L.words;
+  }
 }
 
 // `X` (host image of the extras): barriers become the dense rows of the warp-cooperative

@@ -62,10 +62,14 @@ struct TreeDual {
     const float* Rd = W + L.o_rd;
     const float* Ru = W + L.o_ru;
     const float* y = W + L.o_y;
-    // J = R^-1, column c by back-substitution (upper triangular)
+    // J = R^-1, column by column by back-substitution (upper triangular).  The work of
+    // column c grows like c^2 / 2, so lane l takes the pair (l, n-1-l): balanced, and no
+    // second pass in which the longest columns run alone (n <= 64).
     PK_LANES(l) {
       #pragma unroll 1
-      for (int c = l; c < n; c += 32) {
+      for (int h = 0; h < 2; ++h) {
+        const int c = h == 0 ? l : n - 1 - l;
+        if (c < 0 || c >= n || 2 * l > n - 1 || (h == 1 && c == l)) continue;
         #pragma unroll 1
         for (int i = n - 1; i >= 0; --i) {
           float s = 0.f;

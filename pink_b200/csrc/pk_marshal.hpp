@@ -418,11 +418,14 @@ inline void tree_layout(TreePlan& L, int ntasks, int stride) {
 }
 
 // `X` (host image of the extras): barriers become the dense rows of the warp-cooperative
-// dual method; equality constraints and the floating-base limit stay on the general path.
+// dual method, like the rows of the floating-base limit; equality constraints stay on the
+// general path.
 inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok, const DevExtras* X = nullptr) {
   TreePlan L;
   memset(&L, 0, sizeof(L));
   if (X) {
+    if (X->fb_enabled)
+      for (int r = 0; r < 6; ++r) L.p += std::isfinite(X->fb_max[r]) ? 2 : 0;
     for (int b = 0; b < X->nbarriers; ++b) {
       L.p += X->barriers[b].dim;
       if (X->barriers[b].type == PK_BARRIER_SELF_COLLISION) L.npairs = std::max(L.npairs, X->barriers[b].npairs);
@@ -458,7 +461,7 @@ inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok
   // sides).  Overlaying the two and packing R roughly halves the footprint, which is
   // what bounds the number of resident warps per SM.
   tree_layout(L, P.ntasks, L.stride);
-  const bool dense_ok = !X || (X->nconstraints == 0 && !X->fb_enabled && L.p <= 32 &&
+  const bool dense_ok = !X || (X->nconstraints == 0 && L.p <= 32 &&
                                !(X->acc_enabled && X->acc_prev_shared && X->acc_prev_off >= 0));
   *ok = dense_ok && m.njoints >= 1 && m.njoints <= kTreeMaxJoints && m.nv <= 64 && P.ntasks <= 32 && K <= 64 &&
         (size_t)L.words * 4 <= 48 * 1024;

@@ -710,6 +710,42 @@ struct TreeStep {
     if (L.p > 0) {
       const DevExtras& X = *P.ext;
       int prow = 0;
+      if (X.fb_enabled) {
+        // FloatingBaseVelocityLimit (pink/limits/floating_base_velocity_limit.py:118-148):
+        // +-J_frame[:, root] dq <= dt * twist_max, rows with an infinite bound dropped
+        const SE3f Tf = compose(load_tw(W, L, X.fb_body), load_se3(M.fX + 12 * X.fb_frame));
+        int nfin = 0;
+        #pragma unroll 1
+        for (int r = 0; r < 6; ++r) nfin += (X.fb_max[r] < 3.0e38f) ? 1 : 0;
+        float* Gb = W + L.o_G;
+        float* hb = W + L.o_hg;
+        PK_LANES(l) {
+          #pragma unroll 1
+          for (int i = l; i < nv; i += 32) {
+            V3 lin = v3(0.f, 0.f, 0.f), ang = v3(0.f, 0.f, 0.f);
+            if (i < rv) jac_col(M, W, L, X.fb_body, Tf, i, lin, ang);
+            const float col[6] = {lin.x, lin.y, lin.z, ang.x, ang.y, ang.z};
+            int rr = 0;
+            #pragma unroll 1
+            for (int r = 0; r < 6; ++r)
+              if (X.fb_max[r] < 3.0e38f) {
+                Gb[rr * L.lda + i] = col[r];
+                Gb[(nfin + rr) * L.lda + i] = -col[r];
+                ++rr;
+              }
+          }
+          if (l == 0) {
+            int rr = 0;
+            for (int r = 0; r < 6; ++r)
+              if (X.fb_max[r] < 3.0e38f) {
+                hb[rr] = hb[nfin + rr] = P.dt * X.fb_max[r];
+                ++rr;
+              }
+          }
+        }
+        prow += 2 * nfin;
+        PK_WSYNC();
+      }
       #pragma unroll 1
       for (int bi = 0; bi < X.nbarriers; ++bi) {
         const DevBarrier& Bd = X.barriers[bi];

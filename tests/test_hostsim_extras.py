@@ -92,11 +92,14 @@ def test_g1_self_collision_barrier_config_matches_oracle():
     hs = HostSim(sc.model)
     prob, targets, _ = sc.problem()
     v, st = hs.solve_ik(prob, sc.q32, targets)
-    assert not hs.used_tree
+    assert hs.used_tree  # floating-base rows and barrier rows: dual QP of the warp kernel
+    v_gen, st_gen = hs.solve_ik(prob, sc.q32, targets, path=1)  # thread-per-instance general path
+    np.testing.assert_array_equal(st, st_gen)
     v_ref, st_ref = sc.oracle_solve()
     feasible = st_ref == 0
     assert feasible.mean() > 0.8
     assert (st[feasible] == 0).all()
+    assert helpers.within_tolerance(v_gen[feasible], v_ref[feasible]).all()
     # infeasible QPs (penetrating spheres that cannot separate within the limits) are flagged
     assert ((st & _cabi.PK_STATUS_NO_SOLUTION) != 0)[~feasible].all() and not feasible.all()
     ok = helpers.within_tolerance(v[feasible], v_ref[feasible])

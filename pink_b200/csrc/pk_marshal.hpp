@@ -366,11 +366,15 @@ inline void tree_layout(TreePlan& L, int ntasks, int stride) {
   L.o_x = take(off, L.nv);
   L.o_y = take(off, L.nv);
   L.o_g = off;  // unused
-  if (L.p > 0) {
+  if (L.p > 0 || L.meq > 0) {
     // dense rows and dual-method state: persistent (not overlaid with the assembly scratch)
-    L.o_G = take(off, L.p * L.lda);
-    L.o_hg = take(off, L.p);
-    L.o_gn = take(off, L.p);
+    L.o_G = take(off, (L.p > 0 ? L.p : 1) * L.lda);
+    L.o_hg = take(off, L.p > 0 ? L.p : 1);
+    L.o_gn = take(off, L.p > 0 ? L.p : 1);
+    L.o_E = take(off, (L.meq > 0 ? L.meq : 1) * L.lda);
+    L.o_fe = take(off, L.meq > 0 ? L.meq : 1);
+    L.o_en = take(off, L.meq > 0 ? L.meq : 1);
+    L.o_asg = take(off, L.nv + 1);
     L.o_J = take(off, L.nv * L.ldj);
     L.o_dv = take(off, L.nv);
     L.o_z = take(off, L.nv);
@@ -394,7 +398,7 @@ inline void tree_layout(TreePlan& L, int ntasks, int stride) {
   L.o_t = take(a, stride);
   L.o_tw = take(a, kTwStride * (L.nj > 0 ? L.nj : 1));
   L.o_root = take(a, 12);
-  L.o_tf = take(a, kTreeTaskWords * (ntasks > 0 ? ntasks : 1));
+  L.o_tf = take(a, kTreeTaskWords * (ntasks + L.nct > 0 ? ntasks + L.nct : 1));
   L.o_cw = take(a, 3 * (L.nj + 1));
   int b2 = shared_base;  // QP view
   L.o_aw = take(b2, Kp * L.ldw);
@@ -407,7 +411,7 @@ inline void tree_layout(TreePlan& L, int ntasks, int stride) {
   L.o_idx = take(b2, L.nv);
   L.o_xa = take(b2, L.nv);
   L.words = a > b2 ? a : b2;
-  if (L.p > 0) {
+  if (L.p > 0 || L.meq > 0) {
     // third use of the region: once J = R^-1 is built the QR scratch is dead, and the
     // triangular factor of the active normals (written from the first entering constraint
     // on) takes its place
@@ -418,14 +422,15 @@ inline void tree_layout(TreePlan& L, int ntasks, int stride) {
 }
 
 // `X` (host image of the extras): barriers become the dense rows of the warp-cooperative
-// dual method, like the rows of the floating-base limit; equality constraints stay on the
-// general path.
+// dual method, like the rows of the floating-base limit and the equality rows of constraint tasks.
 inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok, const DevExtras* X = nullptr) {
   TreePlan L;
   memset(&L, 0, sizeof(L));
   if (X) {
     if (X->fb_enabled)
       for (int r = 0; r < 6; ++r) L.p += std::isfinite(X->fb_max[r]) ? 2 : 0;
+    L.meq = X->n_eq_rows;
+    L.nct = X->nconstraints;
     for (int b = 0; b < X->nbarriers; ++b) {
       L.p += X->barriers[b].dim;
       if (X->barriers[b].type == PK_BARRIER_SELF_COLLISION) L.npairs = std::max(L.npairs, X->barriers[b].npairs);
@@ -461,7 +466,7 @@ inline TreePlan make_tree_plan(const HostModel& m, const DevProblem& P, bool* ok
   // sides).  Overlaying the two and packing R roughly halves the footprint, which is
   // what bounds the number of resident warps per SM.
   tree_layout(L, P.ntasks, L.stride);
-  const bool dense_ok = !X || (X->nconstraints == 0 && L.p <= 32 &&
+  const bool dense_ok = !X || (L.p <= 32 && L.meq <= 32 && L.p + L.meq <= 60 && P.ntasks + L.nct <= 32 &&
                                !(X->acc_enabled && X->acc_prev_shared && X->acc_prev_off >= 0));
   *ok = dense_ok && m.njoints >= 1 && m.njoints <= kTreeMaxJoints && m.nv <= 64 && P.ntasks <= 32 && K <= 64 &&
         (size_t)L.words * 4 <= 48 * 1024;

@@ -25,8 +25,10 @@ struct TreePlan {
   int o_q, o_t, o_tw, o_root, o_tf, o_A, o_b, o_d, o_beta, o_lo, o_hi, o_x, o_y, o_g, o_aw, o_ru, o_rd, o_zt, o_zb,
       o_rho, o_ys, o_idx, o_cw, o_xa, words;
   // dense inequality rows (barriers) and the state of the dual method (pk_treedual.cuh); p = 0: none
-  int p, ldj, npairs;
-  int o_G, o_hg, o_gn, o_J, o_RA, o_dv, o_z, o_r, o_u, o_act, o_xd, o_wd, o_gd, o_rhod, o_ud, o_dist;
+  // meq: equality rows of solve_ik(..., constraints=...); nct: number of constraint tasks
+  int p, ldj, npairs, meq, nct;
+  int o_G, o_hg, o_gn, o_J, o_RA, o_dv, o_z, o_r, o_u, o_act, o_xd, o_wd, o_gd, o_rhod, o_ud, o_dist, o_E, o_fe, o_en,
+      o_asg;
 };
 
 // defined in pk_treedual.cuh
@@ -524,7 +526,10 @@ struct TreeStep {
     // world CoM of every body (only if a CoM task exists)
     bool has_com = false;
     #pragma unroll 1
-    for (int t = 0; t < P.ntasks; ++t) has_com = has_com || (P.tasks[t].type == PK_TASK_COM);
+    const int nt = P.ntasks + L.nct;  // objective tasks, then the tasks used as equality constraints
+    auto task_at = [&](int t) -> const DevTask& { return t < P.ntasks ? P.tasks[t] : P.ext->constraints[t - P.ntasks]; };
+    #pragma unroll 1
+    for (int t = 0; t < nt; ++t) has_com = has_com || (task_at(t).type == PK_TASK_COM);
     if (has_com) {
       PK_LANES(l) {
         for (int b = l; b <= nj; b += 32) {  // index b: body b - 1
@@ -538,8 +543,8 @@ struct TreeStep {
     }
     // ---- per-task quantities, one task per lane ------------------------------------------
     PK_LANES(l) {
-      if (l < P.ntasks) {
-        const DevTask& Kt = P.tasks[l];
+      if (l < nt) {
+        const DevTask& Kt = task_at(l);
         float* F = W + L.o_tf + kTreeTaskWords * l;
         const float* tgt = Kt.tgt_shared ? (P.shared + Kt.tgt_off) : (ts + Kt.tgt_off);
         if (Kt.type == PK_TASK_FRAME || Kt.type == PK_TASK_RELATIVE_FRAME) {
@@ -602,10 +607,12 @@ struct TreeStep {
     PK_WSYNC();
     // ---- rows of A (column-parallel), b, diagonal terms -----------------------------------
     float diag = P.damping;
+    int erow = 0;  // next equality row
     #pragma unroll 1
-    for (int t = 0; t < P.ntasks; ++t) {
-      const DevTask& Kt = P.tasks[t];
+    for (int t = 0; t < nt; ++t) {
+      const DevTask& Kt = task_at(t);
       const float* F = W + L.o_tf + kTreeTaskWords * t;
+      const bool as_constraint = t >= P.ntasks;  // J dq = -gain e (pink/solve_ik.py:143-148)
       if (is_diag_task(Kt.type)) {
         const float* tgt = Kt.tgt_shared ? (P.shared + Kt.tgt_off) : (ts + Kt.tgt_off);
         const float w2 = Kt.cost[0] * Kt.cost[0];
@@ -623,22 +630,30 @@ struct TreeStep {
         continue;
       }
       const int k = (Kt.type == PK_TASK_COM) ? 3 : (Kt.type == PK_TASK_LINEAR ? Kt.rows : 6);
-      float mu = 0.f;
-      #pragma unroll 1
-      for (int r = 0; r < k; ++r) {
-        const float ew = Kt.cost[r] * Kt.gain * F[30 + r];
-        mu = fmaf(ew, ew, mu);
+      int base;
+      if (as_constraint) {
+        base = erow;
+        erow += k;
+      } else {
+        float mu = 0.f;
+        #pragma unroll 1
+        for (int r = 0; r < k; ++r) {
+          const float ew = Kt.cost[r] * Kt.gain * F[30 + r];
+          mu = fmaf(ew, ew, mu);
+        }
+        diag = fmaf(Kt.lm, mu, diag);
+        base = L.row_base[t];
+        if (base < 0) continue;
       }
-      diag = fmaf(Kt.lm, mu, diag);
-      const int base = L.row_base[t];
-      if (base < 0) continue;
       PK_LANES(l) {
         // b entries of this task (rows with non-zero cost are packed in order)
         if (l == 0) {
           int row = base;
           #pragma unroll 1
-          for (int r = 0; r < k; ++r)
-            if (Kt.cost[r] != 0.f) W[L.o_b + row++] = Kt.cost[r] * Kt.gain * F[30 + r];
+          for (int r = 0; r < k; ++r) {
+            if (as_constraint) W[L.o_fe + row++] = -Kt.gain * F[30 + r];
+            else if (Kt.cost[r] != 0.f) W[L.o_b + row++] = Kt.cost[r] * Kt.gain * F[30 + r];
+          }
         }
         #pragma unroll 1
         for (int i = l; i < nv; i += 32) {
@@ -698,8 +713,10 @@ struct TreeStep {
           }
           int row = base;
           #pragma unroll 1
-          for (int r = 0; r < k; ++r)
-            if (Kt.cost[r] != 0.f) A[(row++) * L.lda + i] = Kt.cost[r] * col[r];
+          for (int r = 0; r < k; ++r) {
+            if (as_constraint) W[L.o_E + (row++) * L.lda + i] = col[r];
+            else if (Kt.cost[r] != 0.f) A[(row++) * L.lda + i] = Kt.cost[r] * col[r];
+          }
         }
       }
     }
@@ -922,7 +939,7 @@ struct TreeStep {
     }
     PK_WSYNC();
     // ---- QP -------------------------------------------------------------------------------
-    status |= (L.p > 0) ? tree_dual_solve(W, L) : solve_qp(W, L);
+    status |= (L.p > 0 || L.meq > 0) ? tree_dual_solve(W, L) : solve_qp(W, L);
     PK_LANES(l) {
       #pragma unroll 1
       for (int i = l; i < nv; i += 32) vg[i] = W[L.o_x + i] * P.inv_dt;

@@ -25,9 +25,15 @@
 namespace pk {
 
 struct TreeDual {
-  // constraint ids: [0, p) dense rows G x <= h; p + 2 i: x_i <= hi_i; p + 2 i + 1: x_i >= lo_i
+  // constraint ids: [0, meq) equalities E x = f (solve_ik(..., constraints=...), entered with
+  // the sign that makes them violated and never dropped); [meq, pp) dense rows G x <= h;
+  // pp + 2 i: x_i <= hi_i; pp + 2 i + 1: x_i >= lo_i
   static PK_HD int solve(float* W, const TreePlan& L) {
-    const int n = L.nv, K = L.K, p = L.p, ld = L.ldj;
+    const int n = L.nv, K = L.K, p = L.p, meq = L.meq, pp = L.meq + L.p, ld = L.ldj;
+    const float* E = W + L.o_E;
+    const float* fe = W + L.o_fe;
+    float* en = W + L.o_en;    // 1 / |E_r|
+    float* asg = W + L.o_asg;  // sign an active equality was entered with
     const float* A = W + L.o_A;
     const float* bv = W + L.o_b;
     const float* dg = W + L.o_d;
@@ -90,35 +96,43 @@ struct TreeDual {
         for (int k = 0; k < n; ++k) nn = fmaf(G[l * L.lda + k], G[l * L.lda + k], nn);
         gn[l] = (nn > 0.f) ? rsqrtf(nn) : 0.f;
       }
+      if (l < meq) {
+        float nn = 0.f;
+        #pragma unroll 1
+        for (int k = 0; k < n; ++k) nn = fmaf(E[l * L.lda + k], E[l * L.lda + k], nn);
+        en[l] = (nn > 0.f) ? rsqrtf(nn) : 0.f;
+      }
     }
     PK_WSYNC();
 
     int iq = 0;
-    uint64_t in_hi = 0ull, in_lo = 0ull;
-    uint32_t in_gen = 0u;
-    const int max_iter = 4 * (n + p) + 32;
+    uint64_t in_hi = 0ull, in_lo = 0ull, in_gen = 0ull;
+    const int max_iter = 4 * (n + pp) + 32;
     int iter = 0;
     float vtol = 1e-6f;
 
-    // slack of constraint id (s >= 0 form), computed by the whole warp
+    // slack of constraint id (s >= 0 form; equalities: E x - f, sign applied by the caller),
+    // computed by the whole warp
     auto slack = [&](int id) -> double {
-      if (id >= p) {
-        const int c = (id - p) >> 1;
-        return ((id - p) & 1) ? xd[c] - (double)lo[c] : (double)hi[c] - xd[c];
+      if (id >= pp) {
+        const int c = (id - pp) >> 1;
+        return ((id - pp) & 1) ? xd[c] - (double)lo[c] : (double)hi[c] - xd[c];
       }
+      const float* row = (id < meq) ? E + id * L.lda : G + (id - meq) * L.lda;
       LaneVar<double> part;
       PK_LANES(l) {
         double s = 0.0;
         #pragma unroll 1
-        for (int k = l; k < n; k += 32) s += (double)G[id * L.lda + k] * xd[k];
+        for (int k = l; k < n; k += 32) s += (double)row[k] * xd[k];
         part[l] = s;
       }
-      return (double)hg[id] - lane_sum_d(part);
+      const double dotv = lane_sum_d(part);
+      return (id < meq) ? dotv - (double)fe[id] : (double)hg[id - meq] - dotv;
     };
     auto set_member = [&](int id, bool on) {
-      if (id < p) { if (on) in_gen |= (1u << id); else in_gen &= ~(1u << id); return; }
-      const int c = (id - p) >> 1;
-      uint64_t& w = ((id - p) & 1) ? in_lo : in_hi;
+      if (id < pp) { if (on) in_gen |= (1ull << id); else in_gen &= ~(1ull << id); return; }
+      const int c = (id - pp) >> 1;
+      uint64_t& w = ((id - pp) & 1) ? in_lo : in_hi;
       if (on) w |= (1ull << c); else w &= ~(1ull << c);
     };
     // remove active constraint l (Givens on the Hessenberg part of RA and the same columns of J)
@@ -160,7 +174,7 @@ struct TreeDual {
       PK_LANES(l) {
         // act / u shift; done by one lane (short lists)
         if (l == 0) {
-          for (int c = l0; c < iq - 1; ++c) { act[c] = act[c + 1]; u[c] = u[c + 1]; }
+          for (int c = l0; c < iq - 1; ++c) { act[c] = act[c + 1]; u[c] = u[c + 1]; asg[c] = asg[c + 1]; }
           u[iq - 1] = u[iq];
         }
       }
@@ -179,7 +193,8 @@ struct TreeDual {
         // slacks of the active constraints -> wd[k] (right-hand side -s)
         #pragma unroll 1
         for (int k = 0; k < iq; ++k) {
-          const double sv = slack(act[k]);
+          double sv = slack(act[k]);
+          if (act[k] < meq) sv *= (double)asg[k];
           PK_LANES(l) { if (l == 0) wd[k] = -sv; }
         }
         PK_WSYNC();
@@ -225,8 +240,9 @@ struct TreeDual {
             #pragma unroll 1
             for (int k = 0; k < iq; ++k) {
               const int id = act[k];
-              if (id < p) g += ud[k] * (double)G[id * L.lda + i];
-              else if (((id - p) >> 1) == i) g -= ((id - p) & 1) ? ud[k] : -ud[k];
+              if (id < meq) g -= ud[k] * (double)asg[k] * (double)E[id * L.lda + i];
+              else if (id < pp) g += ud[k] * (double)G[(id - meq) * L.lda + i];
+              else if (((id - pp) >> 1) == i) g -= ((id - pp) & 1) ? ud[k] : -ud[k];
             }
             gd[i] = g;
           }
@@ -286,20 +302,28 @@ struct TreeDual {
             for (int i = l; i < n; i += 32) {
               if ((all || !((in_hi >> i) & 1ull)) && hi[i] < 3.0e38f) {
                 const float s = (float)((double)hi[i] - xd[i]);
-                if (s < -tol_rel * (fabsf(hi[i]) + 1e-3f) && s < best) { best = s; bid = p + 2 * i; }
+                if (s < -tol_rel * (fabsf(hi[i]) + 1e-3f) && s < best) { best = s; bid = pp + 2 * i; }
               }
               if ((all || !((in_lo >> i) & 1ull)) && lo[i] > -3.0e38f) {
                 const float s = (float)(xd[i] - (double)lo[i]);
-                if (s < -tol_rel * (fabsf(lo[i]) + 1e-3f) && s < best) { best = s; bid = p + 2 * i + 1; }
+                if (s < -tol_rel * (fabsf(lo[i]) + 1e-3f) && s < best) { best = s; bid = pp + 2 * i + 1; }
               }
             }
-            if (l < p && (all || !((in_gen >> l) & 1u))) {
+            if (l < p && (all || !((in_gen >> (meq + l)) & 1ull))) {
               double sacc = (double)hg[l];
               #pragma unroll 1
               for (int k = 0; k < n; ++k) sacc -= (double)G[l * L.lda + k] * xd[k];
               const float s = (float)sacc * gn[l];
               if (gn[l] == 0.f) { if (hg[l] < 0.f) { best = -3.0e38f; bid = -1; } }
-              else if (s < -tol_rel * (fabsf(hg[l]) * gn[l] + 1e-3f) && s < best) { best = s; bid = l; }
+              else if (s < -tol_rel * (fabsf(hg[l]) * gn[l] + 1e-3f) && s < best) { best = s; bid = meq + l; }
+            }
+            if (l < meq && (all || !((in_gen >> l) & 1ull))) {
+              double sacc = -(double)fe[l];
+              #pragma unroll 1
+              for (int k = 0; k < n; ++k) sacc += (double)E[l * L.lda + k] * xd[k];
+              const float s = -fabsf((float)sacc) * en[l];
+              if (en[l] == 0.f) { if (fe[l] != 0.f) { best = -3.0e38f; bid = -1; } }
+              else if (s < -tol_rel * (fabsf(fe[l]) * en[l] + 1e-3f) && s < best) { best = s; bid = l; }
             }
             bv_[l] = best;
             bi[l] = bid;
@@ -320,22 +344,29 @@ struct TreeDual {
         if (ip == -1) { status |= PK_STATUS_NO_SOLUTION; break; }  // empty row with h < 0
         if (ip == 0x7fffffff) break;
         ++changed;
+        // an equality enters with the sign that makes it a violated inequality
+        float sgn = 1.f;
+        if (ip < meq) sgn = (slack(ip) > 0.0) ? -1.f : 1.f;
+        // normal of the entering constraint as a dense row (nullptr: box row) and its sign
+        const float* nrow = (ip < meq) ? E + ip * L.lda : (ip < pp ? G + (ip - meq) * L.lda : nullptr);
+        const float nsg = (ip < meq) ? sgn : -1.f;
         PK_LANES(l) { if (l == 0) u[iq] = 0.f; }
         bool added = false;
         #pragma unroll 1
-        for (int inner = 0; inner <= n + p + 2 && !added; ++inner) {
+        for (int inner = 0; inner <= n + pp + 2 && !added; ++inner) {
           // step 2a: d = J^T n+, z = J2 d2, r = Ra^-1 d1
           PK_LANES(l) {
             #pragma unroll 1
             for (int i = l; i < n; i += 32) {
               float s;
-              if (ip >= p) {
-                const int c = (ip - p) >> 1;
-                s = ((ip - p) & 1) ? J[c * ld + i] : -J[c * ld + i];
+              if (ip >= pp) {
+                const int c = (ip - pp) >> 1;
+                s = ((ip - pp) & 1) ? J[c * ld + i] : -J[c * ld + i];
               } else {
                 s = 0.f;
                 #pragma unroll 1
-                for (int k = 0; k < n; ++k) s = fmaf(-J[k * ld + i], G[ip * L.lda + k], s);
+                for (int k = 0; k < n; ++k) s = fmaf(J[k * ld + i], nrow[k], s);
+                s *= nsg;
               }
               dv[i] = s;
             }
@@ -392,7 +423,7 @@ struct TreeDual {
               int bid = 0x7fffffff;
               #pragma unroll 1
               for (int k = l; k < iq; k += 32)
-                if (r[k] > 0.f) {
+                if (act[k] >= meq && r[k] > 0.f) {
                   const float t = fmaxf(u[k], 0.f) / r[k];
                   if (t < best) { best = t; bid = k; }
                 }
@@ -404,20 +435,20 @@ struct TreeDual {
           float t2 = 3.0e38f;
           if (!dependent) {
             float zn;
-            if (ip >= p) {
-              const int c = (ip - p) >> 1;
-              zn = ((ip - p) & 1) ? z[c] : -z[c];
+            if (ip >= pp) {
+              const int c = (ip - pp) >> 1;
+              zn = ((ip - pp) & 1) ? z[c] : -z[c];
             } else {
               LaneVar<float> part;
               PK_LANES(l) {
                 float s = 0.f;
                 #pragma unroll 1
-                for (int k = l; k < n; k += 32) s = fmaf(-G[ip * L.lda + k], z[k], s);
+                for (int k = l; k < n; k += 32) s = fmaf(nrow[k], z[k], s);
                 part[l] = s;
               }
-              zn = lane_sum(part);
+              zn = nsg * lane_sum(part);
             }
-            const float sp = (float)slack(ip);
+            const float sp = (ip < meq) ? sgn * (float)slack(ip) : (float)slack(ip);
             if (zn > 0.f) t2 = fmaxf(-sp, 0.f) / zn;
           }
           const float t = fminf(t1, t2);
@@ -457,6 +488,7 @@ struct TreeDual {
               if (l == 0) {
                 RA[iq * ld + iq] = alpha;
                 act[iq] = ip;
+                asg[iq] = sgn;
               }
             }
             PK_WSYNC();
@@ -486,7 +518,7 @@ struct TreeDual {
             #pragma unroll 1
             for (int k = l; k < iq; k += 32) {
               b2 = fmaxf(b2, fabsf(u[k]));
-              if (u[k] < a) { a = u[k]; bi = k; }
+              if (act[k] >= meq && u[k] < a) { a = u[k]; bi = k; }
             }
             mn[l] = a;
             mi[l] = bi;

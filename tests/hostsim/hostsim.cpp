@@ -221,11 +221,12 @@ int hs_dual_qp(int K, int n, int p, int meq, const float* A, const float* b, con
 
 // Direct access to the warp-cooperative dual QP (pk_treedual.cuh) for unit tests; same
 // problem as hs_dual_qp without equalities.
-int hs_tree_dual_qp(int K, int n, int p, const float* A, const float* b, const float* d, const float* beta,
-                    const float* lo, const float* hi, const float* G, const float* h, float* x) {
+int hs_tree_dual_qp(int K, int n, int p, int meq, const float* A, const float* b, const float* d, const float* beta,
+                    const float* lo, const float* hi, const float* G, const float* h, const float* E, const float* f,
+                    float* x) {
   pk::TreePlan L;
   memset(&L, 0, sizeof(L));
-  L.nj = 1; L.nq = n; L.nv = n; L.K = K; L.p = p; L.npairs = 0;
+  L.nj = 1; L.nq = n; L.nv = n; L.K = K; L.p = p; L.meq = meq; L.npairs = 0;
   pk::tree_layout(L, 1, 0);
   std::vector<float> W(L.words + 8, 0.f);
   float* Wp = W.data();
@@ -237,6 +238,10 @@ int hs_tree_dual_qp(int K, int n, int p, const float* A, const float* b, const f
   for (int r = 0; r < p; ++r) {
     for (int c = 0; c < n; ++c) Wp[L.o_G + r * L.lda + c] = G[r * n + c];
     Wp[L.o_hg + r] = h[r];
+  }
+  for (int r = 0; r < meq; ++r) {
+    for (int c = 0; c < n; ++c) Wp[L.o_E + r * L.lda + c] = E[r * n + c];
+    Wp[L.o_fe + r] = f[r];
   }
   for (int i = 0; i < n; ++i) {
     Wp[L.o_d + i] = d[i]; Wp[L.o_beta + i] = beta[i]; Wp[L.o_lo + i] = lo[i]; Wp[L.o_hi + i] = hi[i];

@@ -135,24 +135,28 @@ def test_ill_conditioned_humanoid_like():
 # ---- the warp-cooperative variant used by the tree kernel (pk_treedual.cuh) ------------
 
 
-def tree_dual_qp(A, b, d, beta, lo, hi, G, h):
+def tree_dual_qp(A, b, d, beta, lo, hi, G, h, E=None, f=None):
     K, n = A.shape
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
-    args = [f32(a) for a in (A, b, d, beta, lo, hi, G, h)]
+    E = np.zeros((0, n)) if E is None else E
+    f = np.zeros(0) if f is None else f
+    args = [f32(a) for a in (A, b, d, beta, lo, hi, G, h, E, f)]
     x = np.zeros(n, dtype=np.float32)
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
-    st = hostsim.lib().hs_tree_dual_qp(K, n, G.shape[0], *[ptr(a) for a in args], ptr(x))
+    st = hostsim.lib().hs_tree_dual_qp(K, n, G.shape[0], E.shape[0], *[ptr(a) for a in args[:8]], ptr(args[8]),
+                                       ptr(args[9]), ptr(x))
     return x.astype(np.float64), st
 
 
-@pytest.mark.parametrize("n,K,p", [(6, 6, 3), (12, 9, 5), (33, 30, 6), (35, 33, 8), (40, 45, 24), (64, 60, 16)])
-def test_warp_cooperative_variant_matches_oracle(n, K, p):
-    rng = np.random.default_rng(1000 * n + p)
+@pytest.mark.parametrize("n,K,p,meq", [(6, 6, 3, 0), (6, 6, 2, 1), (12, 9, 5, 2), (33, 30, 6, 0), (35, 33, 8, 3),
+                                       (35, 33, 0, 9), (40, 45, 24, 12), (64, 60, 16, 4)])
+def test_warp_cooperative_variant_matches_oracle(n, K, p, meq):
+    rng = np.random.default_rng(1000 * n + p + 7 * meq)
     worst, solved, infeasible = 0.0, 0, 0
     for _ in range(30 if n <= 12 else 8):
-        A, b, d, beta, lo, hi, G, h, _, _ = random_problem(rng, n, K, p, 0)
-        ref = reference(A, b, d, beta, lo, hi, G, h)
-        x, st = tree_dual_qp(A, b, d, beta, lo, hi, G, h)
+        A, b, d, beta, lo, hi, G, h, E, f = random_problem(rng, n, K, p, meq)
+        ref = reference(A, b, d, beta, lo, hi, G, h, E, f)
+        x, st = tree_dual_qp(A, b, d, beta, lo, hi, G, h, E, f)
         if not ref.found:
             assert st & STATUS_NO_SOLUTION
             infeasible += 1

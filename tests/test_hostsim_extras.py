@@ -63,7 +63,9 @@ def test_ur5_barriers_constraints_limits_match_oracle():
     hs = HostSim(sc.model)
     prob, targets, _ = sc.problem()
     v, st = hs.solve_ik(prob, sc.q32, targets)
-    assert not hs.used_chain and not hs.used_tree
+    assert hs.used_tree and not hs.used_chain  # barriers + an equality constraint: warp kernel
+    v_gen, st_gen = hs.solve_ik(prob, sc.q32, targets, path=1)  # thread-per-instance general path
+    np.testing.assert_array_equal(st, st_gen)
     v_ref, st_ref = sc.oracle_solve()
     feasible = st_ref == 0
     # infeasible QPs (barrier already violated and unreachable within the velocity box) are flagged alike
@@ -72,6 +74,7 @@ def test_ur5_barriers_constraints_limits_match_oracle():
     assert feasible.mean() > 0.5
     ok = helpers.within_tolerance(v[feasible], v_ref[feasible])
     assert ok.all(), f"{(~ok).sum()} of {feasible.sum()} off, worst {np.abs(v - v_ref)[feasible].max()}"
+    assert helpers.within_tolerance(v_gen[feasible], v_ref[feasible]).all()
     # the barrier rows matter: the same problem without them moves differently
     sc2 = extras.ur5_extras(300, active=False)
     v2_ref, _ = sc2.oracle_solve(60)
@@ -214,7 +217,9 @@ def test_frame_and_com_tasks_as_equality_constraints():
     targets = torch.cat([p.cpu().float() for p in parts], dim=1).numpy()
     hs = HostSim(sc.model)
     v, st = hs.solve_ik(prob, sc.q32, targets)
-    assert not hs.used_tree
+    assert hs.used_tree  # equality rows in the dual QP of the warp kernel
+    v_gen, st_gen = hs.solve_ik(prob, sc.q32, targets, path=1)
+    np.testing.assert_array_equal(st, st_gen)
     v_ref, st_ref = oik.solve_ik_batch(sc.table, sc.q64, otasks, sc.dt, sc.damping, sc.oracle_limits, sc.safety_break,
                                        None, ocons)
     feasible = st_ref == 0
@@ -222,6 +227,7 @@ def test_frame_and_com_tasks_as_equality_constraints():
     assert ((st[~feasible] & _cabi.PK_STATUS_NO_SOLUTION) != 0).all()
     assert helpers.within_tolerance(v[feasible], v_ref[feasible], atol=5e-4, rtol=5e-3).all(), \
         np.abs(v - v_ref)[feasible].max()
+    assert helpers.within_tolerance(v_gen[feasible], v_ref[feasible], atol=5e-4, rtol=5e-3).all()
     # the equalities hold in the exported rows: E dq = f
     _, _, E, f, _, _ = hs.constraint_rows(prob, sc.q32, targets)
     x = v.astype(np.float64) * sc.dt

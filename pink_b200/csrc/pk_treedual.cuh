@@ -1,9 +1,9 @@
 // Warp-cooperative dual active-set QP (Goldfarb-Idnani in square-root form) for the
 // tree kernel: the method of pk_dualqp.cuh with one instance per warp and the state
 // (J = R^-1, the triangular factor Ra of the active normals, multipliers) in the warp's
-// slice of shared memory instead of thread-local memory.  Box rows and dense inequality
-// rows (barriers: pink/barriers/barrier.py:206-254); equality constraints stay on the
-// general path.
+// slice of shared memory instead of thread-local memory.  Box rows, dense inequality rows
+// (barriers: pink/barriers/barrier.py:206-254; floating-base limit) and the equality rows of
+// solve_ik(..., constraints=...) (pink/solve_ik.py:125-149).
 //
 //   * R from TreeStep::eqp with nothing fixed (Householder QR of [diag(d); A]); J = R^-1
 //     by columns (lane c owns column c);

@@ -525,7 +525,6 @@ struct TreeStep {
     }
     // world CoM of every body (only if a CoM task exists)
     bool has_com = false;
-    #pragma unroll 1
     const int nt = P.ntasks + L.nct;  // objective tasks, then the tasks used as equality constraints
     auto task_at = [&](int t) -> const DevTask& { return t < P.ntasks ? P.tasks[t] : P.ext->constraints[t - P.ntasks]; };
     #pragma unroll 1

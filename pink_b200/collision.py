@@ -8,7 +8,8 @@ test and examples use sphere-decomposed URDFs): every sphere is a frame at its
 centre plus a radius, every collision pair a pair of spheres.
 """
 
-from typing import List, Sequence, Tuple
+import xml.etree.ElementTree as ET
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -27,9 +28,43 @@ class SphereCollisionModel:
         self.frames: List[int] = []
         self.radii: List[float] = []
         self.parents: List[int] = []
+        self.links: List[str] = []  # URDF link each sphere belongs to ("" if unknown)
         self.collisionPairs: List[Tuple[int, int]] = []
 
-    def add_sphere(self, name: str, parent_joint: int, center: Sequence[float], radius: float) -> int:
+    @classmethod
+    def from_urdf_string(cls, model, xml: str) -> "SphereCollisionModel":
+        """Spheres of the ``<collision><geometry><sphere radius=.../>`` elements of a
+        sphere-decomposed URDF (such as ``iiwa14_spheres_collision.urdf`` used by
+        ``tests/test_self_collision_barrier.py:26-31`` of the reference), attached to the
+        joints of ``model`` (built from the same URDF by
+        :func:`pink_b200.model.model_from_urdf_string`).  Collision elements with another
+        geometry are skipped."""
+        self = cls(model)
+        for link in ET.fromstring(xml).findall("link"):
+            lname = link.get("name")
+            if not model.existFrame(lname):
+                continue
+            frame = model.frames[model.getFrameId(lname)]
+            k = 0
+            for col in link.findall("collision"):
+                geom = col.find("geometry")
+                sphere = None if geom is None else geom.find("sphere")
+                if sphere is None:
+                    continue
+                origin = col.find("origin")
+                xyz = [0.0, 0.0, 0.0] if origin is None else [float(t) for t in origin.get("xyz", "0 0 0").split()]
+                center = frame.placement * np.asarray(xyz, dtype=float)
+                self.add_sphere(f"{lname}_{k}", frame.parentJoint, center, float(sphere.get("radius")), link=lname)
+                k += 1
+        return self
+
+    @classmethod
+    def from_urdf(cls, model, path: str) -> "SphereCollisionModel":
+        with open(path, "r", encoding="utf-8") as fh:
+            return cls.from_urdf_string(model, fh.read())
+
+    def add_sphere(self, name: str, parent_joint: int, center: Sequence[float], radius: float,
+                   link: str = "") -> int:
         """Attach a sphere to joint ``parent_joint`` (Pinocchio joint id), centre in
         the joint frame; returns the sphere index."""
         if radius < 0.0:
@@ -39,6 +74,7 @@ class SphereCollisionModel:
         self.frames.append(frame)
         self.radii.append(float(radius))
         self.parents.append(int(parent_joint))
+        self.links.append(link)
         return len(self.names) - 1
 
     def add_collision_pair(self, first: int, second: int) -> None:
@@ -57,12 +93,20 @@ class SphereCollisionModel:
                 self.collisionPairs.append((i, j))
 
     def remove_collision_pairs(self, excluded: Sequence[Tuple[str, str]]) -> None:
-        """Drop the pairs whose sphere names (or name prefixes up to the first '_')
-        match an excluded pair, the job of an SRDF ``disable_collisions`` list."""
+        """Drop the pairs whose sphere names or link names match an excluded pair, the job
+        of an SRDF ``disable_collisions`` list (``pin.removeCollisionPairs``)."""
         ex = {frozenset(p) for p in excluded}
         self.collisionPairs = [
-            (i, j) for (i, j) in self.collisionPairs if frozenset((self.names[i], self.names[j])) not in ex
+            (i, j) for (i, j) in self.collisionPairs
+            if frozenset((self.names[i], self.names[j])) not in ex
+            and frozenset((self.links[i], self.links[j])) not in ex
         ]
+
+    def remove_collision_pairs_from_srdf(self, path: str) -> None:
+        """``<disable_collisions link1="a" link2="b"/>`` entries of an SRDF file."""
+        with open(path, "r", encoding="utf-8") as fh:
+            root = ET.fromstring(fh.read())
+        self.remove_collision_pairs([(e.get("link1"), e.get("link2")) for e in root.iter("disable_collisions")])
 
     # arrays for the C-ABI ------------------------------------------------------
     def pair_frames(self) -> np.ndarray:

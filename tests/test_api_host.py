@@ -192,3 +192,47 @@ def test_se3_value_type():
     np.testing.assert_allclose(a.action @ a.actionInverse, np.eye(6), atol=1e-12)
     np.testing.assert_allclose(np.asarray(a), a.homogeneous)
     assert SE3(a.homogeneous).isApprox(a) and SE3(a.as_3x4()).isApprox(a)
+
+
+def test_sphere_collision_model_from_urdf_and_srdf(tmp_path):
+    """Sphere-decomposed URDF -> SphereCollisionModel; process_collision_pairs with an SRDF
+    (pink/utils.py:116-142, tests/test_self_collision_barrier.py:26-43)."""
+    from pink_b200 import SphereCollisionModel
+    from pink_b200.barriers import SelfCollisionBarrier
+    from pink_b200.utils import process_collision_pairs
+
+    urdf = """
+    <robot name="spheres">
+      <link name="base"><collision><origin xyz="0 0 0.1"/><geometry><sphere radius="0.1"/></geometry></collision></link>
+      <link name="l1">
+        <collision><origin xyz="0.1 0 0"/><geometry><sphere radius="0.05"/></geometry></collision>
+        <collision><origin xyz="0.2 0 0"/><geometry><sphere radius="0.04"/></geometry></collision>
+        <collision><geometry><box size="1 1 1"/></geometry></collision>
+      </link>
+      <link name="l2"><collision><origin xyz="0 0.1 0"/><geometry><sphere radius="0.03"/></geometry></collision></link>
+      <joint name="j1" type="revolute"><parent link="base"/><child link="l1"/><origin xyz="0 0 0.3"/>
+        <axis xyz="0 0 1"/><limit lower="-1" upper="1" velocity="2"/></joint>
+      <joint name="j2" type="revolute"><parent link="l1"/><child link="l2"/><origin xyz="0.3 0 0" rpy="0 0 1.5707963"/>
+        <axis xyz="0 1 0"/><limit lower="-1" upper="1" velocity="2"/></joint>
+    </robot>"""
+    model = model_from_urdf_string(urdf)
+    cm = SphereCollisionModel.from_urdf_string(model, urdf)
+    assert cm.names == ["base_0", "l1_0", "l1_1", "l2_0"] and cm.radii == [0.1, 0.05, 0.04, 0.03]
+    assert cm.links == ["base", "l1", "l1", "l2"]
+    # centres in the parent-joint frames (the base link hangs on the universe)
+    table = model.table()
+    f = table.frame_names.index("sphere:l1_1")
+    np.testing.assert_allclose(table.frame_p[f], [0.2, 0.0, 0.0])
+    srdf = tmp_path / "pairs.srdf"
+    srdf.write_text('<robot name="spheres"><disable_collisions link1="base" link2="l1" reason="Adjacent"/></robot>')
+    assert process_collision_pairs(model, cm, str(srdf)) is None
+    names = {(cm.names[i], cm.names[j]) for i, j in cm.collisionPairs}
+    # same-joint pairs are never added; base-l1 pairs are disabled by the SRDF
+    assert names == {("base_0", "l2_0"), ("l1_0", "l2_0"), ("l1_1", "l2_0")}
+    barrier = SelfCollisionBarrier(n_collision_pairs=2, d_min=0.01)
+    prob, parts, _ = describe_problem(model, 4, [], 0.01, 1e-6, [], False, [barrier], None, cm)
+    assert prob.nbarriers == 1 and prob.barriers[0].npairs == 3 and prob.n_pairs == 3 and prob.n_extra == 6
+    from pink_b200.exceptions import InvalidCollisionPairs
+
+    with pytest.raises(InvalidCollisionPairs):
+        describe_problem(model, 4, [], 0.01, 1e-6, [], False, [SelfCollisionBarrier(n_collision_pairs=5)], None, cm)

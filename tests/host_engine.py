@@ -47,6 +47,23 @@ class HostEngine:
     def frame_jacobian(self, frame, q):
         return torch.as_tensor(self.hs.frame_jacobian(frame, self._np(q)))
 
+    def _f32(self, t, cols):
+        t = torch.as_tensor(np.asarray(t), dtype=torch.float32)
+        t = t.unsqueeze(0) if t.dim() == 1 else t
+        assert t.shape[1] == cols
+        return t.contiguous()
+
+    def integrate(self, q, v, dt, out=None):
+        """The device integration kernel lives in pk_cabi.cu (no host build); the harness
+        integrates with the oracle, rounded to the fp32 the kernel stores."""
+        from oracle import kinematics as okin
+
+        res = torch.as_tensor(okin.integrate(self.table, self._np(q), self._np(v).astype(np.float64) * dt).astype(np.float32))
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
 
 @pytest.fixture
 def host_engine(monkeypatch):

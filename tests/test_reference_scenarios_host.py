@@ -1,0 +1,191 @@
+"""The closed-loop scenarios of the reference's ``tests/test_solve_ik.py`` on the unbatched
+drop-in API (``Configuration`` -> ``solve_ik`` -> ``integrate``), with the engine routed
+to the host build of the kernels (tests/host_engine.py; test harness only).  The
+robots are the synthetic G1-/Draco3-class trees of ``pink_b200.robots`` (the
+robot_descriptions the reference uses are not in this image)."""
+
+import numpy as np
+import pytest
+from numpy.linalg import norm
+
+import pink_b200
+from pink_b200 import ComTask, Configuration, FrameTask, build_ik, solve_ik
+from pink_b200.exceptions import NotWithinConfigurationLimits
+from pink_b200.model import JointModelFreeFlyer
+from pink_b200.robots import load_robot_description
+from pink_b200.spatial import SE3
+from tests.host_engine import host_engine  # noqa: F401  (fixture)
+
+
+@pytest.fixture(autouse=True)
+def _cpu(host_engine):  # noqa: F811
+    yield
+
+
+def g1():
+    return load_robot_description("g1_description", root_joint=JointModelFreeFlyer())
+
+
+def test_checks_and_ignores_configuration_limits():
+    """tests/test_solve_ik.py:39-65."""
+    robot = g1()
+    q = robot.q0.copy()
+    q[7] = 20.0  # far above the first actuated joint's limit
+    configuration = Configuration(robot.model, robot.data, q)
+    with pytest.raises(NotWithinConfigurationLimits):
+        solve_ik(configuration, [], dt=1.0, solver="daqp")
+    solve_ik(configuration, [], dt=1.0, solver="daqp", safety_break=False)
+
+
+def test_no_task_gives_zero_velocity():
+    """tests/test_solve_ik.py:79-87."""
+    robot = g1()
+    configuration = Configuration(robot.model, robot.data, robot.q0)
+    v = solve_ik(configuration, [], dt=1e-3, solver="daqp")
+    assert v.shape == (robot.model.nv,) and np.allclose(v, 0.0)
+
+
+def test_single_task_fulfilled():
+    """tests/test_solve_ik.py:89-102."""
+    robot = g1()
+    configuration = Configuration(robot.model, robot.data, robot.q0)
+    task = FrameTask("left_ankle_roll_link", position_cost=1.0, orientation_cost=1.0)
+    task.set_target(configuration.get_transform_frame_to_world("left_ankle_roll_link"))
+    v = solve_ik(configuration, [task], dt=5e-3, solver="daqp")
+    assert np.allclose(v, 0.0, atol=1e-5)
+
+
+def test_single_task_convergence():
+    """tests/test_solve_ik.py:160-210: integrating the velocities brings the frame onto a
+    target 10 cm away, the error decreasing at every step.  fp32 kernels: "at the target"
+    is 1e-5 m instead of the 1e-8 of the fp64 reference."""
+    robot = g1()
+    frame = "left_ankle_roll_link"
+    configuration = Configuration(robot.model, robot.data, robot.q0)
+    task = FrameTask(frame, position_cost=1.0, orientation_cost=1.0)
+    init = configuration.get_transform_frame_to_world(frame)
+    target = init * SE3(np.eye(3), np.array([0.0, 0.0, 0.1]))
+    task.set_target(target)
+    dt = 5e-3
+    velocity = solve_ik(configuration, [task], dt, solver="daqp")
+    assert not np.allclose(velocity, 0.0)
+    assert abs(norm(task.compute_error(configuration)) - 0.1) < 1e-6
+    last_error = 1e6
+    for nb_steps in range(42):
+        error = norm(task.compute_error(configuration))
+        if error < 1e-5 and np.allclose(velocity, 0.0, atol=1e-2):
+            break
+        assert error < last_error
+        last_error = error
+        q = configuration.integrate(velocity, dt)
+        configuration = Configuration(robot.model, robot.data, q)
+        velocity = solve_ik(configuration, [task], dt, solver="daqp")
+    assert norm(task.compute_error(configuration)) < 1e-5
+    assert configuration.get_transform_frame_to_world(frame).isApprox(target, prec=1e-4)
+    assert nb_steps < 4  # the reference asserts < 3 with an fp64 backend; measured here: 2
+
+
+def test_single_task_translation():
+    """tests/test_solve_ik.py:212-247: translating the target gives a pure linear
+    velocity of the frame, along the translated axis."""
+    robot = g1()
+    frame = "right_ankle_roll_link"
+    configuration = Configuration(robot.model, robot.data, robot.q0)
+    task = FrameTask(frame, position_cost=1.0, orientation_cost=1.0)
+    target = configuration.get_transform_frame_to_world(frame).copy()
+    R0 = target.rotation.copy()
+    target.translation[1] -= 0.1
+    task.set_target(target)
+    task.lm_damping = 0.0
+    velocity = solve_ik(configuration, [task], dt=1e-3, damping=1e-12, solver="daqp")
+    twist = configuration.get_frame_jacobian(frame) @ velocity
+    linear_world = R0 @ twist[:3]
+    scale = norm(twist[:3])
+    assert scale > 1e-3
+    assert np.allclose(twist[3:], 0.0, atol=2e-4 * max(1.0, scale))
+    assert abs(linear_world[0]) < 2e-4 * max(1.0, scale) and abs(linear_world[2]) < 2e-4 * max(1.0, scale)
+    assert linear_world[1] < 0.0
+
+
+def _three_tasks(configuration, oc_pelvis):
+    names = ("pelvis", "left_ankle_roll_link", "right_ankle_roll_link")
+    tasks = [FrameTask(names[0], position_cost=1.0, orientation_cost=oc_pelvis),
+             FrameTask(names[1], position_cost=1.0, orientation_cost=3.0),
+             FrameTask(names[2], position_cost=1.0, orientation_cost=3.0)]
+    for t in tasks:
+        t.set_target(configuration.get_transform_frame_to_world(t.frame))
+    return tasks
+
+
+def test_three_tasks_fulfilled():
+    """tests/test_solve_ik.py:249-277."""
+    robot = g1()
+    configuration = Configuration(robot.model, robot.data, robot.q0)
+    velocity = solve_ik(configuration, _three_tasks(configuration, 3.0), dt=5e-3, solver="daqp")
+    assert np.allclose(velocity, 0.0, atol=1e-5)
+
+
+def _closed_loop(robot, configuration, tasks, dt, max_iter=60, conv=2e-3):
+    """Velocity-norm stopping rule of tests/test_solve_ik.py:316-333 (the fp32 kernels sit
+    on a velocity noise floor of about 1e-3 rad/s once the tasks are met, where the
+    reference with an fp64 backend reaches 1e-6)."""
+    for nb_iter in range(max_iter):
+        velocity = solve_ik(configuration, tasks, dt, solver="proxqp")
+        if norm(velocity) < conv:
+            break
+        q = configuration.integrate(velocity, dt)
+        configuration = Configuration(robot.model, robot.data, q)
+    return nb_iter, velocity, configuration
+
+
+def test_three_tasks_convergence():
+    """tests/test_solve_ik.py:279-339: both feet move 10 cm in opposite directions with
+    the pelvis position held."""
+    robot = g1()
+    configuration = Configuration(robot.model, robot.data, robot.q0)
+    pelvis, left, right = tasks = _three_tasks(configuration, 0.0)
+    left.set_target(left.transform_target_to_world * SE3(np.eye(3), np.array([0.1, 0.0, 0.0])))
+    right.set_target(right.transform_target_to_world * SE3(np.eye(3), np.array([-0.1, 0.0, 0.0])))
+    nb_iter, velocity, configuration = _closed_loop(robot, configuration, tasks, dt=4e-3)
+    assert nb_iter < 59 and norm(velocity) < 2e-3
+    assert max(norm(t.compute_error(configuration)) for t in tasks) < 0.5
+
+
+def test_com_task_fulfilled_and_convergence():
+    """tests/test_solve_ik.py:341-423: CoM and ankle tasks."""
+    robot = g1()
+    configuration = Configuration(robot.model, robot.data, robot.q0)
+    left = FrameTask("left_ankle_roll_link", position_cost=1.0, orientation_cost=3.0)
+    right = FrameTask("right_ankle_roll_link", position_cost=1.0, orientation_cost=3.0)
+    com = ComTask(cost=2.0)
+    left.set_target(configuration.get_transform_frame_to_world(left.frame))
+    right.set_target(configuration.get_transform_frame_to_world(right.frame))
+    com.set_target_from_configuration(configuration)
+    tasks = [com, left, right]
+    velocity = solve_ik(configuration, tasks, dt=5e-3, solver="daqp")
+    assert np.allclose(velocity, 0.0, atol=1e-5)
+
+    left.set_target(left.transform_target_to_world * SE3(np.eye(3), np.array([0.1, 0.0, 0.0])))
+    right.set_target(right.transform_target_to_world * SE3(np.eye(3), np.array([-0.1, 0.0, 0.0])))
+    com.set_target(com.target_com + np.array([0.0, 0.0, -0.05]))
+    nb_iter, velocity, configuration = _closed_loop(robot, configuration, tasks, dt=4e-3)
+    assert nb_iter < 59 and norm(velocity) < 2e-3
+    assert max(norm(t.compute_error(configuration)) for t in tasks) < 0.5
+
+
+def test_model_with_no_joint_limit_has_no_inequalities():
+    """tests/test_solve_ik.py:67-77, tests/test_limits.py:35-46: a model whose joints are
+    all unbounded yields G = h = None."""
+    from pink_b200.model import model_from_urdf_string
+
+    urdf = """
+    <robot name="free">
+      <link name="a"/><link name="b"/><link name="c"/>
+      <joint name="j1" type="continuous"><parent link="a"/><child link="b"/><axis xyz="0 0 1"/></joint>
+      <joint name="j2" type="continuous"><parent link="b"/><child link="c"/><origin xyz="0.2 0 0"/><axis xyz="0 1 0"/></joint>
+    </robot>"""
+    model = model_from_urdf_string(urdf)
+    configuration = Configuration(model, model.createData(), np.zeros(model.nq))
+    problem = build_ik(configuration, [], dt=1.0)
+    assert problem.G is None and problem.h is None
+    assert pink_b200.__version__

@@ -48,6 +48,11 @@ class VelocityLimit(Limit):
         """``velocity_limit.py:90-121``, evaluated by the CUDA library."""
         if self.projection_matrix is None:
             return None
+        if configuration is None:
+            # the rows are constants of (model, dt), no configuration to evaluate
+            # (tests/test_velocity_limit.py:46-55 calls it that way)
+            v_max = self.velocity_limit[self.indices]
+            return (np.vstack([self.projection_matrix, -self.projection_matrix]), dt * np.hstack([v_max, v_max]))
         from ..solve_ik import _limit_rows
 
         return _limit_rows(configuration, [self], dt)

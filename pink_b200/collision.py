@@ -108,9 +108,73 @@ class SphereCollisionModel:
             root = ET.fromstring(fh.read())
         self.remove_collision_pairs([(e.get("link1"), e.get("link2")) for e in root.iter("disable_collisions")])
 
+    @property
+    def geometryObjects(self) -> List["SphereObject"]:
+        """``collision_model.geometryObjects[i].parentJoint`` of the reference's barrier
+        (``pink/barriers/self_collision_barrier.py:181-191``)."""
+        return [SphereObject(n, j, r) for n, j, r in zip(self.names, self.parents, self.radii)]
+
     # arrays for the C-ABI ------------------------------------------------------
     def pair_frames(self) -> np.ndarray:
         return np.array([[self.frames[i], self.frames[j]] for i, j in self.collisionPairs], dtype=np.int32).reshape(-1, 2)
 
     def pair_radii(self) -> np.ndarray:
         return np.array([[self.radii[i], self.radii[j]] for i, j in self.collisionPairs], dtype=np.float32).reshape(-1, 2)
+
+
+class SphereObject:
+    """One entry of :attr:`SphereCollisionModel.geometryObjects`."""
+
+    def __init__(self, name: str, parent_joint: int, radius: float):
+        self.name = name
+        self.parentJoint = parent_joint
+        self.radius = radius
+
+
+class DistanceResult:
+    """``collision_data.distanceResults[k]``: signed distance of one sphere pair and its
+    nearest points in the world frame."""
+
+    def __init__(self, min_distance: float, p1: np.ndarray, p2: np.ndarray):
+        self.min_distance = min_distance
+        self._p1, self._p2 = p1, p2
+
+    def getNearestPoint1(self) -> np.ndarray:
+        return self._p1
+
+    def getNearestPoint2(self) -> np.ndarray:
+        return self._p2
+
+
+class SphereCollisionData:
+    """Counterpart of ``pin.GeometryData`` for a :class:`SphereCollisionModel`, returned by
+    :func:`pink_b200.utils.process_collision_pairs`.
+
+    The solver never reads it (the kernels evaluate the pair distances themselves); it
+    serves user code that inspects ``distanceResults`` as the reference's tests do
+    (``tests/test_self_collision_barrier.py:139-159``).  The results are evaluated on
+    access from the sphere-centre frames of the configuration bound last (unbatched
+    configurations only)."""
+
+    def __init__(self, collision_model: SphereCollisionModel):
+        self.collision_model = collision_model
+        self.enable_contact = True
+        self._configuration = None
+
+    def bind(self, configuration) -> None:
+        self._configuration = configuration
+
+    @property
+    def distanceResults(self) -> List[DistanceResult]:
+        cm, cfg = self.collision_model, self._configuration
+        if cfg is None or cfg.batched:
+            return [DistanceResult(float("nan"), np.full(3, np.nan), np.full(3, np.nan)) for _ in cm.collisionPairs]
+        cfg._ensure_fk()
+        out = []
+        for i, j in cm.collisionPairs:
+            ca = cfg.data.oMf[cm.frames[i]].translation
+            cb = cfg.data.oMf[cm.frames[j]].translation
+            gap = np.linalg.norm(cb - ca)
+            n = (cb - ca) / gap if gap > 0.0 else np.array([1.0, 0.0, 0.0])
+            out.append(DistanceResult(float(gap - cm.radii[i] - cm.radii[j]), ca + cm.radii[i] * n, cb - cm.radii[j] * n))
+        return out

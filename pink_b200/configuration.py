@@ -56,10 +56,13 @@ class Configuration:
             data = model.createData()
         self.data = data.copy() if copy_data else data
         self.tangent = model.tangent
-        # sphere collision model (pink_b200.collision.SphereCollisionModel); distances are
-        # evaluated inside the kernels, there is no host-side collision data
+        # sphere collision model (pink_b200.collision.SphereCollisionModel); the kernels
+        # evaluate the pair distances themselves, collision_data only serves user code that
+        # reads distanceResults (pink_b200.collision.SphereCollisionData)
         self.collision_model = collision_model
-        self.collision_data = None
+        self.collision_data = collision_data
+        if collision_data is not None and hasattr(collision_data, "bind"):
+            collision_data.bind(self)
         self._device = device
         self._set_q(q)
         # forward kinematics is lazy: nothing to do here

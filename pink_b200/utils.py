@@ -69,9 +69,12 @@ class VectorSpace:
 def process_collision_pairs(model, collision_model, srdf_path: str = ""):
     """Add every collision pair of ``collision_model`` (a
     :class:`pink_b200.SphereCollisionModel`) and drop the ones an SRDF file disables
-    (``pink/utils.py:116-142``).  Returns ``None``: the CUDA engine evaluates the
-    distances inside the kernels, there is no host-side collision data."""
+    (``pink/utils.py:116-142``).  Returns the collision data to hand to
+    :class:`pink_b200.Configuration` (a :class:`pink_b200.collision.SphereCollisionData`;
+    the solver itself evaluates the distances inside the kernels)."""
+    from .collision import SphereCollisionData
+
     collision_model.add_all_collision_pairs()
     if srdf_path != "":
         collision_model.remove_collision_pairs_from_srdf(srdf_path)
-    return None
+    return SphereCollisionData(collision_model)

@@ -48,7 +48,7 @@ class HostEngine:
         return torch.as_tensor(self.hs.frame_jacobian(frame, self._np(q)))
 
     def _f32(self, t, cols):
-        t = torch.as_tensor(np.asarray(t), dtype=torch.float32)
+        t = torch.tensor(np.asarray(t), dtype=torch.float32)
         t = t.unsqueeze(0) if t.dim() == 1 else t
         assert t.shape[1] == cols
         return t.contiguous()

@@ -225,7 +225,8 @@ def test_sphere_collision_model_from_urdf_and_srdf(tmp_path):
     np.testing.assert_allclose(table.frame_p[f], [0.2, 0.0, 0.0])
     srdf = tmp_path / "pairs.srdf"
     srdf.write_text('<robot name="spheres"><disable_collisions link1="base" link2="l1" reason="Adjacent"/></robot>')
-    assert process_collision_pairs(model, cm, str(srdf)) is None
+    data = process_collision_pairs(model, cm, str(srdf))
+    assert data.enable_contact and len(data.distanceResults) == 3
     names = {(cm.names[i], cm.names[j]) for i, j in cm.collisionPairs}
     # same-joint pairs are never added; base-l1 pairs are disabled by the SRDF
     assert names == {("base_0", "l2_0"), ("l1_0", "l2_0"), ("l1_1", "l2_0")}

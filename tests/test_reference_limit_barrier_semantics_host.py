@@ -320,4 +320,15 @@ def test_self_collision_barrier(sphere_arm):
     assert h_few.shape == (5,)
     for h_i in h_few:
         assert np.sum(h < h_i - 1e-6) < few.dim
+    # collision data is shared and follows the configuration constructed last, as pin.GeometryData does
+    configuration = Configuration(model, model.createData(), np.zeros(model.nq), collision_model=collision_model,
+                                  collision_data=collision_data)
+    distances = np.array([r.min_distance for r in configuration.collision_data.distanceResults]) - 0.02
+    assert configuration.collision_data.enable_contact and distances.shape == (n_pairs,)
+    assert np.allclose(np.sort(distances), np.sort(h), atol=1e-5)
+    for h_i in h_few:
+        assert np.sum(distances < h_i - 1e-6) < few.dim
+    r0 = configuration.collision_data.distanceResults[0]
+    assert abs(np.linalg.norm(r0.getNearestPoint2() - r0.getNearestPoint1()) - abs(r0.min_distance)) < 1e-9
+    assert collision_model.geometryObjects[0].parentJoint == collision_model.parents[0]
     assert pink_b200.__version__

@@ -340,3 +340,53 @@ def test_joint_coupling_task_semantics(humanoid):
     H, c = zero.compute_qp_objective(moved)
     qd = np.random.default_rng(5).random(humanoid.model.nv)
     assert abs(objective_value(H, c, qd)) < 1e-9
+
+
+# ---- Configuration / utils (tests/test_configuration.py:348-476, tests/test_utils.py:27-60) ---------------------
+
+def test_configuration_semantics(humanoid):
+    from pink_b200.exceptions import ConfigurationError, FrameNotFound, NotWithinConfigurationLimits
+    from pink_b200.utils import VectorSpace, custom_configuration_vector
+
+    model = humanoid.model
+    robot = load_robot_description("g1_description", root_joint=JointModelFreeFlyer())
+    # copy_data=False works directly on the caller's data (test_configuration.py:348-380)
+    shared = Configuration(robot.model, robot.data, robot.q0, copy_data=False)
+    assert shared.data is robot.data
+    copied = Configuration(robot.model, robot.data, robot.q0)
+    assert copied.data is not robot.data
+    T = humanoid.get_transform_frame_to_world("pelvis")
+    assert np.allclose(T.np[3, :], [0.0, 0.0, 0.0, 1.0])
+    with pytest.raises(FrameNotFound):
+        humanoid.get_transform_frame_to_world("foo")
+    with pytest.raises(FrameNotFound):
+        humanoid.get_frame_jacobian("does_not_exist")
+    humanoid.check_limits()
+    q = robot.q0.copy()
+    q[-10] += 1e4
+    with pytest.raises(NotWithinConfigurationLimits):
+        Configuration(robot.model, robot.data, q).check_limits()
+    # q is a read-only copy (test_configuration.py:420-432)
+    original_q = robot.q0.copy()
+    configuration = Configuration(robot.model, robot.data, original_q)
+    original_q[2] = 42.0
+    assert configuration.q[2] != 42.0
+    with pytest.raises(ValueError):
+        configuration.q[2] += 3.0
+    # tangent space helpers
+    v = np.arange(model.nv, dtype=float)
+    assert np.allclose(configuration.tangent.eye.dot(v), v)
+    assert np.sum(configuration.tangent.ones) == model.nv
+    assert np.sum(configuration.tangent.zeros) == 0.0 and len(configuration.tangent.zeros) == model.nv
+    tangent = VectorSpace(model.nv)
+    assert tangent.eye.shape == (model.nv, model.nv) and tangent.ones.shape == (model.nv,)
+    # in-place integration (test_configuration.py:469-476)
+    q0 = configuration.q.copy()
+    configuration.integrate_inplace(configuration.tangent.ones, dt=1e-3)
+    assert np.linalg.norm(configuration.q - q0) > 2e-3
+    # custom configuration vectors (test_utils.py:27-49)
+    q = custom_configuration_vector(robot, left_knee_joint=0.2, right_knee_joint=-0.2)
+    assert abs(q[get_joint_idx(model, "left_knee_joint")[0]] - 0.2) < 1e-12
+    assert abs(q[get_joint_idx(model, "right_knee_joint")[0]] + 0.2) < 1e-12
+    with pytest.raises(ConfigurationError):
+        custom_configuration_vector(robot, left_knee_joint=[0.1, 0.2])

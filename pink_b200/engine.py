@@ -68,7 +68,7 @@ class Engine:
     def _f32(self, t, cols: int) -> torch.Tensor:
         """``[B, cols]`` contiguous fp32 tensor on this device."""
         if not isinstance(t, torch.Tensor):
-            t = torch.as_tensor(np.asarray(t))
+            t = torch.tensor(np.asarray(t))  # copy: the source may be read-only
         t = t.to(device=self.device, dtype=torch.float32)
         if t.dim() == 1:
             t = t.unsqueeze(0)

@@ -15,7 +15,10 @@ import numpy as np
 from pink_b200 import _cabi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libpk_hostsim.so")
+# PK_HOSTSIM_SANITIZE=1: AddressSanitizer + UBSan build of the same sources (run the suite
+# with LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0)
+_SANITIZE = os.environ.get("PK_HOSTSIM_SANITIZE", "0") == "1"
+_SO = os.path.join(_HERE, "libpk_hostsim_asan.so" if _SANITIZE else "libpk_hostsim.so")
 _SRC = os.path.join(_HERE, "hostsim.cpp")
 _CSRC = os.path.join(_HERE, "..", "..", "pink_b200", "csrc")
 _lib = None
@@ -27,8 +30,9 @@ def build(force: bool = False) -> str:
     ]
     stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if force or stale:
+        extra = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"] if _SANITIZE else ["-O2"]
         subprocess.check_call(
-            ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+            ["g++", *extra, "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
              "-ffp-contract=off", "-o", _SO, _SRC]
         )
     return _SO

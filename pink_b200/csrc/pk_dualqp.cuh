@@ -179,6 +179,31 @@ struct DualQP {
     int iq = 0;
     // membership of the active set: one bit per general/equality row, two words for the box rows
     uint64_t in_hi = 0ull, in_lo = 0ull, in_gen = 0ull;
+    // Constraints that cannot enter (dependent on the active set, nothing to release) while
+    // violated by less than the final check accepts: opposing rows that pin a direction
+    // (lo == hi, a barrier with p_min == p_max) look like that once rounding leaves x 1e-8 on
+    // the wrong side of one of them.  Up to four ids, 8 bits each, 0xff = free.
+    unsigned skip = 0xffffffffu;
+    auto skipped = [&](int id) {
+      const unsigned v = (unsigned)id;
+      return ((skip & 255u) == v) | (((skip >> 8) & 255u) == v) | (((skip >> 16) & 255u) == v) | ((skip >> 24) == v);
+    };
+    // tolerance base of constraint id: |rhs| in units of its normalised row, + 1e-3
+    auto tol_base = [&](int id, float& scale) {
+      float rhs;
+      scale = 1.f;
+      if (id < P.meq + P.p) {
+        const float* row = (id < P.meq) ? P.E[id] : P.G[id - P.meq];
+        float nn = 0.f;
+        for (int k = 0; k < n; ++k) nn = fmaf(row[k], row[k], nn);
+        scale = (nn > 0.f) ? rsqrtf(nn) : 0.f;
+        rhs = (id < P.meq) ? P.f[id] : P.h[id - P.meq];
+      } else {
+        const int bid = id - P.meq - P.p;
+        rhs = (bid & 1) ? P.lo[bid >> 1] : P.hi[bid >> 1];
+      }
+      return fabsf(rhs) * scale + 1e-3f;
+    };
     const int max_iter = 4 * (n + P.p + P.meq) + 32;
     int iter = 0;
     // x is carried in fp64: slacks are then exact functions of the fp32 data, so that
@@ -318,6 +343,7 @@ struct DualQP {
         float worst = 0.f, sgn = 1.f;
         for (int id = 0; id < m; ++id) {
           float scale, rhs;
+          if (skipped(id)) continue;
           if (id < P.meq + P.p) {
             if ((in_gen >> id) & 1ull) continue;
             const float* row = (id < P.meq) ? P.E[id] : P.G[id - P.meq];
@@ -390,7 +416,19 @@ struct DualQP {
           printf("round %d iter %d ip %d sgn %g iq %d dd %g d2 %g dep %d t1 %g (l %d) t2 %g viol %g\n", round, iter, ip, sgn,
                  iq, dd, d2, (int)dependent, t1, l, t2, worst);
 #endif
-          if (!(t < 3.0e38f)) { status |= PK_STATUS_NO_SOLUTION; break; }
+          if (!(t < 3.0e38f)) {
+            float scale;
+            const float base = tol_base(ip, scale);
+            float viol = (float)slack(ip);
+            viol = ((ip < P.meq) ? fabsf(viol) : -viol) * scale;
+            if (viol <= 1e-4f * base && (skip >> 24) == 255u) {
+              skip = (skip << 8) | (unsigned)ip;  // tolerated: state untouched, look elsewhere
+              added = true;
+              break;
+            }
+            status |= PK_STATUS_NO_SOLUTION;
+            break;
+          }
           if (t2 < 3.0e38f)
             for (int k = 0; k < n; ++k) xd[k] += (double)t * (double)z[k];
           for (int k = 0; k < iq; ++k) u[k] = fmaf(-t, r[k], u[k]);
@@ -469,9 +507,9 @@ struct DualQP {
     // a displacement beyond 1e3 (rad or m, per step) on an unbounded coordinate (floating
     // base) is reported as no solution, like the exactly inconsistent case; also traps NaN.
     {
-      float xmax = 0.f;
-      for (int i = 0; i < n; ++i) xmax = fmaxf(xmax, fabsf(x[i]));
-      if (!(xmax < 1e3f)) return status | PK_STATUS_NO_SOLUTION;
+      bool sane = true;  // (fmaxf would drop a NaN)
+      for (int i = 0; i < n; ++i) sane = sane && (fabsf(x[i]) < 1e3f);
+      if (!sane) return status | PK_STATUS_NO_SOLUTION;
     }
     // coordinates on a bound sit exactly on it
     for (int i = 0; i < n; ++i) {

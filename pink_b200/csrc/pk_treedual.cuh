@@ -288,6 +288,14 @@ struct TreeDual {
       PK_WSYNC();
     };
 
+    // Constraints that cannot enter (dependent on the active set, nothing to release) while
+    // violated by less than the final check accepts (see pk_dualqp.cuh): up to four ids,
+    // 8 bits each, 0xff = free.
+    unsigned skip = 0xffffffffu;
+    auto skipped = [&](int id) {
+      const unsigned v = (unsigned)id;
+      return ((skip & 255u) == v) | (((skip >> 8) & 255u) == v) | (((skip >> 16) & 255u) == v) | ((skip >> 24) == v);
+    };
     // most violated constraint at xd (dense rows normalised by their norm); ip = 0x7fffffff:
     // none beyond the tolerance, ip = -1: an empty row that can never hold
     auto most_violated = [&](float tol_rel, int& ip, float& worst, bool all = false) {
@@ -300,16 +308,16 @@ struct TreeDual {
             int bid = 0x7fffffff;
             #pragma unroll 1
             for (int i = l; i < n; i += 32) {
-              if ((all || !((in_hi >> i) & 1ull)) && hi[i] < 3.0e38f) {
+              if ((all || !(((in_hi >> i) & 1ull) | skipped(pp + 2 * i))) && hi[i] < 3.0e38f) {
                 const float s = (float)((double)hi[i] - xd[i]);
                 if (s < -tol_rel * (fabsf(hi[i]) + 1e-3f) && s < best) { best = s; bid = pp + 2 * i; }
               }
-              if ((all || !((in_lo >> i) & 1ull)) && lo[i] > -3.0e38f) {
+              if ((all || !(((in_lo >> i) & 1ull) | skipped(pp + 2 * i + 1))) && lo[i] > -3.0e38f) {
                 const float s = (float)(xd[i] - (double)lo[i]);
                 if (s < -tol_rel * (fabsf(lo[i]) + 1e-3f) && s < best) { best = s; bid = pp + 2 * i + 1; }
               }
             }
-            if (l < p && (all || !((in_gen >> (meq + l)) & 1ull))) {
+            if (l < p && (all || !(((in_gen >> (meq + l)) & 1ull) | skipped(meq + l)))) {
               double sacc = (double)hg[l];
               #pragma unroll 1
               for (int k = 0; k < n; ++k) sacc -= (double)G[l * L.lda + k] * xd[k];
@@ -317,7 +325,7 @@ struct TreeDual {
               if (gn[l] == 0.f) { if (hg[l] < 0.f) { best = -3.0e38f; bid = -1; } }
               else if (s < -tol_rel * (fabsf(hg[l]) * gn[l] + 1e-3f) && s < best) { best = s; bid = meq + l; }
             }
-            if (l < meq && (all || !((in_gen >> l) & 1ull))) {
+            if (l < meq && (all || !(((in_gen >> l) & 1ull) | skipped(l)))) {
               double sacc = -(double)fe[l];
               #pragma unroll 1
               for (int k = 0; k < n; ++k) sacc += (double)E[l * L.lda + k] * xd[k];
@@ -452,7 +460,27 @@ struct TreeDual {
             if (zn > 0.f) t2 = fmaxf(-sp, 0.f) / zn;
           }
           const float t = fminf(t1, t2);
-          if (!(t < 3.0e38f)) { status |= PK_STATUS_NO_SOLUTION; break; }
+          if (!(t < 3.0e38f)) {
+            float viol, base;
+            if (ip >= pp) {
+              const int c = (ip - pp) >> 1;
+              base = fabsf(((ip - pp) & 1) ? lo[c] : hi[c]) + 1e-3f;
+              viol = -(float)slack(ip);
+            } else if (ip >= meq) {
+              base = fabsf(hg[ip - meq]) * gn[ip - meq] + 1e-3f;
+              viol = -(float)slack(ip) * gn[ip - meq];
+            } else {
+              base = fabsf(fe[ip]) * en[ip] + 1e-3f;
+              viol = fabsf((float)slack(ip)) * en[ip];
+            }
+            if (viol <= 1e-4f * base && (skip >> 24) == 255u) {
+              skip = (skip << 8) | (unsigned)ip;  // tolerated: state untouched, look elsewhere
+              added = true;
+              break;
+            }
+            status |= PK_STATUS_NO_SOLUTION;
+            break;
+          }
           PK_WSYNC();
           PK_LANES(l) {
             if (t2 < 3.0e38f) {

@@ -332,3 +332,32 @@ def test_self_collision_barrier(sphere_arm):
     assert abs(np.linalg.norm(r0.getNearestPoint2() - r0.getNearestPoint1()) - abs(r0.min_distance)) < 1e-9
     assert collision_model.geometryObjects[0].parentJoint == collision_model.parents[0]
     assert pink_b200.__version__
+
+
+def test_opposing_barrier_rows_pin_a_direction(humanoid):
+    """A position barrier with p_min == p_max (the frame held on a plane) gives two
+    opposing rows: the QP keeps the frame in the plane and moves it within
+    (the degenerate lo == hi case itself is pinned in test_hostsim_dualqp.py)."""
+    robot, configuration = humanoid
+    frame = "left_wrist_yaw_link"
+    p = configuration.get_transform_frame_to_world(frame).translation
+    task = FrameTask(frame, position_cost=1.0, orientation_cost=0.0)
+    T = configuration.get_transform_frame_to_world(frame)
+    T.translation[:] = p + np.array([0.05, 0.02, 0.08])
+    task.set_target(T)
+    barrier = PositionBarrier(frame, indices=[2], p_min=np.array([p[2]]), p_max=np.array([p[2]]), gain=1.0)
+    dt = 5e-3
+    limits = [robot.model.configuration_limit, robot.model.velocity_limit]
+    for force_generic in (False, True):
+        import os
+        if force_generic:
+            os.environ["PK_TREE"] = "0"
+        try:
+            v = solve_ik(configuration, [task], dt, solver="quadprog", barriers=[barrier], limits=limits)
+        finally:
+            os.environ.pop("PK_TREE", None)
+        J = configuration.get_frame_jacobian(frame)
+        R = configuration.get_transform_frame_to_world(frame).rotation
+        world_linear = R @ (J[:3] @ v)
+        assert np.linalg.norm(world_linear[:2]) > 1e-2  # moves in the plane
+        assert abs(world_linear[2]) < 1e-3 * max(1.0, np.linalg.norm(world_linear))  # not out of it

@@ -247,8 +247,15 @@ PK_HD void ik_step_chain(const ChainParams<NJ>& P, const float (&q)[NJ], const f
   for (int j = 0; j < NJ; ++j) x[j] = 0.f;
   if (!skip && !(status & PK_STATUS_NO_SOLUTION))
     status |= BoxLSQChol<6 * NFT, NJ>::run(C.A, C.b, C.d, C.beta, C.lo, C.hi, x, flags);
+  // a NaN / Inf in q or in a target passes every comparison above and ends up in x:
+  // report it (the reference's QP back-end fails on such a problem) instead of returning it
+  float sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) v[j] = x[j] * P.inv_dt;
+  for (int j = 0; j < NJ; ++j) sum += x[j];
+  const bool finite = fabsf(sum) < 3.0e38f;
+  if (!finite) status |= PK_STATUS_NO_SOLUTION;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) v[j] = finite ? x[j] * P.inv_dt : 0.f;
   status_out = status;
 }
 

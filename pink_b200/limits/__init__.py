@@ -11,10 +11,7 @@ from .floating_base_velocity_limit import FloatingBaseVelocityLimit
 from .limit import Limit
 from .velocity_limit import VelocityLimit
 
-__all__ = [
-    "AccelerationLimit",
-    "ConfigurationLimit",
-    "FloatingBaseVelocityLimit",
-    "Limit",
-    "VelocityLimit",
-]
+__all__ = [cls.__name__ for cls in (
+    AccelerationLimit, ConfigurationLimit,
+    FloatingBaseVelocityLimit, Limit, VelocityLimit,
+)]

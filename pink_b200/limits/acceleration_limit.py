@@ -1,11 +1,11 @@
 """Acceleration limit (``/root/reference/pink/limits/acceleration_limit.py``)."""
 
-from typing import List, Optional
+from typing import Optional
 
 import numpy as np
 
 from ..tasks._targets import as_vector_target
-from .limit import Limit
+from .limit import Limit, magnitude_limited, range_limited_coordinates, select_joints, selection_matrix
 
 
 class AccelerationLimit(Limit):
@@ -23,36 +23,18 @@ class AccelerationLimit(Limit):
 
     def __init__(self, model, acceleration_limit: np.ndarray):
         acceleration_limit = np.asarray(acceleration_limit, dtype=float).flatten()
-        has_acceleration_limit = np.logical_and(acceleration_limit < 1e20, acceleration_limit > 1e-10)
-        joints = [
-            joint
-            for joint in model.joints
-            if joint.idx_v >= 0
-            and has_acceleration_limit[slice(joint.idx_v, joint.idx_v + joint.nv)].all()
-        ]
-        has_configuration_limit = np.logical_and(
-            model.hasConfigurationLimit(),
-            np.logical_and(
-                model.upperPositionLimit < 1e20,
-                model.upperPositionLimit > model.lowerPositionLimit + 1e-10,
-            ),
-        )
-        index_list: List[int] = []
-        config_limit_list: List[bool] = []
-        for joint in joints:
-            index_list.extend(range(joint.idx_v, joint.idx_v + joint.nv))
-            joint_has_config_limit = bool(has_configuration_limit[slice(joint.idx_q, joint.idx_q + joint.nq)].all())
-            config_limit_list.extend([joint_has_config_limit] * joint.nv)
-        indices = np.array(index_list, dtype=np.int64)
-        indices.setflags(write=False)
-        dim = len(indices)
+        joints, indices = select_joints(model, magnitude_limited(acceleration_limit), "v")
+        # per selected tangent coordinate: does its joint also have a position range (the
+        # braking-distance term applies only there, acceleration_limit.py:88-100)
+        ranged = range_limited_coordinates(model)
+        with_range = [bool(ranged[j.idx_q:j.idx_q + j.nq].all()) for j in joints for _ in range(j.nv)]
         self.Delta_q_prev = np.zeros(model.nv)
-        self.a_max = acceleration_limit[indices] if dim > 0 else np.empty(0)
+        self.a_max = acceleration_limit[indices] if len(indices) > 0 else np.empty(0)
         self.acceleration_limit = acceleration_limit
-        self.has_configuration_limit = np.array(config_limit_list, dtype=bool)
+        self.has_configuration_limit = np.array(with_range, dtype=bool)
         self.indices = indices
         self.model = model
-        self.projection_matrix = np.eye(model.nv)[indices] if dim > 0 else None
+        self.projection_matrix = selection_matrix(model.nv, indices)
 
     def set_last_integration(self, v_prev, dt) -> None:
         """Latest integrated velocity (``[nv]`` or ``[B, nv]``) and its timestep."""

@@ -1,10 +1,10 @@
 """Configuration limit (``/root/reference/pink/limits/configuration_limit.py``)."""
 
-from typing import List, Optional, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 
-from .limit import Limit
+from .limit import Limit, range_limited_coordinates, select_joints, selection_matrix
 
 
 class ConfigurationLimit(Limit):
@@ -17,30 +17,10 @@ class ConfigurationLimit(Limit):
     def __init__(self, model, config_limit_gain: float = 0.5):
         assert 0.0 < config_limit_gain <= 1.0
         # selection at construction time (configuration_limit.py:50-72)
-        has_configuration_limit = np.logical_and(
-            model.hasConfigurationLimit(),
-            np.logical_and(
-                model.upperPositionLimit < 1e20,
-                model.upperPositionLimit > model.lowerPositionLimit + 1e-10,
-            ),
-        )
-        joints = [
-            joint
-            for joint in model.joints
-            if joint.idx_q >= 0
-            and has_configuration_limit[slice(joint.idx_q, joint.idx_q + joint.nq)].all()
-        ]
-        index_list: List[int] = []
-        for joint in joints:
-            index_list.extend(range(joint.idx_v, joint.idx_v + joint.nv))
-        indices = np.array(index_list, dtype=np.int64)
-        indices.setflags(write=False)
-        dim = len(indices)
+        self.joints, self.indices = select_joints(model, range_limited_coordinates(model), "q")
         self.config_limit_gain = config_limit_gain
-        self.indices = indices
-        self.joints = joints
         self.model = model
-        self.projection_matrix = np.eye(model.nv)[indices] if dim > 0 else None
+        self.projection_matrix = selection_matrix(model.nv, self.indices)
 
     def box_bounds(self) -> Tuple[np.ndarray, np.ndarray]:
         """Per-tangent-index position bounds (+-inf where no row exists), read

@@ -1,11 +1,11 @@
 """Velocity limit (``/root/reference/pink/limits/velocity_limit.py``)."""
 
-from typing import List, Optional, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 
 from ..exceptions import PinkError
-from .limit import Limit
+from .limit import Limit, magnitude_limited, select_joints, selection_matrix
 
 
 class VelocityLimit(Limit):
@@ -18,23 +18,9 @@ class VelocityLimit(Limit):
             velocity_limit = np.asarray(velocity_limit, dtype=float).flatten()
             if model.nv > 0 and velocity_limit.shape[0] != model.nv:
                 raise PinkError(f"{velocity_limit.shape=} but {model.nv=}")
-        has_velocity_limit = np.logical_and(velocity_limit < 1e20, velocity_limit > 1e-10)
-        joints = [
-            joint
-            for joint in model.joints
-            if joint.idx_v >= 0
-            and has_velocity_limit[slice(joint.idx_v, joint.idx_v + joint.nv)].all()
-        ]
-        index_list: List[int] = []
-        for joint in joints:
-            index_list.extend(range(joint.idx_v, joint.idx_v + joint.nv))
-        indices = np.array(index_list, dtype=np.int64)
-        indices.setflags(write=False)
-        dim = len(indices)
-        self.indices = indices
-        self.joints = joints
+        self.joints, self.indices = select_joints(model, magnitude_limited(velocity_limit), "v")
         self.model = model
-        self.projection_matrix = np.eye(model.nv)[indices] if dim > 0 else None
+        self.projection_matrix = selection_matrix(model.nv, self.indices)
         self.velocity_limit = velocity_limit
 
     def box_bounds(self) -> np.ndarray:

@@ -16,15 +16,7 @@ from .posture_task import PostureTask
 from .relative_frame_task import RelativeFrameTask
 from .task import Task
 
-__all__ = [
-    "ComTask",
-    "DampingTask",
-    "FrameTask",
-    "JointCouplingTask",
-    "JointVelocityTask",
-    "LinearHolonomicTask",
-    "LowAccelerationTask",
-    "PostureTask",
-    "RelativeFrameTask",
-    "Task",
-]
+__all__ = [cls.__name__ for cls in (
+    ComTask, DampingTask, FrameTask, JointCouplingTask, JointVelocityTask,
+    LinearHolonomicTask, LowAccelerationTask, PostureTask, RelativeFrameTask, Task,
+)]

@@ -335,46 +335,7 @@ __global__ void integrate_kernel(int nq, int nv, int free_flyer, const float* __
                                  const float* __restrict__ v, float dt, float* __restrict__ qo, int64_t B) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
-  const float* qi = q + i * nq;
-  const float* vi = v + i * nv;
-  float* o = qo + i * nq;
-  int rq = 0, rv = 0;
-  if (free_flyer) {
-    rq = 7; rv = 6;
-    // M <- M exp6(v dt): translation += R V(w) vlin, quaternion <- quaternion * exp(w/2)
-    const M3 R = quat_to_matrix(qi[3], qi[4], qi[5], qi[6]);
-    const V3 vl = dt * v3(vi[0], vi[1], vi[2]);
-    const V3 w = dt * v3(vi[3], vi[4], vi[5]);
-    const float x = dot(w, w);
-    const float th = sqrtf(x);
-    float b, c;  // (1 - cos)/th^2, (th - sin)/th^3
-    if (th < 1e-2f) {
-      b = 0.5f - x / 24.f + x * x / 720.f;
-      c = 1.f / 6.f - x / 120.f + x * x / 5040.f;
-    } else {
-      float s, co;
-      sincos_f(th, &s, &co);
-      b = (1.f - co) / x;
-      c = (th - s) / (x * th);
-    }
-    const V3 wv = cross(w, vl);
-    const V3 t = vl + b * wv + c * cross(w, wv);
-    const V3 p = mul(R, t);
-    o[0] = qi[0] + p.x; o[1] = qi[1] + p.y; o[2] = qi[2] + p.z;
-    float sh, ch;
-    sincos_f(0.5f * th, &sh, &ch);
-    const float k = th < 1e-4f ? 0.5f : sh / th;
-    const float dx = k * w.x, dy = k * w.y, dz = k * w.z, dw = ch;
-    const float n0 = rsqrtf(qi[3] * qi[3] + qi[4] * qi[4] + qi[5] * qi[5] + qi[6] * qi[6]);
-    const float ax = qi[3] * n0, ay = qi[4] * n0, az = qi[5] * n0, aw = qi[6] * n0;
-    float rx = aw * dx + ax * dw + ay * dz - az * dy;
-    float ry = aw * dy - ax * dz + ay * dw + az * dx;
-    float rz = aw * dz + ax * dy - ay * dx + az * dw;
-    float rw = aw * dw - ax * dx - ay * dy - az * dz;
-    const float n1 = rsqrtf(rx * rx + ry * ry + rz * rz + rw * rw);
-    o[3] = rx * n1; o[4] = ry * n1; o[5] = rz * n1; o[6] = rw * n1;
-  }
-  for (int j = 0; j < nq - rq; ++j) o[rq + j] = fmaf(vi[rv + j], dt, qi[rq + j]);
+  integrate_configuration(nq, free_flyer, q + i * nq, v + i * nv, dt, qo + i * nq);
 }
 
 }  // namespace pk

@@ -54,11 +54,7 @@ class HostEngine:
         return t.contiguous()
 
     def integrate(self, q, v, dt, out=None):
-        """The device integration kernel lives in pk_cabi.cu (no host build); the harness
-        integrates with the oracle, rounded to the fp32 the kernel stores."""
-        from oracle import kinematics as okin
-
-        res = torch.as_tensor(okin.integrate(self.table, self._np(q), self._np(v).astype(np.float64) * dt).astype(np.float32))
+        res = torch.as_tensor(self.hs.integrate(self._np(q), self._np(v), float(dt)))
         if out is not None:
             out.copy_(res)
             return out

@@ -136,6 +136,12 @@ class HostSim:
         self._chk(lib().hs_forward_kinematics(self.handle, _p(q), _p(oMf), _p(com), C.c_int64(B)))
         return oMf, com
 
+    def integrate(self, q, v, dt):
+        q, v = self._f32(q), self._f32(v)
+        out = np.zeros_like(q)
+        self._chk(lib().hs_integrate(self.handle, _p(q), _p(v), C.c_float(dt), _p(out), C.c_int64(q.shape[0])))
+        return out
+
     def frame_jacobian(self, frame, q):
         q = self._f32(q)
         B = q.shape[0]

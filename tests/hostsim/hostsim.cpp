@@ -200,6 +200,14 @@ int hs_frame_jacobian(void* model, int frame, const float* q, float* J, int64_t 
   return 0;
 }
 
+// q (+) v dt with the body of integrate_kernel (pk_math.cuh)
+int hs_integrate(void* model, const float* q, const float* v, float dt, float* q_out, int64_t B) {
+  const pk::HostModel& hm = *(pk::HostModel*)model;
+  for (int64_t i = 0; i < B; ++i)
+    pk::integrate_configuration(hm.nq, hm.free_flyer, q + i * hm.nq, v + i * hm.nv, dt, q_out + i * hm.nq);
+  return 0;
+}
+
 // Direct access to the dual active-set QP (pk_dualqp.cuh) for unit tests:
 //   min 1/2 |A x + b|^2 + 1/2 sum (d_i x_i + beta_i)^2,  lo <= x <= hi,  G x <= h,  E x = f
 // A[K][n], G[p][n], E[meq][n] row-major; returns the solver's status bits.

@@ -264,3 +264,27 @@ def test_model_larger_than_the_abi_maximum_is_rejected():
     model = helpers.random_tree_model(59, rng, free_flyer=True)
     with pytest.raises(RuntimeError):
         HostSim(model)
+
+
+@pytest.mark.parametrize("name", ["ur5_description", "g1_description"])
+def test_integration_body_matches_oracle(name):
+    """q (+) v dt (Configuration.integrate, pink/configuration.py:273-283): the body of
+    integrate_kernel against the oracle's SE(3) x R^n integration, small and large steps,
+    in place as the closed-loop entry point uses it."""
+    from oracle import kinematics as okin
+    from pink_b200 import workloads
+
+    robot, model, table = helpers.load(name)
+    rng = np.random.default_rng(21)
+    q = workloads.sample_configurations(table, 300, rng)
+    hs = HostSim(model)
+    for scale, dt in ((1.0, 5e-3), (30.0, 0.1), (1e-6, 1e-3)):
+        v = rng.normal(size=(300, model.nv)) * scale
+        out = hs.integrate(q, v, dt)
+        ref = okin.integrate(table, q.astype(np.float32).astype(np.float64), v.astype(np.float32).astype(np.float64) * np.float32(dt))
+        if table.free_flyer:
+            # quaternions up to sign
+            sign = np.sign(np.sum(out[:, 3:7] * ref[:, 3:7], axis=1, keepdims=True))
+            ref[:, 3:7] *= sign
+            np.testing.assert_allclose(np.linalg.norm(out[:, 3:7], axis=1), 1.0, atol=3e-7)
+        np.testing.assert_allclose(out, ref, rtol=2e-6, atol=2e-6 * max(1.0, scale * dt))

@@ -189,3 +189,63 @@ def test_model_with_no_joint_limit_has_no_inequalities():
     problem = build_ik(configuration, [], dt=1.0)
     assert problem.G is None and problem.h is None
     assert pink_b200.__version__
+
+
+# ---- batch extension of the same API (SURVEY section 8b "Batch extension") --------------------
+
+
+def test_batched_calls_follow_the_unbatched_semantics():
+    import torch
+
+    from pink_b200 import PostureTask
+    from pink_b200.exceptions import NoSolutionFound, PinkError
+
+    robot = load_robot_description("ur5_description")
+    model = robot.model
+    rng = np.random.default_rng(8)
+    B = 5
+    q = np.clip(rng.normal(size=(B, 6)) * 0.5 + [0.0, -1.2, 1.4, -0.3, 0.6, 0.0], model.lowerPositionLimit * 0.9,
+                model.upperPositionLimit * 0.9)
+    batch = Configuration(model, robot.data, q)
+    assert batch.batched and batch.batch_size == B
+    # per-instance targets [B, 3, 4] and a target shared by all instances
+    poses = batch.get_transform_frame_to_world("tool0")
+    assert tuple(poses.shape) == (B, 3, 4)
+    poses[:, 1, 3] += 0.05
+    task = FrameTask("tool0", position_cost=1.0, orientation_cost=1.0, lm_damping=1.0)
+    task.set_target(poses)
+    posture = PostureTask(cost=1e-3)
+    posture.set_target(q[0])
+    v = solve_ik(batch, [task, posture], dt=5e-3, solver="quadprog")
+    assert isinstance(v, torch.Tensor) and tuple(v.shape) == (B, 6)
+    # each row equals the unbatched call on that instance
+    for i in range(B):
+        single = Configuration(model, robot.data, q[i])
+        t_i = FrameTask("tool0", position_cost=1.0, orientation_cost=1.0, lm_damping=1.0)
+        t_i.set_target(SE3(poses[i, :, :3].numpy().astype(float), poses[i, :, 3].numpy().astype(float)))
+        v_i = solve_ik(single, [t_i, posture], dt=5e-3, solver="quadprog")
+        assert isinstance(v_i, np.ndarray) and v_i.shape == (6,)
+        np.testing.assert_allclose(v[i].numpy(), v_i, rtol=1e-5, atol=1e-6)
+    # errors / Jacobians come back with the batch dimension
+    e = task.compute_error(batch)
+    J = task.compute_jacobian(batch)
+    assert tuple(e.shape) == (B, 6) and tuple(J.shape) == (B, 6, 6)
+    # a target batch of the wrong size is rejected
+    task.set_target(poses[:3])
+    with pytest.raises(PinkError):
+        solve_ik(batch, [task, posture], dt=5e-3)
+    # status instead of exceptions: one instance outside its limits
+    task.set_target(poses)
+    q_bad = q.copy()
+    q_bad[2, 2] = model.upperPositionLimit[2] + 0.5
+    bad = Configuration(model, robot.data, q_bad)
+    with pytest.raises(NotWithinConfigurationLimits) as info:
+        solve_ik(bad, [task, posture], dt=5e-3)
+    assert "2" in str(info.value)  # the offending instance is named
+    v, status = solve_ik(bad, [task, posture], dt=5e-3, return_status=True)
+    assert status.tolist() == [0, 0, 2, 0, 0] and float(v[2].abs().max()) == 0.0
+    # out= receives the result
+    out = torch.zeros((B, 6), dtype=torch.float32)
+    v2 = solve_ik(batch, [task, posture], dt=5e-3, out=out)
+    assert v2.data_ptr() == out.data_ptr() and float(out.abs().max()) > 0.0
+    assert NoSolutionFound is not None

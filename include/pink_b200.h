@@ -50,7 +50,8 @@ extern "C" {
 
 /* per-instance status bits written by the solve entry points */
 #define PK_STATUS_OK 0
-#define PK_STATUS_NO_SOLUTION 1   /* pink.exceptions.NoSolutionFound (solve_ik.py:271-273) */
+#define PK_STATUS_NO_SOLUTION 1   /* pink.exceptions.NoSolutionFound (solve_ik.py:271-273): infeasible rows, or a
+                                     NaN / Inf in q or a target (bit 1 or 4 is set then); v = 0 for the instance */
 #define PK_STATUS_OUT_OF_LIMITS 2 /* NotWithinConfigurationLimits (configuration.py:186-194) */
 #define PK_STATUS_NOT_POSDEF 4    /* Hessian not positive definite in fp32 */
 #define PK_STATUS_ITER_LIMIT 8    /* active-set iteration cap hit; v is feasible, maybe sub-optimal */

@@ -249,3 +249,26 @@ def test_batched_calls_follow_the_unbatched_semantics():
     v2 = solve_ik(batch, [task, posture], dt=5e-3, out=out)
     assert v2.data_ptr() == out.data_ptr() and float(out.abs().max()) > 0.0
     assert NoSolutionFound is not None
+
+
+def test_non_finite_target_raises_no_solution_found():
+    """A NaN in a target makes the QP unsolvable; the reference's back-end returns nothing
+    and ``solve_ik`` raises (pink/solve_ik.py:271-273)."""
+    from pink_b200.exceptions import NoSolutionFound
+
+    robot = load_robot_description("ur5_description")
+    configuration = Configuration(robot.model, robot.data, np.array([0.3, -1.0, 1.2, -0.4, 0.5, 0.1]))
+    task = FrameTask("tool0", position_cost=1.0, orientation_cost=1.0)
+    target = configuration.get_transform_frame_to_world("tool0")
+    target.translation[0] = np.nan
+    task.set_target(target)
+    with pytest.raises(NoSolutionFound):
+        solve_ik(configuration, [task], dt=5e-3, solver="quadprog")
+    humanoid = g1()
+    configuration = Configuration(humanoid.model, humanoid.data, humanoid.q0)
+    task = FrameTask("pelvis", position_cost=1.0, orientation_cost=1.0)
+    target = configuration.get_transform_frame_to_world("pelvis")
+    target.translation[2] = np.inf
+    task.set_target(target)
+    with pytest.raises(NoSolutionFound):
+        solve_ik(configuration, [task], dt=5e-3, solver="quadprog")

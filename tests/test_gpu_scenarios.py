@@ -39,3 +39,7 @@ def test_com_task_fulfilled_and_convergence():
 
 def test_model_with_no_joint_limit_has_no_inequalities():
     s.test_model_with_no_joint_limit_has_no_inequalities()
+
+
+def test_non_finite_target_raises_no_solution_found():
+    s.test_non_finite_target_raises_no_solution_found()

@@ -56,3 +56,22 @@ def test_compute_without_gpu_fails_loudly():
 
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         require_cuda()
+
+
+def test_c_entry_point_without_gpu_reports_an_error():
+    """Straight through the C ABI on a CPU-only box: a non-zero return code and a message,
+    never a silent fallback."""
+    import pytest
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pink_b200.robots import load_robot_description
+
+    lib = _cabi.load()
+    holder = _cabi.ModelDescHolder(load_robot_description("ur5_description").model.table())
+    handle = ctypes.c_void_p()
+    rc = lib.pk_model_create(ctypes.byref(holder.desc), 0, ctypes.byref(handle))
+    assert rc != 0 and not handle.value
+    lib.pk_last_error.restype = ctypes.c_char_p
+    assert len(lib.pk_last_error()) > 0

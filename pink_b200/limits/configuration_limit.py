@@ -28,10 +28,10 @@ class ConfigurationLimit(Limit):
         nv = self.model.nv
         lo = np.full(nv, -np.inf)
         hi = np.full(nv, np.inf)
-        shift = self.model.nq - nv
-        for i in self.indices:
-            lo[i] = self.model.lowerPositionLimit[i + shift]
-            hi[i] = self.model.upperPositionLimit[i + shift]
+        if len(self.indices) > 0:
+            shift = self.model.nq - nv
+            lo[self.indices] = self.model.lowerPositionLimit[self.indices + shift]
+            hi[self.indices] = self.model.upperPositionLimit[self.indices + shift]
         return lo, hi
 
     def compute_qp_inequalities(self, configuration, dt: float) -> Optional[Tuple]:

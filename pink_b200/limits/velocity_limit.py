@@ -26,8 +26,8 @@ class VelocityLimit(Limit):
     def box_bounds(self) -> np.ndarray:
         """Per-tangent-index velocity bound (+inf where no row exists)."""
         v = np.full(self.model.nv, np.inf)
-        for i in self.indices:
-            v[i] = self.velocity_limit[i]
+        if len(self.indices) > 0:
+            v[self.indices] = self.velocity_limit[self.indices]
         return v
 
     def compute_qp_inequalities(self, configuration, dt: float) -> Optional[Tuple]:

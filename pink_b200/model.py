@@ -236,14 +236,22 @@ class Model:
     def hasConfigurationLimit(self) -> np.ndarray:
         return np.array(self._has_cfg_limit, dtype=bool)
 
+    def _frame_index(self) -> dict:
+        """name -> first frame id, rebuilt when frames were added."""
+        cache = self.__dict__.get("_frame_ids")
+        if cache is None or cache[0] != len(self.frames):
+            ids: dict = {}
+            for i, f in enumerate(self.frames):
+                ids.setdefault(f.name, i)
+            cache = (len(self.frames), ids)
+            self.__dict__["_frame_ids"] = cache
+        return cache[1]
+
     def existFrame(self, name: str) -> bool:
-        return any(f.name == name for f in self.frames)
+        return name in self._frame_index()
 
     def getFrameId(self, name: str) -> int:
-        for i, f in enumerate(self.frames):
-            if f.name == name:
-                return i
-        return len(self.frames)  # Pinocchio returns nframes when absent
+        return self._frame_index().get(name, len(self.frames))  # Pinocchio returns nframes when absent
 
     def existJointName(self, name: str) -> bool:
         return name in self.names

@@ -74,43 +74,42 @@ def _fill_limits(prob: _cabi.PkProblemDesc, model, limits: Sequence[Limit], safe
         )
     if len(cfg) > 1 or len(vel) > 1 or len(acc) > 1 or len(fb) > 1:
         raise NotImplementedError("at most one limit of each kind per solve")
-    inf = float("inf")
-    for i in range(_cabi.PK_MAX_NV):
-        prob.cfg_lo[i], prob.cfg_hi[i], prob.vel[i] = -inf, inf, inf
-        prob.chk_lo[i], prob.chk_hi[i] = -inf, inf
-        prob.acc_max[i], prob.acc_qlo[i], prob.acc_qhi[i] = inf, -inf, inf
+    # numpy views onto the fixed-size arrays of the descriptor (filled in bulk: this runs on
+    # every solve_ik call)
+    def view(field):
+        return np.frombuffer(field, dtype=np.float32)
+
+    cfg_lo, cfg_hi, vel_v = view(prob.cfg_lo), view(prob.cfg_hi), view(prob.vel)
+    chk_lo, chk_hi = view(prob.chk_lo), view(prob.chk_hi)
+    acc_max, acc_qlo, acc_qhi = view(prob.acc_max), view(prob.acc_qlo), view(prob.acc_qhi)
+    cfg_lo[:], cfg_hi[:], vel_v[:] = -np.inf, np.inf, np.inf
+    chk_lo[:], chk_hi[:] = -np.inf, np.inf
+    acc_max[:], acc_qlo[:], acc_qhi[:] = np.inf, -np.inf, np.inf
     prob.cfg_gain = 0.5
     if cfg:
         lo, hi = cfg[0].box_bounds()
         prob.cfg_gain = float(cfg[0].config_limit_gain)
-        for i in range(nv):
-            prob.cfg_lo[i], prob.cfg_hi[i] = float(lo[i]), float(hi[i])
+        cfg_lo[:nv], cfg_hi[:nv] = lo, hi
     if vel:
-        v = vel[0].box_bounds()
-        for i in range(nv):
-            prob.vel[i] = float(v[i])
+        vel_v[:nv] = vel[0].box_bounds()
     prob.acc_enabled = 0
     prob.acc_prev_offset = -1
     if acc and acc[0].projection_matrix is not None:
         a, qlo, qhi = acc[0].box_arrays()
         prob.acc_enabled = 1
-        for i in range(nv):
-            prob.acc_max[i], prob.acc_qlo[i], prob.acc_qhi[i] = float(a[i]), float(qlo[i]), float(qhi[i])
+        acc_max[:nv], acc_qlo[:nv], acc_qhi[:nv] = a, qlo, qhi
     prob.fb_enabled = 0
     if fb:
         prob.fb_enabled = 1
         prob.fb_frame = int(fb[0].frame_id)
-        for r in range(6):
-            prob.fb_max[r] = float(fb[0].twist_max[r])
+        view(prob.fb_max)[:] = fb[0].twist_max
     # Configuration.check_limits (configuration.py:181-201)
     root_nq, _ = get_root_joint_dim(model)
     shift = model.nq - nv
-    q_max, q_min = model.upperPositionLimit, model.lowerPositionLimit
-    for iq in range(root_nq, model.nq):
-        if q_max[iq] <= q_min[iq] + check_tol:
-            continue
-        prob.chk_lo[iq - shift] = float(q_min[iq] - check_tol)
-        prob.chk_hi[iq - shift] = float(q_max[iq] + check_tol)
+    q_max, q_min = model.upperPositionLimit[root_nq:], model.lowerPositionLimit[root_nq:]
+    ranged = q_max > q_min + check_tol
+    chk_lo[root_nq - shift:nv] = np.where(ranged, q_min - check_tol, -np.inf)
+    chk_hi[root_nq - shift:nv] = np.where(ranged, q_max + check_tol, np.inf)
     prob.safety_break = 1 if safety_break else 0
     return acc[0] if prob.acc_enabled else None
 

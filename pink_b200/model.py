@@ -367,6 +367,13 @@ def model_from_urdf_string(xml: str, root_joint=None, name: Optional[str] = None
     children = {}
     child_links = set()
     for j in joints:
+        for end in ("parent", "child"):
+            el = j.find(end)
+            if el is None or el.get("link") not in links:
+                raise ValueError(f"URDF joint {j.get('name')!r}: {end} link "
+                                 f"{None if el is None else el.get('link')!r} is not declared")
+        if j.find("child").get("link") in child_links:
+            raise ValueError(f"URDF link {j.find('child').get('link')!r} has two parent joints (kinematic loop)")
         children.setdefault(j.find("parent").get("link"), []).append(j)
         child_links.add(j.find("child").get("link"))
     roots = [n for n in links if n not in child_links]

@@ -237,3 +237,23 @@ def test_sphere_collision_model_from_urdf_and_srdf(tmp_path):
 
     with pytest.raises(InvalidCollisionPairs):
         describe_problem(model, 4, [], 0.01, 1e-6, [], False, [SelfCollisionBarrier(n_collision_pairs=5)], None, cm)
+
+
+def test_urdf_loader_rejects_malformed_trees():
+    bad = {
+        "undeclared link": '<robot name="r"><link name="a"/><joint name="j" type="revolute"><parent link="a"/>'
+                           '<child link="zz"/><axis xyz="0 0 1"/></joint></robot>',
+        "two roots": '<robot name="r"><link name="a"/><link name="b"/></robot>',
+        "loop": '<robot name="r"><link name="a"/><link name="b"/><link name="c"/>'
+                '<joint name="j1" type="revolute"><parent link="a"/><child link="c"/><axis xyz="0 0 1"/></joint>'
+                '<joint name="j2" type="revolute"><parent link="b"/><child link="c"/><axis xyz="0 0 1"/></joint></robot>',
+        "zero axis": '<robot name="r"><link name="a"/><link name="b"/><joint name="j" type="revolute">'
+                     '<parent link="a"/><child link="b"/><axis xyz="0 0 0"/></joint></robot>',
+    }
+    for what, xml in bad.items():
+        with pytest.raises(ValueError):
+            model_from_urdf_string(xml)
+    for jtype in ("planar", "floating"):
+        with pytest.raises(NotImplementedError):
+            model_from_urdf_string(f'<robot name="r"><link name="a"/><link name="b"/><joint name="j" type="{jtype}">'
+                                   '<parent link="a"/><child link="b"/></joint></robot>')

@@ -288,3 +288,20 @@ def test_integration_body_matches_oracle(name):
             ref[:, 3:7] *= sign
             np.testing.assert_allclose(np.linalg.norm(out[:, 3:7], axis=1), 1.0, atol=3e-7)
         np.testing.assert_allclose(out, ref, rtol=2e-6, atol=2e-6 * max(1.0, scale * dt))
+
+
+@pytest.mark.parametrize("nj,free_flyer,seed", [(8, False, 3), (15, True, 4), (32, False, 5), (32, True, 3)])
+def test_warp_kernel_on_random_trees(nj, free_flyer, seed):
+    """Topologies other than the two humanoids on the warp-per-instance kernel: random joint
+    trees with prismatic joints, fixed or floating base, up to its 32-joint maximum; frame,
+    relative-frame, posture and CoM tasks."""
+    sc = helpers.tree_scenario(nj, 24, free_flyer, seed=seed)
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v, st = hs.solve_ik(prob, sc.q32, targets)
+    assert hs.used_tree
+    v_gen, st_gen = hs.solve_ik(prob, sc.q32, targets, general_path=True)
+    v_ref, st_ref = sc.oracle_solve()
+    assert (st == 0).all() and (st_gen == 0).all() and (st_ref == 0).all()
+    assert helpers.within_tolerance(v, v_ref).all(), np.abs(v - v_ref).max()
+    np.testing.assert_allclose(v, v_gen, rtol=2e-3, atol=2e-4)

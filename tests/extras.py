@@ -182,3 +182,61 @@ def g1_extras(B, seed=5, floating_base_limit=True):
     ocb = {"type": "self_collision", "pairs": [(int(a), int(b), float(ra), float(rb)) for (a, b), (ra, rb) in zip(pf, pr)],
            "n_pairs": 8, "d_min": 0.05, "gain": 20.0, "safe_displacement_gain": 1.0}
     return ExtraScenario(model, table, q, tasks, otasks, limits, olimits, [cb], [ocb], [], [], 1.0 / 200.0, 0.01, cm)
+
+
+def tree_extras(nj, B, free_flyer, seed=7):
+    """Random joint tree (prismatic joints, fixed or floating base): two frame tasks + posture,
+    a position barrier near one tip, a distance barrier between two tips, equality constraints
+    (a joint coupling; on floating trees of 12+ joints also a tip frame held in place) and, with a
+    floating base, its velocity limit."""
+    rng = np.random.default_rng(seed)
+    model = helpers.random_tree_model(nj, rng, free_flyer)
+    table = model.table()
+    q = workloads.sample_configurations(table, B, rng)
+    qt = workloads.perturb_configurations(table, q, rng, sigma=0.2)
+    tasks, otasks = [], []
+    for frame, pc, oc in [("tip0", 1.0, 0.5), ("tip1", 2.0, 0.0)]:
+        t, o = _frame_task(table, frame, qt, pc, oc, lm_damping=0.05)
+        tasks.append(t)
+        otasks.append(o)
+    q_ref = q[0].copy()
+    pt = PostureTask(cost=0.05)
+    pt.set_target(q_ref)
+    tasks.append(pt)
+    otasks.append({"type": "posture", "cost": 0.05, "gain": 1.0, "lm_damping": 0.0, "target": q_ref})
+    limits = [ConfigurationLimit(model), VelocityLimit(model)]
+    olimits = [("configuration", 0.5), ("velocity", None)]
+    if free_flyer:
+        base = next(f.name for f in model.frames if f.parentJoint == model.getJointId("root_joint"))
+        fb = FloatingBaseVelocityLimit(model, base, [0.5, 0.5, 0.3], [1.0, np.inf, 1.0])
+        limits.append(fb)
+        olimits.append(("floating_base", table.frame_names.index(base), np.array([0.5, 0.5, 0.3, 1.0, np.inf, 1.0])))
+    # barriers placed relative to the first instance's pose so that a good share is active
+    fk = okin.forward_kinematics(table, q)
+    f2, f0, f3 = (table.frame_names.index(n) for n in ("tip2", "tip0", "tip3"))
+    _, p2 = okin.frame_placement(table, fk, f2)
+    z_med = float(np.median(p2[:, 2]))
+    pb = PositionBarrier("tip2", indices=[2], p_max=np.array([z_med + 0.02]), gain=2.0, safe_displacement_gain=1.0)
+    opb = {"type": "position", "frame": f2, "indices": [2], "p_min": None, "p_max": np.array([z_med + 0.02]),
+           "gain": np.array([2.0]), "safe_displacement_gain": 1.0}
+    _, p0 = okin.frame_placement(table, fk, f0)
+    _, p3 = okin.frame_placement(table, fk, f3)
+    d_med = float(np.median(np.linalg.norm(p0 - p3, axis=1)))
+    sb = BodySphericalBarrier(("tip0", "tip3"), d_min=0.8 * d_med, gain=3.0, safe_displacement_gain=0.5)
+    osb = {"type": "body_spherical", "frames": (f0, f3), "d_min": 0.8 * d_med, "gain": 3.0, "safe_displacement_gain": 0.5}
+    # equality constraints: a coupling of two joint coordinates and, with a floating base (full
+    # row rank whatever the tree), tip3 held where it is (six rows J dq = 0).  On a fixed base
+    # the tip may hang from fewer than six joints: six rows of rank < 6 with a right-hand side
+    # of rounding size, which the fp64 oracle calls inconsistent and the fp32 kernels accept.
+    rq, rv = (7, 6) if free_flyer else (0, 0)
+    A = np.zeros((1, table.nv))
+    A[0, rv + 1], A[0, rv + 2] = 1.0, -0.5
+    lc = LinearHolonomicTask(A, np.zeros(1), None, cost=[1.0], gain=0.005)
+    olc = {"type": "linear", "A": A, "b": np.zeros(1), "q0": None, "cost": np.ones(1), "gain": 0.005, "lm_damping": 0.0}
+    constraints, oconstraints = [lc], [olc]
+    if free_flyer and nj >= 12:
+        hold, ohold = _frame_task(table, "tip3", q, 1.0, 1.0)
+        constraints.append(hold)
+        oconstraints.append(ohold)
+    return ExtraScenario(model, table, q, tasks, otasks, limits, olimits, [pb, sb], [opb, osb], constraints, oconstraints,
+                         1.0 / 100.0, 1e-6)

@@ -272,3 +272,24 @@ def test_barriers_run_on_the_tree_kernel_body():
     assert feasible.mean() > 0.5
     assert (st[feasible] == 0).all() and ((st[~feasible] & _cabi.PK_STATUS_NO_SOLUTION) != 0).all()
     assert helpers.within_tolerance(v[feasible], v_ref[feasible]).all(), np.abs(v - v_ref)[feasible].max()
+
+
+def test_random_trees_with_barriers_constraints_and_base_limit():
+    """Barriers, equality constraints and the floating-base limit on topologies other than UR5 /
+    G1: random trees with prismatic joints, fixed and floating base, on the warp-cooperative
+    dual QP and on the general path, against the oracle."""
+    for nj, free_flyer, seed in [(7, False, 7), (12, True, 8), (20, False, 9), (28, True, 7)]:
+        sc = extras.tree_extras(nj, 40, free_flyer, seed=seed)
+        hs = HostSim(sc.model)
+        prob, targets, _ = sc.problem()
+        v, st = hs.solve_ik(prob, sc.q32, targets)
+        assert hs.used_tree
+        v_gen, st_gen = hs.solve_ik(prob, sc.q32, targets, path=1)
+        v_ref, st_ref = sc.oracle_solve()
+        feasible = st_ref == 0
+        assert feasible.mean() > 0.5
+        for vk, sk in ((v, st), (v_gen, st_gen)):
+            np.testing.assert_array_equal((sk & _cabi.PK_STATUS_NO_SOLUTION) != 0, ~feasible)
+            assert (sk[feasible] == 0).all()
+            assert helpers.within_tolerance(vk[feasible], v_ref[feasible], atol=5e-4, rtol=5e-3).all()
+    _check_rows(sc, hs, prob, targets, 6)

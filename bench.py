@@ -6,6 +6,14 @@
 A "step" is one ``solve_ik`` pass over one batch of B = 65536 UR5 instances per
 GPU (FrameTask(tool0) + PostureTask + default limits, examples/arm_ur5.py).
 Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement".
+
+How the K steps are timed (all of it holds for any K, the driver's K = 20 included):
+the K launches of the fused kernel are submitted as CUDA-graph replays (one graph of
+exactly K launches, or replays of a 512-launch graph plus a remainder graph for large
+K), behind a short device-side spin so that the host has queued everything before the
+start event fires; the region is bracketed by barrier + synchronize, repeated
+``--regions`` times with an L2 flush in between, and the MEDIAN region is reported
+(max over ranks).  ``roofline.timing`` says what ran.
 """
 
 import argparse
@@ -26,16 +34,18 @@ METRIC = "IK solves/sec (batch=65536 per GPU, UR5 6-DOF, FrameTask+PostureTask, 
 UNIT = "IK steps/s"
 BYTES_PER_STEP = 96  # q 24 B + frame target 48 B read, v 24 B written
 L2_BYTES = 126 * 1024 * 1024
+GRAPH_CHUNK = 512    # launches per captured graph when K is larger than this
 
 
 def committed_traffic():
-    """dram bytes per launch of the dominant kernel, from the committed ncu --set full
-    capture (profiles/traffic.json names the capture); None when absent."""
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full
+    capture (profiles/traffic.json names the capture and its conditions); None when absent."""
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
-            return json.load(f)["dram_bytes_per_launch"]
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            d = json.load(f)
+        return d["dram_bytes_per_launch"], d.get("capture")
     except (OSError, KeyError, ValueError):
-        return None
+        return None, None
 
 
 def load_peaks():
@@ -46,6 +56,54 @@ def load_peaks():
     return 6650.0, "fallback"
 
 
+def host_topology():
+    """(logical CPUs this process may run on, physical cores among them)."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        cpus = list(range(os.cpu_count() or 1))
+    cores = set()
+    for c in cpus:
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as fh:
+                cores.add(fh.read().strip())
+        except OSError:
+            cores.add(str(c))
+    return len(cpus), len(cores)
+
+
+def bind_to_gpu_numa_node(index: int):
+    """Run this process (and therefore first-touch its pinned buffers) on the NUMA node the
+    GPU hangs off: host<->device DMA that crosses the socket interconnect runs well below
+    the PCIe rate.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # 00000000:17:00.0 -> 0000:17:00.0
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return "numa node unknown (single node or virtualised)"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return f"numa node {node}: no allowed CPU there"
+        os.sched_setaffinity(0, allowed)
+        return f"numa node {node} ({len(allowed)} CPUs)"
+    except Exception as exc:  # best effort; never fail the bench on a topology quirk
+        return f"not bound ({type(exc).__name__})"
+
+
 # ---------------------------------------------------------------------------
 # CPU arm: the oracle's C port of the reference path, all host cores
 # ---------------------------------------------------------------------------
@@ -53,8 +111,8 @@ def load_peaks():
 
 class CpuArm:
     """fp64 CPU implementation of the same step (oracle/c/pink_oracle.c: dense H,
-    Goldfarb-Idnani QP with Givens updates, pthreads).  Pink + Pinocchio + quadprog
-    cannot be installed offline, so this port stands in for them."""
+    Goldfarb-Idnani QP with Givens updates, persistent pinned pthread pool).  Pink +
+    Pinocchio + quadprog cannot be installed offline, so this port stands in for them."""
 
     def __init__(self, batch, seed=20260922):
         from oracle import cport
@@ -69,8 +127,9 @@ class CpuArm:
         q = wl.sample_configurations(table, batch, rng)
         qt = wl.perturb_configurations(table, q, rng)
         R, p = okin.frame_placement(table, okin.forward_kinematics(table, qt), f)
-        self.T = np.concatenate([R, p[:, :, None]], axis=2).astype(np.float32).astype(np.float64)[:, None]
-        self.q = q.astype(np.float32).astype(np.float64)
+        self.T = np.ascontiguousarray(
+            np.concatenate([R, p[:, :, None]], axis=2).astype(np.float32).astype(np.float64)[:, None])
+        self.q = np.ascontiguousarray(q.astype(np.float32).astype(np.float64))
         tasks = [
             {"type": "frame", "frame": f, "cost": np.ones(6), "gain": 1.0, "lm_damping": 1.0},
             {"type": "posture", "cost": 1e-3, "gain": 1.0, "lm_damping": 0.0,
@@ -82,7 +141,7 @@ class CpuArm:
 
     def step(self, threads):
         t0 = time.perf_counter()
-        v, st = self.port.solve(self.q, self.T, threads=threads)
+        v, st = self.port.solve(self.q, self.T, threads=threads, reuse_outputs=True)
         return time.perf_counter() - t0, v, st
 
     def python_port_rate(self, n=200):
@@ -101,17 +160,29 @@ class CpuArm:
         return n / (time.perf_counter() - t0)
 
 
-def cpu_baseline_block(batch, passes=5):
-    cores = os.cpu_count() or 1
+def cpu_scaling(arm, passes, logical, physical):
+    """All-core and one-core rates of the C port and the parallel efficiency against
+    `physical cores x one core` (hyper-threads add little to dense fp64 code)."""
+    arm.step(logical)  # warm-up: pool creation, page faults
+    arm.step(logical)
+    wall = sum(arm.step(logical)[0] for _ in range(passes))
+    one = min(arm.step(1)[0] for _ in range(2))
+    value = arm.batch * passes / wall
+    one_core = arm.batch / one
+    return value, one_core, value / (one_core * physical)
+
+
+def cpu_baseline_block(batch, passes=10):
+    logical, physical = host_topology()
     arm = CpuArm(batch)
-    arm.step(cores)  # warm-up (page faults, thread start)
-    wall = sum(arm.step(cores)[0] for _ in range(passes))
-    one = arm.step(1)[0]
+    value, one_core, eff = cpu_scaling(arm, passes, logical, physical)
     return {
-        "value": batch * passes / wall, "unit": UNIT, "cores": cores, "kind": "port",
+        "value": value, "unit": UNIT, "cores": logical, "physical_cores": physical, "kind": "port",
         "sample": f"{passes} passes over the same {batch}-instance UR5 workload, fp64 C port of the reference path "
-                  f"(dense H, Goldfarb-Idnani QP), {cores} pthreads; Pink/Pinocchio/quadprog are not installable offline",
-        "one_core": batch / one,
+                  f"(dense H, Goldfarb-Idnani QP), persistent pool of {logical} pinned pthreads, dynamic chunks; "
+                  "Pink/Pinocchio/quadprog are not installable offline",
+        "one_core": one_core,
+        "parallel_efficiency": eff,
         "python_loop_one_core": arm.python_port_rate(),
     }
 
@@ -122,40 +193,43 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    logical, physical = host_topology()
     arm = CpuArm(args.batch)
-    for _ in range(max(args.warmup, 1)):
-        arm.step(cores)
+    for _ in range(max(args.warmup, 2)):
+        arm.step(logical)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        arm.step(cores)
+        arm.step(logical)
     wall = time.perf_counter() - t0
     value = args.batch * args.steps / wall
+    one = min(arm.step(1)[0] for _ in range(2))
+    one_core = args.batch / one
     sample = (f"every step = the full {args.batch}-instance workload, fp64 C port of the reference path "
-              f"(oracle/c/pink_oracle.c), {cores} pthreads")
+              f"(oracle/c/pink_oracle.c), persistent pool of {logical} pinned pthreads")
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, cpu=True),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": logical, "physical_cores": physical, "kind": "port",
+                         "sample": sample, "one_core": one_core,
+                         "parallel_efficiency": value / (one_core * physical)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, cpu=False):
-    cfg = {
+def workload_config(args):
+    """Identical for both arms (the driver compares them); the GPU arm's cache policy
+    lives in ``roofline.l2``."""
+    return {
         "workload": "UR5 6-DOF (hand-authored URDF), FrameTask(tool0, 1, 1, lm_damping=1) + PostureTask(1e-3), "
                     "ConfigurationLimit + VelocityLimit, dt=1/200, damping=1e-12 (examples/arm_ur5.py)",
         "batch_per_gpu": args.batch,
         "targets": "reachable: FK(q + N(0, 0.3^2)) clipped to limits; seed 20260922",
     }
-    if not cpu:
-        cfg["l2"] = f"rotating {args.nbuf} input/output sets ({args.nbuf * args.batch * BYTES_PER_STEP / 2**20:.0f} MiB > 126 MiB L2)"
-    return cfg
 
 
 # ---------------------------------------------------------------------------
@@ -164,29 +238,64 @@ def workload_config(args, cpu=False):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed regions run.  In-process NVML
+    (no subprocess per sample: an `nvidia-smi` spawned every 100 ms competes with the
+    thread that issues the launches); falls back to nvidia-smi when NVML is missing."""
 
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index = index
-        self.samples = []
+    def __init__(self, index: int, period: float = 0.02):
+        self.index, self.period = index, period
+        self.sm, self.mx, self.reasons = [], [], set()
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
+        self.source = "nvml"
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+            self.source = "nvidia-smi"
+            self.period = 0.25
+
+    def _sample_nvml(self):
+        nv = self._nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        self.mx.append(self._max)
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for bit, name in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(
+            ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
+            capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            s = [x.strip() for x in out.split(",")]
+            self.sm.append(float(s[0]))
+            self.mx.append(float(s[1]))
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[3:7]):
+                if val.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
-                    capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                (self._sample_nvml if self._nv else self._sample_smi)()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(self.period)
 
     def __enter__(self):
         self._thread.start()
@@ -197,23 +306,195 @@ class ClockSampler:
         self._thread.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            try:
-                sm.append(float(s[0]))
-                mx.append(float(s[1]))
-                for name, val in zip(names, s[3:7]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
         return {
-            "sm_mhz": float(np.median(sm)) if sm else None,
-            "sm_max_mhz": float(max(mx)) if mx else None,
-            "reasons": sorted(reasons),
-            "samples": len(sm),
+            "sm_mhz": float(np.median(self.sm)) if self.sm else None,
+            "sm_max_mhz": float(max(self.mx)) if self.mx else None,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.sm),
+            "source": self.source,
         }
+
+
+class GraphedSteps:
+    """K launches of `step(k)` as CUDA-graph replays: one graph of exactly K launches when
+    K <= GRAPH_CHUNK, else replays of a GRAPH_CHUNK-launch graph plus a remainder graph."""
+
+    def __init__(self, torch, device, step, n_steps, chunk=GRAPH_CHUNK):
+        self.torch, self.device, self.n = torch, device, n_steps
+        self.full, self.rem = divmod(n_steps, chunk) if n_steps > chunk else (0, n_steps)
+        self.chunk = chunk
+        self.g_full = self._capture(step, 0, chunk) if self.full else None
+        self.g_rem = self._capture(step, self.full * chunk, self.rem) if self.rem else None
+
+    def _capture(self, step, k0, n):
+        torch = self.torch
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            # thread-local capture mode: the NCCL watchdog thread of a multi-rank run may
+            # issue CUDA calls (event queries) while this thread is capturing
+            with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                for k in range(n):
+                    step(k0 + k)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        return g
+
+    def run(self):
+        for _ in range(self.full):
+            self.g_full.replay()
+        if self.g_rem is not None:
+            self.g_rem.replay()
+
+    def describe(self):
+        if self.full:
+            return (f"{self.full} replays of a {self.chunk}-launch CUDA graph"
+                    + (f" + one {self.rem}-launch graph" if self.rem else ""))
+        return f"one replay of a {self.rem}-launch CUDA graph"
+
+
+def kkt_selfcheck(ik, eng, q, targets, v, status, sample=512):
+    """fp64 optimality certificate of the fp32 velocities on the QP the library itself
+    exports (pk_build_ik_batched / pk_constraint_rows_batched) for the first `sample`
+    instances: stationarity relative to the gradient's rounding scale, worst violation of
+    the box and of the dense rows.  A self-consistency check of the solver inside the run;
+    parity against the oracle is `pytest -m gpu`."""
+    n = min(sample, q.shape[0])
+    qs, ts = q[:n].contiguous(), targets[:n].contiguous()
+    H, c, _ = eng.build_ik(ik.prob, qs, ts)
+    G, hG, E, f, lo, hi = eng.constraint_rows(ik.prob, qs, ts)
+    import torch
+
+    torch.cuda.synchronize()
+    ok = (status[:n] == 0).cpu().numpy()
+    H, c = H.double().cpu().numpy()[ok], c.double().cpu().numpy()[ok]
+    lo, hi = lo.double().cpu().numpy()[ok], hi.double().cpu().numpy()[ok]
+    G, hG = G.double().cpu().numpy()[ok], hG.double().cpu().numpy()[ok]
+    x = v[:n].double().cpu().numpy()[ok] * float(ik.prob.dt)
+    g = np.einsum("bij,bj->bi", H, x) + c
+    rows = np.abs(G).sum(axis=2) > 0  # unused dense rows are zero
+    slack = hG - np.einsum("brj,bj->br", G, x)
+    dense_viol = float(np.where(rows, np.maximum(-slack, 0.0), 0.0).max()) if rows.any() else 0.0
+    # multipliers of active dense rows by least squares on the stationarity equation
+    tol = 1e-9 + 1e-6 * np.abs(x) + 3e-7
+    at_hi, at_lo = x >= hi - tol, x <= lo + tol
+    resid = np.array(g)
+    if rows.any():
+        for b in range(x.shape[0]):
+            act = rows[b] & (slack[b] <= 1e-6 * (1.0 + np.abs(hG[b])))
+            if act.any():
+                free = ~(at_hi[b] | at_lo[b])
+                if free.any():
+                    lam, *_ = np.linalg.lstsq(G[b][act][:, free].T, -g[b][free], rcond=None)
+                    lam = np.maximum(lam, 0.0)
+                    resid[b] = g[b] + G[b][act].T @ lam
+    viol = np.abs(resid)
+    viol = np.where(at_hi & (resid <= 0), 0.0, viol)
+    viol = np.where(at_lo & (resid >= 0), 0.0, viol)
+    scale = np.einsum("bij,bj->bi", np.abs(H), np.abs(x)).max(axis=1) + np.abs(c).max(axis=1)
+    ratio = viol.max(axis=1) / scale
+    return {
+        "instances": int(ok.sum()), "stationarity_over_scale_p999": float(np.quantile(ratio, 0.999)),
+        "stationarity_over_scale_max": float(ratio.max()),
+        "box_violation_max": float(np.maximum(np.maximum(x - hi, lo - x), 0.0).max()),
+        "dense_row_violation_max": dense_viol,
+        "nonzero_status": int((~ok).sum()),
+    }
+
+
+def humanoid_configs(torch, device, peak, regions=5, steps=5):
+    """BASELINE configs 3 and 4 (without and with the self-collision barrier): ms per step
+    (median of `regions` timed regions of `steps` graph-replayed launches), algorithmic
+    GB/s, status counts and the in-run KKT self-check."""
+    from pink_b200 import workloads
+    from pink_b200.engine import get_engine
+
+    out = []
+    for label, name, barrier in [("config 3: Draco3-class 27 joints + free-flyer, 4 FrameTasks + PostureTask", "draco3_description", False),
+                                 ("config 4 without the barrier: G1-class 29 joints + free-flyer, ComTask + 5 FrameTasks + PostureTask", "g1_description", False),
+                                 ("config 4: G1-class + sphere self-collision barrier (36 pairs, 8 closest)", "g1_description", True)]:
+        ik, q_d, targets, model = workloads.humanoid_problem(name, device, with_barrier=barrier)
+        B = q_d.shape[0]
+        v = torch.empty((B, model.nv), dtype=torch.float32, device=device)
+        st = torch.empty((B,), dtype=torch.int32, device=device)
+        for _ in range(3):
+            ik.solve(q_d, targets, v, st)
+        torch.cuda.synchronize()
+        graphed = GraphedSteps(torch, device, lambda k: ik.solve(q_d, targets, v, st), steps)
+        graphed.run()
+        torch.cuda.synchronize()
+        times = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(regions):
+            torch.cuda.synchronize()
+            torch.cuda._sleep(200000)
+            e0.record()
+            graphed.run()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) / steps)
+        ms = float(np.median(times))
+        nbytes = workloads.HUMANOID_BYTES_PER_STEP[name]
+        ach = B * nbytes / (ms * 1e-3) / 1e9
+        counts = {int(k): int(c) for k, c in zip(*np.unique(st.cpu().numpy(), return_counts=True))}
+        out.append({
+            "config": label, "robot": name + " (synthetic model of that class)", "batch": B, "nv": model.nv,
+            "ms_per_step": ms, "ik_steps_per_s": B / (ms * 1e-3), "algorithmic_bytes_per_step": nbytes,
+            "hbm_gbs_algorithmic": ach, "hbm_frac": ach / peak, "status_counts": counts,
+            "kkt_selfcheck": kkt_selfcheck(ik, get_engine(model, device), q_d, targets, v, st),
+            "timing": f"median of {regions} regions of {steps} graph-replayed launches",
+        })
+        del graphed, ik
+    return out
+
+
+def gather_variants(torch, dist, device, world, B, NBUF, step, vs, args, timed_regions):
+    """solve + all-gather of v on every rank (the one data-path collective north_star names),
+    two schedules, both timed like the headline (median of regions, max over ranks):
+    `serial`  - ncclAllGather issued on the solve stream after every step;
+    `overlapped` - the gather of step k runs on a side stream (double-buffered output)
+    while step k+1 solves; the region ends when the last gather has landed."""
+    gathered = [torch.empty((world * B, 6), dtype=torch.float32, device=device) for _ in range(2)]
+    side = torch.cuda.Stream(device)
+    done = [torch.cuda.Event() for _ in range(2)]
+    solved = [torch.cuda.Event() for _ in range(NBUF)]
+
+    def serial():
+        for k in range(args.steps):
+            step(k)
+            dist.all_gather_into_tensor(gathered[0], vs[k % NBUF])
+
+    def overlapped():
+        cur = torch.cuda.current_stream(device)
+        for k in range(args.steps):
+            step(k)
+            solved[k % NBUF].record(cur)
+            with torch.cuda.stream(side):
+                side.wait_event(solved[k % NBUF])
+                dist.all_gather_into_tensor(gathered[k % 2], vs[k % NBUF])
+                done[k % 2].record(side)
+        cur.wait_stream(side)
+
+    out = {}
+    for name, fn in (("serial", serial), ("overlapped", overlapped)):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ms, _ = timed_regions(fn, max(3, args.regions // 2), pre_spin=False)
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        out[name] = {"value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps}
+    # every rank must hold every shard: compare the gathered buffer with an all-gather of checksums
+    step(0)
+    dist.all_gather_into_tensor(gathered[0], vs[0])
+    torch.cuda.synchronize()
+    mine = gathered[0][dist.get_rank() * B:(dist.get_rank() + 1) * B]
+    out["bit_equal_to_local_shard"] = bool(torch.equal(mine, vs[0]))
+    inbound = (world - 1) * B * 6 * 4
+    out["inbound_bytes_per_rank_per_step"] = inbound
+    out["nvlink_floor_us_at_900GBs"] = inbound / 900e9 * 1e6
+    return out
 
 
 def run_gpu_arm(args):
@@ -224,24 +505,24 @@ def run_gpu_arm(args):
     from pink_b200.engine import get_engine
     from pink_b200.limits import ConfigurationLimit, VelocityLimit
     from pink_b200.robots import load_robot_description
-    from pink_b200.solve_ik import describe_problem
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device; pink_b200 has no CPU fallback")
+    full_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local) if not args.no_numa_bind else "off"
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     real_stdout = None
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner on fd 1 at
-        # communicator creation (NCCL_DEBUG >= VERSION); everything written to fd 1 from here
-        # on goes to stderr, the JSON line is written to the saved descriptor at the end
+        # keep stdout to the one JSON line: NCCL prints its banner / INFO log on fd 1;
+        # everything written to fd 1 from here on goes to stderr, the JSON line is written to
+        # the saved descriptor at the end.  NCCL_DEBUG / NCCL_DEBUG_FILE are left as the caller set them.
         sys.stdout.flush()
         real_stdout = os.dup(1)
         os.dup2(2, 1)
-        os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
 
     # model constants: built on rank 0, broadcast over NCCL (north_star), then
@@ -276,6 +557,7 @@ def run_gpu_arm(args):
 
     ik = BatchedIK(model, [frame_task, posture_task], workloads.UR5_DT, damping=workloads.UR5_DAMPING,
                    limits=limits, safety_break=True, device=device, batch_size=B)
+    flush_buf = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=device)
     torch.cuda.synchronize()
 
     def barrier():
@@ -283,84 +565,67 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def flush_l2():
+        flush_buf.zero_()
+
     def step(k):
         i = k % NBUF
         ik.solve(qs[i], ts[i], vs[i], ss[i])
 
+    def timed_regions(run, n_regions, pre_spin=True):
+        """median and all times (ms) of `n_regions` regions, each bracketed by barrier +
+        synchronize, L2 flushed before each"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        out = []
+        for _ in range(n_regions):
+            flush_l2()
+            barrier()
+            if pre_spin:
+                torch.cuda._sleep(300000)  # ~150 us: the host queues the whole region meanwhile
+            e0.record()
+            run()
+            e1.record()
+            barrier()
+            out.append(e0.elapsed_time(e1))
+        return float(np.median(out)), out
+
     # ---- device-resident throughput ("value") ---------------------------------
-    # The K timed steps are K launches of the fused kernel on rotating buffer sets.  They
-    # are submitted as replays of a CUDA graph holding NBUF consecutive steps (plus K mod
-    # NBUF direct launches), so that the figure measures the device, not how fast this
-    # host thread can issue 20 us kernels; `eager_ms_per_step` reports the direct-launch
-    # loop next to it.
     for k in range(args.warmup):
         step(k)
     barrier()
-    graph = None
+    launches0 = _cabi.load().pk_launch_count()
+    graphed = None
     try:
-        graph = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream(device)
-        side.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(side):
-            # thread-local capture mode: the NCCL watchdog thread of a multi-rank run may
-            # issue CUDA calls (event queries) while this thread is capturing
-            with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
-                for k in range(NBUF):
-                    step(k)
-        torch.cuda.current_stream(device).wait_stream(side)
-        graph.replay()
+        graphed = GraphedSteps(torch, device, step, args.steps)
+        graphed.run()  # upload / first-replay cost outside the timed regions
         barrier()
     except Exception as exc:  # pragma: no cover - graph capture is an optimisation only
-        graph = None
+        graphed = None
         print(f"[bench] CUDA graph submission unavailable, direct launches: {exc}", file=sys.stderr)
 
-    def run_steps(n):
-        """exactly n steps; returns the number of launches issued outside graphs"""
-        reps, tail = (n // NBUF, n % NBUF) if graph is not None else (0, n)
-        for _ in range(reps):
-            graph.replay()
-        for k in range(tail):
+    def run_eager():
+        for k in range(args.steps):
             step(k)
-        return tail
 
-    launches0 = _cabi.load().pk_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
-        barrier()
-        e0.record()
-        direct = run_steps(args.steps)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
+        ms, region_ms = timed_regions(graphed.run if graphed is not None else run_eager, args.regions)
         # keep the GPU under the same load a little longer so the sampler sees it
-        t_end = time.time() + 0.6
+        t_end = time.time() + 0.5
         while time.time() < t_end:
-            run_steps(NBUF)
-        torch.cuda.synchronize()
-    # launches inside the timed region: every step is one launch of the fused kernel
-    # (graph replays launch the captured kernels; pk_launch_count only sees direct calls)
-    launches = args.steps
-    assert _cabi.load().pk_launch_count() - launches0 >= direct
-    bad = int(sum(int((s != 0).sum().item()) for s in ss))
+            (graphed.run if graphed is not None else run_eager)()
+            torch.cuda.synchronize()
+    assert _cabi.load().pk_launch_count() - launches0 >= min(args.steps, GRAPH_CHUNK)
+    bad = int(sum(int((s != 0).sum().item()) for s in ss[: min(NBUF, args.steps)]))
 
     # direct-launch loop (host launch latency included), for reference
-    barrier()
-    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_direct = min(args.steps, 2000)
-    d0.record()
-    for k in range(n_direct):
-        step(k)
-    d1.record()
-    barrier()
-    eager_ms = d0.elapsed_time(d1) / n_direct
-    g_ms = ms / args.steps if graph is not None else None
+    eager_total, _ = timed_regions(lambda: [step(k) for k in range(n_direct)], 3, pre_spin=False)
+    eager_ms = eager_total / n_direct
 
     # ---- end to end through host buffers ("e2e") ---------------------------------
     # Every step copies its inputs from pinned host memory and its results back, inside
-    # the timed region.  Steps are submitted round-robin on `--e2e-streams` CUDA streams
-    # with one pinned buffer set per stream (double buffering): step k+1's H2D overlaps
-    # step k's D2H on the full-duplex link; all streams are joined before the stop event.
-    NS = max(1, args.e2e_streams)
+    # the timed region (BatchedIK.solve_host -> pk_solve_ik_prepared_host).
+    NS = max(1, args.e2e_sets)
     q_h = [torch.empty((B, 6), dtype=torch.float32).pin_memory() for _ in range(NS)]
     t_h = [torch.empty((B, 12), dtype=torch.float32).pin_memory() for _ in range(NS)]
     v_h = [torch.empty((B, 6), dtype=torch.float32).pin_memory() for _ in range(NS)]
@@ -368,102 +633,88 @@ def run_gpu_arm(args):
     for i in range(NS):
         q_h[i].copy_(qs[i % NBUF].cpu())
         t_h[i].copy_(ts[i % NBUF].cpu())
-    e2e_streams = [torch.cuda.Stream(device=device) for _ in range(NS)] if NS > 1 else [torch.cuda.current_stream(device)]
 
-    def e2e_step(k):
-        i = k % NS
-        with torch.cuda.stream(e2e_streams[i]):
+    def e2e_run():
+        for k in range(args.steps):
+            i = k % NS
             ik.solve_host(q_h[i], t_h[i], v_h[i], s_h[i])
 
-    def e2e_join():
-        cur = torch.cuda.current_stream(device)
-        for st_ in e2e_streams:
-            if st_ is not cur:
-                cur.wait_stream(st_)
-
-    for k in range(max(3, args.warmup)):
-        e2e_step(k)
-    e2e_join()
+    for k in range(max(3, min(args.warmup, 10))):
+        ik.solve_host(q_h[k % NS], t_h[k % NS], v_h[k % NS], s_h[k % NS])
     barrier()
-    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_steps = args.steps
-    h0.record()
-    for st_ in e2e_streams:
-        st_.wait_event(h0)
-    for k in range(e2e_steps):
-        e2e_step(k)
-    e2e_join()
-    h1.record()
-    barrier()
-    e2e_ms = h0.elapsed_time(h1)
-    e2e_ok = bool(torch.allclose(v_h[0], vs[0].cpu(), atol=0, rtol=0)) if NBUF >= 1 else True
-
-    # ---- max over ranks -----------------------------------------------------------
-    times = torch.tensor([ms, e2e_ms, g_ms if g_ms is not None else 0.0], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, g_ms_max = (float(x) for x in times.cpu())
-    if g_ms is not None:
-        g_ms = g_ms_max
+    e2e_ms, e2e_region_ms = timed_regions(e2e_run, args.regions, pre_spin=False)
+    step(0)
+    torch.cuda.synchronize()
+    e2e_ok = bool(torch.equal(v_h[0], vs[0].cpu()))
 
     # ---- solve + gather variant (multi-GPU only): v gathered on every rank --------
-    gather_ms = None
+    gather = None
     if world > 1:
-        gathered = torch.empty((world * B, 6), dtype=torch.float32, device=device)
-        for k in range(3):
-            step(k)
-            dist.all_gather_into_tensor(gathered, vs[k % NBUF])
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for k in range(args.steps):
-            step(k)
-            dist.all_gather_into_tensor(gathered, vs[k % NBUF])
-        a1.record()
-        barrier()
-        t = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gather_ms = float(t.item())
+        gather = gather_variants(torch, dist, device, world, B, NBUF, step, vs, args, timed_regions)
+
+    # ---- max over ranks -----------------------------------------------------------
+    times = torch.tensor([ms, e2e_ms, eager_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, eager_ms = (float(x) for x in times.cpu())
 
     if rank == 0:
         peak, peak_kind = load_peaks()
         total_steps = world * B * args.steps
         value = total_steps / (ms * 1e-3)
-        kern_ms = g_ms if g_ms is not None else ms / args.steps
+        kern_ms = ms / args.steps
         achieved = B * BYTES_PER_STEP / (kern_ms * 1e-3) / 1e9
+        traffic, traffic_src = committed_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": kern_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args),
-            "gpu_launches": int(launches) * world,
+            "gpu_launches": int(args.steps) * world,
             "clocks": clocks.summary(),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": committed_traffic(), "peak_kind": peak_kind,
-                "kernel": "pk::ik_chain_kernel<6>", "kernel_ms": kern_ms,
-                "timing": "CUDA graph replay of %d launches" % NBUF if g_ms is not None else "eager launches",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
+                "kernel": ik.kernel_name() if hasattr(ik, "kernel_name") else "pk::ik_chain_kernel<6,1>",
+                "kernel_ms": kern_ms,
+                "timing": (f"{graphed.describe()} per timed region" if graphed is not None else "direct launches")
+                          + f"; median of {args.regions} regions of {args.steps} steps, L2 flushed before each",
+                "region_ms": region_ms,
                 "eager_ms_per_step": eager_ms,
                 "algorithmic_bytes_per_launch": B * BYTES_PER_STEP,
+                "l2": f"{NBUF} rotating input/output sets ({NBUF * B * BYTES_PER_STEP / 2**20:.0f} MiB) and a "
+                      f"{2 * L2_BYTES / 2**20:.0f} MiB write between regions (L2 = 126 MiB)",
             },
             "e2e": {
-                "value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+                "value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": B * (6 + 12) * 4, "d2h_bytes_per_step": B * (6 + 1) * 4,
-                "ms_per_step": e2e_ms / e2e_steps, "bitwise_equal_to_device_path": e2e_ok,
-                "api": "BatchedIK.solve_host -> pk_solve_ik_prepared_host (pinned host buffers; mode %s; %d submission stream(s))" % (os.environ.get("PK_HOST_MODE", "0"), NS),
+                "ms_per_step": e2e_ms / args.steps, "region_ms": e2e_region_ms,
+                "bitwise_equal_to_device_path": e2e_ok,
+                "api": "BatchedIK.solve_host -> pk_solve_ik_prepared_host (pinned host buffers, %d set(s); %s)"
+                       % (NS, _cabi.host_schedule() if hasattr(_cabi, "host_schedule") else "mode %s" % os.environ.get("PK_HOST_MODE", "0")),
+                "numa": numa,
             },
             "nonzero_status": bad,
         }
-        if gather_ms is not None:
-            line["solve_plus_allgather"] = {"value": total_steps / (gather_ms * 1e-3), "unit": UNIT}
+        if gather is not None:
+            line["solve_plus_allgather"] = gather
+            for g in gather.values():
+                if isinstance(g, dict) and "value" in g:
+                    g["efficiency_vs_solve_only"] = g["value"] / value
+        if not args.no_configs and world == 1:
+            try:
+                line["configs"] = humanoid_configs(torch, device, peak)
+            except Exception as exc:  # the headline line must survive a failure here
+                line["configs"] = {"error": f"{type(exc).__name__}: {exc}"}
         if not args.no_cpu and world == 1:
+            os.sched_setaffinity(0, full_affinity)  # the CPU arm gets every core again
             line["cpu_baseline"] = cpu_baseline_block(B)
         if real_stdout is not None:
             os.write(real_stdout, (json.dumps(line) + "\n").encode())
         else:
             print(json.dumps(line), flush=True)
-    # release the captured graph and the prepared problem before the process group goes
-    graph = None
+    # release the captured graphs and the prepared problem before the process group goes
+    graphed = None
     ik = None
     torch.cuda.synchronize()
     if world > 1:
@@ -474,13 +725,16 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--nbuf", type=int, default=32)
+    ap.add_argument("--regions", type=int, default=7, help="timed regions of K steps each; the median is reported")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-streams", type=int, default=1, help="CUDA streams the e2e steps are submitted on (double buffering)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the humanoid configs block (N = 1 only)")
+    ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--e2e-sets", type=int, default=2, help="pinned host buffer sets the e2e steps rotate over")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -19,6 +19,7 @@
  */
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -361,28 +362,113 @@ static int solve_one(const OcModel *M, const OcProblem *P, const double *q, cons
 
 /* ---- batch entry points ----------------------------------------------------------- */
 typedef struct {
-  const OcModel *M; const OcProblem *P; const double *q, *targets; double *v; int32_t *status; int64_t lo, hi; int tstride;
+  const OcModel *M; const OcProblem *P; const double *q, *targets; double *v; int32_t *status; int64_t B; int tstride;
+  int64_t chunk; int threads;
 } Job;
 
-static void *worker(void *arg) {
-  Job *j = (Job *)arg;
+/* Persistent worker pool: created once (grown when a call asks for more threads), every
+ * worker pinned to one CPU of the process's affinity set, instances handed out in chunks
+ * from a shared counter (dynamic load balance: active-set iteration counts differ per
+ * instance, and sibling hyper-threads run at different speeds).  A call costs one
+ * broadcast wake-up and one completion wait instead of `threads` pthread_create/join. */
+#define POOL_MAX 512
+static struct {
+  pthread_t th[POOL_MAX];
+  int id[POOL_MAX];
+  int n;                 /* workers created */
+  pthread_mutex_t mu;
+  pthread_cond_t cv_start, cv_done;
+  uint64_t epoch;        /* bumped once per job */
+  int pending;           /* workers that have not finished the current job */
+  Job job;
+  int64_t next;          /* next unclaimed instance (atomic) */
+} g_pool = {.mu = PTHREAD_MUTEX_INITIALIZER, .cv_start = PTHREAD_COND_INITIALIZER, .cv_done = PTHREAD_COND_INITIALIZER};
+static pthread_mutex_t g_call_mu = PTHREAD_MUTEX_INITIALIZER; /* one batch call at a time */
+
+static void run_chunks(const Job *j) {
   const int n = j->M->njoints;
-  for (int64_t i = j->lo; i < j->hi; ++i)
-    j->status[i] = solve_one(j->M, j->P, j->q + i * n, j->targets + i * j->tstride, j->v + i * n);
+  for (;;) {
+    const int64_t lo = __atomic_fetch_add(&g_pool.next, j->chunk, __ATOMIC_RELAXED);
+    if (lo >= j->B) break;
+    const int64_t hi = lo + j->chunk < j->B ? lo + j->chunk : j->B;
+    for (int64_t i = lo; i < hi; ++i)
+      j->status[i] = solve_one(j->M, j->P, j->q + i * n, j->targets + i * j->tstride, j->v + i * n);
+  }
+}
+
+static void *pool_worker(void *arg) {
+  const int id = *(int *)arg;
+  uint64_t seen = 0;
+  for (;;) {
+    /* short spin before blocking: consecutive bench steps arrive back to back */
+    for (int spin = 0; spin < 4000 && __atomic_load_n(&g_pool.epoch, __ATOMIC_ACQUIRE) == seen; ++spin) __builtin_ia32_pause();
+    pthread_mutex_lock(&g_pool.mu);
+    while (g_pool.epoch == seen) pthread_cond_wait(&g_pool.cv_start, &g_pool.mu);
+    seen = g_pool.epoch;
+    const Job job = g_pool.job;
+    pthread_mutex_unlock(&g_pool.mu);
+    if (id < job.threads) run_chunks(&job);
+    pthread_mutex_lock(&g_pool.mu);
+    if (--g_pool.pending == 0) pthread_cond_signal(&g_pool.cv_done);
+    pthread_mutex_unlock(&g_pool.mu);
+  }
   return 0;
 }
 
-/* Solve B instances with `threads` pthreads. targets: [B][12 * n_frame_tasks]. Returns 0. */
+static void pool_grow(int threads) {
+  cpu_set_t allowed;
+  int cpus[CPU_SETSIZE], ncpu = 0;
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0)
+    for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &allowed)) cpus[ncpu++] = c;
+  while (g_pool.n < threads && g_pool.n < POOL_MAX) {
+    const int t = g_pool.n;
+    g_pool.id[t] = t;
+    if (pthread_create(&g_pool.th[t], 0, pool_worker, &g_pool.id[t])) break;
+    if (ncpu > 0) {
+      cpu_set_t one; CPU_ZERO(&one); CPU_SET(cpus[t % ncpu], &one);
+      pthread_setaffinity_np(g_pool.th[t], sizeof(one), &one);
+    }
+    g_pool.n++;
+  }
+}
+
+/* Number of pool workers alive (diagnostics for the bench line). */
+int oc_pool_size(void) { return g_pool.n; }
+
+/* Solve B instances with `threads` workers. targets: [B][12 * n_frame_tasks]. Returns 0. */
 int oc_solve_ik_batch(const OcModel *M, const OcProblem *P, const double *q, const double *targets, double *v,
                       int32_t *status, int64_t B, int threads) {
   if (M->njoints > MAXJ || P->n_frame_tasks > MAXT) return 1;
   if (threads < 1) threads = 1;
-  if (threads > 256) threads = 256;
-  pthread_t th[256]; Job jobs[256];
-  for (int t = 0; t < threads; ++t) {
-    jobs[t] = (Job){M, P, q, targets, v, status, B * t / threads, B * (t + 1) / threads, 12 * P->n_frame_tasks};
-    if (threads == 1) worker(&jobs[t]); else pthread_create(&th[t], 0, worker, &jobs[t]);
+  if (threads > POOL_MAX) threads = POOL_MAX;
+  Job job = {M, P, q, targets, v, status, B, 12 * P->n_frame_tasks, 0, threads};
+  /* ~16 chunks per worker, at least 16 instances each */
+  job.chunk = B / ((int64_t)threads * 16);
+  if (job.chunk < 16) job.chunk = 16;
+  pthread_mutex_lock(&g_call_mu);
+  if (threads == 1) {
+    job.chunk = B > 0 ? B : 1;
+    g_pool.next = 0;
+    run_chunks(&job);
+    pthread_mutex_unlock(&g_call_mu);
+    return 0;
   }
-  if (threads > 1) for (int t = 0; t < threads; ++t) pthread_join(th[t], 0);
+  pthread_mutex_lock(&g_pool.mu);
+  pool_grow(threads);
+  if (job.threads > g_pool.n) job.threads = g_pool.n;
+  if (g_pool.n == 0) { /* no worker could be created: run inline */
+    pthread_mutex_unlock(&g_pool.mu);
+    job.chunk = B > 0 ? B : 1; g_pool.next = 0; run_chunks(&job);
+    pthread_mutex_unlock(&g_call_mu);
+    return 0;
+  }
+  g_pool.job = job;
+  __atomic_store_n(&g_pool.next, 0, __ATOMIC_RELAXED);
+  g_pool.pending = g_pool.n;
+  __atomic_add_fetch(&g_pool.epoch, 1, __ATOMIC_RELEASE);
+  pthread_cond_broadcast(&g_pool.cv_start);
+  while (g_pool.pending != 0) pthread_cond_wait(&g_pool.cv_done, &g_pool.mu);
+  pthread_mutex_unlock(&g_pool.mu);
+  pthread_mutex_unlock(&g_call_mu);
   return 0;
 }

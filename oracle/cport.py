@@ -126,13 +126,19 @@ class CPort:
         self.problem = P
         self.nft = k
 
-    def solve(self, q, targets, threads=1):
+    def solve(self, q, targets, threads=1, reuse_outputs=False):
         """``q [B, nj]``, ``targets [B, nft, 3, 4]`` (fp64) -> ``v [B, nj]``, ``status [B]``."""
         q = np.ascontiguousarray(q, dtype=np.float64)
         B = q.shape[0]
         t = np.ascontiguousarray(np.asarray(targets, dtype=np.float64).reshape(B, 12 * self.nft))
-        v = np.zeros_like(q)
-        st = np.zeros(B, dtype=np.int32)
+        if reuse_outputs:
+            # repeated timing calls: no 3 MB allocation + page faults per step
+            if getattr(self, "_out", None) is None or self._out[0].shape != q.shape:
+                self._out = (np.zeros_like(q), np.zeros(B, dtype=np.int32))
+            v, st = self._out
+        else:
+            v = np.zeros_like(q)
+            st = np.zeros(B, dtype=np.int32)
         rc = lib().oc_solve_ik_batch(C.byref(self.model), C.byref(self.problem), q.ctypes.data_as(C.c_void_p),
                                      t.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p),
                                      st.ctypes.data_as(C.c_void_p), C.c_int64(B), int(threads))

@@ -37,8 +37,10 @@ class BatchedIK:
 
         if not hasattr(model, "configuration_limit"):
             Configuration(model, None, np.zeros(model.nq))
-        if limits is None:
+        if limits is None:  # the same defaults as solve_ik (pink/solve_ik.py:94-105)
             limits = [model.configuration_limit, model.velocity_limit]
+            if getattr(model, "floating_base_velocity_limit", None) is not None:
+                limits.append(model.floating_base_velocity_limit)
         tasks = list(tasks)
         if batch_size is None:
             sizes = [d.shape[0] for d in (t._pk_describe(model)["target"] for t in tasks) if isinstance(d, torch.Tensor)]

@@ -392,8 +392,14 @@ int launch_generic(const PkModel* m, const pk::DevProblem& P, const pk::GenericA
 struct PkProblem {
   pk::DevProblem P;
   void* dev_ext = nullptr;  // DevExtras + extra floats + pair indices (one allocation)
+  // temporary problems of the un-prepared entry points: the image is allocated, filled and
+  // released in stream order (no device-wide synchronisation per call)
+  bool ext_async = false;
+  cudaStream_t ext_stream = nullptr;
   ~PkProblem() {
-    if (dev_ext) cudaFree(dev_ext);
+    if (!dev_ext) return;
+    if (ext_async) cudaFreeAsync(dev_ext, ext_stream);
+    else cudaFree(dev_ext);
   }
   bool chain = false;
   bool tree = false;
@@ -442,6 +448,8 @@ int prepare_problem(const PkModel* m, const PkProblemDesc* desc, PkProblem* pr, 
   if (!perr.empty()) return fail(perr);
   if (hx.present) {
     if (upload_extras(hx, stream, async, &pr->dev_ext)) return 1;
+    pr->ext_async = async;
+    pr->ext_stream = stream;
     pr->P.ext = reinterpret_cast<const pk::DevExtras*>(pr->dev_ext);
   }
   static const int force_generic = env_int("PK_FORCE_GENERIC", 0);
@@ -488,10 +496,17 @@ int solve_device(const PkModel* m, const PkProblem& pr, const float* q, const fl
   }
   if (pr.tree) {
     const size_t smem = (size_t)pr.plan.words * 4 * pk::kTreeWarpsPerBlock;
-    static size_t configured = 0;
-    if (smem > configured) {
-      PK_CUDA(cudaFuncSetAttribute(pk::ik_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
+    // the opt-in is per device (and this entry point may run on several host threads): keep
+    // the size granted so far per device ordinal, under a lock
+    {
+      static std::mutex cfg_mu;
+      static size_t configured[64] = {};
+      std::lock_guard<std::mutex> lock(cfg_mu);
+      const int dev = (m->device >= 0 && m->device < 64) ? m->device : 0;
+      if (smem > configured[dev] || m->device >= 64) {
+        PK_CUDA(cudaFuncSetAttribute(pk::ik_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = smem;
+      }
     }
     const int64_t grid = (B + pk::kTreeWarpsPerBlock - 1) / pk::kTreeWarpsPerBlock;
     pk::ik_tree_kernel<<<(unsigned)grid, 32 * pk::kTreeWarpsPerBlock, smem, stream>>>(m->dev, pr.P, pr.plan, q, targets, v,
@@ -593,7 +608,7 @@ extern "C" int pk_solve_ik_batched(const PkModel* m, const PkProblemDesc* prob, 
   if (check_common(m, q, B)) return 1;
   if (B > 0 && !v) return fail("null v");
   PkProblem pr;
-  if (prepare_problem(m, prob, &pr)) return 1;
+  if (prepare_problem(m, prob, &pr, (cudaStream_t)stream, true)) return 1;
   if (B > 0 && pr.P.target_stride > 0 && !targets) return fail("null targets");
   return solve_device(m, pr, q, targets, v, status, B, (cudaStream_t)stream);
 }
@@ -604,7 +619,7 @@ extern "C" int pk_solve_ik_batched_host(PkModel* m, const PkProblemDesc* prob, c
   if (check_common(m, q_host, B)) return 1;
   if (B > 0 && !v_host) return fail("null v");
   PkProblem pr;
-  if (prepare_problem(m, prob, &pr)) return 1;
+  if (prepare_problem(m, prob, &pr, (cudaStream_t)stream_, true)) return 1;
   if (B > 0 && pr.P.target_stride > 0 && !targets_host) return fail("null targets");
   return solve_host_impl(m, pr, q_host, targets_host, v_host, status_host, B, (cudaStream_t)stream_);
 }
@@ -782,7 +797,7 @@ extern "C" int pk_build_ik_batched(const PkModel* m, const PkProblemDesc* prob, 
                                    const float* targets, float* H, float* c, float* h, int64_t B, void* stream) {
   if (check_common(m, q, B)) return 1;
   PkProblem pr;
-  if (prepare_problem(m, prob, &pr)) return 1;
+  if (prepare_problem(m, prob, &pr, (cudaStream_t)stream, true)) return 1;
   const pk::DevProblem& P = pr.P;
   if (B == 0) return 0;
   if (!H) return fail("null H");
@@ -801,7 +816,7 @@ extern "C" int pk_constraint_rows_batched(const PkModel* m, const PkProblemDesc*
                                           float* hi, int64_t B, void* stream) {
   if (check_common(m, q, B)) return 1;
   PkProblem pr;
-  if (prepare_problem(m, prob, &pr)) return 1;
+  if (prepare_problem(m, prob, &pr, (cudaStream_t)stream, true)) return 1;
   if ((G == nullptr) != (hG == nullptr) || (E == nullptr) != (f == nullptr) || (lo == nullptr) != (hi == nullptr))
     return fail("G/hG, E/f and lo/hi come in pairs");
   if (B == 0) return 0;
@@ -824,7 +839,7 @@ extern "C" int pk_task_terms_batched(const PkModel* m, const PkProblemDesc* prob
                                      void* stream) {
   if (check_common(m, q, B)) return 1;
   PkProblem pr;
-  if (prepare_problem(m, prob, &pr)) return 1;
+  if (prepare_problem(m, prob, &pr, (cudaStream_t)stream, true)) return 1;
   const pk::DevProblem& P = pr.P;
   if (task_index < 0 || task_index >= P.ntasks) return fail("task_index out of range");
   if (B == 0) return 0;

@@ -105,7 +105,10 @@ struct GenericOut {
   float* hi;       // [nv]
 };
 
-constexpr int kGenericMaxRows = 48;  // stacked task rows (6 per frame task, 3 per CoM task)
+// stacked task rows: 6 per frame task, 3 per CoM task; every task set the ABI can describe fits
+// (nothing is ever truncated)
+constexpr int kGenericMaxRows = 6 * PK_MAX_TASKS;
+static_assert(kGenericMaxRows >= 6 * PK_MAX_TASKS, "a describable task set must fit the row buffer");
 
 template <int NJMAX, int NVMAX>
 struct Generic {

@@ -249,7 +249,7 @@ def describe_problem(model, batch_size: int, tasks: Iterable, dt: float, damping
         _fill_barrier(prob.barriers[k], barrier, d, not raw_barriers, extra, pairs)
     acc = _fill_limits(prob, model, limits, safety_break)
     if acc is not None:
-        prev = acc.Delta_q_prev
+        prev = acc._delta_q_prev_full
         if isinstance(prev, torch.Tensor) or np.any(np.asarray(prev) != 0.0):
             prob.acc_prev_offset, prob.acc_prev_shared = layout.place(prev, acc)
     prob.target_stride = layout.inst_off

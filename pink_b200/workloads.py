@@ -139,3 +139,51 @@ def humanoid_task_set(name: str, model, oMf_target, com_target=None):
         com.set_target(com_target)
         tasks.append(com)
     return tasks, damping
+
+
+# sphere set of BASELINE config 4 (joint, radius): 9 spheres -> 36 pairs, the 8 closest enter
+# the barrier (gain 20, safe displacement gain 1, d_min 0.05 as
+# examples/barriers/kukas_self_collision.py:167-172)
+G1_COLLISION_SPHERES = [
+    ("left_wrist_yaw_joint", 0.06), ("right_wrist_yaw_joint", 0.06), ("left_elbow_joint", 0.06),
+    ("right_elbow_joint", 0.06), ("waist_yaw_joint", 0.13), ("left_knee_joint", 0.07),
+    ("right_knee_joint", 0.07), ("left_ankle_roll_joint", 0.06), ("right_ankle_roll_joint", 0.06),
+]
+HUMANOID_BYTES_PER_STEP = {"draco3_description": 460, "g1_description": 536}
+HUMANOID_BATCH = {"draco3_description": 32768, "g1_description": 16384}      # BASELINE configs 3, 4
+
+
+def humanoid_problem(name: str, device, batch: int | None = None, with_barrier: bool = False, seed: int = SEED):
+    """BASELINE config 3 (``draco3_description``) / config 4 (``g1_description``, optionally
+    with the sphere self-collision barrier) as a prepared :class:`BatchedIK` plus its seeded
+    device inputs.  Returns ``(ik, q [B, nq], targets [B, stride], model)``."""
+    import torch
+
+    import pink_b200
+    from .engine import get_engine
+    from .model import JointModelFreeFlyer
+    from .robots import load_robot_description
+
+    robot = load_robot_description(name, root_joint=JointModelFreeFlyer())
+    model = robot.model
+    barriers, cm = None, None
+    if with_barrier:
+        cm = pink_b200.SphereCollisionModel(model)
+        for k, (joint, radius) in enumerate(G1_COLLISION_SPHERES):
+            cm.add_sphere(f"s{k}", model.getJointId(joint), (0.0, 0.0, 0.0), radius)
+        cm.add_all_collision_pairs()
+        barriers = [pink_b200.barriers.SelfCollisionBarrier(8, gain=20.0, safe_displacement_gain=1.0, d_min=0.05)]
+    eng = get_engine(model, device)
+    B = int(batch or HUMANOID_BATCH[name])
+    rng = np.random.default_rng(seed)
+    q = sample_configurations(eng.table, B, rng)
+    qt = perturb_configurations(eng.table, q, rng, sigma=0.15)
+    q_d = torch.as_tensor(q, dtype=torch.float32, device=device)
+    oMf, com = eng.forward_kinematics(torch.as_tensor(qt, dtype=torch.float32, device=device), want_com=True)
+    tasks, damping = humanoid_task_set(name, model, oMf, com)
+    ik = pink_b200.BatchedIK(model, tasks, 1.0 / 200.0, damping=damping, safety_break=False, device=device,
+                             batch_size=B, barriers=barriers, collision_model=cm)
+    targets = torch.cat([t._pk_describe(model)["target"].to(device) for t in tasks
+                         if isinstance(t._pk_describe(model)["target"], torch.Tensor)], dim=1).contiguous()
+    ik._bench_tasks = (tasks, damping, barriers, cm)  # kept for checks that rebuild the QP
+    return ik, q_d, targets, model

@@ -19,7 +19,12 @@
  */
 #include <math.h>
 #include <pthread.h>
+#include <limits.h>
+#include <linux/futex.h>
 #include <sched.h>
+#include <stdio.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -363,112 +368,136 @@ static int solve_one(const OcModel *M, const OcProblem *P, const double *q, cons
 /* ---- batch entry points ----------------------------------------------------------- */
 typedef struct {
   const OcModel *M; const OcProblem *P; const double *q, *targets; double *v; int32_t *status; int64_t B; int tstride;
-  int64_t chunk; int threads;
+  int threads;
 } Job;
 
-/* Persistent worker pool: created once (grown when a call asks for more threads), every
- * worker pinned to one CPU of the process's affinity set, instances handed out in chunks
- * from a shared counter (dynamic load balance: active-set iteration counts differ per
- * instance, and sibling hyper-threads run at different speeds).  A call costs one
- * broadcast wake-up and one completion wait instead of `threads` pthread_create/join. */
+/* Persistent worker pool.
+ *  - Workers are created once (the pool grows when a call asks for more), each pinned to one
+ *    CPU of the process's affinity set (distinct physical cores first, then their
+ *    hyper-thread siblings).
+ *  - A job is published by bumping a futex word; workers claim chunks of instances from one
+ *    64-bit counter that carries the job's epoch in its high bits (guided self-scheduling:
+ *    chunk = remaining / (4 threads), at least 8), so a worker that wakes up late - or still
+ *    holds an older job - can never touch the current job's index space.
+ *  - The caller works too and the call returns when all INSTANCES are done, not when all
+ *    workers have checked in: a worker whose CPU is busy with somebody else's process (the
+ *    GPU boxes are shared) costs at most its one chunk in flight.
+ * The first version of this pool woke the workers through a condition variable and waited
+ * for every one of them to report back: on a 128-thread box the mutex convoy and the
+ * stragglers made a 2 ms job take 15-20 ms (parallel efficiency 0.11).                   */
 #define POOL_MAX 512
-static struct {
-  pthread_t th[POOL_MAX];
-  int id[POOL_MAX];
-  int n;                 /* workers created */
-  pthread_mutex_t mu;
-  pthread_cond_t cv_start, cv_done;
-  uint64_t epoch;        /* bumped once per job */
-  int pending;           /* workers that have not finished the current job */
-  Job job;
-  int64_t next;          /* next unclaimed instance (atomic) */
-} g_pool = {.mu = PTHREAD_MUTEX_INITIALIZER, .cv_start = PTHREAD_COND_INITIALIZER, .cv_done = PTHREAD_COND_INITIALIZER};
+#define EPOCH_SHIFT 40
+#define INDEX_MASK ((1ull << EPOCH_SHIFT) - 1ull)
+static pthread_t g_th[POOL_MAX];
+static int g_tid[POOL_MAX];
+static int g_nworkers = 0;
+static uint32_t g_epoch = 0;   /* futex word: current job number */
+static uint64_t g_ctr = 0;     /* (epoch << 40) | next unclaimed instance */
+static int64_t g_done = 0;     /* instances finished in the current job */
+static Job g_job;
 static pthread_mutex_t g_call_mu = PTHREAD_MUTEX_INITIALIZER; /* one batch call at a time */
 
-static void run_chunks(const Job *j) {
+static void futex_wait(uint32_t *addr, uint32_t val) { syscall(SYS_futex, addr, FUTEX_WAIT_PRIVATE, val, 0, 0, 0); }
+static void futex_wake_all(uint32_t *addr) { syscall(SYS_futex, addr, FUTEX_WAKE_PRIVATE, INT_MAX, 0, 0, 0); }
+
+static void run_chunks(const Job *j, uint64_t epoch) {
   const int n = j->M->njoints;
   for (;;) {
-    const int64_t lo = __atomic_fetch_add(&g_pool.next, j->chunk, __ATOMIC_RELAXED);
-    if (lo >= j->B) break;
-    const int64_t hi = lo + j->chunk < j->B ? lo + j->chunk : j->B;
-    for (int64_t i = lo; i < hi; ++i)
+    uint64_t c = __atomic_load_n(&g_ctr, __ATOMIC_ACQUIRE);
+    if ((c >> EPOCH_SHIFT) != epoch) return;          /* a newer job owns the counter */
+    const int64_t lo = (int64_t)(c & INDEX_MASK);
+    if (lo >= j->B) return;
+    int64_t chunk = (j->B - lo) / (4 * (int64_t)j->threads);
+    if (chunk < 8) chunk = 8;
+    if (chunk > j->B - lo) chunk = j->B - lo;
+    if (!__atomic_compare_exchange_n(&g_ctr, &c, c + (uint64_t)chunk, 1, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) continue;
+    for (int64_t i = lo; i < lo + chunk; ++i)
       j->status[i] = solve_one(j->M, j->P, j->q + i * n, j->targets + i * j->tstride, j->v + i * n);
+    __atomic_add_fetch(&g_done, chunk, __ATOMIC_ACQ_REL);
   }
 }
 
 static void *pool_worker(void *arg) {
   const int id = *(int *)arg;
-  uint64_t seen = 0;
+  uint32_t seen = 0;
   for (;;) {
-    /* short spin before blocking: consecutive bench steps arrive back to back */
-    for (int spin = 0; spin < 4000 && __atomic_load_n(&g_pool.epoch, __ATOMIC_ACQUIRE) == seen; ++spin) __builtin_ia32_pause();
-    pthread_mutex_lock(&g_pool.mu);
-    while (g_pool.epoch == seen) pthread_cond_wait(&g_pool.cv_start, &g_pool.mu);
-    seen = g_pool.epoch;
-    const Job job = g_pool.job;
-    pthread_mutex_unlock(&g_pool.mu);
-    if (id < job.threads) run_chunks(&job);
-    pthread_mutex_lock(&g_pool.mu);
-    if (--g_pool.pending == 0) pthread_cond_signal(&g_pool.cv_done);
-    pthread_mutex_unlock(&g_pool.mu);
+    uint32_t e;
+    int spin = 0;
+    while ((e = __atomic_load_n(&g_epoch, __ATOMIC_ACQUIRE)) == seen) {
+      if (++spin < 200) __builtin_ia32_pause();      /* consecutive bench steps arrive back to back */
+      else futex_wait(&g_epoch, seen);
+    }
+    seen = e;
+    const Job job = g_job;                             /* complete: written before the epoch was published */
+    if (__atomic_load_n(&g_epoch, __ATOMIC_ACQUIRE) != e) continue; /* already superseded */
+    if (id < job.threads) run_chunks(&job, (uint64_t)e);
   }
   return 0;
 }
 
-static void pool_grow(int threads) {
+/* CPUs of the affinity set, one hyper-thread per physical core first. */
+static int ordered_cpus(int *out) {
   cpu_set_t allowed;
-  int cpus[CPU_SETSIZE], ncpu = 0;
-  if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0)
-    for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &allowed)) cpus[ncpu++] = c;
-  while (g_pool.n < threads && g_pool.n < POOL_MAX) {
-    const int t = g_pool.n;
-    g_pool.id[t] = t;
-    if (pthread_create(&g_pool.th[t], 0, pool_worker, &g_pool.id[t])) break;
-    if (ncpu > 0) {
-      cpu_set_t one; CPU_ZERO(&one); CPU_SET(cpus[t % ncpu], &one);
-      pthread_setaffinity_np(g_pool.th[t], sizeof(one), &one);
+  int n = 0, cpus[CPU_SETSIZE], ncpu = 0;
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return 0;
+  for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &allowed)) cpus[ncpu++] = c;
+  char taken[CPU_SETSIZE]; memset(taken, 0, sizeof(taken));
+  for (int pass = 0; pass < 2; ++pass)
+    for (int k = 0; k < ncpu; ++k) {
+      const int c = cpus[k];
+      if (taken[c]) continue;
+      int first = c;  /* lowest sibling id */
+      char path[128]; snprintf(path, sizeof(path), "/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list", c);
+      FILE *f = fopen(path, "r");
+      if (f) { if (fscanf(f, "%d", &first) != 1) first = c; fclose(f); }
+      if (pass == 0 && first != c) continue;   /* siblings go to the second pass */
+      taken[c] = 1; out[n++] = c;
     }
-    g_pool.n++;
+  return n;
+}
+
+static void pool_grow(int threads) {
+  int cpus[CPU_SETSIZE];
+  const int ncpu = ordered_cpus(cpus);
+  const char *pin = getenv("OC_POOL_PIN");
+  const int do_pin = !(pin && pin[0] == '0');
+  while (g_nworkers < threads && g_nworkers < POOL_MAX) {
+    const int t = g_nworkers;
+    g_tid[t] = t;
+    if (pthread_create(&g_th[t], 0, pool_worker, &g_tid[t])) break;
+    if (do_pin && ncpu > 0) {
+      /* worker t shares the machine with the calling thread, which works too: shift by one */
+      cpu_set_t one; CPU_ZERO(&one); CPU_SET(cpus[(t + 1) % ncpu], &one);
+      pthread_setaffinity_np(g_th[t], sizeof(one), &one);
+    }
+    g_nworkers++;
   }
 }
 
 /* Number of pool workers alive (diagnostics for the bench line). */
-int oc_pool_size(void) { return g_pool.n; }
+int oc_pool_size(void) { return g_nworkers; }
 
-/* Solve B instances with `threads` workers. targets: [B][12 * n_frame_tasks]. Returns 0. */
+/* Solve B instances with `threads` threads (the caller + threads - 1 workers).
+ * targets: [B][12 * n_frame_tasks]. Returns 0. */
 int oc_solve_ik_batch(const OcModel *M, const OcProblem *P, const double *q, const double *targets, double *v,
                       int32_t *status, int64_t B, int threads) {
   if (M->njoints > MAXJ || P->n_frame_tasks > MAXT) return 1;
+  if (B >= (int64_t)INDEX_MASK) return 1;
   if (threads < 1) threads = 1;
   if (threads > POOL_MAX) threads = POOL_MAX;
-  Job job = {M, P, q, targets, v, status, B, 12 * P->n_frame_tasks, 0, threads};
-  /* ~16 chunks per worker, at least 16 instances each */
-  job.chunk = B / ((int64_t)threads * 16);
-  if (job.chunk < 16) job.chunk = 16;
   pthread_mutex_lock(&g_call_mu);
-  if (threads == 1) {
-    job.chunk = B > 0 ? B : 1;
-    g_pool.next = 0;
-    run_chunks(&job);
-    pthread_mutex_unlock(&g_call_mu);
-    return 0;
-  }
-  pthread_mutex_lock(&g_pool.mu);
-  pool_grow(threads);
-  if (job.threads > g_pool.n) job.threads = g_pool.n;
-  if (g_pool.n == 0) { /* no worker could be created: run inline */
-    pthread_mutex_unlock(&g_pool.mu);
-    job.chunk = B > 0 ? B : 1; g_pool.next = 0; run_chunks(&job);
-    pthread_mutex_unlock(&g_call_mu);
-    return 0;
-  }
-  g_pool.job = job;
-  __atomic_store_n(&g_pool.next, 0, __ATOMIC_RELAXED);
-  g_pool.pending = g_pool.n;
-  __atomic_add_fetch(&g_pool.epoch, 1, __ATOMIC_RELEASE);
-  pthread_cond_broadcast(&g_pool.cv_start);
-  while (g_pool.pending != 0) pthread_cond_wait(&g_pool.cv_done, &g_pool.mu);
-  pthread_mutex_unlock(&g_pool.mu);
+  if (threads > 1) pool_grow(threads - 1);
+  Job job = {M, P, q, targets, v, status, B, 12 * P->n_frame_tasks, threads - 1};
+  if (job.threads > g_nworkers) job.threads = g_nworkers;
+  const uint32_t e = g_epoch + 1;
+  g_job = job;                                     /* workers with id < job.threads take part */
+  Job mine = job; mine.threads = job.threads + 1;  /* the caller's chunk sizing counts itself */
+  __atomic_store_n(&g_done, 0, __ATOMIC_RELAXED);
+  __atomic_store_n(&g_ctr, (uint64_t)e << EPOCH_SHIFT, __ATOMIC_RELEASE);
+  __atomic_store_n(&g_epoch, e, __ATOMIC_RELEASE);
+  if (job.threads > 0) futex_wake_all(&g_epoch);
+  run_chunks(&mine, (uint64_t)e);
+  while (__atomic_load_n(&g_done, __ATOMIC_ACQUIRE) < B) __builtin_ia32_pause();
   pthread_mutex_unlock(&g_call_mu);
   return 0;
 }

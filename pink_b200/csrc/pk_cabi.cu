@@ -15,6 +15,7 @@
 
 #include "../../include/pink_b200.h"
 #include "pk_chain.cuh"
+#include "pk_coop_kernel.cuh"
 #include "pk_generic.cuh"
 #include "pk_marshal.hpp"
 
@@ -406,14 +407,28 @@ struct PkProblem {
   pk::TreePlan plan;
   int nj = 0;
   alignas(16) unsigned char chain_params[sizeof(pk::ChainParams<7>)];
+  // parameter blocks of the sub-warp chain kernel, one per lanes-per-instance variant
+  // (index log2 L); the padding joints depend on L
+  alignas(16) unsigned char coop_params[4][sizeof(pk::CoopParams<8>)];
 };
 
 namespace {
+
+template <int NJ, int L>
+void fill_coop(const PkModel* m, PkProblem* pr, const pk::DevExtras* X, int slot) {
+  constexpr int NJP = pk::CoopStep<NJ, 1, L>::NJP;
+  static_assert(sizeof(pk::CoopParams<NJP>) <= sizeof(pr->coop_params[0]), "parameter block too small");
+  pk::make_coop_params<NJ, L>(m->hm, pr->P, reinterpret_cast<pk::CoopParams<NJP>*>(pr->coop_params[slot]), X);
+}
 
 template <int NJ>
 void fill_chain(const PkModel* m, PkProblem* pr, const pk::DevExtras* X) {
   static_assert(sizeof(pk::ChainParams<NJ>) <= sizeof(pr->chain_params), "parameter block too small");
   pk::make_chain_params<NJ>(m->hm, pr->P, reinterpret_cast<pk::ChainParams<NJ>*>(pr->chain_params), X);
+  fill_coop<NJ, 1>(m, pr, X, 0);
+  fill_coop<NJ, 2>(m, pr, X, 1);
+  fill_coop<NJ, 4>(m, pr, X, 2);
+  fill_coop<NJ, 8>(m, pr, X, 3);
 }
 
 // Device image of the optional problem parts: [DevExtras | extra | pairs] in one buffer.
@@ -473,9 +488,43 @@ int prepare_problem(const PkModel* m, const PkProblemDesc* desc, PkProblem* pr, 
   return 0;
 }
 
+template <int NJ, int NFT, int L>
+int launch_coop_nft(const PkProblem& pr, int slot, const float* q, const float* targets, float* v, int32_t* status,
+                    int64_t B, cudaStream_t stream, int n_steps, float* q_out) {
+  using Step = pk::CoopStep<NJ, NFT, L>;
+  const auto& C = *reinterpret_cast<const pk::CoopParams<Step::NJP>*>(pr.coop_params[slot]);
+  const int64_t grid = (B * L + pk::kCoopThreads - 1) / pk::kCoopThreads;
+  pk::ik_coop_kernel<NJ, NFT, L><<<(unsigned)grid, pk::kCoopThreads, 0, stream>>>(C, q, targets, v, status, B, n_steps, q_out);
+  g_launches.fetch_add(1);
+  PK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int NJ, int L>
+int launch_coop(const PkProblem& pr, int slot, const float* q, const float* targets, float* v, int32_t* status,
+                int64_t B, cudaStream_t stream, int n_steps, float* q_out) {
+  const int nft = reinterpret_cast<const pk::CoopParams<pk::CoopStep<NJ, 1, L>::NJP>*>(pr.coop_params[slot])->n_frame_tasks;
+  switch (nft) {
+    case 0: return launch_coop_nft<NJ, 0, L>(pr, slot, q, targets, v, status, B, stream, n_steps, q_out);
+    case 1: return launch_coop_nft<NJ, 1, L>(pr, slot, q, targets, v, status, B, stream, n_steps, q_out);
+    default: return launch_coop_nft<NJ, 2, L>(pr, slot, q, targets, v, status, B, stream, n_steps, q_out);
+  }
+}
+
 template <int NJ>
 int launch_chain_prepared(const PkProblem& pr, const float* q, const float* targets, float* v, int32_t* status,
                           int64_t B, cudaStream_t stream, int n_steps = 1, float* q_out = nullptr) {
+  // PK_CHAIN_LANES: 0 = round-1 kernel (one instance per thread, pk_chain.cuh); 1 / 2 / 4 / 8 =
+  // sub-warp kernel (pk_coop.cuh) with that many lanes per instance (4 and 8: UR5-class study
+  // variants, 6 joints + 1 frame task only)
+  static const int lanes = env_int("PK_CHAIN_LANES", 0);
+  if (lanes == 1) return launch_coop<NJ, 1>(pr, 0, q, targets, v, status, B, stream, n_steps, q_out);
+  if (lanes == 2) return launch_coop<NJ, 2>(pr, 1, q, targets, v, status, B, stream, n_steps, q_out);
+  if constexpr (NJ == 6) {
+    const int nft = reinterpret_cast<const pk::ChainParams<NJ>*>(pr.chain_params)->n_frame_tasks;
+    if (lanes == 4 && nft == 1) return launch_coop_nft<NJ, 1, 4>(pr, 2, q, targets, v, status, B, stream, n_steps, q_out);
+    if (lanes == 8 && nft == 1) return launch_coop_nft<NJ, 1, 8>(pr, 3, q, targets, v, status, B, stream, n_steps, q_out);
+  }
   return launch_chain<NJ>(*reinterpret_cast<const pk::ChainParams<NJ>*>(pr.chain_params), q, targets, v, status, B,
                           stream, n_steps, q_out);
 }

@@ -11,6 +11,7 @@
 
 #include "../../include/pink_b200.h"
 #include "pk_chain.cuh"
+#include "pk_coop.cuh"
 #include "pk_generic.cuh"
 #include "pk_tree.cuh"
 #include "pk_treedual.cuh"
@@ -555,6 +556,134 @@ void make_chain_params(const HostModel& m, const DevProblem& P, ChainParams<NJ>*
   C.target_stride = P.target_stride;
   C.safety_break = P.safety_break;
   memcpy(C.shared, P.shared, sizeof(C.shared));
+}
+
+// Parameter block of the sub-warp chain kernel (pk_coop.cuh): joint frames re-oriented so
+// that every joint axis is the local z axis.  With A_j the rotation that takes e_z to the
+// axis a_j, T~_j = oMi[j] A_j satisfies T~_j = T~_{j-1} X~_j M_z(q_j), X~_j = A_{j-1}^T X_j A_j
+// (A_{-1} = I), and a frame fixed to joint b sits at A_b^T X_f in T~_b.  All folding in double.
+template <int NJ, int L>
+void make_coop_params(const HostModel& m, const DevProblem& P, CoopParams<((NJ + L - 1) / L) * L>* out,
+                      const DevExtras* X = nullptr) {
+  constexpr int NJP = ((NJ + L - 1) / L) * L;
+  CoopParams<NJP>& C = *out;
+  memset(&C, 0, sizeof(C));
+  C.acc_prev_off = -1;
+  if (X && X->acc_enabled) {
+    C.acc_enabled = 1;
+    C.acc_prev_off = X->acc_prev_shared ? -1 : X->acc_prev_off;
+  }
+  double Aprev[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  std::vector<double> Aall(9 * NJ);
+  for (int j = 0; j < NJ; ++j) {
+    const double a[3] = {m.axis[3 * j], m.axis[3 * j + 1], m.axis[3 * j + 2]};
+    double A[9];
+    const double c = a[2];  // e_z . a
+    if (c > 1.0 - 1e-12) {
+      const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      memcpy(A, I, sizeof(A));
+    } else if (c < -1.0 + 1e-12) {
+      const double Rx[9] = {1, 0, 0, 0, -1, 0, 0, 0, -1};  // half turn about x
+      memcpy(A, Rx, sizeof(A));
+    } else {
+      // Rodrigues about v = e_z x a = (-a_y, a_x, 0): A = I + [v]x + [v]x^2 / (1 + c)
+      const double vx = -a[1], vy = a[0];
+      const double k = 1.0 / (1.0 + c);
+      const double Kx[9] = {0, 0, vy, 0, 0, -vx, -vy, vx, 0};
+      for (int r = 0; r < 3; ++r)
+        for (int cc = 0; cc < 3; ++cc) {
+          double k2 = 0.0;
+          for (int t = 0; t < 3; ++t) k2 += Kx[3 * r + t] * Kx[3 * t + cc];
+          A[3 * r + cc] = (r == cc ? 1.0 : 0.0) + Kx[3 * r + cc] + k * k2;
+        }
+    }
+    memcpy(&Aall[9 * j], A, sizeof(A));
+    const float* Xj = &m.jX[12 * j];
+    CoopJoint& J = C.joint[j];
+    // X~.R = Aprev^T X.R A, X~.p = Aprev^T X.p
+    double XA[9];
+    for (int r = 0; r < 3; ++r)
+      for (int cc = 0; cc < 3; ++cc) {
+        double s = 0.0;
+        for (int t = 0; t < 3; ++t) s += (double)Xj[4 * r + t] * A[3 * t + cc];
+        XA[3 * r + cc] = s;
+      }
+    for (int r = 0; r < 3; ++r) {
+      for (int cc = 0; cc < 3; ++cc) {
+        double s = 0.0;
+        for (int t = 0; t < 3; ++t) s += Aprev[3 * t + r] * XA[3 * t + cc];
+        J.Xr[3 * r + cc] = (float)s;
+      }
+      double sp = 0.0;
+      for (int t = 0; t < 3; ++t) sp += Aprev[3 * t + r] * (double)Xj[4 * t + 3];
+      J.Xp[r] = (float)sp;
+    }
+    memcpy(Aprev, A, sizeof(A));
+    J.prismatic = (m.jtype[j] == PK_JOINT_REVOLUTE) ? 0.f : 1.f;
+    J.cfg_lo = P.cfg_lo[j];
+    J.cfg_hi = P.cfg_hi[j];
+    J.vel = P.vel[j];
+    J.chk_lo = P.chk_lo[j];
+    J.chk_hi = P.chk_hi[j];
+    J.acc_max = (X && X->acc_enabled) ? X->acc_max[j] : INFINITY;
+    J.acc_qlo = (X && X->acc_enabled) ? X->acc_qlo[j] : -INFINITY;
+    J.acc_qhi = (X && X->acc_enabled) ? X->acc_qhi[j] : INFINITY;
+    J.valid = 1.f;
+  }
+  for (int j = NJ; j < NJP; ++j) {  // padding: identity joints that never move
+    CoopJoint& J = C.joint[j];
+    J.Xr[0] = J.Xr[4] = J.Xr[8] = 1.f;
+    J.cfg_lo = J.chk_lo = J.acc_qlo = -INFINITY;
+    J.cfg_hi = J.chk_hi = J.acc_qhi = J.vel = J.acc_max = INFINITY;
+    J.valid = 0.f;
+  }
+  for (int t = 0; t < kCoopMaxFrameTasks; ++t) {
+    const float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    memcpy(C.ft[t].X, I, sizeof(I));
+    C.ft[t].body = -1;
+  }
+  bool vec4 = (P.target_stride % 4) == 0;
+  for (int t = 0; t < P.ntasks; ++t) {
+    const DevTask& d = P.tasks[t];
+    if (d.type == PK_TASK_FRAME) {
+      CoopFrameTask& f = C.ft[C.n_frame_tasks++];
+      f.body = d.body;
+      const float* Xf = &m.fX[12 * d.frame];
+      if (d.body >= 0) {
+        const double* A = &Aall[9 * d.body];
+        for (int r = 0; r < 3; ++r)
+          for (int cc = 0; cc < 4; ++cc) {
+            double s = 0.0;
+            for (int k = 0; k < 3; ++k) s += A[3 * k + r] * (double)Xf[4 * k + cc];
+            f.X[4 * r + cc] = (float)s;
+          }
+      } else {
+        memcpy(f.X, Xf, sizeof(float) * 12);
+      }
+      memcpy(f.cost, d.cost, sizeof(float) * 6);
+      f.gain = d.gain;
+      f.lm = d.lm;
+      f.tgt_off = d.tgt_off;
+      f.tgt_shared = d.tgt_shared;
+      if (!d.tgt_shared && (d.tgt_off % 4) != 0) vec4 = false;
+    } else {
+      C.has_posture = 1;
+      C.posture_w2 = d.cost[0] * d.cost[0];
+      C.posture_gain = d.gain;
+      C.posture_lm = d.lm;
+      C.posture_off = d.tgt_off;
+      C.posture_shared = d.tgt_shared;
+    }
+  }
+  C.dt = P.dt;
+  C.inv_dt = P.inv_dt;
+  C.damping = P.damping;
+  C.cfg_gain = P.cfg_gain;
+  C.target_stride = P.target_stride;
+  C.target_vec4 = vec4 ? 1 : 0;
+  C.safety_break = P.safety_break;
+  static_assert(sizeof(C.shared) >= sizeof(float) * (12 * kChainMaxFrameTasks + NJ), "shared target block too small");
+  memcpy(C.shared, P.shared, sizeof(float) * (12 * kChainMaxFrameTasks + NJ));
 }
 
 }  // namespace pk

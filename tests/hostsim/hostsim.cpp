@@ -36,6 +36,60 @@ void run_chain(const pk::HostModel& hm, const pk::DevProblem& P, const float* q,
   }
 }
 
+// Sub-warp chain kernel body (pk_coop.cuh) with L lanes per instance, lanes emulated by loops.
+template <int NJ, int NFT, int L>
+void run_coop_nft(const pk::HostModel& hm, const pk::DevProblem& P, const float* q, const float* targets, float* v,
+                  int32_t* status, int64_t B) {
+  using Step = pk::CoopStep<NJ, NFT, L>;
+  typename Step::Params C;
+  pk::make_coop_params<NJ, L>(hm, P, &C, P.ext);
+  const pk::Group<L> G{};
+  auto jc = [&](int j) -> const pk::CoopJoint& { return C.joint[j]; };
+  for (int64_t i = 0; i < B; ++i) {
+    pk::GVar<typename Step::Lane, L> S;
+    for (int h = 0; h < L; ++h)
+      for (int k = 0; k < Step::NC; ++k) {
+        const int j = h * Step::NC + k;
+        S[h].q[k] = j < NJ ? q[i * NJ + j] : 0.f;
+      }
+    int st = 0;
+    const float* trow = targets + i * (int64_t)P.target_stride;
+    pk::ik_step_coop<NJ, NFT, L>(G, C, jc, trow, S, st);
+    for (int h = 0; h < L; ++h)
+      for (int k = 0; k < Step::NC; ++k) {
+        const int j = h * Step::NC + k;
+        if (j < NJ) v[i * NJ + j] = S[h].x[k];
+      }
+    if (status) status[i] = st;
+  }
+}
+
+template <int NJ, int L>
+void run_coop(const pk::HostModel& hm, const pk::DevProblem& P, const float* q, const float* targets, float* v,
+              int32_t* status, int64_t B) {
+  int nft = 0;
+  for (int t = 0; t < P.ntasks; ++t) nft += P.tasks[t].type == PK_TASK_FRAME;
+  switch (nft) {
+    case 0: run_coop_nft<NJ, 0, L>(hm, P, q, targets, v, status, B); break;
+    case 1: run_coop_nft<NJ, 1, L>(hm, P, q, targets, v, status, B); break;
+    default: run_coop_nft<NJ, 2, L>(hm, P, q, targets, v, status, B); break;
+  }
+}
+
+template <int L>
+bool run_coop_nj(const pk::HostModel& hm, const pk::DevProblem& P, const float* q, const float* targets, float* v,
+                 int32_t* status, int64_t B) {
+  switch (hm.njoints) {
+    case 2: run_coop<2, L>(hm, P, q, targets, v, status, B); return true;
+    case 3: run_coop<3, L>(hm, P, q, targets, v, status, B); return true;
+    case 4: run_coop<4, L>(hm, P, q, targets, v, status, B); return true;
+    case 5: run_coop<5, L>(hm, P, q, targets, v, status, B); return true;
+    case 6: run_coop<6, L>(hm, P, q, targets, v, status, B); return true;
+    case 7: run_coop<7, L>(hm, P, q, targets, v, status, B); return true;
+  }
+  return false;
+}
+
 struct Args {
   const float* q; const float* targets; float* v; int32_t* status; float* H; float* c; float* h;
   float* e; float* J; int task_index; int task_k; float* oMf; float* com; float* Jf; int jac_frame;
@@ -101,6 +155,19 @@ int hs_solve_ik(void* model, const PkProblemDesc* prob, const float* q, const fl
   if (!e.empty()) return fail(e);
   const bool chain = path == 0 && pk::chain_eligible(hm, P, hx.present && !hx.box_only());
   if (used_chain) *used_chain = chain ? 1 : 0;
+  // path 11 / 12 / 14 / 18: the sub-warp chain kernel body with 1 / 2 / 4 / 8 lanes per instance
+  if (path > 10) {
+    if (!pk::chain_eligible(hm, P, hx.present && !hx.box_only())) return fail("problem does not fit the chain kernel");
+    if (used_chain) *used_chain = 1;
+    bool ok = false;
+    switch (path - 10) {
+      case 1: ok = run_coop_nj<1>(hm, P, q, targets, v, status, B); break;
+      case 2: ok = run_coop_nj<2>(hm, P, q, targets, v, status, B); break;
+      case 4: ok = run_coop_nj<4>(hm, P, q, targets, v, status, B); break;
+      case 8: ok = run_coop_nj<8>(hm, P, q, targets, v, status, B); break;
+    }
+    return ok ? 0 : fail("unsupported lanes per instance");
+  }
   if (chain) {
     switch (hm.njoints) {
       case 2: run_chain<2>(hm, P, q, targets, v, status, B); return 0;

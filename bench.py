@@ -72,6 +72,41 @@ def host_topology():
     return len(cpus), len(cores)
 
 
+def cpu_quota():
+    """CPUs' worth of run time the container may use per period (cgroup CFS quota), or None.
+    On the GPU boxes of this pool the container sees 128 logical CPUs but `cpu.max` is
+    `1600000 100000`: 16 CPUs sustained.  More runnable threads than that burn the period's
+    budget in a burst and are then throttled for tens of milliseconds (measured with
+    scripts/cpu_pool_diag.py: 128 threads alternate 2.6 ms steps with 45-85 ms stalls)."""
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:  # cgroup v2
+            quota, period = fh.read().split()[:2]
+        if quota != "max":
+            return float(quota) / float(period)
+    except (OSError, ValueError):
+        pass
+    try:  # cgroup v1
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as fh:
+            quota = float(fh.read())
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as fh:
+            period = float(fh.read())
+        if quota > 0:
+            return quota / period
+    except (OSError, ValueError):
+        pass
+    return None
+
+
+def cpu_threads():
+    """(threads the CPU arm runs on, logical CPUs, physical cores, quota): every CPU the process may
+    use, capped by the CFS quota (running more threads than the quota allows only adds
+    throttling stalls)."""
+    logical, physical = host_topology()
+    quota = cpu_quota()
+    threads = logical if quota is None else max(1, min(logical, int(quota)))
+    return threads, logical, physical, quota
+
+
 def bind_to_gpu_numa_node(index: int):
     """Run this process (and therefore first-touch its pinned buffers) on the NUMA node the
     GPU hangs off: host<->device DMA that crosses the socket interconnect runs well below
@@ -160,31 +195,39 @@ class CpuArm:
         return n / (time.perf_counter() - t0)
 
 
-def cpu_scaling(arm, passes, logical, physical):
-    """All-core and one-core rates of the C port and the parallel efficiency against
-    `physical cores x one core` (hyper-threads add little to dense fp64 code)."""
-    arm.step(logical)  # warm-up: pool creation, page faults
-    arm.step(logical)
-    wall = sum(arm.step(logical)[0] for _ in range(passes))
+def cpu_scaling(arm, passes, threads, cores_available):
+    """All-thread and one-thread rates of the C port and the parallel efficiency against
+    `cores available x one core` (available = physical cores, capped by the CFS quota)."""
+    arm.step(threads)  # warm-up: pool creation, page faults
+    arm.step(threads)
+    wall = sum(arm.step(threads)[0] for _ in range(passes))
     one = min(arm.step(1)[0] for _ in range(2))
     value = arm.batch * passes / wall
     one_core = arm.batch / one
-    return value, one_core, value / (one_core * physical)
+    return value, one_core, value / (one_core * cores_available)
 
 
-def cpu_baseline_block(batch, passes=10):
-    logical, physical = host_topology()
-    arm = CpuArm(batch)
-    value, one_core, eff = cpu_scaling(arm, passes, logical, physical)
+def cpu_baseline_fields(value, one_core, threads, logical, physical, quota):
+    avail = physical if quota is None else min(physical, quota)
     return {
-        "value": value, "unit": UNIT, "cores": logical, "physical_cores": physical, "kind": "port",
-        "sample": f"{passes} passes over the same {batch}-instance UR5 workload, fp64 C port of the reference path "
-                  f"(dense H, Goldfarb-Idnani QP), persistent pool of {logical} pinned pthreads, dynamic chunks; "
-                  "Pink/Pinocchio/quadprog are not installable offline",
-        "one_core": one_core,
-        "parallel_efficiency": eff,
-        "python_loop_one_core": arm.python_port_rate(),
+        "value": value, "unit": UNIT, "cores": threads, "logical_cpus_visible": logical, "physical_cores_visible": physical,
+        "cfs_quota_cpus": quota, "kind": "port", "one_core": one_core,
+        "parallel_efficiency": value / (one_core * avail),
     }
+
+
+def cpu_baseline_block(batch, passes=20):
+    threads, logical, physical, quota = cpu_threads()
+    arm = CpuArm(batch)
+    avail = physical if quota is None else min(physical, quota)
+    value, one_core, _ = cpu_scaling(arm, passes, threads, avail)
+    out = cpu_baseline_fields(value, one_core, threads, logical, physical, quota)
+    out["sample"] = (f"{passes} passes over the same {batch}-instance UR5 workload, fp64 C port of the reference path "
+                     f"(dense H, Goldfarb-Idnani QP), persistent pool of {threads} pinned threads (futex wake-up, guided "
+                     "chunks); thread count = CPUs the container may use (cgroup cpu.max); "
+                     "Pink/Pinocchio/quadprog are not installable offline")
+    out["python_loop_one_core"] = arm.python_port_rate()
+    return out
 
 
 def run_reference_arm(args):
@@ -193,28 +236,29 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    logical, physical = host_topology()
+    threads, logical, physical, quota = cpu_threads()
     arm = CpuArm(args.batch)
     for _ in range(max(args.warmup, 2)):
-        arm.step(logical)
+        arm.step(threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        arm.step(logical)
+        arm.step(threads)
     wall = time.perf_counter() - t0
     value = args.batch * args.steps / wall
     one = min(arm.step(1)[0] for _ in range(2))
     one_core = args.batch / one
     sample = (f"every step = the full {args.batch}-instance workload, fp64 C port of the reference path "
-              f"(oracle/c/pink_oracle.c), persistent pool of {logical} pinned pthreads")
+              f"(oracle/c/pink_oracle.c), persistent pool of {threads} pinned threads = the CPUs the container may use "
+              f"({logical} logical CPUs visible, cgroup quota {quota})")
+    cpu_block = cpu_baseline_fields(value, one_core, threads, logical, physical, quota)
+    cpu_block["sample"] = sample
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": logical, "physical_cores": physical, "kind": "port",
-                         "sample": sample, "one_core": one_core,
-                         "parallel_efficiency": value / (one_core * physical)},
+        "cpu_baseline": cpu_block,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -448,12 +492,14 @@ def humanoid_configs(torch, device, peak, regions=5, steps=5):
     return out
 
 
-def gather_variants(torch, dist, device, world, B, NBUF, step, vs, args, timed_regions):
+def gather_variants(torch, dist, device, world, B, NBUF, step, vs, args, timed_regions, ik, qs, ts, ss):
     """solve + all-gather of v on every rank (the one data-path collective north_star names),
     two schedules, both timed like the headline (median of regions, max over ranks):
     `serial`  - ncclAllGather issued on the solve stream after every step;
     `overlapped` - the gather of step k runs on a side stream (double-buffered output)
     while step k+1 solves; the region ends when the last gather has landed."""
+    from pink_b200 import parallel
+
     gathered = [torch.empty((world * B, 6), dtype=torch.float32, device=device) for _ in range(2)]
     side = torch.cuda.Stream(device)
     done = [torch.cuda.Event() for _ in range(2)]
@@ -475,8 +521,19 @@ def gather_variants(torch, dist, device, world, B, NBUF, step, vs, args, timed_r
                 done[k % 2].record(side)
         cur.wait_stream(side)
 
+    # `fused` - the solve kernel stores its rows into every peer's gather buffer itself
+    # (NVLink peer memory, pink_b200.parallel.PeerGather), one flag-barrier kernel per step
+    peer = parallel.PeerGather(B, 6, device, n_buffers=2)
+    fused_views = []
+
+    def fused():
+        for k in range(args.steps):
+            i = k % NBUF
+            fused_views.append(peer.solve(ik, qs[i], ts[i], ss[i], vs[i])[0])
+            del fused_views[:-2]
+
     out = {}
-    for name, fn in (("serial", serial), ("overlapped", overlapped)):
+    for name, fn in (("serial", serial), ("overlapped", overlapped), ("fused", fused)):
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
@@ -485,12 +542,17 @@ def gather_variants(torch, dist, device, world, B, NBUF, step, vs, args, timed_r
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         out[name] = {"value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps}
-    # every rank must hold every shard: compare the gathered buffer with an all-gather of checksums
+    # every rank must hold every shard, bit for bit: the fused buffer against an NCCL all-gather
     step(0)
     dist.all_gather_into_tensor(gathered[0], vs[0])
+    v_all, _ = peer.solve(ik, qs[0], ts[0], ss[0], vs[0])
     torch.cuda.synchronize()
     mine = gathered[0][dist.get_rank() * B:(dist.get_rank() + 1) * B]
-    out["bit_equal_to_local_shard"] = bool(torch.equal(mine, vs[0]))
+    ok = torch.tensor([int(torch.equal(mine, vs[0])), int(torch.equal(v_all, gathered[0]))], device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    out["bit_equal_to_local_shard"] = bool(ok[0].item())
+    out["fused_bit_equal_to_nccl_all_gather"] = bool(ok[1].item())
+    peer.close()
     inbound = (world - 1) * B * 6 * 4
     out["inbound_bytes_per_rank_per_step"] = inbound
     out["nvlink_floor_us_at_900GBs"] = inbound / 900e9 * 1e6
@@ -668,7 +730,7 @@ def run_gpu_arm(args):
     # ---- solve + gather variant (multi-GPU only): v gathered on every rank --------
     gather = None
     if world > 1:
-        gather = gather_variants(torch, dist, device, world, B, NBUF, step, vs, args, timed_regions)
+        gather = gather_variants(torch, dist, device, world, B, NBUF, step, vs, args, timed_regions, ik, qs, ts, ss)
 
     # ---- max over ranks -----------------------------------------------------------
     times = torch.tensor([ms, e2e_ms, eager_ms], dtype=torch.float64, device=device)

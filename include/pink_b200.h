@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PK_ABI_VERSION 2
+#define PK_ABI_VERSION 3
 
 #define PK_MAX_JOINTS 58  /* 1-dof joints (free-flyer excluded)            */
 #define PK_MAX_NV 64      /* PK_MAX_JOINTS + 6 (active sets are 64-bit masks) */
@@ -235,6 +235,34 @@ int pk_rollout_prepared(const PkModel* model, const PkProblem* problem,
                         const float* q, const float* targets, int32_t n_steps,
                         float* q_out, float* v, int32_t* status, int64_t B,
                         void* stream);
+
+/* ---- multi-GPU: all-gather of v through NVLink peer memory ----
+ * One process per GPU; instances are independent, so the only exchange is the one
+ * BASELINE north_star names: collecting v.  Instead of a collective after the kernel, the
+ * solve kernel itself stores every velocity row into the gather buffer of every peer
+ * (posted NVLink writes from the epilogue, overlapped with the remaining instances), and a
+ * one-warp flag kernel tells the peers when a rank's rows are complete.
+ *   pk_peer_alloc   device buffer that other processes can map + its 64-byte IPC handle
+ *   pk_peer_open    map a peer's buffer from its handle (enables peer access)
+ *   pk_solve_ik_prepared_gather   pk_solve_ik_prepared + store v[i] to row (row_offset + i)
+ *                   of each of the n_peers buffers (peer_v[k] = base of [rows][nv] floats;
+ *                   the caller's own buffer is one of them); v may be NULL
+ *   pk_peer_barrier every rank writes `epoch` to slot [rank] of each peer's flag array
+ *                   (uint32[n_peers], zero-initialised, epochs increase) and waits until
+ *                   all slots of its own array carry >= epoch: after it, all rows of all
+ *                   ranks are visible.  Every rank must call it, with the same epoch.      */
+#define PK_MAX_PEERS 16
+#define PK_IPC_HANDLE_BYTES 64
+int pk_peer_alloc(int device, int64_t bytes, void** ptr, unsigned char* handle /*[64]*/);
+int pk_peer_open(int device, const unsigned char* handle /*[64]*/, void** ptr);
+int pk_peer_close(int device, void* ptr);
+int pk_peer_free(int device, void* ptr);
+int pk_solve_ik_prepared_gather(const PkModel* model, const PkProblem* problem,
+                                const float* q, const float* targets, float* v,
+                                int32_t* status, int64_t B, void* const* peer_v,
+                                int32_t n_peers, int64_t row_offset, void* stream);
+int pk_peer_barrier(int device, void* const* peer_flags, int32_t n_peers, int32_t rank,
+                    uint32_t epoch, void* stream);
 
 /* Same through HOST buffers: H2D of q/targets, solve, D2H of v/status, all on
  * `stream`, chunked so copies overlap the kernels.  Returns after enqueueing;

@@ -23,7 +23,9 @@ PK_MAX_EQ_ROWS = 12
 PK_MAX_BARRIERS = 8
 PK_MAX_CONSTRAINTS = 4
 PK_MAX_PAIRS = 256
-PK_ABI_VERSION = 2
+PK_MAX_PEERS = 16
+PK_IPC_HANDLE_BYTES = 64
+PK_ABI_VERSION = 3
 
 PK_STATUS_NO_SOLUTION = 1
 PK_STATUS_OUT_OF_LIMITS = 2
@@ -194,6 +196,13 @@ def declare(lib: C.CDLL, prefix: str = "pk_") -> None:
     lib.pk_forward_kinematics_batched.argtypes = [C.c_void_p, _FP, _FP, _FP, C.c_int64, C.c_void_p]
     lib.pk_frame_jacobian_batched.argtypes = [C.c_void_p, C.c_int32, _FP, _FP, C.c_int64, C.c_void_p]
     lib.pk_integrate_batched.argtypes = [C.c_void_p, _FP, _FP, C.c_float, _FP, C.c_int64, C.c_void_p]
+    lib.pk_peer_alloc.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.pk_peer_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.pk_peer_close.argtypes = [C.c_int, C.c_void_p]
+    lib.pk_peer_free.argtypes = [C.c_int, C.c_void_p]
+    lib.pk_solve_ik_prepared_gather.argtypes = [C.c_void_p, C.c_void_p, _FP, _FP, _FP, _FP, C.c_int64,
+                                                C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_void_p]
+    lib.pk_peer_barrier.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]
 
 
 EXPORTED_SYMBOLS = [
@@ -216,6 +225,12 @@ EXPORTED_SYMBOLS = [
     "pk_forward_kinematics_batched",
     "pk_frame_jacobian_batched",
     "pk_integrate_batched",
+    "pk_peer_alloc",
+    "pk_peer_open",
+    "pk_peer_close",
+    "pk_peer_free",
+    "pk_solve_ik_prepared_gather",
+    "pk_peer_barrier",
 ]
 
 

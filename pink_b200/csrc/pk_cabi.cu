@@ -208,11 +208,20 @@ namespace pk {
 // start and the closed-form releases settle 99.3 % of the benchmark instances in the
 // uniform part, that machinery (barriers, slot traffic) cost more than the sparse warps
 // it saved (21.6 us vs 18.4 us per 65536-instance launch) and was removed.
+// Gather targets of the fused epilogue (pk_solve_ik_prepared_gather): velocity row i goes to
+// row (row_offset + i) of each peer buffer.  n == 0: no gather.
+struct PeerOut {
+  float* ptr[PK_MAX_PEERS];
+  int n;
+  int64_t row_offset;
+};
+
 template <int NJ, int NFT>
 __global__ void __launch_bounds__(128, 4)
     ik_chain_kernel(const __grid_constant__ ChainParams<NJ> P, const float* __restrict__ q,
                     const float* __restrict__ targets, float* __restrict__ v, int32_t* __restrict__ status,
-                    int64_t B, int flags, int n_steps, float* __restrict__ q_out) {
+                    int64_t B, int flags, int n_steps, float* __restrict__ q_out,
+                    const __grid_constant__ PeerOut peers) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   float qi[NJ], vi[NJ];
@@ -245,13 +254,28 @@ __global__ void __launch_bounds__(128, 4)
       for (int k = 0; k < NJ; ++k) qi[k] = fmaf(vi[k], P.dt, qi[k]);  // 1-dof joints: q (+) v dt = q + v dt
     }
   }
-  float* vrow = v + i * NJ;
-  if constexpr (NJ % 2 == 0) {
+  if (v) {
+    float* vrow = v + i * NJ;
+    if constexpr (NJ % 2 == 0) {
 #pragma unroll
-    for (int k = 0; k < NJ / 2; ++k) reinterpret_cast<float2*>(vrow)[k] = make_float2(vi[2 * k], vi[2 * k + 1]);
-  } else {
+      for (int k = 0; k < NJ / 2; ++k) reinterpret_cast<float2*>(vrow)[k] = make_float2(vi[2 * k], vi[2 * k + 1]);
+    } else {
 #pragma unroll
-    for (int k = 0; k < NJ; ++k) vrow[k] = vi[k];
+      for (int k = 0; k < NJ; ++k) vrow[k] = vi[k];
+    }
+  }
+  // fused all-gather: posted stores into every peer's buffer (NVLink), straight from the
+  // registers that hold the result
+#pragma unroll 1
+  for (int p = 0; p < peers.n; ++p) {
+    float* prow = peers.ptr[p] + (peers.row_offset + i) * NJ;
+    if constexpr (NJ % 2 == 0) {
+#pragma unroll
+      for (int k = 0; k < NJ / 2; ++k) reinterpret_cast<float2*>(prow)[k] = make_float2(vi[2 * k], vi[2 * k + 1]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < NJ; ++k) prow[k] = vi[k];
+    }
   }
   if (q_out) {
     float* orow = q_out + i * NJ;
@@ -339,6 +363,43 @@ __global__ void integrate_kernel(int nq, int nv, int free_flyer, const float* __
   integrate_configuration(nq, free_flyer, q + i * nq, v + i * nv, dt, qo + i * nq);
 }
 
+// Gather for the kernels without a fused epilogue: rows of the local v to every peer buffer.
+__global__ void peer_scatter_kernel(const float* __restrict__ v, int64_t n_floats, const __grid_constant__ PeerOut peers,
+                                    int nv) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_floats; k += stride) {
+    const float x = v[k];
+    for (int p = 0; p < peers.n; ++p) peers.ptr[p][peers.row_offset * nv + k] = x;
+  }
+}
+
+// Flag barrier over peer memory: one thread per peer.  Stores of earlier kernels of this
+// stream (the gather epilogue) are complete when this kernel starts; the release store
+// orders them before the flag for a peer that acquires it.  Gives up after ~2 s (a peer that
+// never arrives must not hang the GPU) and reports through *timed_out.
+struct PeerFlags {
+  unsigned* ptr[PK_MAX_PEERS];
+};
+__global__ void peer_barrier_kernel(const __grid_constant__ PeerFlags F, int n, int rank, unsigned epoch,
+                                    int* __restrict__ timed_out) {
+  const int t = threadIdx.x;
+  if (t >= n) return;
+  __threadfence_system();
+  unsigned* remote = F.ptr[t] + rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+  const unsigned* mine = F.ptr[rank] + t;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned seen;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+    if ((int)(seen - epoch) >= 0) break;
+    if (clock64() - t0 > 4000000000ll) {
+      if (timed_out) *timed_out = 1;
+      break;
+    }
+  }
+}
+
 }  // namespace pk
 
 namespace {
@@ -350,12 +411,12 @@ int env_int(const char* name, int dflt) {
 
 template <int NJ, int NFT>
 int launch_chain_nft(const pk::ChainParams<NJ>& C, const float* q, const float* targets, float* v, int32_t* status,
-                     int64_t B, cudaStream_t stream, int n_steps, float* q_out) {
+                     int64_t B, cudaStream_t stream, int n_steps, float* q_out, const pk::PeerOut& peers) {
   // A/B and probe switches (timing experiments; see scripts/ab.sh)
   static const int flags = (env_int("PK_CLOSED_FORM", 1) ? 0 : 1) | (env_int("PK_PROBE_SKIP_ROUNDS", 0) ? 2 : 0);
   static const int block = env_int("PK_CHAIN_BLOCK", 128);
   const int64_t grid = (B + block - 1) / block;
-  pk::ik_chain_kernel<NJ, NFT><<<(unsigned)grid, block, 0, stream>>>(C, q, targets, v, status, B, flags, n_steps, q_out);
+  pk::ik_chain_kernel<NJ, NFT><<<(unsigned)grid, block, 0, stream>>>(C, q, targets, v, status, B, flags, n_steps, q_out, peers);
   g_launches.fetch_add(1);
   PK_CUDA(cudaGetLastError());
   return 0;
@@ -363,11 +424,14 @@ int launch_chain_nft(const pk::ChainParams<NJ>& C, const float* q, const float* 
 
 template <int NJ>
 int launch_chain(const pk::ChainParams<NJ>& C, const float* q, const float* targets, float* v, int32_t* status,
-                 int64_t B, cudaStream_t stream, int n_steps = 1, float* q_out = nullptr) {
+                 int64_t B, cudaStream_t stream, int n_steps = 1, float* q_out = nullptr,
+                 const pk::PeerOut* peers = nullptr) {
+  static const pk::PeerOut none{};
+  const pk::PeerOut& po = peers ? *peers : none;
   switch (C.n_frame_tasks) {
-    case 0: return launch_chain_nft<NJ, 0>(C, q, targets, v, status, B, stream, n_steps, q_out);
-    case 1: return launch_chain_nft<NJ, 1>(C, q, targets, v, status, B, stream, n_steps, q_out);
-    default: return launch_chain_nft<NJ, 2>(C, q, targets, v, status, B, stream, n_steps, q_out);
+    case 0: return launch_chain_nft<NJ, 0>(C, q, targets, v, status, B, stream, n_steps, q_out, po);
+    case 1: return launch_chain_nft<NJ, 1>(C, q, targets, v, status, B, stream, n_steps, q_out, po);
+    default: return launch_chain_nft<NJ, 2>(C, q, targets, v, status, B, stream, n_steps, q_out, po);
   }
 }
 
@@ -513,11 +577,13 @@ int launch_coop(const PkProblem& pr, int slot, const float* q, const float* targ
 
 template <int NJ>
 int launch_chain_prepared(const PkProblem& pr, const float* q, const float* targets, float* v, int32_t* status,
-                          int64_t B, cudaStream_t stream, int n_steps = 1, float* q_out = nullptr) {
+                          int64_t B, cudaStream_t stream, int n_steps = 1, float* q_out = nullptr,
+                          const pk::PeerOut* peers = nullptr) {
   // PK_CHAIN_LANES: 0 = round-1 kernel (one instance per thread, pk_chain.cuh); 1 / 2 / 4 / 8 =
   // sub-warp kernel (pk_coop.cuh) with that many lanes per instance (4 and 8: UR5-class study
   // variants, 6 joints + 1 frame task only)
-  static const int lanes = env_int("PK_CHAIN_LANES", 0);
+  static const int lanes_env = env_int("PK_CHAIN_LANES", 0);
+  const int lanes = peers ? 0 : lanes_env;  // the fused gather epilogue lives in the thread-per-instance kernel
   if (lanes == 1) return launch_coop<NJ, 1>(pr, 0, q, targets, v, status, B, stream, n_steps, q_out);
   if (lanes == 2) return launch_coop<NJ, 2>(pr, 1, q, targets, v, status, B, stream, n_steps, q_out);
   if constexpr (NJ == 6) {
@@ -526,7 +592,7 @@ int launch_chain_prepared(const PkProblem& pr, const float* q, const float* targ
     if (lanes == 8 && nft == 1) return launch_coop_nft<NJ, 1, 8>(pr, 3, q, targets, v, status, B, stream, n_steps, q_out);
   }
   return launch_chain<NJ>(*reinterpret_cast<const pk::ChainParams<NJ>*>(pr.chain_params), q, targets, v, status, B,
-                          stream, n_steps, q_out);
+                          stream, n_steps, q_out, peers);
 }
 
 int solve_device(const PkModel* m, const PkProblem& pr, const float* q, const float* targets, float* v,
@@ -620,6 +686,106 @@ extern "C" int pk_solve_ik_prepared_host(PkModel* m, const PkProblem* pr, const 
   if (B > 0 && !v_host) return fail("null v");
   if (B > 0 && pr->P.target_stride > 0 && !targets_host) return fail("null targets");
   return solve_host_impl(m, *pr, q_host, targets_host, v_host, status_host, B, (cudaStream_t)stream);
+}
+
+// ---- multi-GPU gather over peer memory -------------------------------------------------
+
+extern "C" int pk_peer_alloc(int device, int64_t bytes, void** ptr, unsigned char* handle) {
+  if (!ptr || !handle || bytes <= 0) return fail("pk_peer_alloc: bad arguments");
+  PK_CUDA(cudaSetDevice(device));
+  void* p = nullptr;
+  PK_CUDA(cudaMalloc(&p, (size_t)bytes));
+  PK_CUDA(cudaMemset(p, 0, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == PK_IPC_HANDLE_BYTES, "IPC handle size");
+  if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
+    cudaFree(p);
+    return fail(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(cudaGetLastError()));
+  }
+  memcpy(handle, &h, sizeof(h));
+  *ptr = p;
+  return 0;
+}
+
+extern "C" int pk_peer_open(int device, const unsigned char* handle, void** ptr) {
+  if (!ptr || !handle) return fail("pk_peer_open: bad arguments");
+  PK_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  PK_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+extern "C" int pk_peer_close(int device, void* ptr) {
+  if (!ptr) return 0;
+  PK_CUDA(cudaSetDevice(device));
+  PK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+
+extern "C" int pk_peer_free(int device, void* ptr) {
+  if (!ptr) return 0;
+  PK_CUDA(cudaSetDevice(device));
+  PK_CUDA(cudaFree(ptr));
+  return 0;
+}
+
+extern "C" int pk_solve_ik_prepared_gather(const PkModel* m, const PkProblem* pr, const float* q, const float* targets,
+                                           float* v, int32_t* status, int64_t B, void* const* peer_v,
+                                           int32_t n_peers, int64_t row_offset, void* stream_) {
+  if (check_common(m, q, B)) return 1;
+  if (!pr) return fail("null problem");
+  if (n_peers < 0 || n_peers > PK_MAX_PEERS) return fail("n_peers out of range");
+  if (n_peers > 0 && !peer_v) return fail("null peer_v");
+  if (row_offset < 0) return fail("negative row_offset");
+  if (B > 0 && pr->P.target_stride > 0 && !targets) return fail("null targets");
+  if (B == 0) return 0;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  pk::PeerOut po{};
+  po.n = n_peers;
+  po.row_offset = row_offset;
+  for (int k = 0; k < n_peers; ++k) {
+    if (!peer_v[k]) return fail("null peer buffer");
+    po.ptr[k] = static_cast<float*>(peer_v[k]);
+  }
+  if (pr->chain) {
+    switch (pr->nj) {
+      case 2: return launch_chain_prepared<2>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po);
+      case 3: return launch_chain_prepared<3>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po);
+      case 4: return launch_chain_prepared<4>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po);
+      case 5: return launch_chain_prepared<5>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po);
+      case 6: return launch_chain_prepared<6>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po);
+      case 7: return launch_chain_prepared<7>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po);
+      default: break;
+    }
+  }
+  // kernels without the fused epilogue: solve into v, then one scatter kernel
+  if (!v) return fail("this model needs a local v buffer for the gather");
+  if (solve_device(m, *pr, q, targets, v, status, B, stream)) return 1;
+  if (n_peers > 0) {
+    const int64_t n = B * m->nv;
+    const int block = 256;
+    const int64_t grid = std::min<int64_t>((n + block - 1) / block, 148 * 8);
+    pk::peer_scatter_kernel<<<(unsigned)grid, block, 0, stream>>>(v, n, po, m->nv);
+    g_launches.fetch_add(1);
+    PK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+extern "C" int pk_peer_barrier(int device, void* const* peer_flags, int32_t n_peers, int32_t rank, uint32_t epoch,
+                               void* stream_) {
+  if (n_peers < 1 || n_peers > PK_MAX_PEERS || !peer_flags) return fail("pk_peer_barrier: bad arguments");
+  if (rank < 0 || rank >= n_peers) return fail("pk_peer_barrier: rank out of range");
+  PK_CUDA(cudaSetDevice(device));
+  pk::PeerFlags F{};
+  for (int k = 0; k < n_peers; ++k) {
+    if (!peer_flags[k]) return fail("null flag array");
+    F.ptr[k] = static_cast<unsigned*>(peer_flags[k]);
+  }
+  pk::peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(F, n_peers, rank, epoch, nullptr);
+  PK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int pk_rollout_prepared(const PkModel* m, const PkProblem* pr, const float* q, const float* targets,

@@ -7,7 +7,13 @@ for exactly two things (BASELINE north_star):
 
 * :func:`broadcast_model` - model constants from rank 0, once;
 * :func:`gather_velocities` / :func:`all_gather_velocities` - collecting ``v``
-  when a single consumer needs the whole batch.
+  when a single consumer needs the whole batch (plain NCCL collectives);
+* :class:`PeerGather` - the same all-gather FUSED into the solve kernel: every rank's
+  kernel stores its velocity rows straight into the gather buffers of all peers over
+  NVLink peer memory (``pk_solve_ik_prepared_gather``), a one-warp flag kernel replaces
+  the collective's synchronisation.  NCCL only carries the 64-byte IPC handles, once.
+* :func:`solve_ik_all_ranks` - one call that shards a batch over the box, solves and
+  returns the whole ``v`` on every rank.
 
 Works with any initialised ``torch.distributed`` backend (``nccl`` on GPUs,
 ``gloo`` in the CPU tests).
@@ -106,3 +112,145 @@ def solve_ik_sharded(configuration_factory, tasks_factory, q_global, dt, **kwarg
     configuration = configuration_factory(q_global[lo:hi])
     v = solve_ik(configuration, tasks_factory(lo, hi), dt, **kwargs)
     return v, (lo, hi)
+
+
+class PeerGather:
+    """All-gather of ``v`` through NVLink peer memory, written by the solve kernel itself.
+
+    Every rank owns ``n_buffers`` gather buffers ``[world * B, nv]`` (rotated per call, so that
+    a rank one step ahead never overwrites rows a slower consumer is still reading) and one
+    flag array; the buffers of all ranks are mapped into every process through CUDA IPC
+    handles exchanged once over the process group.  ``solve(ik, q, targets)`` runs the IK step
+    of this rank's shard with the gather fused into the kernel epilogue, then the flag barrier;
+    it returns this rank's view of the full ``[world * B, nv]`` velocities (valid on the
+    current stream).  Equal shard sizes ``B`` on all ranks.
+    """
+
+    def __init__(self, shard_rows: int, nv: int, device, n_buffers: int = 2):
+        import ctypes as C
+
+        from . import _cabi
+
+        rank, world = _world()
+        if world > _cabi.PK_MAX_PEERS:
+            raise ValueError(f"at most {_cabi.PK_MAX_PEERS} ranks")
+        self.rank, self.world, self.B, self.nv = rank, world, int(shard_rows), int(nv)
+        self.device = torch.device(device)
+        self.lib = _cabi.load()
+        self.n_buffers = n_buffers
+        self._epoch = 0
+        self._call = 0
+        dev = self.device.index
+        nbytes = self.world * self.B * self.nv * 4
+        # local allocations: n_buffers gather buffers + one flag array
+        self._local, handles = [], []
+        for k in range(n_buffers + 1):
+            ptr = C.c_void_p()
+            h = C.create_string_buffer(_cabi.PK_IPC_HANDLE_BYTES)
+            _cabi.check(self.lib.pk_peer_alloc(dev, nbytes if k < n_buffers else 4 * _cabi.PK_MAX_PEERS, C.byref(ptr), h))
+            self._local.append(ptr)
+            handles.append(h.raw)
+        # exchange the handles (64 bytes each) over the process group
+        mine = torch.tensor(list(b"".join(handles)), dtype=torch.uint8,
+                            device=self.device if dist.is_initialized() and dist.get_backend() == "nccl" else "cpu")
+        if world > 1:
+            everyone = torch.empty(world * mine.numel(), dtype=torch.uint8, device=mine.device)
+            dist.all_gather_into_tensor(everyone, mine)
+            everyone = bytes(everyone.cpu().numpy().tobytes())
+        else:
+            everyone = bytes(mine.cpu().numpy().tobytes())
+        per = (n_buffers + 1) * _cabi.PK_IPC_HANDLE_BYTES
+        self._opened = []
+        # ptrs[k][r]: buffer k of rank r as seen from this process
+        self.ptrs = [[None] * world for _ in range(n_buffers + 1)]
+        for r in range(world):
+            for k in range(n_buffers + 1):
+                if r == rank:
+                    self.ptrs[k][r] = self._local[k]
+                    continue
+                h = everyone[r * per + k * _cabi.PK_IPC_HANDLE_BYTES: r * per + (k + 1) * _cabi.PK_IPC_HANDLE_BYTES]
+                ptr = C.c_void_p()
+                _cabi.check(self.lib.pk_peer_open(dev, h, C.byref(ptr)))
+                self._opened.append(ptr)
+                self.ptrs[k][r] = ptr
+        self._arrays = [(C.c_void_p * world)(*[p.value for p in self.ptrs[k]]) for k in range(n_buffers + 1)]
+        # torch views of the local gather buffers
+        self.views = [self._view(self._local[k], (self.world * self.B, self.nv)) for k in range(n_buffers)]
+        if world > 1:
+            dist.barrier()  # everyone has mapped everyone before the first store
+
+    def _view(self, ptr, shape):
+        class _Holder:
+            pass
+
+        hld = _Holder()
+        hld.__cuda_array_interface__ = {
+            "shape": tuple(shape), "typestr": "<f4", "data": (int(ptr.value), False), "version": 3, "strides": None,
+        }
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(hld, device=self.device)
+
+    def solve(self, ik, q: torch.Tensor, targets, status=None, v_local=None):
+        """IK step of this rank's shard, gathered on every rank.  Returns ``(v_all, status)``:
+        ``v_all`` is this rank's ``[world * B, nv]`` buffer of the current rotation slot."""
+        from .engine import _addr, _stream
+        from . import _cabi
+
+        eng = ik.engine
+        B = q.shape[0]
+        if B != self.B:
+            raise ValueError(f"shard has {B} rows, PeerGather was built for {self.B}")
+        if status is None:
+            status = torch.empty((B,), device=eng.device, dtype=torch.int32)
+        if v_local is None:
+            # the shard's own rows, also kept locally (kernels without the fused epilogue solve
+            # into this buffer and scatter from it)
+            if getattr(self, "_v_local", None) is None:
+                self._v_local = torch.empty((B, self.nv), device=eng.device, dtype=torch.float32)
+            v_local = self._v_local
+        k = self._call % self.n_buffers
+        self._call += 1
+        self._epoch += 1
+        with torch.cuda.device(eng.device):
+            st = _stream(eng.device)
+            _cabi.check(self.lib.pk_solve_ik_prepared_gather(
+                eng.handle, ik._handle, _addr(q), _addr(targets), _addr(v_local), _addr(status), B,
+                self._arrays[k], self.world, self.rank * self.B, st))
+            _cabi.check(self.lib.pk_peer_barrier(self.device.index, self._arrays[self.n_buffers], self.world,
+                                                 self.rank, self._epoch, st))
+        return self.views[k], status
+
+    def close(self):
+        dev = self.device.index
+        torch.cuda.synchronize(self.device)
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier()  # nobody still writes into a buffer that is about to go
+        for p in self._opened:
+            self.lib.pk_peer_close(dev, p)
+        for p in self._local:
+            self.lib.pk_peer_free(dev, p)
+        self._opened, self._local = [], []
+
+    def __del__(self):
+        try:
+            if self._local:
+                self.close()
+        except Exception:
+            pass
+
+
+def solve_ik_all_ranks(ik, q_global, targets_global, gather: Optional["PeerGather"] = None):
+    """Shard ``q_global [B, nq]`` / ``targets_global [B, stride]`` (host or device tensors,
+    identical on every rank) over the ranks, solve, and return the full ``v [B, nv]`` on every
+    rank (``B`` divisible by the world size).  ``ik`` is this rank's :class:`BatchedIK`.
+    With a :class:`PeerGather` the gather is fused into the kernel; without, NCCL all-gather."""
+    rank, world = _world()
+    lo, hi = shard_bounds(q_global.shape[0])
+    dev = ik.engine.device
+    q = q_global[lo:hi].to(dev, dtype=torch.float32).contiguous()
+    t = None if targets_global is None else targets_global[lo:hi].to(dev, dtype=torch.float32).contiguous()
+    if gather is not None and world > 1:
+        v_all, _ = gather.solve(ik, q, t)
+        return v_all
+    v, _ = ik.solve(q, t)
+    return all_gather_velocities(v)

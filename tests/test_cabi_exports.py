@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     lib.pk_abi_version.restype = ctypes.c_int
-    assert lib.pk_abi_version() == _cabi.PK_ABI_VERSION == 2
+    assert lib.pk_abi_version() == _cabi.PK_ABI_VERSION == 3
 
 
 def test_struct_layouts_match_the_header_constants():

@@ -363,8 +363,9 @@ class GraphedSteps:
     """K launches of `step(k)` as CUDA-graph replays: one graph of exactly K launches when
     K <= GRAPH_CHUNK, else replays of a GRAPH_CHUNK-launch graph plus a remainder graph."""
 
-    def __init__(self, torch, device, step, n_steps, chunk=GRAPH_CHUNK):
+    def __init__(self, torch, device, step, n_steps, chunk=GRAPH_CHUNK, end=None):
         self.torch, self.device, self.n = torch, device, n_steps
+        self.end = end  # called at the end of every captured graph (joins side streams)
         self.full, self.rem = divmod(n_steps, chunk) if n_steps > chunk else (0, n_steps)
         self.chunk = chunk
         self.g_full = self._capture(step, 0, chunk) if self.full else None
@@ -381,6 +382,8 @@ class GraphedSteps:
             with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
                 for k in range(n):
                     step(k0 + k)
+                if self.end is not None:
+                    self.end()
         torch.cuda.current_stream(self.device).wait_stream(side)
         return g
 
@@ -494,54 +497,90 @@ def humanoid_configs(torch, device, peak, regions=5, steps=5):
 
 def gather_variants(torch, dist, device, world, B, NBUF, step, vs, args, timed_regions, ik, qs, ts, ss):
     """solve + all-gather of v on every rank (the one data-path collective north_star names),
-    two schedules, both timed like the headline (median of regions, max over ranks):
-    `serial`  - ncclAllGather issued on the solve stream after every step;
-    `overlapped` - the gather of step k runs on a side stream (double-buffered output)
-    while step k+1 solves; the region ends when the last gather has landed."""
+    three schedules, all submitted as CUDA-graph replays like the headline (median of regions,
+    max over ranks):
+    `serial`     - ncclAllGather on the solve stream after every step;
+    `overlapped` - the gather of step k on a side stream (double-buffered output) while step
+                   k + 1 solves; the region ends when the last gather has landed;
+    `fused`      - the solve kernel stores its rows into every peer's gather buffer itself
+                   (NVLink peer memory, pink_b200.parallel.PeerGather) and publishes "gather
+                   k complete"; the wait for the peers' rows runs on a side stream, a
+                   produced / released count per rank keeps a fast rank from overwriting a slot
+                   a slower one still reads;
+    `fused_wait_inline` - the same with the wait on the compute stream."""
     from pink_b200 import parallel
 
     gathered = [torch.empty((world * B, 6), dtype=torch.float32, device=device) for _ in range(2)]
-    side = torch.cuda.Stream(device)
-    done = [torch.cuda.Event() for _ in range(2)]
-    solved = [torch.cuda.Event() for _ in range(NBUF)]
-
-    def serial():
-        for k in range(args.steps):
-            step(k)
-            dist.all_gather_into_tensor(gathered[0], vs[k % NBUF])
-
-    def overlapped():
-        cur = torch.cuda.current_stream(device)
-        for k in range(args.steps):
-            step(k)
-            solved[k % NBUF].record(cur)
-            with torch.cuda.stream(side):
-                side.wait_event(solved[k % NBUF])
-                dist.all_gather_into_tensor(gathered[k % 2], vs[k % NBUF])
-                done[k % 2].record(side)
-        cur.wait_stream(side)
-
-    # `fused` - the solve kernel stores its rows into every peer's gather buffer itself
-    # (NVLink peer memory, pink_b200.parallel.PeerGather), one flag-barrier kernel per step
     peer = parallel.PeerGather(B, 6, device, n_buffers=2)
-    fused_views = []
 
-    def fused():
-        for k in range(args.steps):
+    def serial(k):
+        step(k)
+        dist.all_gather_into_tensor(gathered[0], vs[k % NBUF])
+
+    class Overlapped:
+        def __init__(self):
+            self.side = torch.cuda.Stream(device)
+
+        def __call__(self, k):
+            cur = torch.cuda.current_stream(device)
+            step(k)
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                dist.all_gather_into_tensor(gathered[k % 2], vs[k % NBUF])
+
+        def end(self):
+            torch.cuda.current_stream(device).wait_stream(self.side)
+
+    class Fused:
+        """solve (+ fused gather) on the compute stream, the matching wait / release on a side
+        stream: the next solve overlaps this one's NVLink drain and flag round trip"""
+
+        def __init__(self):
+            self.side = torch.cuda.Stream(device)
+
+        def __call__(self, k):
             i = k % NBUF
-            fused_views.append(peer.solve(ik, qs[i], ts[i], ss[i], vs[i])[0])
-            del fused_views[:-2]
+            cur = torch.cuda.current_stream(device)
+            peer.solve(ik, qs[i], ts[i], ss[i], vs[i], wait=False)
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                peer.wait()
+
+        def end(self):
+            torch.cuda.current_stream(device).wait_stream(self.side)
+
+    class FusedSerial:
+        """the same with the wait on the compute stream (what PeerGather.solve does by default)"""
+
+        def __call__(self, k):
+            i = k % NBUF
+            peer.solve(ik, qs[i], ts[i], ss[i], vs[i])
 
     out = {}
-    for name, fn in (("serial", serial), ("overlapped", overlapped), ("fused", fused)):
+    for name, fn in (("serial", serial), ("overlapped", Overlapped()), ("fused", Fused()), ("fused_wait_inline", FusedSerial())):
+        how = "graph"
+        try:
+            g = GraphedSteps(torch, device, fn, args.steps, end=getattr(fn, "end", None))
+            run = g.run
+        except Exception as exc:  # capture of the collective not possible: direct submission
+            print(f"[bench] {name}: graph capture failed ({exc}); direct launches", file=sys.stderr)
+            how = "direct launches"
+
+            def run(fn=fn):
+                for k in range(args.steps):
+                    fn(k)
+                if hasattr(fn, "end"):
+                    fn.end()
         for _ in range(2):
-            fn()
+            run()
         torch.cuda.synchronize()
-        ms, _ = timed_regions(fn, max(3, args.regions // 2), pre_spin=False)
+        ms, _ = timed_regions(run, max(3, args.regions // 2))
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        out[name] = {"value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps}
+        out[name] = {"value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps,
+                     "submission": how}
+        g = None
     # every rank must hold every shard, bit for bit: the fused buffer against an NCCL all-gather
     step(0)
     dist.all_gather_into_tensor(gathered[0], vs[0])
@@ -552,6 +591,7 @@ def gather_variants(torch, dist, device, world, B, NBUF, step, vs, args, timed_r
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     out["bit_equal_to_local_shard"] = bool(ok[0].item())
     out["fused_bit_equal_to_nccl_all_gather"] = bool(ok[1].item())
+    out["fused_spin_timeouts"] = peer.timeouts()
     peer.close()
     inbound = (world - 1) * B * 6 * 4
     out["inbound_bytes_per_rank_per_step"] = inbound

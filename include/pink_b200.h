@@ -240,19 +240,30 @@ int pk_rollout_prepared(const PkModel* model, const PkProblem* problem,
  * One process per GPU; instances are independent, so the only exchange is the one
  * BASELINE north_star names: collecting v.  Instead of a collective after the kernel, the
  * solve kernel itself stores every velocity row into the gather buffer of every peer
- * (posted NVLink writes from the epilogue, overlapped with the remaining instances), and a
- * one-warp flag kernel tells the peers when a rank's rows are complete.
- *   pk_peer_alloc   device buffer that other processes can map + its 64-byte IPC handle
+ * (posted NVLink writes from the epilogue, overlapped with the remaining instances); a
+ * one-warp kernel behind it publishes "gather k complete" in every peer's flag block and
+ * waits for the peers' - on a side stream if the next solve should not wait for it.
+ *   pk_peer_alloc   zero-filled device buffer that other processes can map + its IPC handle
  *   pk_peer_open    map a peer's buffer from its handle (enables peer access)
  *   pk_solve_ik_prepared_gather   pk_solve_ik_prepared + store v[i] to row (row_offset + i)
  *                   of each of the n_peers buffers (peer_v[k] = base of [rows][nv] floats;
- *                   the caller's own buffer is one of them); v may be NULL
- *   pk_peer_barrier every rank writes `epoch` to slot [rank] of each peer's flag array
- *                   (uint32[n_peers], zero-initialised, epochs increase) and waits until
- *                   all slots of its own array carry >= epoch: after it, all rows of all
- *                   ranks are visible.  Every rank must call it, with the same epoch.      */
+ *                   the caller's own buffer is one of them; v may be NULL for serial chains).
+ *                   peer_flags (NULL: no flow control, the caller synchronises by other means)
+ *                   = the flag blocks of all ranks, PK_PEER_FLAG_WORDS uint32 each, allocated
+ *                   with pk_peer_alloc: in its first instructions the kernel checks that every
+ *                   peer has released the gather that used the same buffer slot n_buffers
+ *                   calls ago (normally long done: n local words per CTA).
+ *   pk_peer_sync    one-warp kernel, queued behind the gather kernel (same stream, or another
+ *                   stream that waits for it - then the next solve overlaps it):
+ *                   post: publish "my gather k is complete" in every rank's flag block;
+ *                   wait: hold the stream until the oldest gather this rank has not waited
+ *                   for yet has been published by every rank (its rows are then visible);
+ *                   release: tell the peers that this rank is done with that buffer slot.
+ * Every rank issues the same sequence of gathers, one post and one wait + release per gather.
+ * All counters live in device memory: every launch can be replayed from a CUDA graph.      */
 #define PK_MAX_PEERS 16
 #define PK_IPC_HANDLE_BYTES 64
+#define PK_PEER_FLAG_WORDS 48
 int pk_peer_alloc(int device, int64_t bytes, void** ptr, unsigned char* handle /*[64]*/);
 int pk_peer_open(int device, const unsigned char* handle /*[64]*/, void** ptr);
 int pk_peer_close(int device, void* ptr);
@@ -260,9 +271,11 @@ int pk_peer_free(int device, void* ptr);
 int pk_solve_ik_prepared_gather(const PkModel* model, const PkProblem* problem,
                                 const float* q, const float* targets, float* v,
                                 int32_t* status, int64_t B, void* const* peer_v,
-                                int32_t n_peers, int64_t row_offset, void* stream);
-int pk_peer_barrier(int device, void* const* peer_flags, int32_t n_peers, int32_t rank,
-                    uint32_t epoch, void* stream);
+                                int32_t n_peers, int64_t row_offset,
+                                void* const* peer_flags, int32_t rank, int32_t n_buffers,
+                                void* stream);
+int pk_peer_sync(int device, void* const* peer_flags, int32_t n_peers, int32_t rank,
+                 int32_t post, int32_t wait, int32_t release, void* stream);
 
 /* Same through HOST buffers: H2D of q/targets, solve, D2H of v/status, all on
  * `stream`, chunked so copies overlap the kernels.  Returns after enqueueing;

@@ -25,6 +25,7 @@ PK_MAX_CONSTRAINTS = 4
 PK_MAX_PAIRS = 256
 PK_MAX_PEERS = 16
 PK_IPC_HANDLE_BYTES = 64
+PK_PEER_FLAG_WORDS = 48
 PK_ABI_VERSION = 3
 
 PK_STATUS_NO_SOLUTION = 1
@@ -201,8 +202,10 @@ def declare(lib: C.CDLL, prefix: str = "pk_") -> None:
     lib.pk_peer_close.argtypes = [C.c_int, C.c_void_p]
     lib.pk_peer_free.argtypes = [C.c_int, C.c_void_p]
     lib.pk_solve_ik_prepared_gather.argtypes = [C.c_void_p, C.c_void_p, _FP, _FP, _FP, _FP, C.c_int64,
-                                                C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_void_p]
-    lib.pk_peer_barrier.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]
+                                                C.POINTER(C.c_void_p), C.c_int32, C.c_int64,
+                                                C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p]
+    lib.pk_peer_sync.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_void_p]
 
 
 EXPORTED_SYMBOLS = [
@@ -230,7 +233,7 @@ EXPORTED_SYMBOLS = [
     "pk_peer_close",
     "pk_peer_free",
     "pk_solve_ik_prepared_gather",
-    "pk_peer_barrier",
+    "pk_peer_sync",
 ]
 
 

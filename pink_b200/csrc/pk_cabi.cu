@@ -214,7 +214,61 @@ struct PeerOut {
   float* ptr[PK_MAX_PEERS];
   int n;
   int64_t row_offset;
+  // flow control (optional, flags[0] != nullptr): flags[p] = flag block of rank p (peer-mapped)
+  unsigned* flags[PK_MAX_PEERS];
+  int rank;
+  int n_buffers;  // gather buffers the caller rotates through
 };
+
+// Flag block of a rank (uint32 words; written by peers with release stores, zero at start):
+//   [p]       produced[p]: gathers rank p has completed (its rows of that gather are visible)
+//   [16 + p]  consumed[p]: gathers rank p has released (it no longer reads that buffer slot)
+//   [32] gathers this rank has published, [33] waits it has issued, [34] CTA counter, [35] time-outs,
+//   [36] gather kernels this rank has run
+constexpr int kPeerProduced = 0, kPeerConsumed = PK_MAX_PEERS, kPeerCalls = 2 * PK_MAX_PEERS,
+              kPeerWaits = 2 * PK_MAX_PEERS + 1, kPeerCtas = 2 * PK_MAX_PEERS + 2, kPeerTimeouts = 2 * PK_MAX_PEERS + 3,
+              kPeerLaunched = 2 * PK_MAX_PEERS + 4;
+constexpr long long kPeerSpinLimit = 4000000000ll;  // ~2 s: a peer that never arrives must not hang the GPU
+
+__device__ __forceinline__ unsigned peer_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void peer_st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// First instructions of a kernel that stores gather number k (= kernels run so far + 1) into
+// slot k % n_buffers of the peers' buffers: every peer must have released gather k - n_buffers,
+// which used the same slot.  Almost always true already: one pass over n local words per CTA.
+__device__ __forceinline__ void peer_gate(const PeerOut& peers) {
+  if (peers.n > 0 && peers.flags[0] != nullptr) {
+    if (threadIdx.x < (unsigned)peers.n) {
+      unsigned* mine = peers.flags[peers.rank];
+      const unsigned k = mine[kPeerLaunched] + 1u;  // stable: written at the end of the previous kernel
+      const long long t0 = clock64();
+      while ((int)(peer_ld_acquire(mine + kPeerConsumed + threadIdx.x) + (unsigned)peers.n_buffers - k) < 0) {
+        if (clock64() - t0 > kPeerSpinLimit) {
+          atomicAdd(mine + kPeerTimeouts, 1u);
+          break;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+// Last instructions of that kernel (thread 0 of every CTA): count the kernel once all CTAs are through.
+// No fence: only the next kernel of the stream reads the count.
+__device__ __forceinline__ void peer_count_kernel(const PeerOut& peers) {
+  if (peers.n > 0 && peers.flags[0] != nullptr && threadIdx.x == 0) {
+    unsigned* mine = peers.flags[peers.rank];
+    if (atomicAdd(mine + kPeerCtas, 1u) == gridDim.x - 1u) {
+      mine[kPeerCtas] = 0u;
+      mine[kPeerLaunched] += 1u;
+    }
+  }
+}
 
 template <int NJ, int NFT>
 __global__ void __launch_bounds__(128, 4)
@@ -223,6 +277,7 @@ __global__ void __launch_bounds__(128, 4)
                     int64_t B, int flags, int n_steps, float* __restrict__ q_out,
                     const __grid_constant__ PeerOut peers) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  peer_gate(peers);
   if (i >= B) return;
   float qi[NJ], vi[NJ];
   const float* qrow = q + i * NJ;
@@ -283,6 +338,7 @@ __global__ void __launch_bounds__(128, 4)
     for (int k = 0; k < NJ; ++k) orow[k] = qi[k];
   }
   if (status) status[i] = st_all;
+  peer_count_kernel(peers);
 }
 
 // General path: one instance per thread, per-thread arrays in local memory.
@@ -366,37 +422,56 @@ __global__ void integrate_kernel(int nq, int nv, int free_flyer, const float* __
 // Gather for the kernels without a fused epilogue: rows of the local v to every peer buffer.
 __global__ void peer_scatter_kernel(const float* __restrict__ v, int64_t n_floats, const __grid_constant__ PeerOut peers,
                                     int nv) {
+  peer_gate(peers);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_floats; k += stride) {
     const float x = v[k];
     for (int p = 0; p < peers.n; ++p) peers.ptr[p][peers.row_offset * nv + k] = x;
   }
+  peer_count_kernel(peers);
 }
 
-// Flag barrier over peer memory: one thread per peer.  Stores of earlier kernels of this
-// stream (the gather epilogue) are complete when this kernel starts; the release store
-// orders them before the flag for a peer that acquires it.  Gives up after ~2 s (a peer that
-// never arrives must not hang the GPU) and reports through *timed_out.
 struct PeerFlags {
   unsigned* ptr[PK_MAX_PEERS];
 };
-__global__ void peer_barrier_kernel(const __grid_constant__ PeerFlags F, int n, int rank, unsigned epoch,
-                                    int* __restrict__ timed_out) {
+
+// One warp, one thread per peer; queued behind the kernel that stored a gather (whose stores
+// are complete at the kernel boundary), on that stream or on any stream that waits for it.
+//   post:    publish "gather k complete" (k = this rank's own count) in every peer's block;
+//   wait:    hold the stream until the next gather this rank has not waited for yet has been
+//            published by every rank;
+//   release: then tell all peers that this rank is done with that gather's buffer slot.
+__global__ void peer_sync_kernel(const __grid_constant__ PeerFlags F, int n, int rank, int post, int wait, int release) {
   const int t = threadIdx.x;
-  if (t >= n) return;
-  __threadfence_system();
-  unsigned* remote = F.ptr[t] + rank;
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
-  const unsigned* mine = F.ptr[rank] + t;
-  const long long t0 = clock64();
-  for (;;) {
-    unsigned seen;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-    if ((int)(seen - epoch) >= 0) break;
-    if (clock64() - t0 > 4000000000ll) {
-      if (timed_out) *timed_out = 1;
-      break;
+  unsigned* mine = F.ptr[rank];
+  if (post) {
+    unsigned k = 0;
+    if (t == 0) {
+      k = mine[kPeerCalls] + 1u;
+      mine[kPeerCalls] = k;
+      __threadfence_system();
     }
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (t < n) peer_st_release(F.ptr[t] + kPeerProduced + rank, k);
+  }
+  if (wait) {
+    unsigned w = 0;
+    if (t == 0) {
+      w = mine[kPeerWaits] + 1u;
+      mine[kPeerWaits] = w;
+    }
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (t < n) {
+      const long long t0 = clock64();
+      while ((int)(peer_ld_acquire(mine + kPeerProduced + t) - w) < 0) {
+        if (clock64() - t0 > kPeerSpinLimit) {
+          atomicAdd(mine + kPeerTimeouts, 1u);
+          break;
+        }
+      }
+    }
+    __syncwarp();
+    if (release && t < n) peer_st_release(F.ptr[t] + kPeerConsumed + rank, w);
   }
 }
 
@@ -730,60 +805,84 @@ extern "C" int pk_peer_free(int device, void* ptr) {
   return 0;
 }
 
-extern "C" int pk_solve_ik_prepared_gather(const PkModel* m, const PkProblem* pr, const float* q, const float* targets,
-                                           float* v, int32_t* status, int64_t B, void* const* peer_v,
-                                           int32_t n_peers, int64_t row_offset, void* stream_) {
-  if (check_common(m, q, B)) return 1;
-  if (!pr) return fail("null problem");
+static int fill_peer_out(pk::PeerOut* po, void* const* peer_v, int32_t n_peers, int64_t row_offset,
+                         void* const* peer_flags, int32_t rank, int32_t n_buffers) {
   if (n_peers < 0 || n_peers > PK_MAX_PEERS) return fail("n_peers out of range");
   if (n_peers > 0 && !peer_v) return fail("null peer_v");
   if (row_offset < 0) return fail("negative row_offset");
-  if (B > 0 && pr->P.target_stride > 0 && !targets) return fail("null targets");
-  if (B == 0) return 0;
-  cudaStream_t stream = (cudaStream_t)stream_;
-  pk::PeerOut po{};
-  po.n = n_peers;
-  po.row_offset = row_offset;
+  memset(po, 0, sizeof(*po));
+  po->n = n_peers;
+  po->row_offset = row_offset;
   for (int k = 0; k < n_peers; ++k) {
     if (!peer_v[k]) return fail("null peer buffer");
-    po.ptr[k] = static_cast<float*>(peer_v[k]);
+    po->ptr[k] = static_cast<float*>(peer_v[k]);
   }
-  if (pr->chain) {
-    switch (pr->nj) {
-      case 2: return launch_chain_prepared<2>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po);
-      case 3: return launch_chain_prepared<3>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po);
-      case 4: return launch_chain_prepared<4>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po);
-      case 5: return launch_chain_prepared<5>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po);
-      case 6: return launch_chain_prepared<6>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po);
-      case 7: return launch_chain_prepared<7>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po);
-      default: break;
+  if (peer_flags) {
+    if (rank < 0 || rank >= n_peers) return fail("rank out of range");
+    if (n_buffers < 1) return fail("n_buffers must be >= 1");
+    for (int k = 0; k < n_peers; ++k) {
+      if (!peer_flags[k]) return fail("null flag block");
+      po->flags[k] = static_cast<unsigned*>(peer_flags[k]);
     }
-  }
-  // kernels without the fused epilogue: solve into v, then one scatter kernel
-  if (!v) return fail("this model needs a local v buffer for the gather");
-  if (solve_device(m, *pr, q, targets, v, status, B, stream)) return 1;
-  if (n_peers > 0) {
-    const int64_t n = B * m->nv;
-    const int block = 256;
-    const int64_t grid = std::min<int64_t>((n + block - 1) / block, 148 * 8);
-    pk::peer_scatter_kernel<<<(unsigned)grid, block, 0, stream>>>(v, n, po, m->nv);
-    g_launches.fetch_add(1);
-    PK_CUDA(cudaGetLastError());
+    po->rank = rank;
+    po->n_buffers = n_buffers;
   }
   return 0;
 }
 
-extern "C" int pk_peer_barrier(int device, void* const* peer_flags, int32_t n_peers, int32_t rank, uint32_t epoch,
-                               void* stream_) {
-  if (n_peers < 1 || n_peers > PK_MAX_PEERS || !peer_flags) return fail("pk_peer_barrier: bad arguments");
-  if (rank < 0 || rank >= n_peers) return fail("pk_peer_barrier: rank out of range");
+extern "C" int pk_solve_ik_prepared_gather(const PkModel* m, const PkProblem* pr, const float* q, const float* targets,
+                                           float* v, int32_t* status, int64_t B, void* const* peer_v,
+                                           int32_t n_peers, int64_t row_offset, void* const* peer_flags,
+                                           int32_t rank, int32_t n_buffers, void* stream_) {
+  if (check_common(m, q, B)) return 1;
+  if (!pr) return fail("null problem");
+  if (B > 0 && pr->P.target_stride > 0 && !targets) return fail("null targets");
+  if (B == 0) return 0;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  pk::PeerOut po;
+  if (fill_peer_out(&po, peer_v, n_peers, row_offset, peer_flags, rank, n_buffers)) return 1;
+  bool launched = false;
+  if (pr->chain) {
+    int rc = -1;
+    switch (pr->nj) {
+      case 2: rc = launch_chain_prepared<2>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po); break;
+      case 3: rc = launch_chain_prepared<3>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po); break;
+      case 4: rc = launch_chain_prepared<4>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po); break;
+      case 5: rc = launch_chain_prepared<5>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po); break;
+      case 6: rc = launch_chain_prepared<6>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po); break;
+      case 7: rc = launch_chain_prepared<7>(*pr, q, targets, v, status, B, stream, 1, nullptr, &po); break;
+      default: break;
+    }
+    if (rc > 0) return rc;
+    launched = rc == 0;
+  }
+  if (!launched) {
+    // kernels without the fused epilogue: solve into v, then one scatter kernel
+    if (!v) return fail("this model needs a local v buffer for the gather");
+    if (solve_device(m, *pr, q, targets, v, status, B, stream)) return 1;
+    if (n_peers > 0) {
+      const int64_t n = B * m->nv;
+      const int block = 256;
+      const int64_t grid = std::min<int64_t>((n + block - 1) / block, 148 * 8);
+      pk::peer_scatter_kernel<<<(unsigned)grid, block, 0, stream>>>(v, n, po, m->nv);
+      g_launches.fetch_add(1);
+      PK_CUDA(cudaGetLastError());
+    }
+  }
+  return 0;
+}
+
+extern "C" int pk_peer_sync(int device, void* const* peer_flags, int32_t n_peers, int32_t rank, int32_t post,
+                            int32_t wait, int32_t release, void* stream_) {
+  if (n_peers < 1 || n_peers > PK_MAX_PEERS || !peer_flags) return fail("pk_peer_sync: bad arguments");
+  if (rank < 0 || rank >= n_peers) return fail("pk_peer_sync: rank out of range");
   PK_CUDA(cudaSetDevice(device));
   pk::PeerFlags F{};
   for (int k = 0; k < n_peers; ++k) {
-    if (!peer_flags[k]) return fail("null flag array");
+    if (!peer_flags[k]) return fail("null flag block");
     F.ptr[k] = static_cast<unsigned*>(peer_flags[k]);
   }
-  pk::peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(F, n_peers, rank, epoch, nullptr);
+  pk::peer_sync_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(F, n_peers, rank, post ? 1 : 0, wait ? 1 : 0, release ? 1 : 0);
   PK_CUDA(cudaGetLastError());
   return 0;
 }

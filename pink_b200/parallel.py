@@ -10,8 +10,8 @@ for exactly two things (BASELINE north_star):
   when a single consumer needs the whole batch (plain NCCL collectives);
 * :class:`PeerGather` - the same all-gather FUSED into the solve kernel: every rank's
   kernel stores its velocity rows straight into the gather buffers of all peers over
-  NVLink peer memory (``pk_solve_ik_prepared_gather``), a one-warp flag kernel replaces
-  the collective's synchronisation.  NCCL only carries the 64-byte IPC handles, once.
+  NVLink peer memory (``pk_solve_ik_prepared_gather``); produced / released counters in peer
+  memory replace the collective's synchronisation.  NCCL only carries the IPC handles, once.
 * :func:`solve_ik_all_ranks` - one call that shards a batch over the box, solves and
   returns the whole ``v`` on every rank.
 
@@ -117,13 +117,18 @@ def solve_ik_sharded(configuration_factory, tasks_factory, q_global, dt, **kwarg
 class PeerGather:
     """All-gather of ``v`` through NVLink peer memory, written by the solve kernel itself.
 
-    Every rank owns ``n_buffers`` gather buffers ``[world * B, nv]`` (rotated per call, so that
-    a rank one step ahead never overwrites rows a slower consumer is still reading) and one
-    flag array; the buffers of all ranks are mapped into every process through CUDA IPC
-    handles exchanged once over the process group.  ``solve(ik, q, targets)`` runs the IK step
-    of this rank's shard with the gather fused into the kernel epilogue, then the flag barrier;
-    it returns this rank's view of the full ``[world * B, nv]`` velocities (valid on the
-    current stream).  Equal shard sizes ``B`` on all ranks.
+    Every rank owns ``n_buffers`` gather buffers ``[world * B, nv]`` (rotated per call) and
+    one flag block; the buffers of all ranks are mapped into every process through CUDA IPC
+    handles exchanged once over the process group.  :meth:`solve` runs the IK step of this
+    rank's shard with the gather fused into the kernel epilogue: the kernel stores its rows
+    into slot ``k % n_buffers`` of every rank (after checking, in its first instructions, that
+    every rank has released gather ``k - n_buffers``); :meth:`wait` queues a one-warp kernel that
+    publishes "gather k complete", blocks its stream until gather ``k`` has arrived from every
+    rank and releases the slot.  ``solve(..., wait=True)`` (default) does both on the current stream;
+    for throughput, call ``solve(..., wait=False)`` on the compute stream and :meth:`wait` on
+    the stream that consumes the gathered velocities - the next solve then overlaps the
+    NVLink transfer of this one.  Every rank must issue the same sequence of ``solve`` calls
+    and exactly one ``wait`` per ``solve``.  Equal shard sizes ``B`` on all ranks.
     """
 
     def __init__(self, shard_rows: int, nv: int, device, n_buffers: int = 2):
@@ -138,21 +143,22 @@ class PeerGather:
         self.device = torch.device(device)
         self.lib = _cabi.load()
         self.n_buffers = n_buffers
-        self._epoch = 0
         self._call = 0
+        self._waited = 0
         dev = self.device.index
         nbytes = self.world * self.B * self.nv * 4
-        # local allocations: n_buffers gather buffers + one flag array
+        # local allocations: n_buffers gather buffers + one flag block
         self._local, handles = [], []
         for k in range(n_buffers + 1):
             ptr = C.c_void_p()
             h = C.create_string_buffer(_cabi.PK_IPC_HANDLE_BYTES)
-            _cabi.check(self.lib.pk_peer_alloc(dev, nbytes if k < n_buffers else 4 * _cabi.PK_MAX_PEERS, C.byref(ptr), h))
+            size = nbytes if k < n_buffers else 4 * _cabi.PK_PEER_FLAG_WORDS
+            _cabi.check(self.lib.pk_peer_alloc(dev, size, C.byref(ptr), h))
             self._local.append(ptr)
             handles.append(h.raw)
         # exchange the handles (64 bytes each) over the process group
-        mine = torch.tensor(list(b"".join(handles)), dtype=torch.uint8,
-                            device=self.device if dist.is_initialized() and dist.get_backend() == "nccl" else "cpu")
+        on_gpu = dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
+        mine = torch.tensor(list(b"".join(handles)), dtype=torch.uint8, device=self.device if on_gpu else "cpu")
         if world > 1:
             everyone = torch.empty(world * mine.numel(), dtype=torch.uint8, device=mine.device)
             dist.all_gather_into_tensor(everyone, mine)
@@ -161,7 +167,7 @@ class PeerGather:
             everyone = bytes(mine.cpu().numpy().tobytes())
         per = (n_buffers + 1) * _cabi.PK_IPC_HANDLE_BYTES
         self._opened = []
-        # ptrs[k][r]: buffer k of rank r as seen from this process
+        # ptrs[k][r]: buffer k of rank r as seen from this process (k = n_buffers: flag block)
         self.ptrs = [[None] * world for _ in range(n_buffers + 1)]
         for r in range(world):
             for k in range(n_buffers + 1):
@@ -190,9 +196,10 @@ class PeerGather:
         with torch.cuda.device(self.device):
             return torch.as_tensor(hld, device=self.device)
 
-    def solve(self, ik, q: torch.Tensor, targets, status=None, v_local=None):
-        """IK step of this rank's shard, gathered on every rank.  Returns ``(v_all, status)``:
-        ``v_all`` is this rank's ``[world * B, nv]`` buffer of the current rotation slot."""
+    def solve(self, ik, q: torch.Tensor, targets, status=None, v_local=None, wait: bool = True):
+        """IK step of this rank's shard with the fused gather.  Returns ``(v_all, status)``:
+        ``v_all`` is this rank's ``[world * B, nv]`` buffer of the current rotation slot,
+        complete once the matching :meth:`wait` has run (``wait=True``: on the current stream)."""
         from .engine import _addr, _stream
         from . import _cabi
 
@@ -210,15 +217,35 @@ class PeerGather:
             v_local = self._v_local
         k = self._call % self.n_buffers
         self._call += 1
-        self._epoch += 1
         with torch.cuda.device(eng.device):
-            st = _stream(eng.device)
             _cabi.check(self.lib.pk_solve_ik_prepared_gather(
                 eng.handle, ik._handle, _addr(q), _addr(targets), _addr(v_local), _addr(status), B,
-                self._arrays[k], self.world, self.rank * self.B, st))
-            _cabi.check(self.lib.pk_peer_barrier(self.device.index, self._arrays[self.n_buffers], self.world,
-                                                 self.rank, self._epoch, st))
+                self._arrays[k], self.world, self.rank * self.B,
+                self._arrays[self.n_buffers], self.rank, self.n_buffers, _stream(eng.device)))
+        if wait:
+            self.wait()
         return self.views[k], status
+
+    def wait(self, release: bool = True):
+        """Queue, on the current stream, the one-warp kernel that publishes this rank's oldest
+        unpublished gather, waits until that gather has arrived from every rank and (``release``)
+        frees its buffer slot for the gather ``n_buffers`` calls later.  The current stream must
+        be ordered after the matching :meth:`solve` (same stream, or ``wait_stream``)."""
+        from .engine import _stream
+        from . import _cabi
+
+        if self._waited >= self._call:
+            raise RuntimeError("PeerGather.wait without a matching solve")
+        self._waited += 1
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.pk_peer_sync(self.device.index, self._arrays[self.n_buffers], self.world, self.rank,
+                                              1, 1, 1 if release else 0, _stream(self.device)))
+
+    def timeouts(self) -> int:
+        """Number of spin-wait time-outs recorded in this rank's flag block (0 in a healthy run)."""
+        torch.cuda.synchronize(self.device)
+        flags = self._view(self._local[self.n_buffers], (48,)).view(torch.int32)
+        return int(flags[35].item())
 
     def close(self):
         dev = self.device.index

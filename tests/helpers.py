@@ -157,6 +157,47 @@ def within_tolerance(v, v_ref, atol=V_ATOL, rtol=V_RTOL):
     return (err <= atol + rtol * np.abs(v_ref)).all(axis=-1)
 
 
+# Parity statement of BASELINE.md section 6, by conditioning of the QP's Hessian.  The kernels
+# work on the square-root form [diag(d); A] (cond ~ sqrt(cond(H))), so fp32 keeps the standard
+# tolerance up to cond(H) ~ 1e5; the G1 example weights (CoM cost 200 next to posture cost 0.1)
+# give cond(H) of 1e6..1e7, where the measured distribution (host build and GPU, 1000-instance
+# samples) is 98.9 % inside the standard tolerance, 99.8 % inside 2.5x of it, all inside 5x.
+PARITY_BINS = [
+    # (cond(H) lower edge, upper edge, [(atol, rtol, minimum fraction inside), ...])
+    (0.0, 1e5, [(V_ATOL, V_RTOL, 0.999)]),
+    (1e5, 1e9, [(V_ATOL, V_RTOL, 0.975), (5e-4, 5e-3, 0.99), (1e-3, 1e-2, 1.0)]),
+]
+
+
+def parity_by_condition(v, v_ref, H, min_bin=20):
+    """Checks the binned parity statement; returns a report (list of dicts, one per
+    populated bin) with the outliers of the standard tolerance listed.  Bins with fewer than
+    ``min_bin`` instances are checked against the loosest bound of their bin only (a fraction
+    of a handful of instances is not a statistic)."""
+    v = np.asarray(v, dtype=np.float64)
+    cond = np.linalg.cond(np.asarray(H, dtype=np.float64))
+    err = np.abs(v - v_ref)
+    report = []
+    for lo, hi, bounds in PARITY_BINS:
+        m = (cond >= lo) & (cond < hi)
+        if not m.any():
+            continue
+        entry = {"cond": (lo, hi), "n": int(m.sum()), "fractions": [], "worst_abs_err": float(err[m].max())}
+        checks = bounds if m.sum() >= min_bin else bounds[-1:]
+        for atol, rtol, need in checks:
+            ok = (err[m] <= atol + rtol * np.abs(v_ref[m])).all(axis=-1)
+            need_n = need if m.sum() >= min_bin else (1.0 if need == 1.0 else 0.0)
+            entry["fractions"].append((atol, rtol, float(ok.mean()), need))
+            assert ok.mean() >= need_n, (
+                f"cond(H) in [{lo:g}, {hi:g}): {ok.mean():.4f} of {m.sum()} inside {atol:g} + {rtol:g}|v|, "
+                f"need {need}; worst |dv| {err[m].max():.3e}")
+        std = (err[m] <= V_ATOL + V_RTOL * np.abs(v_ref[m])).all(axis=-1)
+        entry["outliers_of_standard_tolerance"] = [int(i) for i in np.nonzero(m)[0][~std]][:32]
+        report.append(entry)
+    assert (cond < PARITY_BINS[-1][1]).all(), "cond(H) beyond the stated range"
+    return report
+
+
 def random_chain_model(nj, rng, prismatic=(), name="chain"):
     """Fixed-base serial chain with random placements / axes, a tool frame on the last
     joint and an elbow frame mid-chain (exercises NJ = 2..7, prismatic joints, two

@@ -34,8 +34,13 @@ def _check(name, v, st, gold):
     ok = gold["status"] == 0
     assert ((st[~ok] & _cabi.PK_STATUS_NO_SOLUTION) != 0).all()
     assert (st[ok] == 0).all()
-    good = helpers.within_tolerance(v[ok], gold["v"][ok], **TOL.get(name, {}))
-    assert good.mean() >= (0.97 if name in TOL else 1.0), np.abs(v[ok] - gold["v"][ok]).max()
+    if name in TOL:
+        # humanoid fixtures (32 / 48 instances, cond(H) up to 1e7): every instance inside the
+        # loosest bound of helpers.PARITY_BINS, >= 97 % inside the middle one
+        assert helpers.within_tolerance(v[ok], gold["v"][ok], atol=1e-3, rtol=1e-2).all(), np.abs(v[ok] - gold["v"][ok]).max()
+        assert helpers.within_tolerance(v[ok], gold["v"][ok], **TOL[name]).mean() >= 0.97
+    else:
+        assert helpers.within_tolerance(v[ok], gold["v"][ok]).all(), np.abs(v[ok] - gold["v"][ok]).max()
 
 
 @pytest.mark.parametrize("name", sorted(CASES))

@@ -123,8 +123,10 @@ def test_humanoids_match_oracle(name, kw):
     v_ref, st_ref = sc.oracle_solve()
     np.testing.assert_array_equal(st & 1, st_ref & 1)
     good = (st & 1) == 0
-    ok = helpers.within_tolerance(v[good], v_ref[good], atol=5e-4, rtol=5e-3)
-    assert ok.mean() >= 0.97, f"only {ok.mean():.3f} within tolerance, worst {np.abs(v - v_ref)[good].max()}"
+    # binned by cond(H): >= 99.9 % inside the standard tolerance below 1e5, the stated looser
+    # distribution for the G1-class weights (helpers.PARITY_BINS)
+    H_ref = sc.oracle_build()[0]
+    helpers.parity_by_condition(v[good], v_ref[good], H_ref[good])
     # task terms through Task.compute_error / compute_jacobian
     cfg = pink_b200.Configuration(sc.model, sc.robot.data, torch.as_tensor(sc.q32, device="cuda"))
     fk = okin.forward_kinematics(sc.table, sc.q64)
@@ -364,6 +366,22 @@ def test_humanoid_full_batch_kkt_certificate(name, B, kw):
     assert worst_prim <= 1e-6
     assert np.quantile(ratios, 0.999) <= 5e-5, np.quantile(ratios, 0.999)
     assert ratios.max() <= 5e-4, ratios.max()
+
+
+@pytest.mark.parametrize("name,B,kw", [
+    ("draco3_description", 1500, {}),
+    ("g1_description", 1000, {"with_com": True}),
+])
+def test_humanoid_parity_distribution_by_condition_number(name, B, kw):
+    """The BASELINE.md section 6 statement, generated by the test: fraction of instances inside
+    the tolerance per cond(H) bin, outliers listed in the report."""
+    sc = helpers.humanoid_scenario(name, B, **kw)
+    v, st = _gpu_solve(sc)
+    v_ref, st_ref = sc.oracle_solve()
+    assert (st == 0).all() and (st_ref == 0).all()
+    report = helpers.parity_by_condition(v, v_ref, sc.oracle_build()[0])
+    print(name, report)
+    assert sum(r["n"] for r in report) == B
 
 
 @pytest.mark.parametrize("nj,free_flyer", [(40, False), (58, True)])

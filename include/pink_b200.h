@@ -229,8 +229,9 @@ int pk_solve_ik_prepared_host(PkModel* model, const PkProblem* problem,
  * (the loop of examples/arm_ur5.py:65-86 with fixed targets): q_out[B][nq] final
  * configurations, v[B][nv] last velocities, status = OR over steps; an instance
  * that fails a step keeps its configuration.  Serial chains run all steps in one
- * launch with q resident in registers; other models alternate solve / integrate
- * launches (status then reports the last step only).                        */
+ * launch with q resident in registers, joint trees (warp kernel) in one launch with
+ * the instance's rows re-read by the warp that wrote them; models beyond the warp
+ * kernel alternate solve / integrate launches (status then reports the last step).   */
 int pk_rollout_prepared(const PkModel* model, const PkProblem* problem,
                         const float* q, const float* targets, int32_t n_steps,
                         float* q_out, float* v, int32_t* status, int64_t B,

@@ -429,6 +429,39 @@ __global__ void __launch_bounds__(32 * kTreeWarpsPerBlock)
                 status ? status + i : nullptr);
 }
 
+// Closed-loop rollout of the tree kernel in ONE launch: n_steps iterations of
+// v = solve_ik(q); q <- q (+) v dt (pink/configuration.py:285-293 after pink/solve_ik.py:274)
+// per warp, the instance's q / v rows re-read by the warp that wrote them (they stay in
+// L1 / L2; the per-step launch pair and its two full passes over HBM are gone).  An instance
+// that fails a step (no solution / outside limits with safety_break) is frozen, as on chains.
+__global__ void __launch_bounds__(32 * kTreeWarpsPerBlock)
+    ik_tree_rollout_kernel(const DevModel M, const __grid_constant__ DevProblem P, const __grid_constant__ TreePlan L,
+                           const float* __restrict__ q, const float* __restrict__ targets, int n_steps,
+                           float* __restrict__ q_out, float* __restrict__ v, int32_t* __restrict__ status, int64_t B) {
+  extern __shared__ __align__(16) float tree_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * kTreeWarpsPerBlock + warp;
+  if (i >= B) return;
+  float* W = tree_smem + (size_t)warp * L.words;
+  float* qrow = q_out + i * L.nq;
+  float* vrow = v + i * L.nv;
+  for (int k = lane; k < L.nq; k += 32) qrow[k] = q[i * L.nq + k];
+  __syncwarp();
+  int st_all = 0;
+  for (int s = 0; s < n_steps; ++s) {
+    int32_t st = 0;
+    TreeStep::run(M, P, L, qrow, targets ? targets + i * (int64_t)L.stride : nullptr, W, vrow, &st);
+    __syncwarp();
+    st = __shfl_sync(0xffffffffu, st, 0);  // run() reports through lane 0
+    st_all |= st;
+    const bool failed = (st & (PK_STATUS_NO_SOLUTION | PK_STATUS_NOT_POSDEF)) || ((st & PK_STATUS_OUT_OF_LIMITS) && P.safety_break);
+    if (failed) break;
+    if (lane == 0) integrate_configuration(L.nq, M.free_flyer, qrow, vrow, P.dt, qrow);
+    __syncwarp();
+  }
+  if (status && lane == 0) status[i] = st_all;
+}
+
 // q (+) v dt
 __global__ void integrate_kernel(int nq, int nv, int free_flyer, const float* __restrict__ q,
                                  const float* __restrict__ v, float dt, float* __restrict__ qo, int64_t B) {
@@ -925,6 +958,26 @@ extern "C" int pk_rollout_prepared(const PkModel* m, const PkProblem* pr, const 
       case 7: return launch_chain_prepared<7>(*pr, q, targets, v, status, B, stream, n_steps, q_out);
       default: break;
     }
+  }
+  if (pr->tree) {
+    // joint trees: the whole loop in one launch of the warp kernel
+    const size_t smem = (size_t)pr->plan.words * 4 * pk::kTreeWarpsPerBlock;
+    {
+      static std::mutex cfg_mu;
+      static size_t configured[64] = {};
+      std::lock_guard<std::mutex> lock(cfg_mu);
+      const int dev = (m->device >= 0 && m->device < 64) ? m->device : 0;
+      if (smem > configured[dev] || m->device >= 64) {
+        PK_CUDA(cudaFuncSetAttribute(pk::ik_tree_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = smem;
+      }
+    }
+    const int64_t grid = (B + pk::kTreeWarpsPerBlock - 1) / pk::kTreeWarpsPerBlock;
+    pk::ik_tree_rollout_kernel<<<(unsigned)grid, 32 * pk::kTreeWarpsPerBlock, smem, stream>>>(
+        m->dev, pr->P, pr->plan, q, targets, n_steps, q_out, v, status, B);
+    g_launches.fetch_add(1);
+    PK_CUDA(cudaGetLastError());
+    return 0;
   }
   // other models: the same closed loop as separate launches (solve, then integrate in place)
   if (q_out != q) PK_CUDA(cudaMemcpyAsync(q_out, q, sizeof(float) * B * m->nq, cudaMemcpyDeviceToDevice, stream));

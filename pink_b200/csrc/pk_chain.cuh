@@ -55,6 +55,7 @@ struct ChainParams {
   float cfg_gain;
   float cfg_lo[NJ], cfg_hi[NJ], vel[NJ], chk_lo[NJ], chk_hi[NJ];
   int target_stride;
+  int target_vec4;  // per-instance frame targets are 16-byte aligned: three 128-bit loads per target
   int safety_break;
   float shared[12 * kChainMaxFrameTasks + NJ];
   // AccelerationLimit (pink/limits/acceleration_limit.py:119-200): a box as well
@@ -134,7 +135,7 @@ struct ChainStep {
 #pragma unroll
   for (int t = 0; t < NFT; ++t) {
     const ChainFrameTask& Kt = P.ft[t];
-    const SE3f Tt = load_se3(Kt.tgt_shared ? (P.shared + Kt.tgt_off) : (trow + Kt.tgt_off));
+    const SE3f Tt = Kt.tgt_shared ? load_se3(P.shared + Kt.tgt_off) : load_se3_vec4(trow + Kt.tgt_off, P.target_vec4 != 0);
     // e = log6(T_b^-1 T_t)
     const SE3f Tbt = act_inv(Tf[t], Tt);
     Log3 L = log3(Tbt.R);

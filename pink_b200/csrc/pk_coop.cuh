@@ -46,7 +46,7 @@ struct alignas(16) CoopJoint {
   float Xr[9];  // rotation of the z-aligned placement X~_j = A_{j-1}^T X_j A_j (row-major)
   float Xp[3];  // its translation A_{j-1}^T X_j.p
   float prismatic;  // 1.0 prismatic, 0.0 revolute
-  float cfg_lo, cfg_hi, vel;
+  float cfg_lo, cfg_hi, vel;  // q_min, q_max, dt * v_max (box: lo = max(gain (q_min - q), -vel), hi = min(gain (q_max - q), vel))
   float chk_lo, chk_hi;
   float acc_max, acc_qlo, acc_qhi;
   float valid;  // 0 for padding joints beyond NJ
@@ -79,25 +79,9 @@ struct CoopParams {
   int safety_break;
   float shared[12 * kCoopMaxFrameTasks + NJP];
   int acc_enabled, acc_prev_off;
+  int any_prismatic;    // 0: every joint is revolute (the common case skips the per-joint selects)
+  int frames_on_last;   // 1: every frame task sits on the last joint (no mid-chain / world frames)
 };
-
-PK_HD SE3f load_se3_vec4(const float* t, bool vec4) {
-#if defined(__CUDA_ARCH__)
-  if (vec4) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(t));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(t) + 1);
-    const float4 c = __ldg(reinterpret_cast<const float4*>(t) + 2);
-    SE3f T;
-    T.R.m[0] = a.x; T.R.m[1] = a.y; T.R.m[2] = a.z; T.p.x = a.w;
-    T.R.m[3] = b.x; T.R.m[4] = b.y; T.R.m[5] = b.z; T.p.y = b.w;
-    T.R.m[6] = c.x; T.R.m[7] = c.y; T.R.m[8] = c.z; T.p.z = c.w;
-    return T;
-  }
-#else
-  (void)vec4;
-#endif
-  return load_se3(t);
-}
 
 template <int NJ, int NFT, int L>
 struct CoopStep {
@@ -172,10 +156,13 @@ struct CoopStep {
         // motion about / along the local z axis
         float sn, cs;
         sincos_f(s.q[k], &sn, &cs);
-        const bool pris = J.prismatic != 0.f;
-        sn = pris ? 0.f : sn;
-        cs = pris ? 1.f : cs;
-        const float dz = pris ? s.q[k] : 0.f;
+        float dz = 0.f;
+        if (P.any_prismatic) {  // uniform: chains without prismatic joints skip the selects
+          const bool pris = J.prismatic != 0.f;
+          sn = pris ? 0.f : sn;
+          cs = pris ? 1.f : cs;
+          dz = pris ? s.q[k] : 0.f;
+        }
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           const float y0 = Y.R.m[3 * r], y1 = Y.R.m[3 * r + 1];
@@ -184,18 +171,25 @@ struct CoopStep {
           T.R.m[3 * r + 2] = Y.R.m[3 * r + 2];
         }
         const V3 z = v3(T.R.m[2], T.R.m[5], T.R.m[8]);
-        T.p = Y.p + dz * z;
+        T.p = P.any_prismatic ? Y.p + dz * z : Y.p;
         s.pj[k] = T.p;
         s.zj[k] = z;
+        if (!P.frames_on_last) {  // uniform: remember the joint that carries each task frame
 #pragma unroll
-        for (int t = 0; t < NFT; ++t) {
-          const bool here = P.ft[t].body == j;
+          for (int t = 0; t < NFT; ++t) {
+            const bool here = P.ft[t].body == j;
 #pragma unroll
-          for (int i = 0; i < 9; ++i) Tb[t].R.m[i] = here ? T.R.m[i] : Tb[t].R.m[i];
-          Tb[t].p.x = here ? T.p.x : Tb[t].p.x;
-          Tb[t].p.y = here ? T.p.y : Tb[t].p.y;
-          Tb[t].p.z = here ? T.p.z : Tb[t].p.z;
+            for (int i = 0; i < 9; ++i) Tb[t].R.m[i] = here ? T.R.m[i] : Tb[t].R.m[i];
+            Tb[t].p.x = here ? T.p.x : Tb[t].p.x;
+            Tb[t].p.y = here ? T.p.y : Tb[t].p.y;
+            Tb[t].p.z = here ? T.p.z : Tb[t].p.z;
+          }
         }
+      }
+      if (P.frames_on_last) {
+        // the frame's joint is the last one of the chain: it lives in the last lane's segment
+#pragma unroll
+        for (int t = 0; t < NFT; ++t) Tb[t] = T;
       }
       // segment factor of the suffix product: the whole segment before the frame's joint, the
       // prefix up to that joint times the frame offset in its segment, identity after it
@@ -293,16 +287,20 @@ struct CoopStep {
         for (int k = 0; k < NC; ++k) {
           const int j = h * NC + k;
           const CoopJoint& J = jc(j);
-          const bool pris = J.prismatic != 0.f;
           const V3 z = s.zj[k];
           const V3 cr = cross(z, F.p - s.pj[k]);
-          const V3 lin = pris ? z : cr;
-          const V3 ang = pris ? v3(0.f, 0.f, 0.f) : z;
+          V3 lin = cr, ang = z;
+          if (P.any_prismatic) {
+            const bool pris = J.prismatic != 0.f;
+            lin = pris ? z : cr;
+            ang = pris ? v3(0.f, 0.f, 0.f) : z;
+          }
           const V3 jl = mulT(F.R, lin);
           const V3 ja = mulT(F.R, ang);
           const V3 tl = mul(WA, jl) + mul(WB, ja);
           const V3 ta = mul(WC, ja);
-          const bool on = (j <= Kt.body) && (J.valid != 0.f);  // joints past the frame do not move it
+          // joints past the frame do not move it; padding joints never do
+          const bool on = (P.frames_on_last || j <= Kt.body) && (NJP == NJ || J.valid != 0.f);
           s.A[k][6 * t + 0] = on ? tl.x : 0.f;
           s.A[k][6 * t + 1] = on ? tl.y : 0.f;
           s.A[k][6 * t + 2] = on ? tl.z : 0.f;
@@ -349,9 +347,8 @@ struct CoopStep {
         const int j = h * NC + k;
         const CoopJoint& J = jc(j);
         s.beta[k] *= kf;
-        const float vb = P.dt * J.vel;
-        s.hi[k] = fminf(P.cfg_gain * (J.cfg_hi - s.q[k]), vb);
-        s.lo[k] = fmaxf(P.cfg_gain * (J.cfg_lo - s.q[k]), -vb);
+        s.hi[k] = fminf(P.cfg_gain * (J.cfg_hi - s.q[k]), J.vel);  // the difference first: exact near a limit
+        s.lo[k] = fmaxf(P.cfg_gain * (J.cfg_lo - s.q[k]), -J.vel);
         if (P.acc_enabled) {
           // AccelerationLimit (pink/limits/acceleration_limit.py:119-200): a box as well
           const float a = J.acc_max;
@@ -366,14 +363,16 @@ struct CoopStep {
             s.lo[k] = fmaxf(s.lo[k], -hl);
           }
         }
-        if (J.valid == 0.f) {  // padding joint: pinned at zero, never part of the problem
+        if (NJP != NJ && J.valid == 0.f) {  // padding joint: pinned at zero, never part of the problem
           s.lo[k] = 0.f;
           s.hi[k] = 0.f;
         }
+        // |A[:, k]| for the rounding scale of the multipliers (a tolerance: the rsqrt
+        // approximation is plenty)
         float n2 = 0.f;
 #pragma unroll
         for (int r = 0; r < K; ++r) n2 = fmaf(s.A[k][r], s.A[k][r], n2);
-        s.nrm[k] = sqrtf(n2);
+        s.nrm[k] = n2 * rsqrtf(fmaxf(n2, 1e-30f));
       }
     }
     if (P.acc_enabled && g_any(G, S, [](const Lane& s) { return (s.flags & PK_STATUS_NO_SOLUTION) != 0; }))

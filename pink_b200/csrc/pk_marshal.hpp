@@ -554,6 +554,9 @@ void make_chain_params(const HostModel& m, const DevProblem& P, ChainParams<NJ>*
   C.damping = P.damping;
   C.cfg_gain = P.cfg_gain;
   C.target_stride = P.target_stride;
+  C.target_vec4 = (P.target_stride % 4) == 0;
+  for (int t = 0; t < C.n_frame_tasks; ++t)
+    if (!C.ft[t].tgt_shared && (C.ft[t].tgt_off % 4) != 0) C.target_vec4 = 0;
   C.safety_break = P.safety_break;
   memcpy(C.shared, P.shared, sizeof(C.shared));
 }
@@ -620,9 +623,10 @@ void make_coop_params(const HostModel& m, const DevProblem& P, CoopParams<((NJ +
     }
     memcpy(Aprev, A, sizeof(A));
     J.prismatic = (m.jtype[j] == PK_JOINT_REVOLUTE) ? 0.f : 1.f;
+    if (m.jtype[j] != PK_JOINT_REVOLUTE) C.any_prismatic = 1;
     J.cfg_lo = P.cfg_lo[j];
     J.cfg_hi = P.cfg_hi[j];
-    J.vel = P.vel[j];
+    J.vel = P.dt * P.vel[j];  // the same fp32 product the kernel used to form
     J.chk_lo = P.chk_lo[j];
     J.chk_hi = P.chk_hi[j];
     J.acc_max = (X && X->acc_enabled) ? X->acc_max[j] : INFINITY;
@@ -675,6 +679,9 @@ void make_coop_params(const HostModel& m, const DevProblem& P, CoopParams<((NJ +
       C.posture_shared = d.tgt_shared;
     }
   }
+  C.frames_on_last = 1;
+  for (int t = 0; t < C.n_frame_tasks; ++t)
+    if (C.ft[t].body != NJ - 1) C.frames_on_last = 0;
   C.dt = P.dt;
   C.inv_dt = P.inv_dt;
   C.damping = P.damping;

@@ -114,6 +114,28 @@ PK_HD SE3f load_se3(const float* t) {  // 12 floats, row-major [R | p]
   T.R.m[6] = t[8]; T.R.m[7] = t[9]; T.R.m[8] = t[10]; T.p.z = t[11];
   return T;
 }
+// 12 floats from global memory; `vec4`: the address is 16-byte aligned (three 128-bit
+// read-only loads instead of twelve scalar ones)
+PK_HD SE3f load_se3_vec4(const float* t, bool vec4) {
+#if defined(__CUDA_ARCH__)
+  // the caller's `vec4` covers stride and offsets; the base pointer is checked here (a
+  // sliced tensor may start anywhere)
+  if (vec4 && (reinterpret_cast<uintptr_t>(t) & 15u) == 0u) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(t));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(t) + 1);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(t) + 2);
+    SE3f T;
+    T.R.m[0] = a.x; T.R.m[1] = a.y; T.R.m[2] = a.z; T.p.x = a.w;
+    T.R.m[3] = b.x; T.R.m[4] = b.y; T.R.m[5] = b.z; T.p.y = b.w;
+    T.R.m[6] = c.x; T.R.m[7] = c.y; T.R.m[8] = c.z; T.p.z = c.w;
+    return T;
+  }
+#else
+  (void)vec4;
+#endif
+  return load_se3(t);
+}
+
 PK_HD void store_se3(const SE3f& T, float* t) {
   t[0] = T.R.m[0]; t[1] = T.R.m[1]; t[2] = T.R.m[2];  t[3] = T.p.x;
   t[4] = T.R.m[3]; t[5] = T.R.m[4]; t[6] = T.R.m[5];  t[7] = T.p.y;

@@ -300,6 +300,34 @@ def test_fused_rollout_equals_step_by_step_loop():
     np.testing.assert_allclose(q_f.cpu().numpy()[:n], q_o, atol=2e-4)
 
 
+def test_tree_rollout_in_one_launch_equals_step_by_step_loop():
+    """pk_rollout_prepared on a humanoid (warp kernel, whole loop in one launch) against the
+    same closed loop made of separate solve + integrate calls."""
+    from pink_b200 import _cabi as cabi
+
+    sc = helpers.humanoid_scenario("g1_description", 192, with_com=True)
+    ik = pink_b200.BatchedIK(sc.model, sc.tasks, sc.dt, damping=sc.damping, limits=sc.limits,
+                             safety_break=False, batch_size=sc.B)
+    _, targets, _ = sc.problem()
+    q0 = torch.as_tensor(sc.q32, device="cuda")
+    t_d = torch.as_tensor(targets, device="cuda")
+    K = 5
+    n0 = cabi.load().pk_launch_count()
+    q_f, v_f, st_f = ik.rollout(q0, t_d, K)
+    assert cabi.load().pk_launch_count() - n0 == 1
+    q = q0.clone()
+    v = None
+    for _ in range(K):
+        v, st = ik.solve(q, t_d)
+        q = ik.engine.integrate(q, v, sc.dt)
+    torch.cuda.synchronize()
+    assert (st_f.cpu().numpy() & 1 == 0).all()
+    # same arithmetic; the integration is inlined into a different kernel, so FMA contraction
+    # may differ in the last bit and the difference rides along for the remaining steps
+    np.testing.assert_allclose(q_f.cpu().numpy(), q.cpu().numpy(), atol=2e-5)
+    np.testing.assert_allclose(v_f.cpu().numpy(), v.cpu().numpy(), atol=5e-3, rtol=5e-3)
+
+
 @pytest.mark.parametrize("nj,kw", [
     (2, {}), (3, {"prismatic": (1,)}), (4, {"two_tasks": True}), (5, {"shared_target": True}),
     (7, {"two_tasks": True, "prismatic": (2,)}), (7, {}),

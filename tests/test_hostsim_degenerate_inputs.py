@@ -75,6 +75,23 @@ def test_ur5_kernels_on_hostile_inputs(kind, general_path):
 
 
 @pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8])
+def test_ur5_sub_warp_kernel_on_hostile_inputs(kind, lanes):
+    """The same on the sub-warp chain kernel body (pk_coop.cuh), every lanes-per-instance variant."""
+    sc = helpers.ur5_scenario(64, "reachable", seed=11)
+    _, targets, _ = sc.problem()
+    rng = np.random.default_rng(5)
+    t, q, rows = poison(targets, sc.q32, kind, rng)
+    v, st, prob = run(sc, q, t, path=10 + lanes)
+    check_clean(v, st, prob, 6, sc.dt, rows)
+    v0, st0, _ = run(sc, sc.q32, targets, path=10 + lanes)
+    clean = np.ones(64, dtype=bool)
+    if rows is not None:
+        clean[rows] = False
+        np.testing.assert_array_equal(v[clean], v0[clean])
+
+
+@pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("general_path", [False, True])
 def test_humanoid_kernels_on_hostile_inputs(kind, general_path):
     sc = helpers.humanoid_scenario("g1_description", 16, seed=3, with_com=True)
@@ -96,9 +113,9 @@ def test_extreme_costs(cost):
             t.set_orientation_cost(cost)
         else:
             t.cost = cost
-    for general_path in (False, True):
+    for kw in ({"general_path": False}, {"general_path": True}, {"path": 11}, {"path": 12}, {"path": 18}):
         _, targets, _ = sc.problem()
-        v, st, prob = run(sc, sc.q32, targets, general_path=general_path)
+        v, st, prob = run(sc, sc.q32, targets, **kw)
         check_clean(v, st, prob, 6, sc.dt)
         if cost == 0.0:
             assert (st == 0).all() and np.abs(v).max() < 1e-3

@@ -761,6 +761,8 @@ def run_gpu_arm(args):
         elapsed = time.time() - t_warm
         if elapsed > 2.0 or (elapsed > 0.4 and len(recent) == 3 and max(recent) <= 1.05 * best_batch):
             break
+    # start-up probe of the library's host schedules on these buffers (same results either way)
+    host_probe = ik.tune_host_path(q_h[0], t_h[0], v_h[0], s_h[0]) if "PK_HOST_MODE" not in os.environ else None
     barrier()
     e2e_ms, e2e_region_ms = timed_regions(e2e_run, args.regions, pre_spin=False)
     step(0)
@@ -810,8 +812,9 @@ def run_gpu_arm(args):
                 "h2d_bytes_per_step": B * (6 + 12) * 4, "d2h_bytes_per_step": B * (6 + 1) * 4,
                 "ms_per_step": e2e_ms / args.steps, "region_ms": e2e_region_ms, "warmup_calls": e2e_warm_calls,
                 "bitwise_equal_to_device_path": e2e_ok,
-                "api": "BatchedIK.solve_host -> pk_solve_ik_prepared_host (pinned host buffers, %d set(s); %s)"
-                       % (NS, _cabi.host_schedule() if hasattr(_cabi, "host_schedule") else "mode %s" % os.environ.get("PK_HOST_MODE", "0")),
+                "api": "BatchedIK.solve_host -> pk_solve_ik_prepared_host (pinned host buffers, %d set(s); schedule %s)"
+                       % (NS, getattr(ik, "host_schedule", os.environ.get("PK_HOST_MODE", "0"))),
+                "schedule_probe_us_per_call": host_probe,
                 "numa": numa,
             },
             "nonzero_status": bad,

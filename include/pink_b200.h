@@ -278,6 +278,13 @@ int pk_solve_ik_prepared_gather(const PkModel* model, const PkProblem* problem,
 int pk_peer_sync(int device, void* const* peer_flags, int32_t n_peers, int32_t rank,
                  int32_t post, int32_t wait, int32_t release, void* stream);
 
+/* Schedule of the host-buffer entry points for this model: 0 = uploads and downloads staged
+ * by the copy engines, one direction at a time (default); 2 = staged uploads, results
+ * written by the kernels straight into the caller's pinned host buffers; 1 = zero-copy both
+ * ways; -1 = the PK_HOST_MODE environment default.  Results are identical; which is faster
+ * depends on the platform's PCIe root complex, so the caller measures.                  */
+int pk_model_set_host_schedule(PkModel* model, int mode);
+
 /* Same through HOST buffers: H2D of q/targets, solve, D2H of v/status, all on
  * `stream`, chunked so copies overlap the kernels.  Returns after enqueueing;
  * the caller synchronises the stream before reading v.                     */

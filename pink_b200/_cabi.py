@@ -183,6 +183,7 @@ def declare(lib: C.CDLL, prefix: str = "pk_") -> None:
     lib.pk_model_create.argtypes = [C.POINTER(PkModelDesc), C.c_int, C.POINTER(C.c_void_p)]
     lib.pk_model_destroy.argtypes = [C.c_void_p]
     lib.pk_model_destroy.restype = None
+    lib.pk_model_set_host_schedule.argtypes = [C.c_void_p, C.c_int]
     lib.pk_solve_ik_batched.argtypes = [C.c_void_p, C.POINTER(PkProblemDesc), _FP, _FP, _FP, _FP, C.c_int64, C.c_void_p]
     lib.pk_solve_ik_batched_host.argtypes = [C.c_void_p, C.POINTER(PkProblemDesc), _FP, _FP, _FP, _FP, C.c_int64, C.c_void_p]
     lib.pk_problem_create.argtypes = [C.c_void_p, C.POINTER(PkProblemDesc), C.POINTER(C.c_void_p)]
@@ -215,6 +216,7 @@ EXPORTED_SYMBOLS = [
     "pk_launch_count",
     "pk_model_create",
     "pk_model_destroy",
+    "pk_model_set_host_schedule",
     "pk_solve_ik_batched",
     "pk_solve_ik_batched_host",
     "pk_problem_create",

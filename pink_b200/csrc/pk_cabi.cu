@@ -60,6 +60,10 @@ struct PkModel {
   cudaEvent_t st_fork = nullptr;
   cudaEvent_t st_join[3] = {nullptr, nullptr, nullptr};
   bool st_busy = false;
+  // schedule of the host entry point: -1 = PK_HOST_MODE from the environment (default 0),
+  // 0 = staged uploads and downloads, 1 = zero-copy, 2 = staged uploads, results written by the
+  // kernels straight into the pinned host buffers (pk_model_set_host_schedule)
+  int host_mode = -1;
   static constexpr int kMaxChunks = 64;
   cudaEvent_t st_in[kMaxChunks] = {};    // H2D of chunk k complete
   cudaEvent_t st_kern[kMaxChunks] = {};  // kernel of chunk k complete
@@ -166,6 +170,21 @@ extern "C" int pk_model_create(const PkModelDesc* d, int device, PkModel** out) 
   m->dev.depth = (const int*)(base + o_depth);
   m->dev.maxdepth = m->hm.maxdepth;
   *out = m;
+  return 0;
+}
+
+// Which of the host-buffer schedules pk_solve_ik_*_host uses for this model: 0 = uploads and
+// downloads staged through device buffers by the copy engines, one direction at a time;
+// 2 = staged uploads, the kernels write v / status straight into the caller's pinned host
+// buffers (no download phase; falls back to 0 when a result buffer is not pinned);
+// 1 = zero-copy both ways; -1 = back to the PK_HOST_MODE environment default.  Which one is
+// faster depends on how the platform's PCIe root handles both directions at once, so the
+// caller measures: BatchedIK.tune_host_path() times them on its own buffers.
+extern "C" int pk_model_set_host_schedule(PkModel* m, int mode) {
+  if (!m) return fail("null model");
+  if (mode < -1 || mode > 2) return fail("host schedule must be -1, 0, 1 or 2");
+  std::lock_guard<std::mutex> lock(m->mu);
+  m->host_mode = mode;
   return 0;
 }
 
@@ -1016,7 +1035,8 @@ static int solve_host_impl(PkModel* m, const PkProblem& pr, const float* q_host,
   // Zero-copy mode: when every buffer is pinned (device-addressable under UVA) the
   // kernel can pull q / targets over PCIe itself and push v / status back: one
   // launch, no staging copies.  PK_HOST_MODE=1 selects it; default is staged DMA.
-  static const int host_mode = env_int("PK_HOST_MODE", 0);
+  static const int host_mode_env = env_int("PK_HOST_MODE", 0);
+  const int host_mode = m->host_mode >= 0 ? m->host_mode : host_mode_env;
   if (host_mode == 1) {
     auto pinned = [](const void* ptr) {
       if (!ptr) return true;

@@ -101,6 +101,9 @@ struct TreeStep {
     const int nf = n - __builtin_popcountll(act);
 #endif
     float* xa = W + L.o_xa;  // x with the free entries zeroed
+#ifdef PK_COUNT_ITERS
+    pk_count_nfree(nf, 1000);
+#endif
     PK_LANES(l) {
       #pragma unroll 1
       for (int i = l; i < n; i += 32) {

@@ -719,6 +719,41 @@ def run_gpu_arm(args):
     assert _cabi.load().pk_launch_count() - launches0 >= min(args.steps, GRAPH_CHUNK)
     bad = int(sum(int((s != 0).sum().item()) for s in ss[: min(NBUF, args.steps)]))
 
+    # two independent batches in flight (informational): the same K launches alternated over two
+    # graph branches, so that the tail of one launch (the few warps still in Cholesky rounds)
+    # overlaps the start of the next.  Not the headline: `value` times serial launches.
+    two_ms = None
+    try:
+        class TwoStreams:
+            def __init__(self):
+                self.side = torch.cuda.Stream(device)
+                self.forked = False
+
+            def __call__(self, k):
+                cur = torch.cuda.current_stream(device)
+                if k % 2 == 0:
+                    step(k)
+                else:
+                    if not self.forked:
+                        self.side.wait_stream(cur)
+                        self.forked = True
+                    with torch.cuda.stream(self.side):
+                        step(k)
+
+            def end(self):
+                torch.cuda.current_stream(device).wait_stream(self.side)
+                self.forked = False
+
+        ts_fn = TwoStreams()
+        g2 = GraphedSteps(torch, device, ts_fn, args.steps, end=ts_fn.end)
+        g2.run()
+        barrier()
+        two_ms, _ = timed_regions(g2.run, max(3, args.regions // 2))
+        two_ms /= args.steps
+        g2 = None
+    except Exception as exc:  # pragma: no cover
+        print(f"[bench] two-stream variant unavailable: {exc}", file=sys.stderr)
+
     # direct-launch loop (host launch latency included), for reference
     n_direct = min(args.steps, 2000)
     eager_total, _ = timed_regions(lambda: [step(k) for k in range(n_direct)], 3, pre_spin=False)
@@ -803,6 +838,7 @@ def run_gpu_arm(args):
                           + f"; median of {args.regions} regions of {args.steps} steps, L2 flushed before each",
                 "region_ms": region_ms,
                 "eager_ms_per_step": eager_ms,
+                "two_batches_in_flight_ms_per_step": two_ms,
                 "algorithmic_bytes_per_launch": B * BYTES_PER_STEP,
                 "l2": f"{NBUF} rotating input/output sets ({NBUF * B * BYTES_PER_STEP / 2**20:.0f} MiB) and a "
                       f"{2 * L2_BYTES / 2**20:.0f} MiB write between regions (L2 = 126 MiB)",

@@ -35,6 +35,10 @@ struct TreePlan {
 PK_HD int tree_dual_solve(float* W, const TreePlan& L);
 
 constexpr int kTwStride = 13;     // 12 floats per joint transform, padded against bank conflicts
+#ifdef PK_COUNT_ITERS
+static int g_tree_seq = 0;
+static uint64_t g_tree_prev = 0;
+#endif
 constexpr int kMultiChange = 12;  // iterations with multi-add / multi-release before single steps
 
 struct TreeStep {
@@ -80,7 +84,12 @@ struct TreeStep {
 
   // ---- least squares on the free set (cooperative Householder QR) -------------------
   // Rows of Aw are owned by lanes (r = l, l + 32, ...).  y receives the full solution.
-  static PK_HD bool eqp(float* W, const TreePlan& L, uint64_t act) {
+  // TWO: the task set has more than 32 rows, so a lane owns two of them (l and l + 32); with
+  // K <= 32 (the Draco3 / G1 example task sets: 24 rows) the second slot is compiled out, which
+  // removes a third of the sweep's loads, FMAs and stores (results are bit-identical: the
+  // empty slot only ever contributed zeros).
+  template <bool TWO>
+  static PK_HD bool eqp_impl(float* W, const TreePlan& L, uint64_t act) {
     const int n = L.nv, K = L.K;
     float* A = W + L.o_A;
     float* Aw = W + L.o_aw;
@@ -103,6 +112,9 @@ struct TreeStep {
     float* xa = W + L.o_xa;  // x with the free entries zeroed
 #ifdef PK_COUNT_ITERS
     pk_count_nfree(nf, 1000);
+    if (g_tree_seq > 0) pk_count_nfree(__builtin_popcountll(act ^ g_tree_prev), 2000 + (g_tree_seq < 9 ? g_tree_seq : 9));
+    g_tree_prev = act;
+    ++g_tree_seq;
 #endif
     PK_LANES(l) {
       #pragma unroll 1
@@ -125,7 +137,7 @@ struct TreeStep {
     // right-hand side and compacted copy, row-parallel (two row slots per lane)
     PK_LANES(l) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < (TWO ? 2 : 1); ++h) {
         const int r = l + 32 * h;
         if (r < K) {
           const float* Ar = A + r * L.lda;
@@ -149,7 +161,7 @@ struct TreeStep {
       LaneVar<float> ak0, ak1, part;
       PK_LANES(l) {
         const float a0 = (l < K) ? Aw[l * L.ldw + k] : 0.f;
-        const float a1 = (l + 32 < K) ? Aw[(l + 32) * L.ldw + k] : 0.f;
+        const float a1 = (TWO && l + 32 < K) ? Aw[(l + 32) * L.ldw + k] : 0.f;
         ak0[l] = a0;
         ak1[l] = a1;
         part[l] = fmaf(a0, a0, a1 * a1);
@@ -169,7 +181,7 @@ struct TreeStep {
           for (int c = 0; c < 4; ++c) {
             const bool on = j + c < nf;
             const float a0 = (on && l < K) ? Aw[l * L.ldw + j + c] : 0.f;
-            const float a1 = (on && l + 32 < K) ? Aw[(l + 32) * L.ldw + j + c] : 0.f;
+            const float a1 = (TWO && on && l + 32 < K) ? Aw[(l + 32) * L.ldw + j + c] : 0.f;
             c0[c][l] = a0;
             c1[c][l] = a1;
             p[c][l] = fmaf(ak0[l], a0, ak1[l] * a1);
@@ -184,7 +196,7 @@ struct TreeStep {
           for (int c = 0; c < 4; ++c) {
             if (j + c < nf) {
               if (l < K) Aw[l * L.ldw + j + c] = fmaf(-sc[c], ak0[l], c0[c][l]);
-              if (l + 32 < K) Aw[(l + 32) * L.ldw + j + c] = fmaf(-sc[c], ak1[l], c1[c][l]);
+              if (TWO && l + 32 < K) Aw[(l + 32) * L.ldw + j + c] = fmaf(-sc[c], ak1[l], c1[c][l]);
               if (l == 0) Ru[ru(L, k, j + c)] = -sc[c] * v0;
             }
           }
@@ -192,7 +204,7 @@ struct TreeStep {
       }
       PK_LANES(l) {
         const float z0 = (l < K) ? zb[l] : 0.f;
-        const float z1 = (l + 32 < K) ? zb[l + 32] : 0.f;
+        const float z1 = (TWO && l + 32 < K) ? zb[l + 32] : 0.f;
         part[l] = fmaf(ak0[l], z0, ak1[l] * z1);
       }
       const float ztk = zt[k];
@@ -200,7 +212,7 @@ struct TreeStep {
       PK_WSYNC();
       PK_LANES(l) {
         if (l < K) zb[l] = fmaf(-s, ak0[l], zb[l]);
-        if (l + 32 < K) zb[l + 32] = fmaf(-s, ak1[l], zb[l + 32]);
+        if (TWO && l + 32 < K) zb[l + 32] = fmaf(-s, ak1[l], zb[l + 32]);
         if (l == 0) {
           zt[k] = fmaf(-s, v0, ztk);
           Rd[k] = rdk;
@@ -241,8 +253,15 @@ struct TreeStep {
     return ok;
   }
 
+  static PK_HD bool eqp(float* W, const TreePlan& L, uint64_t act) {
+    return (L.K > 32) ? eqp_impl<true>(W, L, act) : eqp_impl<false>(W, L, act);
+  }
+
   // ---- box-constrained least squares (as BoxLSQ::run, cooperative) ------------------
   static PK_HD int solve_qp(float* W, const TreePlan& L) {
+#ifdef PK_COUNT_ITERS
+    g_tree_seq = 0;
+#endif
     const int n = L.nv, K = L.K;
     const float* A = W + L.o_A;
     const float* bv = W + L.o_b;

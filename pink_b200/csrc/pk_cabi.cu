@@ -354,8 +354,12 @@ __global__ void __launch_bounds__(128, 4)
       for (int k = 0; k < NJ; ++k) st[lane * NJ + k] = vi[k];
       __syncwarp();
       constexpr int NV4 = 32 * NJ / 4;
+      // destinations in a per-rank, per-CTA rotated order: all ranks storing to peer 0 first,
+      // then peer 1, ... would converge on one NVSwitch port at a time
+      const int first = peers.rank + 1 + (int)(blockIdx.x % (unsigned)peers.n);
 #pragma unroll 1
-      for (int p = 0; p < peers.n; ++p) {
+      for (int t = 0; t < peers.n; ++t) {
+        const int p = (first + t) % peers.n;
         float4* dst = reinterpret_cast<float4*>(peers.ptr[p] + (peers.row_offset + row0) * NJ);
 #pragma unroll
         for (int f = lane; f < NV4; f += 32) dst[f] = reinterpret_cast<const float4*>(st)[f];
@@ -887,6 +891,7 @@ static int fill_peer_out(pk::PeerOut* po, void* const* peer_v, int32_t n_peers, 
     if (!peer_v[k]) return fail("null peer buffer");
     po->ptr[k] = static_cast<float*>(peer_v[k]);
   }
+  if (rank >= 0 && rank < n_peers) po->rank = rank;
   if (peer_flags) {
     if (rank < 0 || rank >= n_peers) return fail("rank out of range");
     if (n_buffers < 1) return fail("n_buffers must be >= 1");

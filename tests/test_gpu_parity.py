@@ -300,6 +300,31 @@ def test_fused_rollout_equals_step_by_step_loop():
     np.testing.assert_allclose(q_f.cpu().numpy()[:n], q_o, atol=2e-4)
 
 
+def test_host_schedules_give_identical_results_and_the_probe_picks_one():
+    """pk_model_set_host_schedule: staged downloads (0) and results written straight into the
+    pinned host buffers (2) return the same bits; BatchedIK.tune_host_path keeps one of them."""
+    sc = helpers.ur5_scenario(8192, "reachable")
+    ik = pink_b200.BatchedIK(sc.model, sc.tasks, sc.dt, damping=sc.damping, batch_size=sc.B)
+    _, targets, _ = sc.problem()
+    q_h = torch.as_tensor(sc.q32).pin_memory()
+    t_h = torch.as_tensor(targets).pin_memory()
+    out = {}
+    for mode in (0, 2):
+        ik.set_host_schedule(mode)
+        v_h = torch.empty((sc.B, 6), dtype=torch.float32).pin_memory()
+        s_h = torch.empty((sc.B,), dtype=torch.int32).pin_memory()
+        ik.solve_host(q_h, t_h, v_h, s_h)
+        torch.cuda.synchronize()
+        out[mode] = (v_h.clone(), s_h.clone())
+    assert torch.equal(out[0][0], out[2][0]) and torch.equal(out[0][1], out[2][1])
+    v_h = torch.empty((sc.B, 6), dtype=torch.float32).pin_memory()
+    s_h = torch.empty((sc.B,), dtype=torch.int32).pin_memory()
+    timings = ik.tune_host_path(q_h, t_h, v_h, s_h, calls=5)
+    assert set(timings) == {0, 2} and ik.host_schedule in (0, 2)
+    assert torch.equal(v_h, out[0][0])
+    ik.set_host_schedule(-1)
+
+
 def test_tree_rollout_in_one_launch_equals_step_by_step_loop():
     """pk_rollout_prepared on a humanoid (warp kernel, whole loop in one launch) against the
     same closed loop made of separate solve + integrate calls."""

@@ -439,7 +439,12 @@ __global__ void __launch_bounds__(64) ik_generic_kernel(const DevModel M, const 
 // Tree kernel: one instance per warp, per-instance state in the warp's slice of
 // dynamic shared memory (pk_tree.cuh).
 constexpr int kTreeWarpsPerBlock = 2;
-__global__ void __launch_bounds__(32 * kTreeWarpsPerBlock)
+// resident CTAs per SM the register allocation aims at: 10 (96 registers, 40 B of spills) ran
+// 4 % faster than 8 (128 registers) on configs 3 / 4 (scripts/r2_tree_ab.sh)
+#ifndef PK_TREE_MIN_BLOCKS
+#define PK_TREE_MIN_BLOCKS 10
+#endif
+__global__ void __launch_bounds__(32 * kTreeWarpsPerBlock, PK_TREE_MIN_BLOCKS)
     ik_tree_kernel(const DevModel M, const __grid_constant__ DevProblem P, const __grid_constant__ TreePlan L,
                    const float* __restrict__ q, const float* __restrict__ targets, float* __restrict__ v,
                    int32_t* __restrict__ status, int64_t B) {

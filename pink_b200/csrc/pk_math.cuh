@@ -142,6 +142,15 @@ PK_HD void store_se3(const SE3f& T, float* t) {
   t[8] = T.R.m[6]; t[9] = T.R.m[7]; t[10] = T.R.m[8]; t[11] = T.p.z;
 }
 
+// correctly rounded reciprocal without the slow path of the IEEE division
+PK_HD float rcp_f(float x) {
+#if defined(__CUDA_ARCH__)
+  return __frcp_rn(x);
+#else
+  return 1.0f / x;
+#endif
+}
+
 PK_HD void sincos_f(float x, float* s, float* c) {
 #if defined(__CUDA_ARCH__)
   sincosf(x, s, c);

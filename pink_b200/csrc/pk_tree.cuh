@@ -348,7 +348,7 @@ struct TreeStep {
       const float norm = sqrtf(fmaf(alpha, alpha, sigma));
       ok = ok && (norm > 0.f);
       const float v0 = alpha + norm;                              // alpha >= 0: no cancellation
-      const float tau = (sigma > 0.f) ? 1.f / (norm * v0) : 0.f;  // 2 / |v|^2
+      const float tau = (sigma > 0.f) ? rcp_f(norm * v0) : 0.f;  // 2 / |v|^2
       const float ztk = zt[k];
       PK_WSYNC();
       PK_LANES(l) {
@@ -381,7 +381,7 @@ struct TreeStep {
         const int k = nf - 1 - kk;
         const float rd = Rd[k];
         const float num = lane_bcast(acc0, k);
-        const float yk = (rd != 0.f) ? num / rd : 0.f;
+        const float yk = (rd != 0.f) ? num * rcp_f(rd) : 0.f;
         PK_LANES(l) {
           if (l < k) acc0[l] = fmaf(-Ru[ru(L, l, k)], yk, acc0[l]);
           if (l == k) sol0[l] = yk;

@@ -507,7 +507,10 @@ def gather_variants(torch, dist, device, world, B, NBUF, step, vs, args, timed_r
                    k complete"; the wait for the peers' rows runs on a side stream, a
                    produced / released count per rank keeps a fast rank from overwriting a slot
                    a slower one still reads;
-    `fused_wait_inline` - the same with the wait on the compute stream."""
+    `fused_wait_inline` - the same with the wait on the compute stream;
+    `fused_two_in_flight` - two such sequences alternating over two compute streams (two
+                   independent batches in flight, as `roofline.two_batches_in_flight_ms_per_step`
+                   for the solve alone)."""
     from pink_b200 import parallel
 
     gathered = [torch.empty((world * B, 6), dtype=torch.float32, device=device) for _ in range(2)]
@@ -556,8 +559,46 @@ def gather_variants(torch, dist, device, world, B, NBUF, step, vs, args, timed_r
             i = k % NBUF
             peer.solve(ik, qs[i], ts[i], ss[i], vs[i])
 
+    class FusedTwoInFlight:
+        """two gather sequences in flight: even steps on one compute stream with one PeerGather,
+        odd steps on a second stream with a second PeerGather (own buffers and counters), each
+        with its wait on its own side stream.  A one-wave kernel emits its peer stores as a burst
+        at its end; here the burst of one launch travels under the computation of the next."""
+
+        def __init__(self):
+            self.peers = [peer, parallel.PeerGather(B, 6, device, n_buffers=2)]
+            self.compute = [None, torch.cuda.Stream(device)]
+            self.sides = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
+            self.forked = False
+
+        def __call__(self, k):
+            i = k % NBUF
+            cur = torch.cuda.current_stream(device)
+            which = k % 2
+            if which == 1 and not self.forked:
+                self.compute[1].wait_stream(cur)
+                self.forked = True
+            stream = cur if which == 0 else self.compute[1]
+            with torch.cuda.stream(stream):
+                self.peers[which].solve(ik, qs[i], ts[i], ss[i], vs[i], wait=False)
+                self.sides[which].wait_stream(stream)
+            with torch.cuda.stream(self.sides[which]):
+                self.peers[which].wait()
+
+        def end(self):
+            cur = torch.cuda.current_stream(device)
+            cur.wait_stream(self.compute[1])
+            for sd in self.sides:
+                cur.wait_stream(sd)
+            self.forked = False
+
+        def close(self):
+            self.peers[1].close()
+
+    two = FusedTwoInFlight()
     out = {}
-    for name, fn in (("serial", serial), ("overlapped", Overlapped()), ("fused", Fused()), ("fused_wait_inline", FusedSerial())):
+    for name, fn in (("serial", serial), ("overlapped", Overlapped()), ("fused", Fused()), ("fused_wait_inline", FusedSerial()),
+                     ("fused_two_in_flight", two)):
         how = "graph"
         try:
             g = GraphedSteps(torch, device, fn, args.steps, end=getattr(fn, "end", None))
@@ -591,7 +632,8 @@ def gather_variants(torch, dist, device, world, B, NBUF, step, vs, args, timed_r
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     out["bit_equal_to_local_shard"] = bool(ok[0].item())
     out["fused_bit_equal_to_nccl_all_gather"] = bool(ok[1].item())
-    out["fused_spin_timeouts"] = peer.timeouts()
+    out["fused_spin_timeouts"] = peer.timeouts() + two.peers[1].timeouts()
+    two.close()
     peer.close()
     inbound = (world - 1) * B * 6 * 4
     out["inbound_bytes_per_rank_per_step"] = inbound

@@ -290,6 +290,9 @@ struct TreeStep {
     float* xa = W + L.o_xa;  // x with the free entries zeroed
 #ifdef PK_COUNT_ITERS
     pk_count_nfree(nf, 1000);
+    if (g_tree_seq > 0) pk_count_nfree(__builtin_popcountll(act ^ g_tree_prev), 2000 + (g_tree_seq < 9 ? g_tree_seq : 9));
+    g_tree_prev = act;
+    ++g_tree_seq;
 #endif
     PK_LANES(l) {
       #pragma unroll 1

@@ -813,10 +813,27 @@ def run_gpu_arm(args):
         q_h[i].copy_(qs[i % NBUF].cpu())
         t_h[i].copy_(ts[i % NBUF].cpu())
 
+    # --e2e-streams 2: consecutive calls alternate over two caller streams (one pinned buffer set
+    # each), so that the library's two staging sets pipeline them - the upload of step k + 1
+    # under the kernel and download of step k; all streams are joined before the stop event
+    n_streams = max(1, min(args.e2e_streams, NS))
+    user_streams = [torch.cuda.Stream(device) for _ in range(n_streams)] if n_streams > 1 else None
+
     def e2e_run():
+        if user_streams is None:
+            for k in range(args.steps):
+                i = k % NS
+                ik.solve_host(q_h[i], t_h[i], v_h[i], s_h[i])
+            return
+        cur = torch.cuda.current_stream(device)
+        for st_ in user_streams:
+            st_.wait_stream(cur)
         for k in range(args.steps):
-            i = k % NS
-            ik.solve_host(q_h[i], t_h[i], v_h[i], s_h[i])
+            i = k % n_streams
+            with torch.cuda.stream(user_streams[i]):
+                ik.solve_host(q_h[i], t_h[i], v_h[i], s_h[i])
+        for st_ in user_streams:
+            cur.wait_stream(st_)
 
     # Warm-up of the host path.  The first tens of milliseconds of pinned-buffer DMA in a
     # process run 2-3x below the steady rate (measured, scripts/e2e_burst.py: 300-500 us per
@@ -838,8 +855,23 @@ def run_gpu_arm(args):
         elapsed = time.time() - t_warm
         if elapsed > 2.0 or (elapsed > 0.4 and len(recent) == 3 and max(recent) <= 1.05 * best_batch):
             break
-    # start-up probe of the library's host schedules on these buffers (same results either way)
-    host_probe = ik.tune_host_path(q_h[0], t_h[0], v_h[0], s_h[0]) if "PK_HOST_MODE" not in os.environ else None
+    # start-up probe of the library's host schedules under this submission pattern (same results
+    # either way): three batches of K steps per schedule, the faster one stays
+    host_probe = None
+    if "PK_HOST_MODE" not in os.environ:
+        host_probe = {}
+        for mode in (0, 2):
+            ik.set_host_schedule(mode)
+            e2e_run()
+            torch.cuda.synchronize()
+            best = float("inf")
+            for _ in range(3):
+                w0 = time.perf_counter()
+                e2e_run()
+                torch.cuda.synchronize()
+                best = min(best, (time.perf_counter() - w0) / args.steps)
+            host_probe[mode] = best * 1e6
+        ik.set_host_schedule(min(host_probe, key=host_probe.get))
     barrier()
     e2e_ms, e2e_region_ms = timed_regions(e2e_run, args.regions, pre_spin=False)
     step(0)
@@ -890,8 +922,8 @@ def run_gpu_arm(args):
                 "h2d_bytes_per_step": B * (6 + 12) * 4, "d2h_bytes_per_step": B * (6 + 1) * 4,
                 "ms_per_step": e2e_ms / args.steps, "region_ms": e2e_region_ms, "warmup_calls": e2e_warm_calls,
                 "bitwise_equal_to_device_path": e2e_ok,
-                "api": "BatchedIK.solve_host -> pk_solve_ik_prepared_host (pinned host buffers, %d set(s); schedule %s)"
-                       % (NS, getattr(ik, "host_schedule", os.environ.get("PK_HOST_MODE", "0"))),
+                "api": "BatchedIK.solve_host -> pk_solve_ik_prepared_host (pinned host buffers, %d set(s), %d caller stream(s); schedule %s)"
+                       % (NS, n_streams, getattr(ik, "host_schedule", os.environ.get("PK_HOST_MODE", "0"))),
                 "schedule_probe_us_per_call": host_probe,
                 "numa": numa,
             },
@@ -936,6 +968,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the humanoid configs block (N = 1 only)")
     ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--e2e-sets", type=int, default=2, help="pinned host buffer sets the e2e steps rotate over")
+    ap.add_argument("--e2e-streams", type=int, default=2, help="caller streams the e2e steps alternate over (2: consecutive calls pipeline through the library's two staging sets)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

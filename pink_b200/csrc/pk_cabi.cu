@@ -48,25 +48,32 @@ struct PkModel {
   int njoints = 0, free_flyer = 0, nq = 0, nv = 0, nframes = 0;
   void* dev_buf = nullptr;
   pk::DevModel dev{};
-  // staging of the host entry point
+  // staging of the host entry point: two independent sets (device buffers, internal streams,
+  // events) used alternately, so that two calls submitted on two caller streams pipeline
+  // (the upload of one under the kernel / download of the other); a call on the same caller
+  // stream as its predecessor is ordered behind it by the stream itself
   std::mutex mu;
-  float* st_q = nullptr;
-  float* st_t = nullptr;
-  float* st_v = nullptr;
-  int32_t* st_s = nullptr;
-  int64_t st_cap = 0;
-  int st_tstride = 0;
-  cudaStream_t st_streams[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t st_fork = nullptr;
-  cudaEvent_t st_join[3] = {nullptr, nullptr, nullptr};
-  bool st_busy = false;
+  struct Staging {
+    float* st_q = nullptr;
+    float* st_t = nullptr;
+    float* st_v = nullptr;
+    int32_t* st_s = nullptr;
+    int64_t st_cap = 0;
+    int st_tstride = 0;
+    cudaStream_t st_streams[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t st_fork = nullptr;
+    cudaEvent_t st_join[3] = {nullptr, nullptr, nullptr};
+    bool st_busy = false;
+    cudaEvent_t st_in[64] = {};    // H2D of chunk k complete
+    cudaEvent_t st_kern[64] = {};  // kernel of chunk k complete
+  };
+  Staging st[2];
+  int st_next = 0;
   // schedule of the host entry point: -1 = PK_HOST_MODE from the environment (default 0),
   // 0 = staged uploads and downloads, 1 = zero-copy, 2 = staged uploads, results written by the
   // kernels straight into the pinned host buffers (pk_model_set_host_schedule)
   int host_mode = -1;
   static constexpr int kMaxChunks = 64;
-  cudaEvent_t st_in[kMaxChunks] = {};    // H2D of chunk k complete
-  cudaEvent_t st_kern[kMaxChunks] = {};  // kernel of chunk k complete
 };
 
 namespace {
@@ -192,18 +199,20 @@ extern "C" void pk_model_destroy(PkModel* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   if (m->dev_buf) cudaFree(m->dev_buf);
-  if (m->st_q) cudaFree(m->st_q);
-  if (m->st_t) cudaFree(m->st_t);
-  if (m->st_v) cudaFree(m->st_v);
-  if (m->st_s) cudaFree(m->st_s);
-  for (int i = 0; i < 3; ++i) {
-    if (m->st_streams[i]) cudaStreamDestroy(m->st_streams[i]);
-    if (m->st_join[i]) cudaEventDestroy(m->st_join[i]);
-  }
-  if (m->st_fork) cudaEventDestroy(m->st_fork);
-  for (int i = 0; i < PkModel::kMaxChunks; ++i) {
-    if (m->st_in[i]) cudaEventDestroy(m->st_in[i]);
-    if (m->st_kern[i]) cudaEventDestroy(m->st_kern[i]);
+  for (PkModel::Staging& S : m->st) {
+    if (S.st_q) cudaFree(S.st_q);
+    if (S.st_t) cudaFree(S.st_t);
+    if (S.st_v) cudaFree(S.st_v);
+    if (S.st_s) cudaFree(S.st_s);
+    for (int i = 0; i < 3; ++i) {
+      if (S.st_streams[i]) cudaStreamDestroy(S.st_streams[i]);
+      if (S.st_join[i]) cudaEventDestroy(S.st_join[i]);
+    }
+    if (S.st_fork) cudaEventDestroy(S.st_fork);
+    for (int i = 0; i < PkModel::kMaxChunks; ++i) {
+      if (S.st_in[i]) cudaEventDestroy(S.st_in[i]);
+      if (S.st_kern[i]) cudaEventDestroy(S.st_kern[i]);
+    }
   }
   delete m;
 }
@@ -1061,32 +1070,34 @@ static int solve_host_impl(PkModel* m, const PkProblem& pr, const float* q_host,
   }
   std::lock_guard<std::mutex> lock(m->mu);
   PK_CUDA(cudaSetDevice(m->device));
+  PkModel::Staging& S = m->st[m->st_next];
+  m->st_next ^= 1;
   const int ts = P.target_stride;
-  if (B > m->st_cap || ts > m->st_tstride) {
+  if (B > S.st_cap || ts > S.st_tstride) {
     // (re)size staging; happens on the first call or when the batch grows
     PK_CUDA(cudaStreamSynchronize(stream));
     for (int i = 0; i < 3; ++i)
-      if (m->st_streams[i]) PK_CUDA(cudaStreamSynchronize(m->st_streams[i]));
-    if (m->st_q) cudaFree(m->st_q);
-    if (m->st_t) cudaFree(m->st_t);
-    if (m->st_v) cudaFree(m->st_v);
-    if (m->st_s) cudaFree(m->st_s);
-    m->st_q = m->st_t = m->st_v = nullptr;
-    m->st_s = nullptr;
-    const int64_t cap = std::max<int64_t>(B, m->st_cap);
-    const int tcap = std::max(ts, m->st_tstride);
-    PK_CUDA(cudaMalloc(&m->st_q, sizeof(float) * cap * m->nq));
-    PK_CUDA(cudaMalloc(&m->st_t, sizeof(float) * cap * std::max(tcap, 1)));
-    PK_CUDA(cudaMalloc(&m->st_v, sizeof(float) * cap * m->nv));
-    PK_CUDA(cudaMalloc(&m->st_s, sizeof(int32_t) * cap));
-    m->st_cap = cap;
-    m->st_tstride = tcap;
+      if (S.st_streams[i]) PK_CUDA(cudaStreamSynchronize(S.st_streams[i]));
+    if (S.st_q) cudaFree(S.st_q);
+    if (S.st_t) cudaFree(S.st_t);
+    if (S.st_v) cudaFree(S.st_v);
+    if (S.st_s) cudaFree(S.st_s);
+    S.st_q = S.st_t = S.st_v = nullptr;
+    S.st_s = nullptr;
+    const int64_t cap = std::max<int64_t>(B, S.st_cap);
+    const int tcap = std::max(ts, S.st_tstride);
+    PK_CUDA(cudaMalloc(&S.st_q, sizeof(float) * cap * m->nq));
+    PK_CUDA(cudaMalloc(&S.st_t, sizeof(float) * cap * std::max(tcap, 1)));
+    PK_CUDA(cudaMalloc(&S.st_v, sizeof(float) * cap * m->nv));
+    PK_CUDA(cudaMalloc(&S.st_s, sizeof(int32_t) * cap));
+    S.st_cap = cap;
+    S.st_tstride = tcap;
   }
-  if (!m->st_fork) {
-    PK_CUDA(cudaEventCreateWithFlags(&m->st_fork, cudaEventDisableTiming));
+  if (!S.st_fork) {
+    PK_CUDA(cudaEventCreateWithFlags(&S.st_fork, cudaEventDisableTiming));
     for (int i = 0; i < 3; ++i) {
-      PK_CUDA(cudaStreamCreateWithFlags(&m->st_streams[i], cudaStreamNonBlocking));
-      PK_CUDA(cudaEventCreateWithFlags(&m->st_join[i], cudaEventDisableTiming));
+      PK_CUDA(cudaStreamCreateWithFlags(&S.st_streams[i], cudaStreamNonBlocking));
+      PK_CUDA(cudaEventCreateWithFlags(&S.st_join[i], cudaEventDisableTiming));
     }
   }
   static const int64_t chunk_env = env_int("PK_HOST_CHUNK", 32768);
@@ -1101,29 +1112,29 @@ static int solve_host_impl(PkModel* m, const PkProblem& pr, const float* q_host,
   // (4.7 MiB up with 1.8 MiB down: 290 us together, 125 us back to back;
   // scripts/pcie_probe.py), so serialising the directions is the faster schedule.
   static const int duplex = env_int("PK_HOST_DUPLEX", 0);
-  PK_CUDA(cudaEventRecord(m->st_fork, stream));
+  PK_CUDA(cudaEventRecord(S.st_fork, stream));
   if (duplex) {
     const int nstreams = (int)std::min<int64_t>(3, nchunks);
-    for (int i = 0; i < nstreams; ++i) PK_CUDA(cudaStreamWaitEvent(m->st_streams[i], m->st_fork, 0));
+    for (int i = 0; i < nstreams; ++i) PK_CUDA(cudaStreamWaitEvent(S.st_streams[i], S.st_fork, 0));
     for (int64_t k = 0; k < nchunks; ++k) {
-      cudaStream_t s = m->st_streams[k % nstreams];
+      cudaStream_t s = S.st_streams[k % nstreams];
       const int64_t b0 = k * chunk;
       const int64_t nb = std::min(chunk, B - b0);
-      PK_CUDA(cudaMemcpyAsync(m->st_q + b0 * m->nq, q_host + b0 * m->nq, sizeof(float) * nb * m->nq,
+      PK_CUDA(cudaMemcpyAsync(S.st_q + b0 * m->nq, q_host + b0 * m->nq, sizeof(float) * nb * m->nq,
                               cudaMemcpyHostToDevice, s));
       if (ts > 0)
-        PK_CUDA(cudaMemcpyAsync(m->st_t + b0 * ts, targets_host + b0 * ts, sizeof(float) * nb * ts,
+        PK_CUDA(cudaMemcpyAsync(S.st_t + b0 * ts, targets_host + b0 * ts, sizeof(float) * nb * ts,
                                 cudaMemcpyHostToDevice, s));
-      if (solve_device(m, pr, m->st_q + b0 * m->nq, m->st_t + b0 * ts, m->st_v + b0 * m->nv, m->st_s + b0, nb, s))
+      if (solve_device(m, pr, S.st_q + b0 * m->nq, S.st_t + b0 * ts, S.st_v + b0 * m->nv, S.st_s + b0, nb, s))
         return 1;
-      PK_CUDA(cudaMemcpyAsync(v_host + b0 * m->nv, m->st_v + b0 * m->nv, sizeof(float) * nb * m->nv,
+      PK_CUDA(cudaMemcpyAsync(v_host + b0 * m->nv, S.st_v + b0 * m->nv, sizeof(float) * nb * m->nv,
                               cudaMemcpyDeviceToHost, s));
       if (status_host)
-        PK_CUDA(cudaMemcpyAsync(status_host + b0, m->st_s + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+        PK_CUDA(cudaMemcpyAsync(status_host + b0, S.st_s + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < nstreams; ++i) {
-      PK_CUDA(cudaEventRecord(m->st_join[i], m->st_streams[i]));
-      PK_CUDA(cudaStreamWaitEvent(stream, m->st_join[i], 0));
+      PK_CUDA(cudaEventRecord(S.st_join[i], S.st_streams[i]));
+      PK_CUDA(cudaStreamWaitEvent(stream, S.st_join[i], 0));
     }
     return 0;
   }
@@ -1140,71 +1151,71 @@ static int solve_host_impl(PkModel* m, const PkProblem& pr, const float* q_host,
     int32_t* s_dev = static_cast<int32_t*>(dev_ptr(status_host));
     cudaGetLastError();
     if (v_dev && (s_dev || !status_host)) {
-      cudaStream_t s_in = m->st_streams[0], s_k = m->st_streams[1];
-      for (int i = 0; i < 2; ++i) PK_CUDA(cudaStreamWaitEvent(m->st_streams[i], m->st_fork, 0));
-      if (m->st_busy) PK_CUDA(cudaStreamWaitEvent(s_in, m->st_join[2], 0));
-      m->st_busy = true;
+      cudaStream_t s_in = S.st_streams[0], s_k = S.st_streams[1];
+      for (int i = 0; i < 2; ++i) PK_CUDA(cudaStreamWaitEvent(S.st_streams[i], S.st_fork, 0));
+      if (S.st_busy) PK_CUDA(cudaStreamWaitEvent(s_in, S.st_join[2], 0));
+      S.st_busy = true;
       for (int64_t k = 0; k < nchunks; ++k) {
-        if (!m->st_in[k]) {
-          PK_CUDA(cudaEventCreateWithFlags(&m->st_in[k], cudaEventDisableTiming));
-          PK_CUDA(cudaEventCreateWithFlags(&m->st_kern[k], cudaEventDisableTiming));
+        if (!S.st_in[k]) {
+          PK_CUDA(cudaEventCreateWithFlags(&S.st_in[k], cudaEventDisableTiming));
+          PK_CUDA(cudaEventCreateWithFlags(&S.st_kern[k], cudaEventDisableTiming));
         }
         const int64_t b0 = k * chunk;
         const int64_t nb = std::min(chunk, B - b0);
-        PK_CUDA(cudaMemcpyAsync(m->st_q + b0 * m->nq, q_host + b0 * m->nq, sizeof(float) * nb * m->nq,
+        PK_CUDA(cudaMemcpyAsync(S.st_q + b0 * m->nq, q_host + b0 * m->nq, sizeof(float) * nb * m->nq,
                                 cudaMemcpyHostToDevice, s_in));
         if (ts > 0)
-          PK_CUDA(cudaMemcpyAsync(m->st_t + b0 * ts, targets_host + b0 * ts, sizeof(float) * nb * ts,
+          PK_CUDA(cudaMemcpyAsync(S.st_t + b0 * ts, targets_host + b0 * ts, sizeof(float) * nb * ts,
                                   cudaMemcpyHostToDevice, s_in));
-        PK_CUDA(cudaEventRecord(m->st_in[k], s_in));
-        PK_CUDA(cudaStreamWaitEvent(s_k, m->st_in[k], 0));
-        if (solve_device(m, pr, m->st_q + b0 * m->nq, m->st_t + b0 * ts, v_dev + b0 * m->nv, s_dev ? s_dev + b0 : nullptr,
+        PK_CUDA(cudaEventRecord(S.st_in[k], s_in));
+        PK_CUDA(cudaStreamWaitEvent(s_k, S.st_in[k], 0));
+        if (solve_device(m, pr, S.st_q + b0 * m->nq, S.st_t + b0 * ts, v_dev + b0 * m->nv, s_dev ? s_dev + b0 : nullptr,
                          nb, s_k))
           return 1;
       }
-      PK_CUDA(cudaEventRecord(m->st_join[2], s_k));
-      PK_CUDA(cudaStreamWaitEvent(stream, m->st_join[2], 0));
+      PK_CUDA(cudaEventRecord(S.st_join[2], s_k));
+      PK_CUDA(cudaStreamWaitEvent(stream, S.st_join[2], 0));
       return 0;
     }
   }
-  cudaStream_t s_in = m->st_streams[0], s_k = m->st_streams[1], s_out = m->st_streams[2];
-  for (int i = 0; i < 3; ++i) PK_CUDA(cudaStreamWaitEvent(m->st_streams[i], m->st_fork, 0));
+  cudaStream_t s_in = S.st_streams[0], s_k = S.st_streams[1], s_out = S.st_streams[2];
+  for (int i = 0; i < 3; ++i) PK_CUDA(cudaStreamWaitEvent(S.st_streams[i], S.st_fork, 0));
   // calls submitted on different caller streams share the staging buffers: the next upload
   // waits for the previous call's last download (a no-op for calls on one stream)
-  if (m->st_busy) PK_CUDA(cudaStreamWaitEvent(s_in, m->st_join[2], 0));
-  m->st_busy = true;
+  if (S.st_busy) PK_CUDA(cudaStreamWaitEvent(s_in, S.st_join[2], 0));
+  S.st_busy = true;
   for (int64_t k = 0; k < nchunks; ++k) {
-    if (!m->st_in[k]) {
-      PK_CUDA(cudaEventCreateWithFlags(&m->st_in[k], cudaEventDisableTiming));
-      PK_CUDA(cudaEventCreateWithFlags(&m->st_kern[k], cudaEventDisableTiming));
+    if (!S.st_in[k]) {
+      PK_CUDA(cudaEventCreateWithFlags(&S.st_in[k], cudaEventDisableTiming));
+      PK_CUDA(cudaEventCreateWithFlags(&S.st_kern[k], cudaEventDisableTiming));
     }
     const int64_t b0 = k * chunk;
     const int64_t nb = std::min(chunk, B - b0);
-    PK_CUDA(cudaMemcpyAsync(m->st_q + b0 * m->nq, q_host + b0 * m->nq, sizeof(float) * nb * m->nq,
+    PK_CUDA(cudaMemcpyAsync(S.st_q + b0 * m->nq, q_host + b0 * m->nq, sizeof(float) * nb * m->nq,
                             cudaMemcpyHostToDevice, s_in));
     if (ts > 0)
-      PK_CUDA(cudaMemcpyAsync(m->st_t + b0 * ts, targets_host + b0 * ts, sizeof(float) * nb * ts,
+      PK_CUDA(cudaMemcpyAsync(S.st_t + b0 * ts, targets_host + b0 * ts, sizeof(float) * nb * ts,
                               cudaMemcpyHostToDevice, s_in));
-    PK_CUDA(cudaEventRecord(m->st_in[k], s_in));
-    PK_CUDA(cudaStreamWaitEvent(s_k, m->st_in[k], 0));
-    if (solve_device(m, pr, m->st_q + b0 * m->nq, m->st_t + b0 * ts, m->st_v + b0 * m->nv, m->st_s + b0, nb, s_k))
+    PK_CUDA(cudaEventRecord(S.st_in[k], s_in));
+    PK_CUDA(cudaStreamWaitEvent(s_k, S.st_in[k], 0));
+    if (solve_device(m, pr, S.st_q + b0 * m->nq, S.st_t + b0 * ts, S.st_v + b0 * m->nv, S.st_s + b0, nb, s_k))
       return 1;
-    PK_CUDA(cudaEventRecord(m->st_kern[k], s_k));
+    PK_CUDA(cudaEventRecord(S.st_kern[k], s_k));
   }
   // downloads start once the last upload is through (st_in[nchunks-1] on the in-order s_in)
-  PK_CUDA(cudaStreamWaitEvent(s_out, m->st_in[nchunks - 1], 0));
+  PK_CUDA(cudaStreamWaitEvent(s_out, S.st_in[nchunks - 1], 0));
   for (int64_t k = 0; k < nchunks; ++k) {
     const int64_t b0 = k * chunk;
     const int64_t nb = std::min(chunk, B - b0);
-    PK_CUDA(cudaStreamWaitEvent(s_out, m->st_kern[k], 0));
-    PK_CUDA(cudaMemcpyAsync(v_host + b0 * m->nv, m->st_v + b0 * m->nv, sizeof(float) * nb * m->nv,
+    PK_CUDA(cudaStreamWaitEvent(s_out, S.st_kern[k], 0));
+    PK_CUDA(cudaMemcpyAsync(v_host + b0 * m->nv, S.st_v + b0 * m->nv, sizeof(float) * nb * m->nv,
                             cudaMemcpyDeviceToHost, s_out));
     if (status_host)
-      PK_CUDA(cudaMemcpyAsync(status_host + b0, m->st_s + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s_out));
+      PK_CUDA(cudaMemcpyAsync(status_host + b0, S.st_s + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s_out));
   }
   // the caller's stream resumes when everything is back; s_in / s_k are ordered before s_out
-  PK_CUDA(cudaEventRecord(m->st_join[2], s_out));
-  PK_CUDA(cudaStreamWaitEvent(stream, m->st_join[2], 0));
+  PK_CUDA(cudaEventRecord(S.st_join[2], s_out));
+  PK_CUDA(cudaStreamWaitEvent(stream, S.st_join[2], 0));
   return 0;
 }
 

@@ -881,7 +881,11 @@ def run_gpu_arm(args):
     # ---- solve + gather variant (multi-GPU only): v gathered on every rank --------
     gather = None
     if world > 1:
-        gather = gather_variants(torch, dist, device, world, B, NBUF, step, vs, args, timed_regions, ik, qs, ts, ss)
+        try:
+            gather = gather_variants(torch, dist, device, world, B, NBUF, step, vs, args, timed_regions, ik, qs, ts, ss)
+        except Exception as exc:  # the headline line must survive a failure of the optional leg
+            gather = {"error": f"{type(exc).__name__}: {exc}"}
+            print(f"[bench] solve + gather variants failed: {exc}", file=sys.stderr)
 
     # ---- max over ranks -----------------------------------------------------------
     times = torch.tensor([ms, e2e_ms, eager_ms], dtype=torch.float64, device=device)

@@ -194,6 +194,70 @@ class Model:
         self.coms[joint_id] = (m0 * c0 + mass * c1) / (m0 + mass)
         self._version += 1
 
+    # -- flat image (what travels between ranks) -----------------------------
+    def pack(self):
+        """The model constants as three flat arrays: ``(floats, ints, text)`` - float64 numbers
+        (placements, axes, limits, inertias), int64 structure (parents, kinds, sizes) and a UTF-8
+        blob of the names.  :meth:`unpack` rebuilds an equal model; this is the payload of
+        ``parallel.broadcast_model`` (no pickle: only numbers and names cross the wire)."""
+        import json
+
+        kinds = {"revolute": 0, "prismatic": 1}
+        first = 2 if self.free_flyer else 1
+        jf, ji = [], []
+        for j in range(first, len(self.joints)):
+            jt = self.joints[j]
+            P = self.jointPlacements[j]
+            jf += list(P.rotation.reshape(9)) + list(P.translation) + list(self.axes[j])
+            jf += [self._q_min[jt.idx_q], self._q_max[jt.idx_q], self._v_max[jt.idx_v]]
+            ji += [kinds[jt.kind], self.parents[j], int(self._has_cfg_limit[jt.idx_q])]
+        # every frame, in order (frame ids are part of the model's identity)
+        ff, fi, fnames = [], [], []
+        for f in self.frames:
+            ff += list(f.placement.rotation.reshape(9)) + list(f.placement.translation)
+            fi += [f.parentJoint]
+            fnames.append([f.name, f.type])
+        mf = []
+        for j in range(len(self.joints)):
+            mf += [self.masses[j]] + list(self.coms[j])
+        floats = np.array(jf + ff + mf, dtype=np.float64)
+        ints = np.array([int(self.free_flyer), len(self.joints) - first, len(fnames)] + ji + fi, dtype=np.int64)
+        text = json.dumps({"name": self.name, "joints": self.names[first:], "frames": fnames}).encode("utf-8")
+        return floats, ints, text
+
+    @staticmethod
+    def unpack(floats, ints, text) -> "Model":
+        import json
+
+        floats = np.asarray(floats, dtype=np.float64)
+        ints = [int(x) for x in np.asarray(ints).reshape(-1)]
+        meta = json.loads(bytes(text).decode("utf-8"))
+        free_flyer, nj, nf = bool(ints[0]), ints[1], ints[2]
+        m = Model(meta["name"], free_flyer=free_flyer)
+        kinds = ["revolute", "prismatic"]
+        fpos, ipos = 0, 3
+        for k in range(nj):
+            rec = floats[fpos:fpos + 18]
+            fpos += 18
+            kind, parent, has_cfg = ints[ipos:ipos + 3]
+            ipos += 3
+            jid = m.add_joint(meta["joints"][k], parent, SE3(rec[:9].reshape(3, 3), rec[9:12]), rec[12:15], kinds[kind],
+                              lower=rec[15], upper=rec[16], velocity=rec[17])
+            m._has_cfg_limit[m.joints[jid].idx_q] = bool(has_cfg)
+        frames = []
+        for k in range(nf):
+            rec = floats[fpos:fpos + 12]
+            fpos += 12
+            frames.append(Frame(meta["frames"][k][0], ints[ipos], SE3(rec[:9].reshape(3, 3), rec[9:12]), meta["frames"][k][1]))
+            ipos += 1
+        m.frames = frames  # replaces the frames the constructor and add_joint created, same content, original order
+        for j in range(len(m.joints)):
+            m.masses[j] = float(floats[fpos])
+            m.coms[j] = np.array(floats[fpos + 1:fpos + 4])
+            fpos += 4
+        m._version += 1
+        return m
+
     # -- Pinocchio-style queries ------------------------------------------
     @property
     def njoints(self) -> int:

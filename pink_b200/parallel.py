@@ -47,17 +47,48 @@ def shard_bounds(total: int, rank: Optional[int] = None, world: Optional[int] = 
 
 
 def broadcast_model(model, device=None, src: int = 0):
-    """Broadcast the kinematic model (joint tree, placements, limits, frames,
-    inertias: a few KB) from ``src`` to every rank; returns the model."""
+    """Broadcast the kinematic model (joint tree, placements, limits, frames, inertias: a few
+    KB) from ``src`` to every rank; returns the model.  What travels is the model's flat image
+    (:meth:`pink_b200.model.Model.pack`): one float64 array, one int64 array and the UTF-8 names -
+    three collectives after one for the sizes, no pickled objects.  Objects without ``pack``
+    (tests pass strings) fall back to a pickle broadcast."""
     rank, world = _world()
     if world == 1:
         return model
     device = torch.device("cpu") if device is None else torch.device(device)
     if dist.get_backend() == "gloo":
         device = torch.device("cpu")
+    packable = torch.tensor([1 if (rank == src and hasattr(model, "pack")) else 0], dtype=torch.int64, device=device)
+    dist.broadcast(packable, src)
+    if not int(packable.item()):
+        return _broadcast_pickled(model, device, src)
     if rank == src:
-        model.__dict__.pop("_pk_engines", None)  # device handles do not travel
-        payload = pickle.dumps(model)
+        floats, ints, text = model.pack()
+        sizes = torch.tensor([floats.size, ints.size, len(text)], dtype=torch.int64, device=device)
+    else:
+        sizes = torch.zeros(3, dtype=torch.int64, device=device)
+    dist.broadcast(sizes, src)
+    nf, ni, nt = (int(x) for x in sizes.cpu())
+    if rank == src:
+        bufs = [torch.as_tensor(floats, dtype=torch.float64).to(device), torch.as_tensor(ints, dtype=torch.int64).to(device),
+                torch.frombuffer(bytearray(text), dtype=torch.uint8).to(device)]
+    else:
+        bufs = [torch.empty(nf, dtype=torch.float64, device=device), torch.empty(ni, dtype=torch.int64, device=device),
+                torch.empty(nt, dtype=torch.uint8, device=device)]
+    for buf in bufs:
+        dist.broadcast(buf, src)
+    if rank == src:
+        return model
+    from .model import Model
+
+    return Model.unpack(bufs[0].cpu().numpy(), bufs[1].cpu().numpy(), bufs[2].cpu().numpy().tobytes())
+
+
+def _broadcast_pickled(obj, device, src: int):
+    rank, _ = _world()
+    if rank == src:
+        getattr(obj, "__dict__", {}).pop("_pk_engines", None)  # device handles do not travel
+        payload = pickle.dumps(obj)
         size = torch.tensor([len(payload)], dtype=torch.int64, device=device)
     else:
         size = torch.zeros(1, dtype=torch.int64, device=device)
@@ -68,8 +99,8 @@ def broadcast_model(model, device=None, src: int = 0):
         buf = torch.empty(int(size.item()), dtype=torch.uint8, device=device)
     dist.broadcast(buf, src)
     if rank != src:
-        model = pickle.load(io.BytesIO(buf.cpu().numpy().tobytes()))
-    return model
+        obj = pickle.load(io.BytesIO(buf.cpu().numpy().tobytes()))
+    return obj
 
 
 def all_gather_velocities(v_local: torch.Tensor) -> torch.Tensor:

@@ -257,3 +257,23 @@ def test_urdf_loader_rejects_malformed_trees():
         with pytest.raises(NotImplementedError):
             model_from_urdf_string(f'<robot name="r"><link name="a"/><link name="b"/><joint name="j" type="{jtype}">'
                                    '<parent link="a"/><child link="b"/></joint></robot>')
+
+
+@pytest.mark.parametrize("name,floating", [("ur5_description", False), ("draco3_description", True), ("g1_description", True)])
+def test_model_flat_image_round_trip(name, floating):
+    """Model.pack / Model.unpack (the payload of parallel.broadcast_model): numbers and names
+    only, and the rebuilt model is the same model - tables, frame ids, limits, inertias."""
+    from pink_b200.model import Model
+    from pink_b200.robots import load_robot_description
+
+    m = load_robot_description(name, root_joint=JointModelFreeFlyer() if floating else None).model
+    floats, ints, text = m.pack()
+    assert floats.dtype == np.float64 and ints.dtype == np.int64 and isinstance(text, bytes)
+    m2 = Model.unpack(floats, ints, text)
+    a, b = m.table(), m2.table()
+    for key, val in vars(a).items():
+        assert np.array_equal(np.asarray(val), np.asarray(getattr(b, key))), key
+    assert [f.name for f in m.frames] == [f.name for f in m2.frames]
+    assert m.names == m2.names and (m.nq, m.nv) == (m2.nq, m2.nv)
+    np.testing.assert_array_equal(m.hasConfigurationLimit(), m2.hasConfigurationLimit())
+    np.testing.assert_array_equal(m.velocityLimit, m2.velocityLimit)

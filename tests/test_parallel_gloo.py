@@ -26,6 +26,10 @@ def _worker(rank, world, port, out):
         model = parallel.broadcast_model(model)
         assert model.nq == 6 and model.getFrameId("tool0") < len(model.frames)
         table = model.table()
+        # what arrived (flat image, no pickle) is the model rank 0 holds: same tables, same frame ids
+        local = load_robot_description("ur5_description").model.table()
+        for key, val in vars(local).items():
+            assert np.array_equal(np.asarray(val), np.asarray(getattr(table, key))), key
         B = 11
         lo, hi = parallel.shard_bounds(B)
         v_local = torch.arange(lo, hi, dtype=torch.float32).repeat_interleave(6).reshape(hi - lo, 6)

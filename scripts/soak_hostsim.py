@@ -18,8 +18,9 @@ from tests import extras, helpers  # noqa: E402
 from tests.hostsim import HostSim  # noqa: E402
 
 
-def ur5_kkt(B):
-    print("# UR5 chain kernel: status, primal violation, relative stationarity residual of the fp64 KKT system")
+def ur5_kkt(B, path=None):
+    which = "chain kernel (one instance per thread)" if path is None else f"sub-warp kernel, {path - 10} lane(s) per instance"
+    print(f"# UR5 {which}: status, primal violation, relative stationarity residual of the fp64 KKT system")
     total = 0
     for kind in ("reachable", "unreachable"):
         for seed in (101, 102):
@@ -29,7 +30,7 @@ def ur5_kkt(B):
                     sc.dt = dt
                     hs = HostSim(sc.model)
                     prob, targets, _ = sc.problem()
-                    v, st = hs.solve_ik(prob, sc.q32, targets)
+                    v, st = hs.solve_ik(prob, sc.q32, targets, path=path)
                     H, c, G, h = sc.oracle_build()
                     stat, prim, _, _ = oik.kkt_check_batch(H, c, G, h, v.astype(np.float64) * sc.dt)
                     r = stat / (np.abs(c).max(axis=1) + 1e-12)
@@ -83,9 +84,12 @@ def with_extras(B_ur5, B_g1):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0, help="also soak the sub-warp chain kernel body with this many lanes per instance (UR5 part)")
     a = ap.parse_args()
     t0 = time.time()
     ur5_kkt(4000 if a.quick else 40000)
+    if a.lanes:
+        ur5_kkt(4000 if a.quick else 40000, path=10 + a.lanes)
     humanoids(60 if a.quick else 300)
     with_extras(80 if a.quick else 400, 40 if a.quick else 200)
     print(f"# {time.time() - t0:.0f} s")

@@ -49,6 +49,24 @@ def test_ur5_large_batch_kkt_certificate(lanes):
     assert (stat / scale).max() <= 1e-3
 
 
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_ill_conditioned_free_block_reaches_the_minimiser(lanes):
+    """No Levenberg-Marquardt term, dt = 0.1: a handful of 40000 instances reach the rounds with a
+    5-coordinate free block of cond ~1e7 whose refinement steps leave the box.  Those coordinates
+    must become active (polish<activate_clamped>); clamping alone stalled at a relative
+    stationarity of 2e-2 (profiles/r02i_hostsim_soak.txt is the sweep this came from)."""
+    sc = helpers.ur5_scenario(40000, "reachable", seed=102, lm_damping=0.0, posture_cost=1e-3)
+    sc.dt = 0.1
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v, st = hs.solve_ik(prob, sc.q32, targets, path=10 + lanes)
+    assert (st == 0).all()
+    H, c, G, h = sc.oracle_build()
+    stat, prim, _, _ = oik.kkt_check_batch(H, c, G, h, v.astype(np.float64) * sc.dt)
+    assert prim.max() <= 1e-6
+    assert (stat / np.abs(c).max(axis=1)).max() <= 1e-4
+
+
 @pytest.mark.parametrize("lanes", LANES)
 def test_lane_variants_agree_with_the_thread_per_instance_kernel(lanes):
     sc = helpers.ur5_scenario(1500, "reachable")

@@ -632,7 +632,7 @@ struct CoopStep {
     bool more = true;
     for (;;) {
       while (more) more = Solver::round(St);
-      more = Solver::template polish<true>(O, St);
+      more = Solver::polish(O, St);
       if (!more) break;
     }
     PK_GLANES(G, h) {

@@ -61,6 +61,24 @@ def test_ur5_full_batch_kkt_certificate():
     assert (stat / scale).max() <= 1e-3
 
 
+@pytest.mark.parametrize("seed", [104, 107])
+def test_ur5_refinement_that_leaves_the_box_activates_the_bound(seed):
+    """No Levenberg-Marquardt term, dt = 0.1: one instance of each of these 40000 reaches the
+    Cholesky rounds with an ill-conditioned free block whose fp32 refinement leaves the box.
+    Clamping alone stalled at a relative stationarity of 4e-2 (found by the round-2 soak,
+    profiles/r02i_hostsim_soak.txt); a coordinate left on a bound must become active."""
+    sc = helpers.ur5_scenario(40000, "reachable", seed=seed, lm_damping=0.0, posture_cost=1e-3)
+    sc.dt = 0.1
+    hs = HostSim(sc.model)
+    prob, targets, _ = sc.problem()
+    v, st = hs.solve_ik(prob, sc.q32, targets)
+    assert (st == 0).all()
+    H, c, G, h = sc.oracle_build()
+    stat, prim, _, _ = oik.kkt_check_batch(H, c, G, h, v.astype(np.float64) * sc.dt)
+    assert prim.max() <= 1e-6
+    assert (stat / np.abs(c).max(axis=1)).max() <= 1e-4
+
+
 def test_ur5_out_of_limits_and_safety_break():
     sc = helpers.ur5_scenario(200, "reachable", out_of_limits=7)
     hs = HostSim(sc.model)

@@ -790,6 +790,9 @@ struct BoxLSQChol {
           }
         }
         if ((hit_hi | hit_lo) != 0u) {
+#ifdef PK_COUNT_ITERS
+          pk_count_nfree(200, __builtin_popcount(hit_hi | hit_lo));
+#endif
           S.at_hi |= hit_hi;
           S.at_lo |= hit_lo;
           return true;

@@ -21,6 +21,12 @@ It restates, in plain numpy, what the reference computes on the path
                      ``solver="quadprog"`` runs),
 * ``ik.py``          ``build_ik`` / ``solve_ik`` assembly in the reference's order.
 
+``refshim/`` holds stand-ins for the module NAMES ``pinocchio`` / ``qpsolvers`` so that the
+reference's unmodified Pink-layer Python can be executed in the build container to generate
+``tests/golden/ref_pink_layer_*.npz`` (``scripts/make_reference_golden.py``); with those
+fixtures the Pink layer of this oracle (task composition, weighting, stacking, limit /
+barrier / equality rows) is pinned to the reference's code (1e-10).
+
 PARITY UNPINNED at the third-party boundary: the arithmetic of this path lives
 in Pinocchio (pin 3.8.0, ``uv.lock:495``) and quadprog (unpinned), neither of
 which is vendored under ``/root/reference`` nor installable offline, and the

@@ -12,8 +12,85 @@ import numpy as np
 
 from oracle import kinematics as _kin
 from oracle import lie as _lie
-from pink_b200.model import Data, Frame, JointModelFreeFlyer, Model, RobotWrapper  # noqa: F401
+import unittest
+
+from pink_b200 import model as _host
+from pink_b200.model import JointModelFreeFlyer  # noqa: F401
 from pink_b200.model import SE3, load_urdf, model_from_urdf_string  # noqa: F401
+
+# Pinocchio marks "no limit" with the largest double, not with inf (the reference's tests rely on
+# 0 * limit == 0); the models handed to the reference's code are converted accordingly.
+HUGE = float(np.finfo(np.float64).max)
+
+
+def pinocchio_like_limits(model):
+    for name in ("lowerPositionLimit", "upperPositionLimit", "velocityLimit"):
+        v = np.array(getattr(model, name), dtype=np.float64)
+        v[np.isposinf(v)] = HUGE
+        v[np.isneginf(v)] = -HUGE
+        setattr(model, name, v)
+    return model
+
+
+class FrameType:
+    OP_FRAME, JOINT, FIXED_JOINT, BODY, SENSOR = "OP_FRAME", "JOINT", "FIXED_JOINT", "BODY", "SENSOR"
+
+
+def Frame(name, parent_joint, *rest):
+    """``pin.Frame(name, parentJoint, [parentFrame,] placement, type)``."""
+    placement, frame_type = rest[-2], rest[-1]
+    return _host.Frame(name, parent_joint, placement, frame_type)
+
+
+class _Unsupported:
+    """Joint models outside this repo's scope (1-dof joints + free-flyer)."""
+
+
+class JointModelPlanar(_Unsupported):
+    pass
+
+
+class JointModelSpherical(_Unsupported):
+    pass
+
+
+class JointModelRevoluteUnaligned:
+    def __init__(self, *axis):
+        self.axis = np.array(axis if len(axis) == 3 else (1.0, 0.0, 0.0), dtype=np.float64)
+
+
+class Model(_host.Model):
+    """``pin.Model()`` as the reference's tests build it by hand."""
+
+    def addJoint(self, parent, joint_model, placement, name, max_effort=None, max_velocity=None, min_config=None,
+                 max_config=None):
+        if isinstance(joint_model, _Unsupported):
+            raise unittest.SkipTest(f"{type(joint_model).__name__} is outside the scope of this repo")
+        lo = -np.inf if min_config is None else float(np.asarray(min_config).reshape(-1)[0])
+        hi = np.inf if max_config is None else float(np.asarray(max_config).reshape(-1)[0])
+        vel = np.inf if max_velocity is None else float(np.asarray(max_velocity).reshape(-1)[0])
+        jid = self.add_joint(name, parent, placement, joint_model.axis, "revolute", lo, hi, vel)
+        pinocchio_like_limits(self)
+        return jid
+
+
+class Data(_host.Data):
+    """``pin.Data(model)``: ``J`` exists (zeros) before the first ``computeJointJacobians``."""
+
+    def __init__(self, model=None):
+        super().__init__(model)
+        if model is not None:
+            self.J = np.zeros((6, model.nv))
+
+
+class RobotWrapper(_host.RobotWrapper):
+    def __init__(self, model=None, **unused):
+        super().__init__(model)
+        self.data = Data(model)
+
+    @staticmethod
+    def BuildFromURDF(*a, **k):
+        raise unittest.SkipTest("URDF packages with meshes / collision geometry are not available offline")
 
 __version__ = "0.0.0+oracle.refshim"
 
@@ -43,11 +120,13 @@ class GeometryData(GeometryModel):
 
 
 def _table(model):
-    t = model.__dict__.get("_refshim_table")
-    if t is None:
-        t = model.table()
-        model.__dict__["_refshim_table"] = t
-    return t
+    key = (getattr(model, "_version", 0), len(model.frames), len(model.joints),
+           tuple(np.asarray(model.upperPositionLimit).tolist()), tuple(np.asarray(model.velocityLimit).tolist()))
+    cached = model.__dict__.get("_refshim_table")
+    if cached is None or cached[0] != key:
+        cached = (key, model.table())
+        model.__dict__["_refshim_table"] = cached
+    return cached[1]
 
 
 def _frame_index(model, frame_id):
@@ -72,6 +151,18 @@ def forwardKinematics(model, data, q):
         oMi.append(_se3(R[j], p[j]))
     assert len(oMi) == first + t.njoints
     data.oMi = oMi
+    # data.J: joint Jacobians as spatial velocities in the world frame (columns oMi.act(S))
+    J = np.zeros((6, t.nv))
+    rv = 6 if model.free_flyer else 0
+    if model.free_flyer:
+        J[:, :6] = _lie.action(R_root, p_root)
+    for j in range(t.njoints):
+        a = R[j] @ np.asarray(t.axis[j], dtype=np.float64)
+        if int(t.jtype[j]) == 0:
+            J[:3, rv + j], J[3:, rv + j] = np.cross(p[j], a), a
+        else:
+            J[:3, rv + j] = a
+    data.J = J
 
 
 def computeJointJacobians(model, data, q):
@@ -120,10 +211,11 @@ def neutral(model):
     return np.array(_kin.neutral(_table(model)))
 
 
-def centerOfMass(model, data, q, *unused):
+def centerOfMass(model, data, q=None, *unused):
     """``pink/tasks/com_task.py:103-105,123-125``."""
     t = _table(model)
-    return np.array(_kin.center_of_mass(t, _kin.forward_kinematics(t, np.asarray(q, dtype=np.float64))))
+    q = data._q if q is None or isinstance(q, bool) else np.asarray(q, dtype=np.float64)
+    return np.array(_kin.center_of_mass(t, _kin.forward_kinematics(t, q)))
 
 
 def jacobianCenterOfMass(model, data, q, *unused):
@@ -161,4 +253,6 @@ def skew(v):
 
 
 def buildModelFromXML(xml, root_joint=None):
-    return model_from_urdf_string(xml, root_joint=root_joint)
+    if isinstance(root_joint, _Unsupported):
+        raise unittest.SkipTest(f"{type(root_joint).__name__} is outside the scope of this repo")
+    return pinocchio_like_limits(model_from_urdf_string(xml, root_joint=root_joint))

@@ -10,6 +10,7 @@ case it builds the reference's task / limit / barrier OBJECTS, then calls the re
 velocity and every task's ``compute_error`` / ``compute_jacobian``.
 
     python scripts/make_reference_golden.py          # rewrites the fixtures (deterministic)
+    python scripts/make_reference_golden.py --check  # re-runs the reference and compares with the committed files
 
 ``tests/test_reference_pink_layer_golden.py`` compares the oracle's own assembly (and the
 kernels) with these files; nothing under tests/ imports /root/reference or the shims.
@@ -38,6 +39,7 @@ assert pin.__file__.startswith(os.path.join(ROOT, "oracle", "refshim")), pin.__f
 from tests import ref_pink_layer_cases as cases  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+CHECK = "--check" in sys.argv
 
 
 def reference_task(o, i, table, configuration):
@@ -164,6 +166,13 @@ def run_case(name):
         arrays[f"task{k}_e"] = pad(task_e[k])
         arrays[f"task{k}_J"] = pad(task_J[k])
     path = os.path.join(GOLDEN, f"ref_pink_layer_{name}.npz")
+    if CHECK:  # compare with the committed fixture instead of rewriting it
+        old = np.load(path)
+        assert sorted(old.files) == sorted(arrays), (sorted(old.files), sorted(arrays))
+        for k in arrays:
+            np.testing.assert_allclose(np.asarray(arrays[k], dtype=np.float64), old[k], rtol=1e-12, atol=1e-14, err_msg=f"{name}:{k}")
+        print(f"{name}: committed fixture reproduced")
+        return
     np.savez_compressed(path, **arrays)
     print(f"{name}: {case.B} instances, nv {nv}, G rows {arrays['G'].shape[1]}, A rows {arrays['A'].shape[1]}, "
           f"solved {int(arrays['found'].sum())} -> {os.path.relpath(path, ROOT)} ({os.path.getsize(path) // 1024} KB)")

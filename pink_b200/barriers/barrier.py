@@ -42,6 +42,7 @@ class Barrier(abc.ABC):
         self.gain = gain if isinstance(gain, np.ndarray) else np.ones(dim) * gain
         self.safe_displacement = np.zeros(self.dim)
         self.safe_displacement_gain = safe_displacement_gain
+        self.__q_cache = None
 
     # -- description for the C-ABI (PkBarrierDesc) --------------------------------
     @abc.abstractmethod
@@ -70,6 +71,7 @@ class Barrier(abc.ABC):
         ``H = r / |J_h|_F^2 I`` when ``safe_displacement_gain > 1e-6``, ``c = 0``."""
         from ..solve_ik import _barrier_objective
 
+        self.__remember(configuration)
         return _barrier_objective(configuration, self)
 
     def compute_qp_inequalities(self, configuration, dt: float = 1e-3):
@@ -77,7 +79,14 @@ class Barrier(abc.ABC):
         (``barrier.py:206-254``)."""
         from ..solve_ik import _barrier_rows
 
+        self.__remember(configuration)
         return _barrier_rows(configuration, self, raw=False, dt=dt)
+
+    def __remember(self, configuration) -> None:
+        # the reference caches h(q), J(q) per configuration (``barrier.py:110-129``) and its tests
+        # read the cached ``q``; here every evaluation is one kernel launch, only ``q`` is kept
+        q = configuration.q
+        self.__q_cache = q if hasattr(q, "detach") else np.array(q)  # (no device sync for batched tensors)
 
     def __repr__(self) -> str:
         return (

@@ -33,3 +33,9 @@ class BodySphericalBarrier(Barrier):
             "d_min": float(self.d_min),
             "gain": np.asarray(self.gain, dtype=float),
         }
+
+    def compute_jacobian(self, configuration):
+        """``dh/dq`` as the reference returns it for this barrier: the row itself, ``[nv]``
+        (``body_spherical_barrier.py:139-143``: ``dh_dx.T @ dx_dq``); ``[B, 1, nv]`` batched."""
+        J = super().compute_jacobian(configuration)
+        return J if getattr(configuration, "batched", False) else J.reshape(-1)

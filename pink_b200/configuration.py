@@ -94,7 +94,8 @@ class Configuration:
                 raise ValueError(f"q has shape {arr.shape}, expected [..., {self.model.nq}]")
             self.batched = arr.ndim == 2
             arr.setflags(write=False)
-            self._q_host = arr.reshape(-1, self.model.nq)
+            # (a model without joints, nq = 0, is one instance with an empty vector)
+            self._q_host = arr.reshape(-1, self.model.nq) if self.model.nq else arr.reshape(1, 0)
             self._q_dev = None
             self.q = arr
 

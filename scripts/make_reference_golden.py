@@ -30,7 +30,8 @@ import pinocchio as pin  # noqa: E402  (the shim)
 import pink  # noqa: E402  (the reference)
 from pink.barriers import BodySphericalBarrier, PositionBarrier  # noqa: E402
 from pink.limits import AccelerationLimit, ConfigurationLimit, FloatingBaseVelocityLimit, VelocityLimit  # noqa: E402
-from pink.tasks import ComTask, FrameTask, JointCouplingTask, LinearHolonomicTask, LowAccelerationTask  # noqa: E402
+from pink.tasks import ComTask, DampingTask, FrameTask, JointCouplingTask, JointVelocityTask  # noqa: E402
+from pink.tasks import LinearHolonomicTask, LowAccelerationTask  # noqa: E402
 from pink.tasks import PostureTask, RelativeFrameTask  # noqa: E402
 
 assert pink.__file__.startswith(REFERENCE), pink.__file__
@@ -74,10 +75,17 @@ def reference_task(o, i, table, configuration):
         t.set_target(target[i] if target.ndim == 2 else target)
         return t
     if kind == "joint_velocity":
-        # in the scenarios this record restates a LowAccelerationTask: e = -dt v_prev
-        t = LowAccelerationTask(cost=cost)
         target = np.asarray(o["target"], dtype=np.float64)
-        t.Delta_q_prev = -(target[i] if target.ndim == 2 else target)
+        target = target[i] if target.ndim == 2 else target
+        if o.get("ref_class") == "damping":
+            return DampingTask(cost=cost)
+        if o.get("ref_class") == "joint_velocity":
+            t = JointVelocityTask(cost=cost)
+            t.set_target(target / o["ref_dt"], o["ref_dt"])
+            return t
+        # otherwise the record restates a LowAccelerationTask: e = -dt v_prev
+        t = LowAccelerationTask(cost=cost)
+        t.Delta_q_prev = -target
         return t
     if kind == "linear":
         A = np.asarray(o["A"], dtype=np.float64)

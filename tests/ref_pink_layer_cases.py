@@ -10,7 +10,7 @@ import types
 from tests import extras, helpers
 
 NAMES = ["ur5_arm", "ur5_unreachable", "draco3_relative", "g1_com_relative", "ur5_limits_barriers_constraint",
-         "g1_coupling_floating_base_limit"]
+         "g1_coupling_floating_base_limit", "ur5_velocity_tasks"]
 
 
 def _from_scenario(sc):
@@ -29,7 +29,44 @@ def _from_extras(sc):
         constraints=sc.constraints, oconstraints=sc.oconstraints, collision_model=None, safety_break=False)
 
 
+def _ur5_velocity_tasks(B, seed):
+    """FrameTask with anisotropic costs, gain < 1 and LM term + JointVelocityTask + DampingTask;
+    ConfigurationLimit with a non-default gain (``pink/tasks/joint_velocity_task.py``,
+    ``damping_task.py``, ``limits/configuration_limit.py:40``)."""
+    import numpy as np
+    import torch
+
+    from pink_b200 import workloads
+    from pink_b200.limits import ConfigurationLimit, VelocityLimit
+    from pink_b200.tasks import DampingTask, FrameTask, JointVelocityTask
+
+    robot, model, table = helpers.load("ur5_description")
+    rng = np.random.default_rng(seed)
+    q = workloads.sample_configurations(table, B, rng)
+    qt = workloads.perturb_configurations(table, q, rng, sigma=0.25)
+    T = helpers.frame_targets(table, qt, "tool0")
+    ft = FrameTask("tool0", position_cost=[1.0, 0.5, 2.0], orientation_cost=[0.3, 0.0, 0.7], lm_damping=0.1, gain=0.7)
+    ft.set_target(torch.as_tensor(T))
+    T64 = T.astype(np.float64)
+    oft = {"type": "frame", "frame": table.frame_names.index("tool0"), "cost": np.array(ft.cost), "gain": 0.7, "lm_damping": 0.1,
+           "target": (T64[:, :, :3], T64[:, :, 3])}
+    dt = 0.01
+    target_v = (rng.normal(size=(B, 6)) * 0.4).astype(np.float32)
+    jv = JointVelocityTask(cost=0.2)
+    jv.set_target(torch.as_tensor(target_v), dt)
+    ojv = {"type": "joint_velocity", "cost": 0.2, "gain": 1.0, "lm_damping": 0.0, "target": target_v.astype(np.float64) * dt,
+           "ref_class": "joint_velocity", "ref_dt": dt}
+    dm = DampingTask(cost=0.3)
+    odm = {"type": "joint_velocity", "cost": 0.3, "gain": 1.0, "lm_damping": 0.0, "target": np.zeros(6), "ref_class": "damping"}
+    sc = helpers.Scenario("ur5_velocity_tasks", robot, model, table, q, [ft, jv, dm], [oft, ojv, odm], dt, 1e-6, safety_break=False)
+    sc.limits = [ConfigurationLimit(model, config_limit_gain=0.3), VelocityLimit(model)]
+    sc.oracle_limits = [("configuration", 0.3), ("velocity", None)]
+    return sc
+
+
 def build(name):
+    if name == "ur5_velocity_tasks":
+        return _from_scenario(_ur5_velocity_tasks(10, seed=507))
     if name == "ur5_arm":
         return _from_scenario(helpers.ur5_scenario(12, "reachable", seed=501))
     if name == "ur5_unreachable":

@@ -53,4 +53,6 @@ def test_reference_run_reproduces_the_committed_pink_layer_fixtures():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "make_reference_golden.py"), "--check"],
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert res.stdout.count("committed fixture reproduced") == 6
+    from tests import ref_pink_layer_cases
+
+    assert res.stdout.count("committed fixture reproduced") == len(ref_pink_layer_cases.NAMES)

@@ -110,13 +110,78 @@ ARG0 = ArgumentPosition.ARG0
 ARG1 = ArgumentPosition.ARG1
 
 
-class GeometryModel:  # collision geometry is out of reach of this shim (hpp-fcl / coal)
-    def __init__(self, *a, **k):
-        raise NotImplementedError("collision geometry is not part of the reference shim")
+class CollisionPair:
+    def __init__(self, first, second):
+        self.first, self.second = int(first), int(second)
 
 
-class GeometryData(GeometryModel):
+class GeometryObject:
+    def __init__(self, name, parent_joint, radius):
+        self.name, self.parentJoint, self.radius = name, int(parent_joint), float(radius)
+
+
+class GeometryModel:
+    """Spheres only (SURVEY section 2 scopes the self-collision barrier to sphere pairs; the
+    reference evaluates arbitrary meshes through hpp-fcl / coal): built from a
+    ``pink_b200.collision.SphereCollisionModel`` so that the reference's ``SelfCollisionBarrier``
+    (``pink/barriers/self_collision_barrier.py:85-224``) can be executed on the same spheres."""
+
+    def __init__(self, spheres=None):
+        self.geometryObjects, self.collisionPairs, self._sphere_frames = [], [], []
+        if spheres is not None:
+            # radii as the C ABI carries them (fp32): the scenarios' oracle records hold these values
+            self.geometryObjects = [GeometryObject(n, j, float(np.float32(r))) for n, j, r in zip(spheres.names, spheres.parents, spheres.radii)]
+            self.collisionPairs = [CollisionPair(i, j) for i, j in spheres.collisionPairs]
+            self._sphere_frames = [spheres.model.frames[f].name for f in spheres.frames]
+
+
+class DistanceResult:
+    def __init__(self, min_distance, w1, w2):
+        self.min_distance, self._w1, self._w2 = float(min_distance), np.array(w1), np.array(w2)
+
+    def getNearestPoint1(self):
+        return self._w1
+
+    def getNearestPoint2(self):
+        return self._w2
+
+
+class GeometryData:
+    def __init__(self, collision_model):
+        self.collision_model = collision_model
+        self.distanceResults = []
+
+
+def computeCollisions(model, data, collision_model, collision_data, q, stop_at_first):
+    """``pink/configuration.py:147-154``: nothing to do for analytic sphere pairs."""
+
+
+def updateGeometryPlacements(*unused):
     pass
+
+
+def computeDistances(model, data, collision_model, collision_data, q):
+    """``pink/configuration.py:155-161``: signed distance and nearest points of every pair."""
+    from oracle import barriers as _bar
+
+    t = _table(model)
+    fk = _kin.forward_kinematics(t, np.asarray(q, dtype=np.float64))
+    pairs = []
+    for cp in collision_model.collisionPairs:
+        fa = t.frame_names.index(collision_model._sphere_frames[cp.first])
+        fb = t.frame_names.index(collision_model._sphere_frames[cp.second])
+        pairs.append((fa, fb, collision_model.geometryObjects[cp.first].radius, collision_model.geometryObjects[cp.second].radius))
+    collision_data.distanceResults = [DistanceResult(d, w1, w2) for d, w1, w2 in _bar.sphere_pair_distances(t, fk, pairs)]
+
+
+def getJointJacobian(model, data, joint_id, reference_frame):
+    """``pink/barriers/self_collision_barrier.py:205-214`` (LOCAL_WORLD_ALIGNED): the LOCAL
+    Jacobian of the joint's own frame, rotated into world axes."""
+    if reference_frame != ReferenceFrame.LOCAL_WORLD_ALIGNED:
+        raise NotImplementedError("the in-scope reference code asks for LOCAL_WORLD_ALIGNED joint Jacobians only")
+    J = getFrameJacobian(model, data, model.getFrameId(model.joints[joint_id].name), ReferenceFrame.LOCAL)
+    R = data.oMi[joint_id].rotation
+    return np.vstack([R @ J[:3], R @ J[3:]])
 
 
 def _table(model):

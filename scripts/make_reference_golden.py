@@ -28,7 +28,7 @@ sys.path[:0] = [os.path.join(ROOT, "oracle", "refshim"), ROOT, REFERENCE]
 import numpy as np  # noqa: E402
 import pinocchio as pin  # noqa: E402  (the shim)
 import pink  # noqa: E402  (the reference)
-from pink.barriers import BodySphericalBarrier, PositionBarrier  # noqa: E402
+from pink.barriers import BodySphericalBarrier, PositionBarrier, SelfCollisionBarrier  # noqa: E402
 from pink.limits import AccelerationLimit, ConfigurationLimit, FloatingBaseVelocityLimit, VelocityLimit  # noqa: E402
 from pink.tasks import ComTask, DampingTask, FrameTask, JointCouplingTask, JointVelocityTask  # noqa: E402
 from pink.tasks import LinearHolonomicTask, LowAccelerationTask  # noqa: E402
@@ -131,6 +131,9 @@ def reference_barrier(o, table):
         a, b = o["frames"]
         return BodySphericalBarrier((table.frame_names[a], table.frame_names[b]), d_min=o["d_min"], gain=o["gain"],
                                     safe_displacement_gain=o["safe_displacement_gain"])
+    if o["type"] == "self_collision":
+        return SelfCollisionBarrier(n_collision_pairs=o["n_pairs"], gain=o["gain"], safe_displacement_gain=o["safe_displacement_gain"],
+                                    d_min=o["d_min"])
     raise ValueError(o["type"])
 
 
@@ -146,8 +149,9 @@ def run_case(name):
     data = model.createData()
     out = {k: [] for k in ("P", "q", "G", "h", "A", "b", "v", "found")}
     task_e, task_J = {}, {}
+    geometry = pin.GeometryModel(case.collision_model) if case.collision_model is not None else None
     for i in range(case.B):
-        configuration = pink.Configuration(model, data, case.q64[i].copy())
+        configuration = pink.Configuration(model, data, case.q64[i].copy(), collision_model=geometry)
         tasks = [reference_task(o, i, table, configuration) for o in case.otasks]
         limits = reference_limits(case.olimits, i, model, table, case.dt)
         barriers = [reference_barrier(o, table) for o in case.obarriers]

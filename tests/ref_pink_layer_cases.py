@@ -2,15 +2,17 @@
 Pink-layer Python on them, build container only) and ``tests/test_reference_pink_layer_golden.py``
 (which compares the oracle and the kernels with the frozen outputs).  Each case is one of the
 scenarios the parity suites already use (tests/helpers.py, tests/extras.py), in product form
-(pink_b200 objects) and oracle form (plain records), minus what the reference cannot evaluate
-without hpp-fcl / coal: the sphere self-collision barrier."""
+(pink_b200 objects) and oracle form (plain records).  The sphere self-collision barrier is part
+of the last two cases only: there the reference's ``SelfCollisionBarrier`` runs on the same sphere
+pairs through the sphere-only geometry stand-in of oracle/refshim (the real one needs hpp-fcl /
+coal meshes)."""
 
 import types
 
 from tests import extras, helpers
 
 NAMES = ["ur5_arm", "ur5_unreachable", "draco3_relative", "g1_com_relative", "ur5_limits_barriers_constraint",
-         "g1_coupling_floating_base_limit", "ur5_velocity_tasks"]
+         "g1_coupling_floating_base_limit", "ur5_velocity_tasks", "ur5_all_barriers", "g1_config4_self_collision"]
 
 
 def _from_scenario(sc):
@@ -20,13 +22,16 @@ def _from_scenario(sc):
         barriers=[], obarriers=[], constraints=[], oconstraints=[], collision_model=None, safety_break=False)
 
 
-def _from_extras(sc):
-    keep = [k for k, o in enumerate(sc.obarriers) if o["type"] != "self_collision"]
+def _from_extras(sc, self_collision=False):
+    """``self_collision``: keep the sphere self-collision barrier (the reference then runs its
+    ``SelfCollisionBarrier`` on the same spheres through the sphere-only geometry stand-in)."""
+    keep = [k for k, o in enumerate(sc.obarriers) if self_collision or o["type"] != "self_collision"]
     return types.SimpleNamespace(
         model=sc.model, table=sc.table, B=sc.B, q32=sc.q32, q64=sc.q64, dt=sc.dt, damping=sc.damping,
         tasks=sc.tasks, otasks=sc.otasks, limits=sc.limits, olimits=sc.olimits,
         barriers=[sc.barriers[k] for k in keep], obarriers=[sc.obarriers[k] for k in keep],
-        constraints=sc.constraints, oconstraints=sc.oconstraints, collision_model=None, safety_break=False)
+        constraints=sc.constraints, oconstraints=sc.oconstraints,
+        collision_model=sc.collision_model if self_collision else None, safety_break=False)
 
 
 def _ur5_velocity_tasks(B, seed):
@@ -65,6 +70,10 @@ def _ur5_velocity_tasks(B, seed):
 
 
 def build(name):
+    if name == "ur5_all_barriers":
+        return _from_extras(extras.ur5_extras(10, seed=508), self_collision=True)
+    if name == "g1_config4_self_collision":  # BASELINE config 4 with its barrier
+        return _from_extras(extras.g1_extras(6, seed=509), self_collision=True)
     if name == "ur5_velocity_tasks":
         return _from_scenario(_ur5_velocity_tasks(10, seed=507))
     if name == "ur5_arm":

@@ -5,7 +5,7 @@ oracle (humanoids, extras) or the fp64 KKT conditions of each instance's own QP 
 Prints one line per configuration; `profiles/r01l_hostsim_soak.txt` and
 `profiles/r02i_hostsim_soak.txt` are committed runs.
 
-    PYTHONPATH=. python scripts/soak_hostsim.py [--quick] [--lanes 2] [--wide]
+    PYTHONPATH=. python scripts/soak_hostsim.py [--quick] [--lanes 2] [--wide] [--fma]
 """
 import argparse
 import sys
@@ -142,9 +142,24 @@ def with_extras(B_ur5, B_g1):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--fma", action="store_true", help="host build with -ffp-contract=fast -mfma (the GPU contracts a*b+c into FMAs; "
+                    "the default host build does not): a second rounding pattern for the same source")
     ap.add_argument("--wide", action="store_true", help="also: 10 more UR5 seeds and every chain instantiation on random chains")
     ap.add_argument("--lanes", type=int, default=0, help="also soak the sub-warp chain kernel body with this many lanes per instance (UR5 part)")
     a = ap.parse_args()
+    if a.fma:
+        import ctypes
+        import os
+        import subprocess
+
+        import tests.hostsim as hsmod
+
+        so = "/tmp/libpk_hostsim_fma.so"
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-ffp-contract=fast", "-mfma",
+                               "-o", so, os.path.join(os.path.dirname(os.path.abspath(hsmod.__file__)), "hostsim.cpp")])
+        hsmod._lib = ctypes.CDLL(so)
+        hsmod._lib.hs_last_error.restype = ctypes.c_char_p
+        print("# host build with FMA contraction (-ffp-contract=fast -mfma)")
     t0 = time.time()
     ur5_kkt(4000 if a.quick else 40000)
     if a.lanes:

@@ -53,6 +53,8 @@ PRODUCT_EXPECTED_FAILURES.update({
     "test_com_task.py::TestComTask::test_zero_error_when_target_at_body": "asks for |e| < 1e-10; fp32 gives 4e-9",
     "test_low_acceleration_task.py::TestLowAccelerationTask::test_qp_objective": "asks for 1e-10; fp32 gives 2e-9",
     "test_solve_ik.py::TestSolveIK::test_three_tasks_convergence": "asks for |v| < 1e-6 at convergence; fp32 floor 3e-4",
+    "test_solve_ik.py::TestSolveIK::test_com_task_convergence":
+        "asks for |v| < 2e-5 at convergence, at the fp32 floor: passes on the default host build, 1.2e-4 on the FMA-contracting one",
     "test_frame_task.py::TestFrameTask::test_lm_damping_has_effect_under_error":
         "mu = 1e-8 |e|^2 is below the fp32 resolution of H: H stays singular and the test's own unconstrained solve has no answer",
 })

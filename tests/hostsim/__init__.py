@@ -18,7 +18,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # PK_HOSTSIM_SANITIZE=1: AddressSanitizer + UBSan build of the same sources (run the suite
 # with LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0)
 _SANITIZE = os.environ.get("PK_HOSTSIM_SANITIZE", "0") == "1"
-_SO = os.path.join(_HERE, "libpk_hostsim_asan.so" if _SANITIZE else "libpk_hostsim.so")
+# PK_HOSTSIM_FMA=1: a*b + c contracted into FMAs, as nvcc does for the device build (a second
+# rounding pattern of the same source; `PK_HOSTSIM_FMA=1 python -m pytest tests -m "not gpu"`)
+_FMA = os.environ.get("PK_HOSTSIM_FMA", "0") == "1"
+_SO = os.path.join(_HERE, "libpk_hostsim_asan.so" if _SANITIZE else "libpk_hostsim_fma.so" if _FMA else "libpk_hostsim.so")
 _SRC = os.path.join(_HERE, "hostsim.cpp")
 _CSRC = os.path.join(_HERE, "..", "..", "pink_b200", "csrc")
 _lib = None
@@ -33,7 +36,7 @@ def build(force: bool = False) -> str:
         extra = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"] if _SANITIZE else ["-O2"]
         subprocess.check_call(
             ["g++", *extra, "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
-             "-ffp-contract=off", "-o", _SO, _SRC]
+             *(["-ffp-contract=fast", "-mfma"] if _FMA else ["-ffp-contract=off"]), "-o", _SO, _SRC]
         )
     return _SO
 

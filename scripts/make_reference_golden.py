@@ -190,7 +190,25 @@ def run_case(name):
           f"solved {int(arrays['found'].sum())} -> {os.path.relpath(path, ROOT)} ({os.path.getsize(path) // 1024} KB)")
 
 
+def run_example(name):
+    """Closed loop of a reference example on the URDF the reference vendors for it."""
+    fname, steps = cases.EXAMPLE_LOOPS[name]
+    robot = pin.RobotWrapper(pin.pinocchio_like_limits(pin.load_urdf(os.path.join(REFERENCE, "examples", "robots", fname)).model))
+    q, v = cases.run_example_loop(name, pink, robot, steps)
+    path = os.path.join(GOLDEN, f"ref_example_{name}.npz")
+    if CHECK:
+        old = np.load(path)
+        np.testing.assert_allclose(q, old["q"], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(v, old["v"], rtol=1e-12, atol=1e-13)
+        print(f"example {name}: committed fixture reproduced")
+        return
+    np.savez_compressed(path, q=q, v=v)
+    print(f"example {name}: {steps} steps, q from {q[0]} to {q[-1]} -> {os.path.relpath(path, ROOT)}")
+
+
 if __name__ == "__main__":
     print(f"reference: pink {pink.__version__} from {os.path.dirname(pink.__file__)}")
     for name in cases.NAMES:
         run_case(name)
+    for name in cases.EXAMPLE_LOOPS:
+        run_example(name)

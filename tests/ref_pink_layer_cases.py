@@ -89,3 +89,44 @@ def build(name):
     if name == "g1_coupling_floating_base_limit":
         return _from_extras(extras.g1_extras(6, seed=506))
     raise KeyError(name)
+
+
+# ---- closed loops of two reference examples on robots the reference vendors ---------------------
+# The same function runs with the reference's modules (scripts/make_reference_golden.py) and with
+# this package's (tests/test_reference_pink_layer_golden.py): `api` is the module `pink` /
+# `pink_b200`, `robot` a RobotWrapper-like (.model, .data, .q0) of the example's URDF.
+
+EXAMPLE_LOOPS = {"double_pendulum": ("double_pendulum.urdf", 300), "one_dof_configuration_limit": ("simple_pendulum.urdf", 400)}
+
+
+def run_example_loop(name, api, robot, steps):
+    """``examples/double_pendulum.py:36-76`` / ``examples/one_dof_configuration_limit.py:50-84`` without
+    the visualiser and the rate limiter: returns ``(q[steps + 1, nq], v[steps, nv])``."""
+    import numpy as np
+
+    FrameTask, PostureTask = api.tasks.FrameTask, api.tasks.PostureTask
+    dt = 0.01  # RateLimiter(frequency=100.0).period
+    if name == "double_pendulum":
+        tip = FrameTask("link3", position_cost=1.0, orientation_cost=1e-3)
+        posture = PostureTask(cost=1e-2)
+        tasks = [tip, posture]
+        configuration = api.Configuration(robot.model, robot.data, robot.q0)
+        for task in tasks:
+            task.set_target_from_configuration(configuration)
+        tip.transform_target_to_world.translation[2] -= 0.1
+    else:
+        task = FrameTask("tip", position_cost=1.0, orientation_cost=0.61)
+        tasks = [task]
+        goal_configuration = api.Configuration(robot.model, robot.data, np.array([5.5]))
+        task.set_target_from_configuration(goal_configuration)
+        configuration = api.Configuration(robot.model, robot.data, np.array([0.5]))
+    qs, vs, t = [np.array(configuration.q, dtype=np.float64)], [], 0.0
+    for _ in range(steps):
+        if name == "double_pendulum":
+            tasks[0].transform_target_to_world.translation[1] = 0.1 * np.sin(t)
+        velocity = api.solve_ik(configuration, tasks, dt, solver="quadprog")
+        configuration.integrate_inplace(velocity, dt)
+        vs.append(np.array(velocity, dtype=np.float64))
+        qs.append(np.array(configuration.q, dtype=np.float64))
+        t += dt
+    return np.array(qs), np.array(vs)

@@ -124,3 +124,50 @@ def test_cuda_library_matches_the_reference_velocities(name):
     v, st = eng.solve_ik(prob, torch.as_tensor(case.q32, device=eng.device), None if targets is None else targets.to(eng.device))
     torch.cuda.synchronize()
     _check_kernel(case, gold, v.cpu().numpy(), st.cpu().numpy())
+
+
+# ---- closed loops of two reference examples (tests/golden/ref_example_*.npz) ---------------------
+def _example_robot(fname):
+    from pink_b200.model import RobotWrapper, model_from_urdf_string
+    from tests.test_reference_urdf_closed_forms import SKELETONS  # proven identical to the reference's URDF files
+
+    return RobotWrapper(model_from_urdf_string(SKELETONS[fname]))
+
+
+def _check_example(name, q, v):
+    gold = np.load(os.path.join(GOLDEN, f"ref_example_{name}.npz"))
+    # measured on the host build: 1.7e-4 rad over the 300 steps of the double pendulum (whose first
+    # steps leave a singular pose at up to 400 rad/s), 2.4e-7 rad on the pendulum that runs into its limit
+    assert np.abs(q - gold["q"]).max() <= (2e-3 if name == "double_pendulum" else 1e-5), np.abs(q - gold["q"]).max()
+    assert helpers.within_tolerance(v, gold["v"], atol=5e-3, rtol=5e-3).all(), np.abs(v - gold["v"]).max()
+    if name == "one_dof_configuration_limit":  # the example's point: stuck on the configuration limit
+        assert abs(q[-1, 0]) <= 1e-6 and np.abs(v[-50:]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("name", sorted(cases.EXAMPLE_LOOPS))
+def test_example_closed_loop_on_the_host_build_follows_the_reference_trajectory(name):
+    """``examples/double_pendulum.py`` / ``examples/one_dof_configuration_limit.py`` as the reference's own
+    code ran them (fixture) against the same loop through this package's unbatched API."""
+    import pink_b200
+    from tests.host_engine import HostEngine
+    import pink_b200.configuration as cfgmod
+
+    fname, steps = cases.EXAMPLE_LOOPS[name]
+    cache = {}
+    saved = cfgmod.get_engine
+    cfgmod.get_engine = lambda model, device=None: cache.setdefault(id(model), HostEngine(model))
+    try:
+        q, v = cases.run_example_loop(name, pink_b200, _example_robot(fname), steps)
+    finally:
+        cfgmod.get_engine = saved
+    _check_example(name, q, v)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(cases.EXAMPLE_LOOPS))
+def test_example_closed_loop_on_the_gpu_follows_the_reference_trajectory(name):
+    import pink_b200
+
+    fname, steps = cases.EXAMPLE_LOOPS[name]
+    q, v = cases.run_example_loop(name, pink_b200, _example_robot(fname), steps)
+    _check_example(name, q, v)

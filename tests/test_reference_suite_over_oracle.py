@@ -55,4 +55,4 @@ def test_reference_run_reproduces_the_committed_pink_layer_fixtures():
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     from tests import ref_pink_layer_cases
 
-    assert res.stdout.count("committed fixture reproduced") == len(ref_pink_layer_cases.NAMES)
+    assert res.stdout.count("committed fixture reproduced") == len(ref_pink_layer_cases.NAMES) + len(ref_pink_layer_cases.EXAMPLE_LOOPS)

@@ -12,7 +12,7 @@ import types
 from tests import extras, helpers
 
 NAMES = ["ur5_arm", "ur5_unreachable", "draco3_relative", "g1_com_relative", "ur5_limits_barriers_constraint",
-         "g1_coupling_floating_base_limit", "ur5_velocity_tasks", "ur5_all_barriers", "g1_config4_self_collision"]
+         "g1_coupling_floating_base_limit", "ur5_velocity_tasks", "ur5_all_barriers", "g1_config4_self_collision", "ur5_benchmark_workload"]
 
 
 def _from_scenario(sc):
@@ -70,6 +70,8 @@ def _ur5_velocity_tasks(B, seed):
 
 
 def build(name):
+    if name == "ur5_benchmark_workload":  # BASELINE config 2 (bench.py's generator and seed) at B = 64
+        return _from_scenario(helpers.ur5_scenario(64, "reachable"))
     if name == "ur5_all_barriers":
         return _from_extras(extras.ur5_extras(10, seed=508), self_collision=True)
     if name == "g1_config4_self_collision":  # BASELINE config 4 with its barrier

@@ -171,3 +171,17 @@ def test_example_closed_loop_on_the_gpu_follows_the_reference_trajectory(name):
     fname, steps = cases.EXAMPLE_LOOPS[name]
     q, v = cases.run_example_loop(name, pink_b200, _example_robot(fname), steps)
     _check_example(name, q, v)
+
+
+def test_c_port_of_the_cpu_arm_equals_the_reference_on_the_benchmark_workload():
+    """``bench.py --impl reference`` times oracle/c/pink_oracle.c: on the benchmark workload's generator
+    and seed (B = 64) its velocities are those of the reference's own ``pink.solve_ik``."""
+    from oracle import cport
+
+    case, gold = cases.build("ur5_benchmark_workload"), _load("ur5_benchmark_workload")
+    port = cport.CPort(case.table, case.otasks, case.dt, case.damping)
+    R, p = case.otasks[0]["target"]
+    targets = np.concatenate([R, p[:, :, None]], axis=2)[:, None]
+    v, st = port.solve(case.q64, targets, threads=2)
+    assert (st == 0).all() and gold["found"].all()
+    np.testing.assert_allclose(v, gold["v"], rtol=1e-9, atol=1e-10)
